@@ -1,0 +1,128 @@
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED
+reference (/root/reference) on CPU in the build container.
+
+    python tests/golden/make_golden.py
+
+The GPU box has no /root/reference, so the parity tests there read these files.
+Inputs come from oracle/synth.py generators (seeded); small inputs are stored
+next to the outputs, full-size cases store only counts and SHA-256 digests of
+the tie-canonicalised event bytes.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_harness as rh                     # noqa: E402
+from oracle import synth, ldati_oracle as lo            # noqa: E402
+
+
+def digest(rec):
+    c = lo.canonicalize(rec)
+    return hashlib.sha256(np.ascontiguousarray(c).tobytes()).hexdigest()
+
+
+def ldati_cases():
+    out = {}
+    meta = {}
+    y = np.zeros((1, 2, 10, 1, 1), np.float32)
+    # the only known-answer vector in the reference repo:
+    # train/scripts/stage2/vis_stage2.ipynb cells 1-2 (positive polarity, fps 30)
+    y[0, 0, :, 0, 0] = [0, 0, .9179, .0821, .9962, .0038, .5287, 2.8454, 1.6884, .9375]
+    small = {
+        'kat': (y, 30),
+        'rand': (synth.make_voxels('rand', 2, 40, 52, seed=42), 30),
+        'randint': (synth.make_voxels('randint', 1, 24, 30, seed=43), 30),
+        'sparse': (synth.make_voxels('sparse', 2, 40, 52, seed=44), 30),
+        'mixed24': (synth.make_voxels('mixed', 2, 33, 47, seed=45), 24),
+        'mixed120': (synth.make_voxels('mixed', 1, 33, 47, seed=46), 120),
+    }
+    for name, (v, fps) in small.items():
+        ref = rh.run_reference_ldati(v, fps=fps, seed=42, frame_base=5)
+        out[f'{name}_voxel'] = v
+        for i, r in enumerate(ref):
+            out[f'{name}_events_{i}'] = np.ascontiguousarray(lo.canonicalize(r)).view(np.uint8)
+        meta[name] = dict(fps=fps, seed=42, frame_base=5, frames=len(ref), counts=[int(len(r)) for r in ref])
+    # full-size digests (inputs regenerated from the seed)
+    for kind, seed in (('rand', 42), ('sparse', 7), ('randint', 9)):
+        v = synth.make_voxels(kind, 1, 260, 346, seed=seed)
+        ref = rh.run_reference_ldati(v, fps=30, seed=42, frame_base=0)
+        meta[f'full_{kind}'] = dict(fps=30, seed=42, frame_base=0, voxel_seed=seed, kind=kind,
+                                    counts=[int(len(r)) for r in ref], sha256=[digest(r) for r in ref])
+    np.savez_compressed(os.path.join(HERE, 'ldati_golden.npz'), **out)
+    return meta
+
+
+def ef_cases():
+    out = {}
+    meta = {}
+    rng = np.random.default_rng(3)
+    for name, scale, kp, pct, ceil in (('rgb_small', 0.02, True, 98, 10), ('rgb_mid', 1.0, True, 98, 10),
+                                       ('rgb_ceil', 5.0, True, 98, 10), ('gray_mid', 1.0, False, 90, 10),
+                                       ('gray_small', 0.02, False, 98, 10)):
+        v = (scale * rng.random((4, 2, 10, 30, 38)) ** 2).astype(np.float32)
+        fr = rh.run_reference_event_frames(v, 30, ceil, pct, kp)
+        out[f'{name}_voxel'] = v
+        out[f'{name}_frames'] = fr
+        meta[name] = dict(keep_polarity=kp, percentile=pct, ceil=ceil)
+    np.savez_compressed(os.path.join(HERE, 'ef_golden.npz'), **out)
+    return meta
+
+
+def unet_cases():
+    out = {}
+    meta = {}
+    V2ce3d = rh.V2ce3d()
+    for name, seed, init, shape in (('refinit', 0, 'reference', (1, 4, 2, 36, 44)),
+                                    ('lively', 1, 'lively', (2, 16, 2, 20, 28))):
+        model = V2ce3d().eval()
+        sd = synth.make_state_dict(seed, init)
+        assert set(model.state_dict().keys()) == set(sd.keys()), 'state-dict key layout drifted'
+        model.load_state_dict(sd)
+        g = torch.Generator().manual_seed(100 + seed)
+        x = torch.randn(*shape, generator=g)
+        with torch.no_grad():
+            y0 = model(x).numpy()
+            y1 = model(x).numpy()          # second call: spectral-norm state has advanced
+        out[f'{name}_x'] = x.numpy()
+        out[f'{name}_y0'] = y0
+        out[f'{name}_y1'] = y1
+        meta[name] = dict(seed=seed, init=init, shape=list(shape))
+    np.savez_compressed(os.path.join(HERE, 'unet_golden.npz'), **out)
+    return meta
+
+
+def pipeline_cases():
+    """video_to_voxels through the reference driver with a FakeVideoReader."""
+    out = {}
+    meta = {}
+    main = rh.main_module()
+    V2ce3d = rh.V2ce3d()
+    for name, n_frames, H, W, infer, width, bs in (('center', 20, 28, 40, 'center', 36, 2),
+                                                   ('pano', 18, 28, 52, 'pano', 20, 1)):
+        model = V2ce3d().eval()
+        model.load_state_dict(synth.make_state_dict(2, 'lively'))
+        frames = synth.make_video(n_frames, H, W, seed=5)
+        with rh.cpu_cuda_shims():
+            vox = main.video_to_voxels(model, vidcap=rh.FakeVideoReader(frames), infer_type=infer,
+                                       seq_len=16, width=width, height=H, batch_size=bs)
+        out[f'{name}_voxel'] = vox.astype(np.float32)
+        meta[name] = dict(n_frames=n_frames, H=H, W=W, infer_type=infer, width=width, batch_size=bs,
+                          video_seed=5, sd_seed=2, init='lively')
+    np.savez_compressed(os.path.join(HERE, 'pipeline_golden.npz'), **out)
+    return meta
+
+
+if __name__ == '__main__':
+    import cv2
+    meta = dict(versions=dict(torch=torch.__version__, numpy=np.__version__, cv2=cv2.__version__),
+                ldati=ldati_cases(), ef=ef_cases(), unet=unet_cases(), pipeline=pipeline_cases())
+    with open(os.path.join(HERE, 'golden_meta.json'), 'w') as f:
+        json.dump(meta, f, indent=1)
+    print(json.dumps(meta, indent=1)[:3000])
