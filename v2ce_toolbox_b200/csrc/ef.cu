@@ -1,0 +1,238 @@
+// Event-frame preview on sm_100a: per-pair accumulation of the 10 voxel bins, exact
+// percentile by radix select over float bit patterns, float64 normalisation to BGR uint8.
+// Replaces /root/reference/v2ce.py:241-280 (write_event_frame_video) up to the cv2 encoder.
+//
+// All three kernels are HBM-bound streaming passes (8,906,040 B per 346x260 pair).
+#include "common.cuh"
+
+namespace v2ce {
+namespace ef {
+
+constexpr int kThreads = 256;
+
+// E1 (v2ce.py:255 / 259): s = v0; s += v1; ... sequential fp32 adds, the order numpy uses
+// when it reduces a strided axis.  Gray mode reduces (polarity, bin) polarity-major.
+template <int V>
+__global__ void __launch_bounds__(kThreads) accumulate_kernel(const float* __restrict__ vox, int HW, int keep_polarity,
+                                                               float* __restrict__ sums) {
+  const int plane = blockIdx.y;                    // keep: n*2+p ; gray: n
+  const int pix = (blockIdx.x * kThreads + threadIdx.x) * V;
+  if (pix >= HW) return;
+  const int nterms = keep_polarity ? 10 : 20;
+  const float* src = vox + (size_t)plane * (keep_polarity ? 10 : 20) * HW + pix;
+  if (V == 4) {
+    float4 s = __ldg(reinterpret_cast<const float4*>(src));
+    for (int c = 1; c < nterms; ++c) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * HW));
+      s.x = __fadd_rn(s.x, t.x); s.y = __fadd_rn(s.y, t.y); s.z = __fadd_rn(s.z, t.z); s.w = __fadd_rn(s.w, t.w);
+    }
+    *reinterpret_cast<float4*>(sums + (size_t)plane * HW + pix) = s;
+  } else {
+    float s = __ldg(src);
+    for (int c = 1; c < nterms; ++c) s = __fadd_rn(s, __ldg(src + (size_t)c * HW));
+    sums[(size_t)plane * HW + pix] = s;
+  }
+}
+
+// E2 (v2ce.py:262-264): radix select.  Positive floats are order-isomorphic to their bit
+// patterns, so the k-th smallest positive sum is found with four 8-bit histogram passes.
+struct SelectState {
+  unsigned long long hist[2][256];
+  unsigned long long npos;
+  unsigned long long remaining[2];   // rank still to skip inside the current prefix bucket
+  unsigned int prefix[2];
+  unsigned int pad[2];
+};
+
+__global__ void select_init_kernel(SelectState* st) {
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
+  if (threadIdx.x == 0) {
+    st->npos = 0; st->remaining[0] = st->remaining[1] = 0; st->prefix[0] = st->prefix[1] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) select_hist_kernel(const float* __restrict__ v, long long n, int pass,
+                                                                SelectState* st) {
+  __shared__ unsigned int h[2][256];
+  for (int i = threadIdx.x; i < 512; i += kThreads) (&h[0][0])[i] = 0u;
+  __syncthreads();
+  const int shift = 24 - 8 * pass;
+  const unsigned int p0 = st->prefix[0], p1 = st->prefix[1];
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const float x = __ldg(v + i);
+    if (x > 0.f) {
+      const unsigned int b = __float_as_uint(x);
+      const unsigned int d = (b >> shift) & 255u;
+      if (pass == 0) {
+        atomicAdd(&h[0][d], 1u);
+      } else {
+        const unsigned int hi = b >> (shift + 8);
+        if (hi == p0) atomicAdd(&h[0][d], 1u);
+        if (hi == p1) atomicAdd(&h[1][d], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += kThreads) {
+    const unsigned int c = (&h[0][0])[i];
+    if (c) atomicAdd(&st->hist[0][0] + i, (unsigned long long)c);
+  }
+}
+
+// one thread: pick the bucket of both ranks, extend the prefixes, clear the histograms
+__global__ void select_step_kernel(SelectState* st, int pass, double percentile, int multiplicity,
+                                   long long* __restrict__ result) {
+  if (threadIdx.x != 0) return;
+  if (pass == 0) {
+    unsigned long long n = 0;
+    for (int d = 0; d < 256; ++d) { n += st->hist[0][d]; st->hist[1][d] = st->hist[0][d]; }
+    st->npos = n;
+    result[0] = (long long)n;
+    if (n == 0) { result[1] = 0; result[2] = 0; result[3] = 0; return; }
+    // numpy 'linear' method: virtual index (n-1)*q with q = percentile/100 (float64)
+    const double q = __ddiv_rn(percentile, 100.0);
+    const double nn = (double)(n * (unsigned long long)multiplicity);
+    const double vi = __dmul_rn(nn - 1.0, q);
+    long long lo = (long long)floor(vi);
+    long long last = (long long)(n * (unsigned long long)multiplicity) - 1;
+    if (lo < 0) lo = 0;
+    if (lo > last) lo = last;
+    long long hi = lo + 1 > last ? last : lo + 1;
+    st->remaining[0] = (unsigned long long)(lo / multiplicity);
+    st->remaining[1] = (unsigned long long)(hi / multiplicity);
+    result[1] = lo;
+  }
+  if (st->npos == 0) return;
+  for (int r = 0; r < 2; ++r) {
+    unsigned long long cum = 0;
+    int d = 0;
+    for (; d < 255; ++d) {
+      const unsigned long long c = st->hist[r][d];
+      if (cum + c > st->remaining[r]) break;
+      cum += c;
+    }
+    st->remaining[r] -= cum;
+    st->prefix[r] = (st->prefix[r] << 8) | (unsigned int)d;
+  }
+  for (int i = 0; i < 512; ++i) (&st->hist[0][0])[i] = 0ull;
+  if (pass == 3) {
+    result[2] = (long long)st->prefix[0];
+    result[3] = (long long)st->prefix[1];
+  }
+}
+
+// E3 (v2ce.py:267-277): clip(s,0,ub)/ub in float64, *255, truncate to uint8; channels
+// (R,G,B) = (pos, neg, 0) then RGB->BGR, i.e. stored order B=0, G=neg, R=pos.
+__device__ __forceinline__ unsigned int norm_u8(float s, double ub) {
+  double x = (double)s;
+  x = x < 0.0 ? 0.0 : x;
+  x = x > ub ? ub : x;
+  x = __dmul_rn(__ddiv_rn(x, ub), 255.0);
+  return (unsigned int)(unsigned char)x;
+}
+
+template <int V>
+__global__ void __launch_bounds__(kThreads) normalize_kernel(const float* __restrict__ sums, int HW, int keep_polarity,
+                                                              double ub, uint8_t* __restrict__ frames) {
+  const int n = blockIdx.y;
+  const int pix = (blockIdx.x * kThreads + threadIdx.x) * V;
+  if (pix >= HW) return;
+  unsigned int bytes[V * 3];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    if (keep_polarity) {
+      const float pos = __ldg(sums + ((size_t)n * 2 + 0) * HW + pix + v);
+      const float neg = __ldg(sums + ((size_t)n * 2 + 1) * HW + pix + v);
+      bytes[v * 3 + 0] = 0u;
+      bytes[v * 3 + 1] = norm_u8(neg, ub);
+      bytes[v * 3 + 2] = norm_u8(pos, ub);
+    } else {
+      const unsigned int g = norm_u8(__ldg(sums + (size_t)n * HW + pix + v), ub);
+      bytes[v * 3 + 0] = g; bytes[v * 3 + 1] = g; bytes[v * 3 + 2] = g;
+    }
+  }
+  uint8_t* dst = frames + ((size_t)n * HW + pix) * 3;
+  if (V == 4) {
+    uint32_t w[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      w[i] = bytes[i * 4] | (bytes[i * 4 + 1] << 8) | (bytes[i * 4 + 2] << 16) | (bytes[i * 4 + 3] << 24);
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+    d32[0] = w[0]; d32[1] = w[1]; d32[2] = w[2];
+  } else {
+#pragma unroll
+    for (int i = 0; i < V * 3; ++i) dst[i] = (uint8_t)bytes[i];
+  }
+}
+
+}  // namespace ef
+}  // namespace v2ce
+
+using namespace v2ce;
+using namespace v2ce::ef;
+
+extern "C" int v2ce_ef_accumulate(const float* voxels_dev, int32_t n_pairs, int32_t height, int32_t width,
+                                  int32_t keep_polarity, float* sums_dev, void* stream) {
+  V2CE_REQUIRE(voxels_dev && sums_dev, "NULL device pointer");
+  V2CE_REQUIRE(n_pairs > 0 && height > 0 && width > 0, "bad geometry");
+  const int HW = height * width;
+  const int planes = keep_polarity ? n_pairs * 2 : n_pairs;
+  V2CE_REQUIRE(planes <= 65535, "too many pairs per call (max %d)", keep_polarity ? 32767 : 65535);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (HW % 4 == 0) {
+    dim3 grid((HW / 4 + kThreads - 1) / kThreads, planes);
+    accumulate_kernel<4><<<grid, kThreads, 0, s>>>(voxels_dev, HW, keep_polarity, sums_dev);
+  } else {
+    dim3 grid((HW + kThreads - 1) / kThreads, planes);
+    accumulate_kernel<1><<<grid, kThreads, 0, s>>>(voxels_dev, HW, keep_polarity, sums_dev);
+  }
+  V2CE_LAUNCH_CHECK("ef::accumulate_kernel");
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_ef_select_workspace_bytes(size_t* bytes) {
+  V2CE_REQUIRE(bytes != nullptr, "bytes is NULL");
+  *bytes = align_up(sizeof(SelectState), 256);
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_ef_select(const float* sums_dev, int64_t n_values, double percentile, int32_t multiplicity,
+                              void* ws_dev, size_t ws_bytes, int64_t* result_dev, void* stream) {
+  V2CE_REQUIRE(sums_dev && ws_dev && result_dev, "NULL device pointer");
+  V2CE_REQUIRE(n_values > 0 && multiplicity >= 1, "bad arguments");
+  V2CE_REQUIRE(percentile >= 0.0 && percentile <= 100.0, "percentile must be in [0,100]");
+  if (ws_bytes < sizeof(SelectState))
+    return set_error(V2CE_ERR_WORKSPACE, "select workspace too small: need %zu, got %zu", sizeof(SelectState), ws_bytes);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SelectState* st = static_cast<SelectState*>(ws_dev);
+  select_init_kernel<<<1, 256, 0, s>>>(st);
+  V2CE_LAUNCH_CHECK("ef::select_init_kernel");
+  long long want = (n_values + kThreads * 8 - 1) / (kThreads * 8);
+  const int grid = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+  for (int pass = 0; pass < 4; ++pass) {
+    select_hist_kernel<<<grid, kThreads, 0, s>>>(sums_dev, n_values, pass, st);
+    V2CE_LAUNCH_CHECK("ef::select_hist_kernel");
+    select_step_kernel<<<1, 32, 0, s>>>(st, pass, percentile, multiplicity, reinterpret_cast<long long*>(result_dev));
+    V2CE_LAUNCH_CHECK("ef::select_step_kernel");
+  }
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_ef_normalize(const float* sums_dev, int32_t n_pairs, int32_t height, int32_t width,
+                                 int32_t keep_polarity, double upper_bound, uint8_t* frames_dev, void* stream) {
+  V2CE_REQUIRE(sums_dev && frames_dev, "NULL device pointer");
+  V2CE_REQUIRE(n_pairs > 0 && n_pairs <= 65535 && height > 0 && width > 0, "bad geometry");
+  V2CE_REQUIRE(upper_bound > 0.0, "upper_bound must be positive");
+  const int HW = height * width;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (HW % 4 == 0) {
+    dim3 grid((HW / 4 + kThreads - 1) / kThreads, n_pairs);
+    normalize_kernel<4><<<grid, kThreads, 0, s>>>(sums_dev, HW, keep_polarity, upper_bound, frames_dev);
+  } else {
+    dim3 grid((HW + kThreads - 1) / kThreads, n_pairs);
+    normalize_kernel<1><<<grid, kThreads, 0, s>>>(sums_dev, HW, keep_polarity, upper_bound, frames_dev);
+  }
+  V2CE_LAUNCH_CHECK("ef::normalize_kernel");
+  return V2CE_OK;
+}

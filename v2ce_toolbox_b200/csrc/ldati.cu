@@ -1,0 +1,845 @@
+// LDATI (stage 2) on sm_100a: event-count relocation, slot assignment in the reference's
+// generation order, inverse-CDF timestamps, stable per-(frame,bin) radix sort and 13-byte
+// record packing.  Replaces /root/reference/scripts/LDATI.py:13-51,80-106,126-310.
+//
+// Data layout in HBM
+//   voxels   float32 (F,2,10,H,W): planes of H*W pixels; a thread owns V=4 consecutive
+//            pixels (float4 loads, fully coalesced) of one polarity plane and walks the
+//            10 bins (plane stride H*W).
+//   elements one 32-bit (or 64-bit when H*W or the key range needs it) word per event:
+//            [ sort key = ts - bin_base + BIAS | polarity | pixel ].  Everything a record
+//            needs travels in the word, so the sort moves 4 bytes per event per pass.
+//   records  13-byte packed AoS, written through shared memory with 16-byte stores.
+//
+// Order contract: per frame, bins ascending; inside a bin the events are
+// sorted by (timestamp, g), g = position in the reference's pre-sort concatenation
+// [neg singles][neg multis][pos singles][pos multis] (row-major pixels, j ascending).
+// The emit kernel writes every event straight to slot g (prefix sums from the count
+// pass), so a STABLE sort on the timestamp key alone yields the canonical order.
+//
+// Arithmetic contract: one IEEE rounding per reference torch
+// op -- all float math below goes through __f*_rn / __d*_rn so nvcc cannot contract it.
+#include "common.cuh"
+
+#include <limits.h>
+
+namespace v2ce {
+namespace ldati {
+
+constexpr int kBins = 9;          // event bins per frame pair (10 voxel bins -> 9)
+constexpr int kQ = 18;            // scanned quantities per plane: singles[9], multis[9]
+constexpr int kThreads = 256;
+constexpr int kKeyBias = 8;       // slack below the bin origin (ts may undershoot it by 1 us)
+constexpr int kTile = 2048;       // sort tile: 256 threads x 8 keys
+constexpr int kKeysPerThread = kTile / kThreads;
+
+struct Geometry {
+  int H, W, HW, F;
+  int V;         // pixels per thread (4 when HW % 4 == 0, else 1)
+  int NB;        // blocks per plane
+  int pix_bits;  // bits of the pixel field
+  int key_bits;  // bits of the sort key
+  int wide;      // 1: 64-bit elements
+};
+
+static Geometry make_geometry(const v2ce_ldati_params* p) {
+  Geometry g;
+  g.H = p->height;
+  g.W = p->width;
+  g.HW = p->height * p->width;
+  g.F = p->n_frames;
+  g.V = (g.HW % 4 == 0) ? 4 : 1;
+  g.NB = (g.HW + kThreads * g.V - 1) / (kThreads * g.V);
+  g.pix_bits = 1;
+  while ((1LL << g.pix_bits) < g.HW) ++g.pix_bits;
+  g.key_bits = 1;
+  while ((1LL << g.key_bits) < (long long)p->key_span + 1) ++g.key_bits;
+  g.wide = (g.pix_bits + 1 + g.key_bits > 32) ? 1 : 0;
+  return g;
+}
+
+// count workspace layout
+struct CountWs {
+  int32_t* partial;     // [F][2][NB][18]
+  int32_t* block_base;  // [F][2][NB][18]
+  int32_t* group_base;  // [F][9][4]
+  int64_t* seg_start;   // [F*9+1]
+  size_t bytes;
+};
+
+static CountWs carve_count_ws(void* ws, const Geometry& g) {
+  Arena a(ws, (size_t)-1);
+  CountWs w;
+  size_t n = (size_t)g.F * 2 * g.NB * kQ;
+  w.partial = a.take<int32_t>(n);
+  w.block_base = a.take<int32_t>(n);
+  w.group_base = a.take<int32_t>((size_t)g.F * kBins * 4);
+  w.seg_start = a.take<int64_t>((size_t)g.F * kBins + 1);
+  w.bytes = align_up(a.off, 256);
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+struct DevParams {
+  int H, W, HW, F, NB;
+  int true_div;
+  long long frame_base;
+  unsigned long long seed;
+  double fps64, nbins64, r_fps64, r_nbins64;
+  float fps32, nbins32, r_fps32, r_nbins32;
+  float vs32, inv_vs32, vs2_32, r_vs2_32, six32, r6_32, eps6, eps8;
+  float binstart[kBins];
+  long long bin_base[kBins];
+  int pix_bits, key_bits;
+  int draws_m;
+  int add_frame_offset;
+  long long nan_ts;   // what float NaN -> int64 yields in the flavour: 0 on CUDA (cvt.rzi), INT64_MIN on x86
+};
+
+static DevParams make_dev_params(const v2ce_ldati_params* p, const Geometry& g) {
+  DevParams d;
+  d.H = g.H; d.W = g.W; d.HW = g.HW; d.F = g.F; d.NB = g.NB;
+  d.true_div = p->true_div;
+  d.frame_base = p->frame_base;
+  d.seed = p->seed;
+  d.fps64 = p->fps64; d.nbins64 = p->nbins64; d.r_fps64 = p->r_fps64; d.r_nbins64 = p->r_nbins64;
+  d.fps32 = p->fps32; d.nbins32 = p->nbins32; d.r_fps32 = p->r_fps32; d.r_nbins32 = p->r_nbins32;
+  d.vs32 = p->vs32; d.inv_vs32 = p->inv_vs32; d.vs2_32 = p->vs2_32; d.r_vs2_32 = p->r_vs2_32;
+  d.six32 = p->six32; d.r6_32 = p->r6_32; d.eps6 = p->eps6; d.eps8 = p->eps8;
+  for (int c = 0; c < kBins; ++c) { d.binstart[c] = p->binstart_t0_32[c]; d.bin_base[c] = p->bin_base_us[c]; }
+  d.pix_bits = g.pix_bits; d.key_bits = g.key_bits;
+  d.draws_m = 0;
+  d.add_frame_offset = p->add_frame_offset;
+  d.nan_ts = p->true_div ? LLONG_MIN : 0;
+  return d;
+}
+
+// y_relocate (LDATI.py:96-106) for one pixel: n[9] and the carried debts tend[9].
+__device__ __forceinline__ void relocate_pixel(const float (&y)[10], float eps6, int (&n)[kBins], float (&tend)[kBins]) {
+  float debt = 0.f;
+#pragma unroll
+  for (int c = 0; c < kBins; ++c) {
+    float x = __fsub_rn(y[c], debt);
+    float nc = ceilf(__fsub_rn(x, eps6));
+    debt = __fsub_rn(nc, x);
+    n[c] = __float2int_rz(nc);
+    tend[c] = debt;
+  }
+  n[kBins - 1] += __float2int_rz(__fsub_rn(y[9], debt));   // `.int()` truncation, LDATI.py:106
+}
+
+template <int V>
+__device__ __forceinline__ void load_pixels(const float* __restrict__ plane0, int HW, int pix, float (&y)[V][10]) {
+  if (V == 4) {
+#pragma unroll
+    for (int c = 0; c < 10; ++c) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(plane0 + (size_t)c * HW + pix));
+      y[0][c] = t.x; y[1 % V][c] = t.y; y[2 % V][c] = t.z; y[3 % V][c] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 10; ++c) y[0][c] = __ldg(plane0 + (size_t)c * HW + pix);
+  }
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += t;
+  }
+  return v;
+}
+
+// Philox4x32-10, counter (lo32(idx), hi32(idx), j>>2, 0), key = seed; see oracle/philox.py.
+__device__ __forceinline__ float philox_uniform(unsigned long long idx, unsigned j, unsigned long long seed) {
+  unsigned c0 = (unsigned)idx, c1 = (unsigned)(idx >> 32), c2 = j >> 2, c3 = 0u;
+  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  unsigned sel = j & 3u;
+  unsigned w = sel == 0 ? c0 : sel == 1 ? c1 : sel == 2 ? c2 : c3;
+  return __fmul_rn((float)(w >> 8), 5.9604644775390625e-08f);   // 2^-24
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: count pass.  grid (NB, 2, F), 256 threads, V pixels per thread.
+// ---------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(kThreads) count_kernel(const float* __restrict__ vox, DevParams P,
+                                                          int32_t* __restrict__ partial) {
+  const int blk = blockIdx.x, p = blockIdx.y, f = blockIdx.z;
+  const int pix = (blk * kThreads + threadIdx.x) * V;
+  int tot[kQ];
+#pragma unroll
+  for (int q = 0; q < kQ; ++q) tot[q] = 0;
+  if (pix < P.HW) {
+    float y[V][10];
+    load_pixels<V>(vox + ((size_t)(f * 2 + p) * 10) * P.HW, P.HW, pix, y);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      int n[kBins];
+      float tend[kBins];
+      relocate_pixel(y[v], P.eps6, n, tend);
+#pragma unroll
+      for (int c = 0; c < kBins; ++c) {
+        tot[c] += (n[c] == 1);
+        tot[kBins + c] += (n[c] >= 2) ? n[c] : 0;
+      }
+    }
+  }
+  __shared__ int red[kThreads / 32][kQ];
+#pragma unroll
+  for (int q = 0; q < kQ; ++q) {
+    int v = tot[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kQ) {
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += red[w][threadIdx.x];
+    partial[(((size_t)f * 2 + p) * P.NB + blk) * kQ + threadIdx.x] = s;
+  }
+}
+
+// K4a: per frame, exclusive scan of the block partials over the plane; group bases; segment counts.
+__global__ void scan_planes_kernel(const int32_t* __restrict__ partial, int32_t* __restrict__ block_base,
+                                   int32_t* __restrict__ group_base, int64_t* __restrict__ seg_counts, int NB) {
+  const int f = blockIdx.x;
+  __shared__ int tot[2][kQ];
+  const int t = threadIdx.x;
+  if (t < 2 * kQ) {
+    const int p = t / kQ, q = t % kQ;
+    const size_t base = ((size_t)f * 2 + p) * NB * kQ + q;
+    int run = 0;
+    for (int b = 0; b < NB; ++b) {
+      block_base[base + (size_t)b * kQ] = run;
+      run += partial[base + (size_t)b * kQ];
+    }
+    tot[p][q] = run;
+  }
+  __syncthreads();
+  if (t < kBins) {
+    const int c = t;
+    const int s_neg = tot[1][c], m_neg = tot[1][kBins + c], s_pos = tot[0][c], m_pos = tot[0][kBins + c];
+    int32_t* gb = group_base + ((size_t)f * kBins + c) * 4;
+    gb[0] = 0;                       // negative singles   (p-index 1 -> polarity 0, LDATI.py:290)
+    gb[1] = s_neg;                   // negative multis
+    gb[2] = s_neg + m_neg;           // positive singles
+    gb[3] = s_neg + m_neg + s_pos;   // positive multis
+    seg_counts[(size_t)f * kBins + c] = (int64_t)s_neg + m_neg + s_pos + m_pos;
+  }
+}
+
+// K4b: exclusive scan of n int64 values into out[0..n] (out[n] = total); one block.
+__global__ void scan_i64_kernel(const int64_t* __restrict__ in, int64_t* __restrict__ out, int n) {
+  __shared__ long long wsum[32];
+  __shared__ long long carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    long long v = (i < n) ? in[i] : 0;
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      long long w = (threadIdx.x < (blockDim.x >> 5)) ? wsum[threadIdx.x] : 0;
+      long long wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        long long t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (threadIdx.x >= o) wi += t;
+      }
+      wsum[threadIdx.x] = wi - w;   // exclusive warp offsets
+    }
+    __syncthreads();
+    long long carry = carry_s;
+    long long excl = carry + wsum[threadIdx.x >> 5] + incl - v;
+    if (i < n) out[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+// ---------------------------------------------------------------------------------------
+// K5: emit pass.  Same grid as the count pass; recomputes the counts (the voxel chunk is
+// L2-resident from the count pass), block-scans the 18 quantities and writes one element
+// per event to its generation-order slot.
+// ---------------------------------------------------------------------------------------
+template <typename Elem>
+__device__ __forceinline__ Elem make_elem(long long ts, bool is_nan, long long bin_base, int pol, int pix, int pix_bits,
+                                          int key_bits, int32_t* status) {
+  // key 0 is reserved for "NaN timestamp below the bin": it sorts first (its value, 0 or
+  // INT64_MIN, is smaller than every real timestamp of the bin) and pack restores nan_ts.
+  long long key = ts - bin_base + kKeyBias;
+  if (is_nan) atomicAdd(status + 1, 1);
+  const long long kmax = (1LL << key_bits) - 1;
+  if (is_nan && (ts < bin_base - kKeyBias + 1)) {
+    key = 0;
+  } else if (key < 1 || key > kmax) {   // outside the representable key range: flagged, host raises
+    atomicAdd(status + 0, 1);
+    key = key < 1 ? 1 : kmax;
+  }
+  return (Elem)(((unsigned long long)key << (pix_bits + 1)) | ((unsigned long long)pol << pix_bits) |
+                (unsigned long long)pix);
+}
+
+template <int V, typename Elem>
+__global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict__ vox, DevParams P,
+                                                         const int32_t* __restrict__ block_base,
+                                                         const int32_t* __restrict__ group_base,
+                                                         const int64_t* __restrict__ seg_start,
+                                                         const float* __restrict__ draws, Elem* __restrict__ elems,
+                                                         int32_t* __restrict__ status) {
+  const int blk = blockIdx.x, p = blockIdx.y, f = blockIdx.z;
+  const int pix0 = (blk * kThreads + threadIdx.x) * V;
+  int n[V][kBins];
+  float tend[V][kBins];
+  int tot[kQ];
+#pragma unroll
+  for (int q = 0; q < kQ; ++q) tot[q] = 0;
+  const bool active = pix0 < P.HW;
+  if (active) {
+    float y[V][10];
+    load_pixels<V>(vox + ((size_t)(f * 2 + p) * 10) * P.HW, P.HW, pix0, y);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      relocate_pixel(y[v], P.eps6, n[v], tend[v]);
+#pragma unroll
+      for (int c = 0; c < kBins; ++c) {
+        tot[c] += (n[v][c] == 1);
+        tot[kBins + c] += (n[v][c] >= 2) ? n[v][c] : 0;
+      }
+    }
+  }
+  // block-exclusive scan of the 18 per-thread totals
+  __shared__ int wtot[kThreads / 32][kQ];
+  int excl[kQ];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < kQ; ++q) {
+    int inc = warp_incl_scan(tot[q]);
+    excl[q] = inc - tot[q];
+    if (lane == 31) wtot[warp][q] = inc;
+  }
+  __syncthreads();
+  if (!active) return;
+  const int pol = 1 - p;                         // p-index 0 = positive plane -> polarity 1
+  const int grp = (p == 1) ? 0 : 2;              // negative plane is emitted first
+  const size_t bb = (((size_t)f * 2 + p) * P.NB + blk) * kQ;
+  const unsigned long long frame = (unsigned long long)(P.frame_base + f);
+#pragma unroll
+  for (int c = 0; c < kBins; ++c) {
+    int ws = 0, wm = 0;
+    for (int w = 0; w < warp; ++w) { ws += wtot[w][c]; wm += wtot[w][kBins + c]; }
+    const int32_t* gb = group_base + ((size_t)f * kBins + c) * 4;
+    const long long seg = seg_start[(size_t)f * kBins + c];
+    long long slot_s = seg + gb[grp] + block_base[bb + c] + ws + excl[c];
+    long long slot_m = seg + gb[grp + 1] + block_base[bb + kBins + c] + wm + excl[kBins + c];
+    const long long bin_base = P.bin_base[c];
+    const float bstart = P.binstart[c];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int nc = n[v][c];
+      const int pix = pix0 + v;
+      if (nc == 1) {
+        // single event (LDATI.py:156-165): float64 path
+        double t = (double)tend[v][c];
+        t = P.true_div ? __ddiv_rn(__ddiv_rn(t, P.fps64), P.nbins64)
+                       : __dmul_rn(__dmul_rn(t, P.r_fps64), P.r_nbins64);
+        t = __dadd_rn(t, (double)bstart);
+        t = __dmul_rn(t, 1e6);
+        const long long ts = (long long)t;
+        elems[slot_s++] = make_elem<Elem>(ts, false, bin_base, pol, pix, P.pix_bits, P.key_bits, status);
+      } else if (nc >= 2) {
+        // slope-distributed events (LDATI.py:184-196,209-212): float32 path
+        float S = 0.f;
+        if (c > 0 && c < kBins - 1) S = __fsub_rn((float)n[v][c + 1 < kBins ? c + 1 : c], (float)n[v][c > 0 ? c - 1 : c]);
+        const float num = __fsub_rn(__fmul_rn(3.f, S), 0.f);
+        float kk = P.true_div ? __fdiv_rn(__fdiv_rn(num, P.six32), P.vs2_32)
+                              : __fmul_rn(__fmul_rn(num, P.r6_32), P.r_vs2_32);
+        kk = __fdiv_rn(kk, __fadd_rn((float)nc, P.eps8));
+        const float b = __fsub_rn(P.inv_vs32, __fmul_rn(__fmul_rn(P.vs32, kk), 0.5f));
+        const float bb2 = __fmul_rn(b, b);
+        const float k2 = __fmul_rn(2.f, kk);
+        const unsigned long long idx = ((frame * 2ull + (unsigned)p) * 9ull + (unsigned)c) * (unsigned long long)P.HW + (unsigned)pix;
+        for (int j = 0; j < nc; ++j) {
+          float u;
+          if (draws != nullptr) {
+            const size_t di = ((((size_t)f * 2 + p) * kBins + c) * P.HW + pix) * (size_t)P.draws_m + j;
+            u = (j < P.draws_m) ? __ldg(draws + di) : 0.f;
+          } else {
+            u = philox_uniform(idx, (unsigned)j, P.seed);
+          }
+          float t;
+          if (kk == 0.f) {
+            t = P.true_div ? __fdiv_rn(__fdiv_rn(u, P.fps32), P.nbins32)
+                           : __fmul_rn(__fmul_rn(u, P.r_fps32), P.r_nbins32);
+          } else {
+            const float disc = __fadd_rn(bb2, __fmul_rn(k2, u));
+            t = __fdiv_rn(__fadd_rn(-b, __fsqrt_rn(disc)), kk);
+          }
+          t = __fadd_rn(t, bstart);
+          t = __fmul_rn(t, 1e6f);
+          const bool is_nan = (t != t);
+          const long long ts = is_nan ? P.nan_ts : (long long)t;
+          elems[slot_m++] = make_elem<Elem>(ts, is_nan, bin_base, pol, pix, P.pix_bits, P.key_bits, status);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K6: segmented stable LSD radix sort on the key field.  Tiles never straddle segments.
+// ---------------------------------------------------------------------------------------
+struct SortWs {
+  void* elem_a;
+  void* elem_b;
+  int32_t* tile_first;   // [NS+1] first tile of each segment (exclusive scan of tiles per segment)
+  int32_t* tile_seg;     // [NT_max]
+  int32_t* counts;       // [NT_max * radix]  (segment-major, digit-major, tile-minor)
+  int32_t* block_sums;   // scan scratch
+  size_t bytes;
+  int nt_max;
+};
+
+static SortWs carve_sort_ws(void* ws, const Geometry& g, int64_t total, int elem_bytes) {
+  Arena a(ws, (size_t)-1);
+  SortWs s;
+  const int ns = g.F * kBins;
+  s.nt_max = (int)((total + kTile - 1) / kTile) + ns;
+  s.elem_a = a.take<char>((size_t)(total > 0 ? total : 1) * elem_bytes);
+  s.elem_b = a.take<char>((size_t)(total > 0 ? total : 1) * elem_bytes);
+  s.tile_first = a.take<int32_t>((size_t)ns + 1);
+  s.tile_seg = a.take<int32_t>((size_t)s.nt_max);
+  s.counts = a.take<int32_t>((size_t)s.nt_max * 256 + 1);
+  s.block_sums = a.take<int32_t>((size_t)s.nt_max * 256 / 1024 + 2);
+  s.bytes = align_up(a.off, 256);
+  return s;
+}
+
+// one block: tiles per segment -> tile_first (exclusive scan) and tile_seg
+__global__ void build_tiles_kernel(const int64_t* __restrict__ seg_start, int ns, int32_t* __restrict__ tile_first,
+                                   int32_t* __restrict__ tile_seg) {
+  __shared__ int carry_s;
+  __shared__ int wsum[32];
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < ns; base += blockDim.x) {
+    const int s = base + threadIdx.x;
+    int nt = 0;
+    if (s < ns) nt = (int)((seg_start[s + 1] - seg_start[s] + kTile - 1) / kTile);
+    int inc = warp_incl_scan(nt);
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = (threadIdx.x < (blockDim.x >> 5)) ? wsum[threadIdx.x] : 0;
+      int wi = warp_incl_scan(w);
+      wsum[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    const int first = carry_s + wsum[threadIdx.x >> 5] + inc - nt;
+    if (s < ns) {
+      tile_first[s] = first;
+      for (int i = 0; i < nt; ++i) tile_seg[first + i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = first + nt;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_first[ns] = carry_s;
+}
+
+template <typename Elem>
+__global__ void __launch_bounds__(kThreads) sort_hist_kernel(const Elem* __restrict__ in,
+                                                              const int64_t* __restrict__ seg_start,
+                                                              const int32_t* __restrict__ tile_first,
+                                                              const int32_t* __restrict__ tile_seg, int ns, int shift,
+                                                              int radix_bits, int32_t* __restrict__ counts) {
+  const int tile = blockIdx.x;
+  if (tile >= tile_first[ns]) return;
+  const int seg = tile_seg[tile];
+  const int tin = tile - tile_first[seg];
+  const int ntile_seg = tile_first[seg + 1] - tile_first[seg];
+  const long long start = seg_start[seg] + (long long)tin * kTile;
+  const int cnt = (int)min((long long)kTile, seg_start[seg + 1] - start);
+  const int radix = 1 << radix_bits;
+  __shared__ int hist[256];
+  for (int i = threadIdx.x; i < radix; i += kThreads) hist[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < cnt; i += kThreads) {
+    const unsigned d = (unsigned)(in[start + i] >> shift) & (radix - 1);
+    atomicAdd(&hist[d], 1);
+  }
+  __syncthreads();
+  // layout: [segment][digit][tile in segment]; segment block starts at radix * tile_first[seg]
+  int32_t* dst = counts + (size_t)radix * tile_first[seg];
+  for (int d = threadIdx.x; d < radix; d += kThreads) dst[(size_t)d * ntile_seg + tin] = hist[d];
+}
+
+// generic int32 exclusive scan, three phases (n up to ~10^8)
+__global__ void scan_reduce_kernel(const int32_t* __restrict__ in, int n, int32_t* __restrict__ block_sums) {
+  const int base = blockIdx.x * 1024;
+  int v = 0;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+    if (base + i < n) v += in[base + i];
+  __shared__ int red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    block_sums[blockIdx.x] = s;
+  }
+}
+
+__global__ void scan_block_sums_kernel(int32_t* __restrict__ block_sums, int nb) {
+  // single block, sequential chunks of blockDim.x
+  __shared__ int carry_s;
+  __shared__ int wsum[32];
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < nb) ? block_sums[i] : 0;
+    int inc = warp_incl_scan(v);
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = (threadIdx.x < (blockDim.x >> 5)) ? wsum[threadIdx.x] : 0;
+      int wi = warp_incl_scan(w);
+      wsum[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    const int ex = carry_s + wsum[threadIdx.x >> 5] + inc - v;
+    if (i < nb) block_sums[i] = ex;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = ex + v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) scan_apply_kernel(int32_t* __restrict__ data, int n,
+                                                          const int32_t* __restrict__ block_sums) {
+  // each block scans 1024 values: 256 threads x 4 consecutive
+  const int base = blockIdx.x * 1024 + threadIdx.x * 4;
+  int v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = (base + i < n) ? data[base + i] : 0;
+  const int tsum = v[0] + v[1] + v[2] + v[3];
+  int inc = warp_incl_scan(tsum);
+  __shared__ int wsum[8];
+  if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
+  int run = block_sums[blockIdx.x] + woff + inc - tsum;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (base + i < n) data[base + i] = run;
+    run += v[i];
+  }
+}
+
+template <typename Elem>
+__global__ void __launch_bounds__(kThreads) sort_scatter_kernel(const Elem* __restrict__ in, Elem* __restrict__ out,
+                                                                 const int64_t* __restrict__ seg_start,
+                                                                 const int32_t* __restrict__ tile_first,
+                                                                 const int32_t* __restrict__ tile_seg, int ns, int shift,
+                                                                 int radix_bits, const int32_t* __restrict__ scanned) {
+  const int tile = blockIdx.x;
+  if (tile >= tile_first[ns]) return;
+  const int seg = tile_seg[tile];
+  const int tin = tile - tile_first[seg];
+  const int ntile_seg = tile_first[seg + 1] - tile_first[seg];
+  const long long start = seg_start[seg] + (long long)tin * kTile;
+  const int cnt = (int)min((long long)kTile, seg_start[seg + 1] - start);
+  const int radix = 1 << radix_bits;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kThreads / 32;
+  __shared__ int wcnt[kWarps][256];     // per-warp digit counters -> exclusive bases
+  __shared__ int gbase[256];            // global position of this tile's first key of each digit
+  for (int i = threadIdx.x; i < kWarps * 256; i += kThreads) (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+  // warp w owns keys [w*256, w*256+256) of the tile, 8 rounds of 32 consecutive keys:
+  // memory order == (warp, round, lane), which is what keeps the pass stable.
+  Elem key[kKeysPerThread];
+  int rank[kKeysPerThread];
+  unsigned dig[kKeysPerThread];
+#pragma unroll
+  for (int r = 0; r < kKeysPerThread; ++r) {
+    const int i = warp * (kTile / kWarps) + r * 32 + lane;
+    const bool valid = i < cnt;
+    key[r] = valid ? in[start + i] : (Elem)0;
+    const unsigned d = valid ? ((unsigned)(key[r] >> shift) & (radix - 1)) : 0xFFFFu;
+    dig[r] = d;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    const int before = __popc(peers & ((1u << lane) - 1u));
+    int old = 0;
+    if (valid && lane == leader) {
+      old = wcnt[warp][d];
+      wcnt[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + before;
+    __syncwarp();
+  }
+  __syncthreads();
+  // exclusive prefix over warps per digit; fetch the scanned global base of (seg, digit, tile)
+  for (int d = threadIdx.x; d < radix; d += kThreads) {
+    int run = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const int c = wcnt[w][d];
+      wcnt[w][d] = run;
+      run += c;
+    }
+    gbase[d] = scanned[(size_t)radix * tile_first[seg] + (size_t)d * ntile_seg + tin];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kKeysPerThread; ++r) {
+    if (dig[r] != 0xFFFFu) out[(size_t)gbase[dig[r]] + wcnt[warp][dig[r]] + rank[r]] = key[r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K7: pack sorted elements into 13-byte records, staged through shared memory so the
+// byte stream leaves the SM as aligned 16-byte stores.
+// ---------------------------------------------------------------------------------------
+template <typename Elem>
+__global__ void __launch_bounds__(kThreads) pack_kernel(const Elem* __restrict__ in, const int64_t* __restrict__ seg_start,
+                                                         const int32_t* __restrict__ tile_first,
+                                                         const int32_t* __restrict__ tile_seg, int ns, DevParams P,
+                                                         const int64_t* __restrict__ frame_offset_us,
+                                                         uint8_t* __restrict__ out) {
+  const int tile = blockIdx.x;
+  if (tile >= tile_first[ns]) return;
+  const int seg = tile_seg[tile];
+  const int tin = tile - tile_first[seg];
+  const long long start = seg_start[seg] + (long long)tin * kTile;
+  const int cnt = (int)min((long long)kTile, seg_start[seg + 1] - start);
+  const int f = seg / kBins, c = seg % kBins;
+  long long base_ts = P.bin_base[c] - kKeyBias;
+  long long off = 0;
+  if (P.add_frame_offset && frame_offset_us != nullptr) off = frame_offset_us[f];
+  __shared__ __align__(16) uint8_t stage[kTile * 13 + 32];
+  const unsigned long long gbyte = (unsigned long long)start * 13ull;
+  const unsigned long long gaddr = (unsigned long long)(uintptr_t)out + gbyte;
+  const int mis = (int)(gaddr & 15ull);        // stage[mis + k] <-> out[gbyte + k]
+  const unsigned long long pix_mask = (1ull << P.pix_bits) - 1ull;
+  for (int i = threadIdx.x; i < cnt; i += kThreads) {
+    const unsigned long long e = (unsigned long long)in[start + i];
+    const int pix = (int)(e & pix_mask);
+    const int pol = (int)((e >> P.pix_bits) & 1ull);
+    const long long key = (long long)(e >> (P.pix_bits + 1));
+    long long ts = (key == 0) ? P.nan_ts : (base_ts + key);
+    ts = (long long)((unsigned long long)ts + (unsigned long long)off);
+    const short x = (short)(pix % P.W), y = (short)(pix / P.W);
+    uint8_t* d = stage + mis + i * 13;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) d[b] = (uint8_t)((unsigned long long)ts >> (8 * b));
+    d[8] = (uint8_t)(x & 0xff);  d[9] = (uint8_t)((x >> 8) & 0xff);
+    d[10] = (uint8_t)(y & 0xff); d[11] = (uint8_t)((y >> 8) & 0xff);
+    d[12] = (uint8_t)pol;
+  }
+  __syncthreads();
+  const int nbytes = cnt * 13;
+  const int lo = mis, hi = mis + nbytes;              // valid byte range inside stage
+  uint8_t* gout = out + gbyte - mis;                  // 16-byte aligned
+  const int nvec = (hi + 15) / 16;
+  for (int v = threadIdx.x; v < nvec; v += kThreads) {
+    const int b0 = v * 16;
+    if (b0 >= lo && b0 + 16 <= hi) {
+      *reinterpret_cast<uint4*>(gout + b0) = *reinterpret_cast<const uint4*>(stage + b0);
+    } else {
+      for (int b = max(b0, lo); b < min(b0 + 16, hi); ++b) gout[b] = stage[b];
+    }
+  }
+}
+
+template <int V>
+__global__ void relocate_debug_kernel(const float* __restrict__ vox, int HW, float eps6, int32_t* __restrict__ counts,
+                                      float* __restrict__ tend_out) {
+  const int plane = blockIdx.y;   // f*2+p
+  const int pix = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (pix >= HW) return;
+  float y[V][10];
+  load_pixels<V>(vox + (size_t)plane * 10 * HW, HW, pix, y);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    int n[kBins];
+    float tend[kBins];
+    relocate_pixel(y[v], eps6, n, tend);
+#pragma unroll
+    for (int c = 0; c < kBins; ++c) {
+      counts[((size_t)plane * kBins + c) * HW + pix + v] = n[c];
+      tend_out[((size_t)plane * kBins + c) * HW + pix + v] = tend[c];
+    }
+  }
+}
+
+static int validate(const v2ce_ldati_params* p) {
+  V2CE_REQUIRE(p != nullptr, "params is NULL");
+  V2CE_REQUIRE(p->height > 0 && p->width > 0 && p->n_frames > 0, "bad geometry %dx%d x %d frames", p->height,
+               p->width, p->n_frames);
+  V2CE_REQUIRE(p->width < 32768 && p->height < 32768, "x/y are int16 fields: H,W must be < 32768");
+  V2CE_REQUIRE((long long)p->height * p->width < (1LL << 30), "plane too large");
+  V2CE_REQUIRE(p->n_frames <= 65535, "at most 65535 frames per call (grid.z)");
+  V2CE_REQUIRE(p->key_span > 0 && p->key_span < (1 << 30), "bad key_span %d", p->key_span);
+  return V2CE_OK;
+}
+
+}  // namespace ldati
+}  // namespace v2ce
+
+using namespace v2ce;
+using namespace v2ce::ldati;
+
+extern "C" int v2ce_ldati_count_workspace_bytes(const v2ce_ldati_params* p, size_t* bytes) {
+  if (int e = validate(p)) return e;
+  V2CE_REQUIRE(bytes != nullptr, "bytes is NULL");
+  Geometry g = make_geometry(p);
+  *bytes = carve_count_ws(nullptr, g).bytes;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_ldati_emit_workspace_bytes(const v2ce_ldati_params* p, int64_t total_events, size_t* bytes) {
+  if (int e = validate(p)) return e;
+  V2CE_REQUIRE(bytes != nullptr && total_events >= 0, "bad arguments");
+  V2CE_REQUIRE(total_events < (1LL << 31) - (1LL << 20), "more than 2^31 events in one call; split the frames");
+  Geometry g = make_geometry(p);
+  *bytes = carve_sort_ws(nullptr, g, total_events, g.wide ? 8 : 4).bytes;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_ldati_count(const float* voxels_dev, const v2ce_ldati_params* p, void* count_ws_dev,
+                                size_t count_ws_bytes, int64_t* seg_counts_dev, void* stream) {
+  if (int e = validate(p)) return e;
+  V2CE_REQUIRE(voxels_dev && count_ws_dev && seg_counts_dev, "NULL device pointer");
+  Geometry g = make_geometry(p);
+  CountWs w = carve_count_ws(count_ws_dev, g);
+  if (w.bytes > count_ws_bytes)
+    return set_error(V2CE_ERR_WORKSPACE, "count workspace too small: need %zu, got %zu", w.bytes, count_ws_bytes);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DevParams P = make_dev_params(p, g);
+  dim3 grid(g.NB, 2, g.F);
+  if (g.V == 4) count_kernel<4><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
+  else count_kernel<1><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
+  V2CE_LAUNCH_CHECK("ldati::count_kernel");
+  scan_planes_kernel<<<g.F, 64, 0, s>>>(w.partial, w.block_base, w.group_base, seg_counts_dev, g.NB);
+  V2CE_LAUNCH_CHECK("ldati::scan_planes_kernel");
+  scan_i64_kernel<<<1, 1024, 0, s>>>(seg_counts_dev, w.seg_start, g.F * kBins);
+  V2CE_LAUNCH_CHECK("ldati::scan_i64_kernel");
+  return V2CE_OK;
+}
+
+template <typename Elem>
+static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometry& g, const CountWs& cw, void* emit_ws,
+                     size_t emit_ws_bytes, const float* draws, int draws_m, const int64_t* frame_off, int64_t total,
+                     uint8_t* out, int32_t* status, cudaStream_t s) {
+  SortWs sw = carve_sort_ws(emit_ws, g, total, sizeof(Elem));
+  if (sw.bytes > emit_ws_bytes)
+    return set_error(V2CE_ERR_WORKSPACE, "emit workspace too small: need %zu, got %zu", sw.bytes, emit_ws_bytes);
+  DevParams P = make_dev_params(p, g);
+  P.draws_m = draws_m;
+  const int ns = g.F * kBins;
+  Elem* ea = static_cast<Elem*>(sw.elem_a);
+  Elem* eb = static_cast<Elem*>(sw.elem_b);
+  V2CE_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), s));
+  dim3 grid(g.NB, 2, g.F);
+  if (g.V == 4)
+    emit_kernel<4, Elem><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
+  else
+    emit_kernel<1, Elem><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
+  V2CE_LAUNCH_CHECK("ldati::emit_kernel");
+  if (total == 0) return V2CE_OK;
+  build_tiles_kernel<<<1, 1024, 0, s>>>(cw.seg_start, ns, sw.tile_first, sw.tile_seg);
+  V2CE_LAUNCH_CHECK("ldati::build_tiles_kernel");
+  // LSD passes over the key field, <= 8 bits each
+  const int passes = (g.key_bits + 7) / 8;
+  const int rb = (g.key_bits + passes - 1) / passes;
+  Elem* src = ea;
+  Elem* dst = eb;
+  for (int pass = 0; pass < passes; ++pass) {
+    const int shift = g.pix_bits + 1 + pass * rb;
+    const int radix = 1 << rb;
+    const int ncounts = sw.nt_max * radix;
+    sort_hist_kernel<Elem><<<sw.nt_max, kThreads, 0, s>>>(src, cw.seg_start, sw.tile_first, sw.tile_seg, ns, shift, rb,
+                                                          sw.counts);
+    V2CE_LAUNCH_CHECK("ldati::sort_hist_kernel");
+    const int nblk = (ncounts + 1023) / 1024;
+    scan_reduce_kernel<<<nblk, 256, 0, s>>>(sw.counts, ncounts, sw.block_sums);
+    V2CE_LAUNCH_CHECK("ldati::scan_reduce_kernel");
+    scan_block_sums_kernel<<<1, 1024, 0, s>>>(sw.block_sums, nblk);
+    V2CE_LAUNCH_CHECK("ldati::scan_block_sums_kernel");
+    scan_apply_kernel<<<nblk, 256, 0, s>>>(sw.counts, ncounts, sw.block_sums);
+    V2CE_LAUNCH_CHECK("ldati::scan_apply_kernel");
+    sort_scatter_kernel<Elem><<<sw.nt_max, kThreads, 0, s>>>(src, dst, cw.seg_start, sw.tile_first, sw.tile_seg, ns,
+                                                             shift, rb, sw.counts);
+    V2CE_LAUNCH_CHECK("ldati::sort_scatter_kernel");
+    Elem* t = src; src = dst; dst = t;
+  }
+  pack_kernel<Elem><<<sw.nt_max, kThreads, 0, s>>>(src, cw.seg_start, sw.tile_first, sw.tile_seg, ns, P, frame_off, out);
+  V2CE_LAUNCH_CHECK("ldati::pack_kernel");
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_ldati_emit(const float* voxels_dev, const v2ce_ldati_params* p, const void* count_ws_dev,
+                               void* emit_ws_dev, size_t emit_ws_bytes, const float* draws_dev, int32_t draws_m,
+                               const int64_t* frame_offset_us_dev, int64_t total_events, uint8_t* events_out_dev,
+                               int32_t* status_dev, void* stream) {
+  if (int e = validate(p)) return e;
+  V2CE_REQUIRE(voxels_dev && count_ws_dev && emit_ws_dev && status_dev, "NULL device pointer");
+  V2CE_REQUIRE(total_events >= 0 && total_events < (1LL << 31) - (1LL << 20), "total_events out of range");
+  V2CE_REQUIRE(total_events == 0 || events_out_dev != nullptr, "events_out_dev is NULL");
+  V2CE_REQUIRE(draws_dev == nullptr || draws_m >= 0, "bad draws_m");
+  Geometry g = make_geometry(p);
+  CountWs cw = carve_count_ws(const_cast<void*>(count_ws_dev), g);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (g.wide)
+    return emit_impl<unsigned long long>(voxels_dev, p, g, cw, emit_ws_dev, emit_ws_bytes, draws_dev, draws_m,
+                                         frame_offset_us_dev, total_events, events_out_dev, status_dev, s);
+  return emit_impl<unsigned int>(voxels_dev, p, g, cw, emit_ws_dev, emit_ws_bytes, draws_dev, draws_m,
+                                 frame_offset_us_dev, total_events, events_out_dev, status_dev, s);
+}
+
+extern "C" int v2ce_ldati_relocate(const float* voxels_dev, int32_t n_frames, int32_t height, int32_t width,
+                                   int32_t* counts_dev, float* tend_dev, void* stream) {
+  V2CE_REQUIRE(voxels_dev && counts_dev && tend_dev, "NULL device pointer");
+  V2CE_REQUIRE(n_frames > 0 && height > 0 && width > 0 && n_frames * 2 <= 65535, "bad geometry");
+  const int HW = height * width;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (HW % 4 == 0) {
+    dim3 grid((HW / 4 + 255) / 256, n_frames * 2);
+    relocate_debug_kernel<4><<<grid, 256, 0, s>>>(voxels_dev, HW, 1e-6f, counts_dev, tend_dev);
+  } else {
+    dim3 grid((HW + 255) / 256, n_frames * 2);
+    relocate_debug_kernel<1><<<grid, 256, 0, s>>>(voxels_dev, HW, 1e-6f, counts_dev, tend_dev);
+  }
+  V2CE_LAUNCH_CHECK("ldati::relocate_debug_kernel");
+  return V2CE_OK;
+}

@@ -1,0 +1,56 @@
+"""Drop-in for /root/reference/scripts/LDATI.py: same public name, arguments, defaults and
+return type; the tensor work runs in libv2ce_b200.so (csrc/ldati.cu).
+
+    sample_voxel_statistical(y, t0=0, fps=30, pooling_type='none', pooling_kernel_size=3,
+                             additional_events_strategy='slope', bidirectional=False)
+        -> List[np.recarray]  (len B; dtype timestamp<i8, x<i2, y<i2, polarity i1; itemsize 13;
+                               timestamps relative to the frame start, like LDATI.py:308)
+
+Extra keyword-only arguments (not in the reference): ``seed`` / ``frame_base`` select the
+counter-based Philox stream that replaces ``torch.rand`` (LDATI.py:171), ``draws`` injects a
+dense (B,2,9,H,W,M) tensor of uniforms instead, ``flavor`` picks the torch-CUDA ('cuda',
+default: what the reference computes on a GPU) or torch-CPU ('cpu') scalar semantics.
+"""
+import logging
+from typing import List
+
+import numpy as np
+import torch
+
+from .. import ldati as _ldati
+from .._lib import V2ceError, require_cuda
+
+logger = logging.getLogger(__name__)
+
+
+def sample_voxel_statistical(y, t0=0, fps=30, pooling_type='none', pooling_kernel_size=3,
+                             additional_events_strategy='slope', bidirectional=False, *,
+                             seed=None, frame_base=0, draws=None, flavor='cuda') -> List[np.recarray]:
+    assert pooling_type in ['avg', 'weighted', 'none']
+    assert additional_events_strategy in ['none', 'random', 'slope']
+    if pooling_type != 'none' or additional_events_strategy != 'slope' or bidirectional:
+        raise NotImplementedError('the B200 path implements the configuration v2ce.py:356 uses: '
+                                  "pooling_type='none', additional_events_strategy='slope', bidirectional=False")
+    require_cuda(y, 'y')
+    B, P, C, H, W = y.shape
+    if P != 2 or C != 10:
+        raise V2ceError(f'expected y of shape (B,2,10,H,W), got {tuple(y.shape)}')
+    vox = y.float().contiguous()
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())       # follows torch.manual_seed like torch.rand does
+    if draws is not None:
+        draws = require_cuda(draws, 'draws').float().contiguous()
+        if tuple(draws.shape[:5]) != (B, 2, 9, H, W):
+            raise V2ceError(f'draws must be (B,2,9,H,W,M), got {tuple(draws.shape)}')
+    with torch.cuda.device(vox.device):
+        eng = _ldati.engine_for(vox.device)
+        params = _ldati.make_params(B, H, W, fps=fps, t0=t0, seed=seed, frame_base=frame_base, flavor=flavor,
+                                    device=vox.device)
+        events, seg_counts, status = eng.run(vox, params, draws=draws)
+        total = int(seg_counts.sum())
+        host = torch.empty(total * 13, dtype=torch.uint8, pin_memory=True)
+        host.copy_(events[:total * 13], non_blocking=True)
+        status_host = status.cpu()                                 # synchronises the stream
+    _ldati.check_status(status_host.numpy())
+    logger.debug(f'LDATI: {total} events in {B} frames')
+    return _ldati.split_frames(host.numpy(), seg_counts)
