@@ -161,8 +161,9 @@ def multi_timestamps(kk, b, u, binstart_t0_32, k: Consts):
             warnings.simplefilter('ignore')
             ts = np.trunc(t)
             out = ts.astype(np.int64)
-            # NaN float -> int64: 0x8000000000000000 on x86 (cvttss2si), 0 on the GPU (PTX cvt.rzi.s64.f32)
-            out[np.isnan(ts)] = np.iinfo(np.int64).min if k.flavor == 'cpu' else 0
+            # NaN float -> int64 is 0x8000000000000000 on x86 (cvttss2si) and on torch-CUDA
+            # (measured on B200: tests/test_gpu_torch_semantics.py::test_nan_to_long_on_cuda)
+            out[np.isnan(ts)] = np.iinfo(np.int64).min
     return out
 
 

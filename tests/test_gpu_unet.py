@@ -1,0 +1,164 @@
+"""GPU parity for stage 1: the tcgen05 implicit-GEMM conv (layer hook) against torch fp32 conv3d on
+the same bf16-rounded operands, and the whole V2ce3d forward against the fp32 CPU oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import synth
+from oracle.unet_oracle import UNetOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def conv_hook(src0, src1, hin, win, w, scale, shift, residual, act, ksize, stride):
+    """src0 (B,D,H0,W0,C0) bf16, src1 (B,D,Hin,Win,C1) bf16 | None -> out (B,D,Hout,Wout,Cout) bf16."""
+    from v2ce_toolbox_b200 import _lib
+    lib = _lib.load()
+    B, D, H0, W0, C0 = src0.shape
+    C1 = 0 if src1 is None else src1.shape[-1]
+    cout = w.shape[0]
+    pad = ksize // 2
+    hout = (hin + 2 * pad - ksize) // stride + 1
+    wout = (win + 2 * pad - ksize) // stride + 1
+    out = torch.full((B, D, hout, wout, cout), float('nan'), dtype=torch.bfloat16, device='cuda')
+    wh = np.ascontiguousarray(w.cpu().numpy(), dtype=np.float32)
+    sh = np.ascontiguousarray(scale.cpu().numpy(), dtype=np.float32)
+    th = np.ascontiguousarray(shift.cpu().numpy(), dtype=np.float32)
+    _lib.check(lib.v2ce_conv3d_bf16(_lib.ptr(src0), C0, H0, W0, _lib.ptr(src1), C1, B, D, hin, win, ksize, stride,
+                                    wh.ctypes.data_as(ctypes.c_void_p), cout, sh.ctypes.data_as(ctypes.c_void_p),
+                                    th.ctypes.data_as(ctypes.c_void_p), _lib.ptr(residual), act, _lib.ptr(out),
+                                    _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    return out
+
+
+def torch_ref(src0, src1, hin, win, w, scale, shift, residual, act, ksize, stride):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = src0.float().permute(0, 4, 1, 2, 3)                       # (B,C,D,H,W)
+    if src0.shape[2] != hin or src0.shape[3] != win:
+        hi = (torch.arange(hin, device=x.device) * src0.shape[2]) // hin
+        wi = (torch.arange(win, device=x.device) * src0.shape[3]) // win
+        x = x[:, :, :, hi][:, :, :, :, wi]
+    if src1 is not None:
+        x = torch.cat([x, src1.float().permute(0, 4, 1, 2, 3)], dim=1)
+    wq = w.to(torch.bfloat16).float()
+    y = F.conv3d(x.double(), wq.double().cuda(), None, (1, stride, stride), ksize // 2).float()
+    y = y * scale.cuda().view(1, -1, 1, 1, 1) + shift.cuda().view(1, -1, 1, 1, 1)
+    y = y.permute(0, 2, 3, 4, 1)
+    if residual is not None:
+        y = y + residual.float()
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = F.leaky_relu(y, 0.01)
+    return y
+
+
+CASES = [
+    # name, B, D, Hin, Win, C0, (H0,W0) or None, C1, Cout, k, stride, residual, act
+    ('gemm32', 1, 2, 8, 16, 64, None, 0, 32, 1, 1, False, 0),
+    ('gemm64', 1, 2, 8, 16, 64, None, 0, 64, 1, 1, False, 0),
+    ('gemm128', 1, 2, 8, 16, 128, None, 0, 128, 1, 1, False, 1),
+    ('gemm256', 1, 2, 8, 16, 64, None, 0, 256, 1, 1, False, 0),
+    ('gemm512', 1, 2, 8, 16, 256, None, 0, 512, 1, 1, True, 1),
+    ('k1_cin32', 1, 3, 9, 11, 32, None, 0, 64, 1, 1, False, 0),
+    ('k3_s1', 1, 3, 9, 11, 64, None, 0, 64, 3, 1, False, 1),
+    ('k3_s2_cin32', 2, 3, 9, 11, 32, None, 0, 64, 3, 2, False, 1),
+    ('k1_s2', 1, 3, 9, 11, 64, None, 0, 128, 1, 2, False, 0),
+    ('k3_res_relu', 1, 4, 10, 12, 128, None, 0, 128, 3, 1, True, 1),
+    ('k3_leaky', 1, 2, 7, 9, 64, None, 0, 32, 3, 1, False, 2),
+    ('concat_up_k3', 1, 3, 9, 11, 64, (5, 6), 32, 32, 3, 1, False, 1),
+    ('concat_up_k1', 1, 3, 9, 11, 64, (5, 6), 32, 32, 1, 1, False, 0),
+    ('concat_up_768', 1, 2, 9, 11, 512, (5, 6), 256, 256, 3, 1, False, 1),
+    ('deepk_512', 1, 4, 6, 7, 512, None, 0, 512, 3, 1, True, 1),
+    ('many_tiles', 2, 16, 33, 44, 64, None, 0, 64, 3, 1, True, 1),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+def test_conv_layer_vs_torch(case):
+    name, B, D, hin, win, C0, up, C1, cout, k, stride, use_res, act = case
+    g = torch.Generator(device='cpu').manual_seed(hash(name) % 1000)
+    h0, w0 = up if up else (hin, win)
+    src0 = torch.randn(B, D, h0, w0, C0, generator=g).to(torch.bfloat16).cuda()
+    src1 = torch.randn(B, D, hin, win, C1, generator=g).to(torch.bfloat16).cuda() if C1 else None
+    cin = C0 + C1
+    w = torch.randn(cout, cin, k, k, k, generator=g) / np.sqrt(cin * k ** 3)
+    scale = 0.5 + torch.rand(cout, generator=g)
+    shift = 0.2 * torch.randn(cout, generator=g)
+    pad = k // 2
+    hout, wout = (hin + 2 * pad - k) // stride + 1, (win + 2 * pad - k) // stride + 1
+    res = torch.randn(B, D, hout, wout, cout, generator=g).to(torch.bfloat16).cuda() if use_res else None
+    out = conv_hook(src0, src1, hin, win, w, scale, shift, res, act, k, stride)
+    ref = torch_ref(src0, src1, hin, win, w, scale, shift, res, act, k, stride)
+    assert not torch.isnan(out.float()).any(), 'unwritten outputs'
+    err = (out.float() - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 2e-3          # bf16 output rounding + fp32 accumulation-order noise
+    bad = (err > tol).sum().item()
+    assert bad == 0, f'{name}: {bad} of {err.numel()} outside tolerance, max err {err.max().item():.4g}'
+
+
+def _model(seed, init):
+    from v2ce_toolbox_b200.scripts.v2ce_3d import V2ce3d
+    sd = synth.make_state_dict(seed, init)
+    m = V2ce3d()
+    m.load_state_dict(sd)
+    return m.eval().to('cuda'), sd
+
+
+@pytest.mark.parametrize('init,shape', [('lively', (1, 16, 2, 36, 44)), ('lively', (2, 16, 2, 20, 28)),
+                                        ('reference', (1, 16, 2, 65, 87))])
+def test_forward_vs_fp32_oracle(init, shape):
+    """Tolerance (stated): bf16 operands / fp32 accumulation against the fp32 reference:
+    rel-L2 <= 2e-2 and max-abs <= 5e-2 * max(ref), on two consecutive calls (spectral-norm state)."""
+    m, sd = _model(3, init)
+    orc = UNetOracle(sd)
+    g = torch.Generator(device='cpu').manual_seed(7)
+    x = torch.randn(*shape, generator=g)
+    for call in range(2):
+        y = m(x.cuda()).cpu()
+        ref = orc.forward(x)
+        sig = m.last_sigmas()
+        assert y.shape == ref.shape and (y >= 0).all()
+        rel = float((y - ref).norm() / ref.norm())
+        mx = float((y - ref).abs().max() / ref.abs().max())
+        assert rel <= 2e-2 and mx <= 5e-2, (init, shape, call, rel, mx)
+    assert m.call_count() == 2 and orc.calls == 2
+
+
+def test_spectral_norm_schedule_matches_oracle():
+    m, sd = _model(5, 'lively')
+    orc = UNetOracle(sd)
+    m.sn_advance(1)
+    want = orc.sn_step()
+    got = m.last_sigmas()
+    assert np.allclose(got, np.array(want, dtype=np.float32), rtol=2e-5)
+    m.sn_advance(3)
+    for _ in range(3):
+        want = orc.sn_step()
+    assert np.allclose(m.last_sigmas(), np.array(want, dtype=np.float32), rtol=2e-5)
+
+
+def test_forward_matches_reference_golden(golden, golden_meta):
+    """Same inputs/weights the unmodified reference saw on CPU (tests/golden/make_golden.py)."""
+    g = golden('unet')
+    for name in ('refinit', 'lively'):
+        meta = golden_meta['unet'][name]
+        m, _ = _model(meta['seed'], meta['init'])
+        x = torch.from_numpy(g[f'{name}_x']).cuda()
+        for call in (0, 1):
+            y = m(x).cpu().numpy()
+            ref = g[f'{name}_y{call}']
+            rel = np.linalg.norm(y - ref) / np.linalg.norm(ref)
+            assert rel <= 2e-2, (name, call, rel)
+
+
+def test_rejects_cpu_input():
+    from v2ce_toolbox_b200 import V2ceError
+    m, _ = _model(0, 'reference')
+    with pytest.raises(V2ceError):
+        m(torch.zeros(1, 16, 2, 20, 28))

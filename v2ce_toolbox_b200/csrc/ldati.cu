@@ -95,7 +95,7 @@ struct DevParams {
   int pix_bits, key_bits;
   int draws_m;
   int add_frame_offset;
-  long long nan_ts;   // what float NaN -> int64 yields in the flavour: 0 on CUDA (cvt.rzi), INT64_MIN on x86
+  long long nan_ts;   // float NaN -> int64: INT64_MIN on x86 (cvttss2si) and on torch-CUDA (measured on B200)
 };
 
 static DevParams make_dev_params(const v2ce_ldati_params* p, const Geometry& g) {
@@ -112,7 +112,7 @@ static DevParams make_dev_params(const v2ce_ldati_params* p, const Geometry& g) 
   d.pix_bits = g.pix_bits; d.key_bits = g.key_bits;
   d.draws_m = 0;
   d.add_frame_offset = p->add_frame_offset;
-  d.nan_ts = p->true_div ? LLONG_MIN : 0;
+  d.nan_ts = LLONG_MIN;
   return d;
 }
 
@@ -288,7 +288,7 @@ __global__ void scan_i64_kernel(const int64_t* __restrict__ in, int64_t* __restr
 template <typename Elem>
 __device__ __forceinline__ Elem make_elem(long long ts, bool is_nan, long long bin_base, int pol, int pix, int pix_bits,
                                           int key_bits, int32_t* status) {
-  // key 0 is reserved for "NaN timestamp below the bin": it sorts first (its value, 0 or
+  // key 0 is reserved for "NaN timestamp below the bin": it sorts first (its value,
   // INT64_MIN, is smaller than every real timestamp of the bin) and pack restores nan_ts.
   long long key = ts - bin_base + kKeyBias;
   if (is_nan) atomicAdd(status + 1, 1);

@@ -1,15 +1,703 @@
-// TEMPORARY stubs (replaced by the real stage-1 implementation in the next commit).
-#include "common.cuh"
+// Stage 1 on sm_100a: the V2ce3d 3D-UNet forward (eval mode) as a fixed schedule of fused
+// conv launches.  Replaces /root/reference/scripts/v2ce_3d.py:12-30, scripts/unet_2layer.py:203-379,
+// scripts/submodules.py:85-124,216-264 and scripts/spectral_norm.py:9-64.
+//
+// Activation layout in HBM: NDHWC bf16, (B, D=16, H, W, C), row m = ((b*D+d)*H+h)*W+w.
+// Schedule per forward (36 launches):
+//   4  spectral-norm power-iteration kernels (fp32; 12 convs batched per launch)
+//   1  head conv 2->32 (direct fp32 CUDA-core kernel, K=54 is HBM-bound) + LeakyReLU
+//   30 tcgen05 implicit-GEMM convs (conv_igemm.cuh): per residual block
+//        t = relu(bn1(conv1(x)))            x may be the virtual concat [nearest_up(prev), skip]
+//        r = bn_d(conv_d(x) + bias_d)       1x1x1 shortcut, present on every block
+//        y = relu(bn2(conv2(t)) + r)
+//   1  pred conv 32->20 + ReLU writing the (B,L,20,H,W) float32 output of V2ce3d.forward
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv_igemm.cuh"
+
+namespace v2ce {
+namespace unet {
+
+using conv::ConvArgs;
+
+constexpr float kBnEps = 1e-5f;
+constexpr int kNumSn = 12;
+
+struct LayerSpec {
+  const char* name;
+  int cin, cout, k;
+  bool sn, bias;
+  const char* bn;   // BatchNorm prefix or nullptr
+};
+
+static const LayerSpec kLayers[] = {
+    {"UNet.head.conv3d", 2, 32, 3, false, true, nullptr},
+    {"UNet.encoders.0.conv1", 32, 64, 3, false, false, "UNet.encoders.0.bn1"},
+    {"UNet.encoders.0.conv2", 64, 64, 3, false, false, "UNet.encoders.0.bn2"},
+    {"UNet.encoders.0.downsample.0", 32, 64, 1, false, true, "UNet.encoders.0.downsample.1"},
+    {"UNet.encoders.1.conv1", 64, 128, 3, false, false, "UNet.encoders.1.bn1"},
+    {"UNet.encoders.1.conv2", 128, 128, 3, false, false, "UNet.encoders.1.bn2"},
+    {"UNet.encoders.1.downsample.0", 64, 128, 1, false, true, "UNet.encoders.1.downsample.1"},
+    {"UNet.encoders.2.conv1", 128, 256, 3, false, false, "UNet.encoders.2.bn1"},
+    {"UNet.encoders.2.conv2", 256, 256, 3, false, false, "UNet.encoders.2.bn2"},
+    {"UNet.encoders.2.downsample.0", 128, 256, 1, false, true, "UNet.encoders.2.downsample.1"},
+    {"UNet.encoders.3.conv1", 256, 512, 3, false, false, "UNet.encoders.3.bn1"},
+    {"UNet.encoders.3.conv2", 512, 512, 3, false, false, "UNet.encoders.3.bn2"},
+    {"UNet.encoders.3.downsample.0", 256, 512, 1, false, true, "UNet.encoders.3.downsample.1"},
+    {"UNet.resblocks.0.conv1", 512, 512, 3, true, false, "UNet.resblocks.0.bn1"},
+    {"UNet.resblocks.0.conv2", 512, 512, 3, true, false, "UNet.resblocks.0.bn2"},
+    {"UNet.resblocks.0.downsample.0", 512, 512, 1, false, true, "UNet.resblocks.0.downsample.1"},
+    {"UNet.resblocks.1.conv1", 512, 512, 3, true, false, "UNet.resblocks.1.bn1"},
+    {"UNet.resblocks.1.conv2", 512, 512, 3, true, false, "UNet.resblocks.1.bn2"},
+    {"UNet.resblocks.1.downsample.0", 512, 512, 1, false, true, "UNet.resblocks.1.downsample.1"},
+    {"UNet.decoders.0.conv1", 768, 256, 3, true, false, "UNet.decoders.0.bn1"},
+    {"UNet.decoders.0.conv2", 256, 256, 3, true, false, "UNet.decoders.0.bn2"},
+    {"UNet.decoders.0.downsample.0", 768, 256, 1, false, true, "UNet.decoders.0.downsample.1"},
+    {"UNet.decoders.1.conv1", 384, 128, 3, true, false, "UNet.decoders.1.bn1"},
+    {"UNet.decoders.1.conv2", 128, 128, 3, true, false, "UNet.decoders.1.bn2"},
+    {"UNet.decoders.1.downsample.0", 384, 128, 1, false, true, "UNet.decoders.1.downsample.1"},
+    {"UNet.decoders.2.conv1", 192, 64, 3, true, false, "UNet.decoders.2.bn1"},
+    {"UNet.decoders.2.conv2", 64, 64, 3, true, false, "UNet.decoders.2.bn2"},
+    {"UNet.decoders.2.downsample.0", 192, 64, 1, false, true, "UNet.decoders.2.downsample.1"},
+    {"UNet.decoders.3.conv1", 96, 32, 3, true, false, "UNet.decoders.3.bn1"},
+    {"UNet.decoders.3.conv2", 32, 32, 3, true, false, "UNet.decoders.3.bn2"},
+    {"UNet.decoders.3.downsample.0", 96, 32, 1, false, true, "UNet.decoders.3.downsample.1"},
+    {"UNet.pred.conv3d", 32, 20, 1, false, true, nullptr},
+};
+constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
+
+// ------------------------------------------------------------------------------------------
+// head: Conv3d(2->32, k3, p1, bias) + LeakyReLU(0.01), fp32 in (B,L,2,H,W) -> bf16 NDHWC
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, int B, int D, int H, int W,
+                                                         __nv_bfloat16* __restrict__ out) {
+  __shared__ float sw[27 * 2 * 32];     // [tap][cin][cout]
+  __shared__ float sb[32];
+  for (int i = threadIdx.x; i < 27 * 2 * 32; i += blockDim.x) {
+    const int n = i % 32, ci = (i / 32) % 2, tap = i / 64;
+    sw[i] = w[((size_t)n * 2 + ci) * 27 + tap];
+  }
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long M = (long long)B * D * H * W;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int wo = (int)(m % W);
+  long long t = m / W;
+  const int ho = (int)(t % H);
+  t /= H;
+  const int d = (int)(t % D);
+  const int b = (int)(t / D);
+  float acc[32];
+#pragma unroll
+  for (int n = 0; n < 32; ++n) acc[n] = sb[n];
+  const size_t HW = (size_t)H * W;
+  for (int kd = 0; kd < 3; ++kd) {
+    const int di = d + kd - 1;
+    if (di < 0 || di >= D) continue;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hi = ho + kh - 1;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wi = wo + kw - 1;
+        if (wi < 0 || wi >= W) continue;
+        const size_t base = ((size_t)(b * D + di) * 2) * HW + (size_t)hi * W + wi;
+        const float x0 = __ldg(x + base), x1 = __ldg(x + base + HW);
+        const float* wt = sw + ((kd * 3 + kh) * 3 + kw) * 64;
+#pragma unroll
+        for (int n = 0; n < 32; ++n) acc[n] = fmaf(x0, wt[n], fmaf(x1, wt[32 + n], acc[n]));
+      }
+    }
+  }
+  uint4 o[4];
+  __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float a0 = acc[2 * i], a1 = acc[2 * i + 1];
+    a0 = a0 > 0.f ? a0 : 0.01f * a0;
+    a1 = a1 > 0.f ? a1 : 0.01f * a1;
+    op[i] = __floats2bfloat162_rn(a0, a1);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m * 32);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dst[i] = o[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// pred: Conv3d(32->20, k1, bias) + ReLU, bf16 NDHWC -> float32 (B,L,20,H,W)  (v2ce_3d.py:29)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pred_conv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, long long M, int HW,
+                                                         float* __restrict__ out) {
+  __shared__ float sw[20 * 32];
+  __shared__ float sb[20];
+  for (int i = threadIdx.x; i < 20 * 32; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 20) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float xin[32];
+  const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)m * 32);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 v = __ldg(src + i);
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(p[j]);
+      xin[i * 8 + 2 * j] = f.x;
+      xin[i * 8 + 2 * j + 1] = f.y;
+    }
+  }
+  const long long plane = m / HW;          // b*L + d
+  const int pix = (int)(m % HW);
+  float* dst = out + (size_t)plane * 20 * HW + pix;
+#pragma unroll
+  for (int n = 0; n < 20; ++n) {
+    float acc = sb[n];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc = fmaf(xin[c], sw[n * 32 + c], acc);
+    dst[(size_t)n * HW] = fmaxf(acc, 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Spectral norm: one power iteration per SN conv per forward (spectral_norm.py:19-31), fp32.
+//   t = W^T u ; v = t/(|t|+eps) ; s = W v ; u = s/(|s|+eps) ; sigma = u . s
+// ------------------------------------------------------------------------------------------
+struct SnDesc {
+  const float* W;   // (rows, K) row-major == weight_bar.view(height, -1)
+  float* u;         // rows
+  float* v;         // K
+  float* t;         // K scratch
+  float* s;         // rows scratch
+  float* partial;   // ceil(K/256) partial sums of t^2
+  int rows, K;
+};
+
+__global__ void __launch_bounds__(256) sn_wtu_kernel(const SnDesc* __restrict__ descs) {
+  const SnDesc d = descs[blockIdx.y];
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (blockIdx.x * 256 >= d.K) return;
+  float acc = 0.f;
+  if (k < d.K) {
+    for (int r = 0; r < d.rows; ++r) acc = fmaf(__ldg(d.W + (size_t)r * d.K + k), __ldg(d.u + r), acc);
+    d.t[k] = acc;
+  }
+  float sq = (k < d.K) ? acc * acc : 0.f;
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    d.partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) sn_norm_v_kernel(const SnDesc* __restrict__ descs) {
+  const SnDesc d = descs[blockIdx.x];
+  __shared__ float norm_s;
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    const int nb = (d.K + 255) / 256;
+    for (int i = 0; i < nb; ++i) s += d.partial[i];
+    norm_s = sqrtf(s) + 1e-12f;
+  }
+  __syncthreads();
+  const float nrm = norm_s;
+  for (int k = threadIdx.x; k < d.K; k += 256) d.v[k] = d.t[k] / nrm;
+}
+
+__global__ void __launch_bounds__(256) sn_wv_kernel(const SnDesc* __restrict__ descs) {
+  const SnDesc d = descs[blockIdx.y];
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= d.rows) return;
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int k = lane; k < d.K; k += 32) acc = fmaf(__ldg(d.W + (size_t)row * d.K + k), d.v[k], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) d.s[row] = acc;
+}
+
+__global__ void __launch_bounds__(256) sn_finish_kernel(const SnDesc* __restrict__ descs, float* __restrict__ sigma,
+                                                         float* __restrict__ inv_sigma) {
+  const SnDesc d = descs[blockIdx.x];
+  __shared__ float red[256];
+  float sq = 0.f;
+  for (int r = threadIdx.x; r < d.rows; r += 256) sq += d.s[r] * d.s[r];
+  red[threadIdx.x] = sq;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float nrm = sqrtf(red[0]) + 1e-12f;
+  __syncthreads();
+  float dot = 0.f;
+  for (int r = threadIdx.x; r < d.rows; r += 256) {
+    const float un = d.s[r] / nrm;
+    d.u[r] = un;
+    dot += un * d.s[r];
+  }
+  red[threadIdx.x] = dot;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    sigma[blockIdx.x] = red[0];
+    inv_sigma[blockIdx.x] = 1.f / red[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------
+struct DevLayer {
+  __nv_bfloat16* wpack = nullptr;
+  float* scale = nullptr;
+  float* shift = nullptr;
+  float* w32 = nullptr;     // head / pred fp32 weights, SN weight_bar
+  float* bias = nullptr;    // head / pred bias
+  int bn_tile = 0, num_kb = 0, sn_index = -1;
+};
+
+}  // namespace unet
+}  // namespace v2ce
+
+struct v2ce_model {
+  int device = 0;
+  bool finalized = false;
+  std::map<std::string, std::vector<float>> host;
+  std::map<std::string, std::vector<int64_t>> shapes;
+  v2ce::unet::DevLayer layers[v2ce::unet::kNumLayers];
+  std::vector<void*> allocs;
+  v2ce::unet::SnDesc* sn_descs_dev = nullptr;
+  v2ce::unet::SnDesc sn_descs_host[v2ce::unet::kNumSn];
+  float* sigma_dev = nullptr;
+  float* inv_sigma_dev = nullptr;
+  int* error_flag_dev = nullptr;
+  int max_rows = 0, max_k = 0;
+  int64_t calls = 0;
+  int last_launches = 0;
+};
+
+namespace v2ce {
+namespace unet {
+
+template <typename T>
+static int dev_alloc(v2ce_model* m, T** p, size_t count) {
+  void* q = nullptr;
+  V2CE_CUDA_CHECK(cudaMalloc(&q, count * sizeof(T)));
+  m->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return V2CE_OK;
+}
+
+static int upload(v2ce_model* m, float** dst, const std::vector<float>& v) {
+  if (int e = dev_alloc(m, dst, v.size())) return e;
+  V2CE_CUDA_CHECK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return V2CE_OK;
+}
+
+static const std::vector<float>* find(const v2ce_model* m, const std::string& key) {
+  auto it = m->host.find(key);
+  return it == m->host.end() ? nullptr : &it->second;
+}
+
+static bool known_name(const std::string& name) {
+  for (int i = 0; i < kNumLayers; ++i) {
+    const LayerSpec& L = kLayers[i];
+    const std::string base = L.name;
+    if (L.sn) {
+      if (name == base + ".module.weight_bar" || name == base + ".module.weight_u" || name == base + ".module.weight_v")
+        return true;
+    } else {
+      if (name == base + ".weight") return true;
+      if (L.bias && name == base + ".bias") return true;
+    }
+    if (L.bn) {
+      const std::string bn = L.bn;
+      if (name == bn + ".weight" || name == bn + ".bias" || name == bn + ".running_mean" || name == bn + ".running_var")
+        return true;
+    }
+  }
+  return false;
+}
+
+static int run_sn_step(v2ce_model* m, cudaStream_t s) {
+  dim3 g1((m->max_k + 255) / 256, kNumSn);
+  sn_wtu_kernel<<<g1, 256, 0, s>>>(m->sn_descs_dev);
+  V2CE_LAUNCH_CHECK("sn_wtu_kernel");
+  sn_norm_v_kernel<<<kNumSn, 256, 0, s>>>(m->sn_descs_dev);
+  V2CE_LAUNCH_CHECK("sn_norm_v_kernel");
+  dim3 g3((m->max_rows + 7) / 8, kNumSn);
+  sn_wv_kernel<<<g3, 256, 0, s>>>(m->sn_descs_dev);
+  V2CE_LAUNCH_CHECK("sn_wv_kernel");
+  sn_finish_kernel<<<kNumSn, 256, 0, s>>>(m->sn_descs_dev, m->sigma_dev, m->inv_sigma_dev);
+  V2CE_LAUNCH_CHECK("sn_finish_kernel");
+  m->calls += 1;
+  return V2CE_OK;
+}
+
+struct Dims {
+  int H[5], W[5];
+  long long M[5];
+};
+
+static Dims make_dims(int B, int D, int H, int W) {
+  Dims d;
+  d.H[0] = H; d.W[0] = W;
+  for (int i = 1; i < 5; ++i) { d.H[i] = (d.H[i - 1] - 1) / 2 + 1; d.W[i] = (d.W[i - 1] - 1) / 2 + 1; }
+  for (int i = 0; i < 5; ++i) d.M[i] = (long long)B * D * d.H[i] * d.W[i];
+  return d;
+}
+
+struct Buffers {
+  __nv_bfloat16 *head, *enc[4], *res[2], *dec[4], *tmp_t, *tmp_r;
+  size_t bytes;
+};
+
+static Buffers carve(void* ws, const Dims& d) {
+  Arena a(ws, (size_t)-1);
+  Buffers b;
+  static const int ch[5] = {32, 64, 128, 256, 512};
+  b.head = a.take<__nv_bfloat16>((size_t)d.M[0] * 32);
+  for (int i = 0; i < 4; ++i) b.enc[i] = a.take<__nv_bfloat16>((size_t)d.M[i + 1] * ch[i + 1]);
+  for (int i = 0; i < 2; ++i) b.res[i] = a.take<__nv_bfloat16>((size_t)d.M[4] * 512);
+  for (int i = 0; i < 4; ++i) b.dec[i] = a.take<__nv_bfloat16>((size_t)d.M[3 - i] * ch[3 - i]);
+  size_t tmax = 0;
+  for (int i = 0; i < 5; ++i) tmax = tmax > (size_t)d.M[i] * ch[i] ? tmax : (size_t)d.M[i] * ch[i];
+  b.tmp_t = a.take<__nv_bfloat16>(tmax);
+  b.tmp_r = a.take<__nv_bfloat16>(tmax);
+  b.bytes = align_up(a.off, 256);
+  return b;
+}
+
+static int layer_index(const char* name) {
+  for (int i = 0; i < kNumLayers; ++i)
+    if (std::string(kLayers[i].name) == name) return i;
+  return -1;
+}
+
+// one fused conv launch of layer `li`
+static int run_conv(v2ce_model* m, int li, const __nv_bfloat16* src0, int c0, int h0, int w0, const __nv_bfloat16* src1,
+                    int c1, int B, int D, int hin, int win, int stride, const __nv_bfloat16* residual, int act,
+                    __nv_bfloat16* out, cudaStream_t s) {
+  const LayerSpec& L = kLayers[li];
+  const DevLayer& dl = m->layers[li];
+  ConvArgs a;
+  a.src0 = src0; a.src1 = src1; a.C0 = c0; a.C1 = c1; a.Cin = c0 + c1;
+  a.H0 = h0; a.W0 = w0; a.B = B; a.D = D; a.Hin = hin; a.Win = win;
+  a.stride = stride; a.ksize = L.k; a.pad = L.k / 2;
+  a.Hout = (hin + 2 * a.pad - L.k) / stride + 1;
+  a.Wout = (win + 2 * a.pad - L.k) / stride + 1;
+  a.taps = L.k * L.k * L.k;
+  a.num_kb = dl.num_kb;
+  a.M = B * D * a.Hout * a.Wout;
+  a.Cout = L.cout;
+  a.wpack = dl.wpack; a.scale = dl.scale; a.shift = dl.shift;
+  a.inv_sigma = dl.sn_index >= 0 ? m->inv_sigma_dev + dl.sn_index : nullptr;
+  a.residual = residual; a.out = out; a.act = act;
+  a.error_flag = m->error_flag_dev;
+  if (a.Cin != L.cin) return set_error(V2CE_ERR_STATE, "layer %s: Cin %d != %d", L.name, a.Cin, L.cin);
+  return conv::launch_conv(a, dl.bn_tile, s);
+}
+
+static int pack_layer(v2ce_model* m, int li, const float* w_dev, cudaStream_t s) {
+  const LayerSpec& L = kLayers[li];
+  DevLayer& dl = m->layers[li];
+  const int taps = L.k * L.k * L.k;
+  dl.bn_tile = conv::pick_bn(L.cout);
+  dl.num_kb = (taps * L.cin + conv::kBlockK - 1) / conv::kBlockK;
+  const size_t n = (size_t)L.cout * dl.num_kb * conv::kBlockK;
+  if (int e = dev_alloc(m, &dl.wpack, n)) return e;
+  conv::pack_weights_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(
+      w_dev, L.cout, L.cin, taps, dl.bn_tile, dl.num_kb, dl.wpack);
+  V2CE_LAUNCH_CHECK("pack_weights_kernel");
+  return V2CE_OK;
+}
+
+}  // namespace unet
+}  // namespace v2ce
+
 using namespace v2ce;
-#define STUB return set_error(V2CE_ERR_STATE, "stage 1 not built yet")
-extern "C" int v2ce_model_create(v2ce_model**, int) { STUB; }
-extern "C" int v2ce_model_destroy(v2ce_model*) { STUB; }
-extern "C" int v2ce_model_set_tensor(v2ce_model*, const char*, const float*, const int64_t*, int32_t) { STUB; }
-extern "C" int v2ce_model_finalize(v2ce_model*) { STUB; }
-extern "C" int v2ce_model_workspace_bytes(const v2ce_model*, int32_t, int32_t, int32_t, int32_t, size_t*) { STUB; }
-extern "C" int v2ce_model_forward(v2ce_model*, const float*, float*, int32_t, int32_t, int32_t, int32_t, void*, size_t, void*) { STUB; }
-extern "C" int v2ce_model_last_sigmas(const v2ce_model*, float*) { STUB; }
-extern "C" int v2ce_model_call_count(const v2ce_model*, int64_t*) { STUB; }
-extern "C" int v2ce_model_sn_advance(v2ce_model*, int32_t, void*) { STUB; }
-extern "C" int v2ce_model_last_launches(const v2ce_model*, int32_t*) { STUB; }
-extern "C" int v2ce_conv3d_bf16(const void*, int32_t, int32_t, int32_t, const void*, int32_t, int32_t, int32_t, int32_t, int32_t, int32_t, int32_t, const float*, int32_t, const float*, const float*, const void*, int32_t, void*, void*) { STUB; }
+using namespace v2ce::unet;
+
+extern "C" int v2ce_model_create(v2ce_model** out, int device) {
+  V2CE_REQUIRE(out != nullptr, "out is NULL");
+  if (int e = v2ce_device_check(device, nullptr, nullptr, nullptr)) return e;
+  v2ce_model* m = new v2ce_model();
+  m->device = device;
+  *out = m;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_model_destroy(v2ce_model* m) {
+  if (!m) return V2CE_OK;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_model_set_tensor(v2ce_model* m, const char* name, const float* data_host, const int64_t* shape,
+                                     int32_t ndim) {
+  V2CE_REQUIRE(m && name && data_host && (shape || ndim == 0), "NULL argument");
+  V2CE_REQUIRE(!m->finalized, "model already finalized");
+  const std::string key = name;
+  if (!known_name(key)) return set_error(V2CE_ERR_INVALID, "unknown state_dict entry '%s'", name);
+  size_t n = 1;
+  std::vector<int64_t> shp;
+  for (int i = 0; i < ndim; ++i) { n *= (size_t)shape[i]; shp.push_back(shape[i]); }
+  m->host[key] = std::vector<float>(data_host, data_host + n);
+  m->shapes[key] = shp;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_model_finalize(v2ce_model* m) {
+  V2CE_REQUIRE(m != nullptr, "model is NULL");
+  V2CE_REQUIRE(!m->finalized, "model already finalized");
+  V2CE_CUDA_CHECK(cudaSetDevice(m->device));
+  cudaStream_t s = 0;
+  if (int e = dev_alloc(m, &m->sigma_dev, kNumSn)) return e;
+  if (int e = dev_alloc(m, &m->inv_sigma_dev, kNumSn)) return e;
+  if (int e = dev_alloc(m, &m->error_flag_dev, 1)) return e;
+  V2CE_CUDA_CHECK(cudaMemset(m->error_flag_dev, 0, sizeof(int)));
+  int sn_count = 0;
+  for (int li = 0; li < kNumLayers; ++li) {
+    const LayerSpec& L = kLayers[li];
+    DevLayer& dl = m->layers[li];
+    const std::string base = L.name;
+    const int taps = L.k * L.k * L.k;
+    const size_t wn = (size_t)L.cout * L.cin * taps;
+    const std::vector<float>* w = find(m, base + (L.sn ? ".module.weight_bar" : ".weight"));
+    if (!w || w->size() != wn) return set_error(V2CE_ERR_STATE, "missing or mis-sized weight for %s", L.name);
+    if (int e = upload(m, &dl.w32, *w)) return e;
+    const std::vector<float>* bias = L.bias ? find(m, base + ".bias") : nullptr;
+    if (L.bias && (!bias || (int)bias->size() != L.cout)) return set_error(V2CE_ERR_STATE, "missing bias for %s", L.name);
+    const bool direct = (li == 0 || li == kNumLayers - 1);   // head and pred run on CUDA cores in fp32
+    if (direct) {
+      if (int e = upload(m, &dl.bias, *bias)) return e;
+      continue;
+    }
+    // eval-mode BatchNorm folded into y = acc*scale + shift (scale *= 1/sigma at run time for SN convs)
+    std::vector<float> scale(L.cout, 1.f), shift(L.cout, 0.f);
+    if (L.bn) {
+      const std::string bn = L.bn;
+      const std::vector<float>*g = find(m, bn + ".weight"), *b = find(m, bn + ".bias"), *mu = find(m, bn + ".running_mean"),
+                              *var = find(m, bn + ".running_var");
+      if (!g || !b || !mu || !var || (int)g->size() != L.cout)
+        return set_error(V2CE_ERR_STATE, "missing BatchNorm tensors %s.*", L.bn);
+      for (int c = 0; c < L.cout; ++c) {
+        const float sc = (*g)[c] / sqrtf((*var)[c] + kBnEps);
+        scale[c] = sc;
+        shift[c] = (*b)[c] - (*mu)[c] * sc + (bias ? (*bias)[c] * sc : 0.f);
+      }
+    } else if (bias) {
+      for (int c = 0; c < L.cout; ++c) shift[c] = (*bias)[c];
+    }
+    if (int e = upload(m, &dl.scale, scale)) return e;
+    if (int e = upload(m, &dl.shift, shift)) return e;
+    if (int e = pack_layer(m, li, dl.w32, s)) return e;
+    if (L.sn) {
+      V2CE_REQUIRE(sn_count < kNumSn, "too many spectral-norm layers");
+      dl.sn_index = sn_count;
+      SnDesc& d = m->sn_descs_host[sn_count];
+      d.rows = L.cout;
+      d.K = L.cin * taps;
+      d.W = dl.w32;
+      const std::vector<float>*u = find(m, base + ".module.weight_u"), *v = find(m, base + ".module.weight_v");
+      if (!u || !v || (int)u->size() != d.rows || (int)v->size() != d.K)
+        return set_error(V2CE_ERR_STATE, "missing weight_u / weight_v for %s", L.name);
+      if (int e = upload(m, &d.u, *u)) return e;
+      if (int e = upload(m, &d.v, *v)) return e;
+      if (int e = dev_alloc(m, &d.t, (size_t)d.K)) return e;
+      if (int e = dev_alloc(m, &d.s, (size_t)d.rows)) return e;
+      if (int e = dev_alloc(m, &d.partial, (size_t)(d.K + 255) / 256)) return e;
+      m->max_rows = m->max_rows > d.rows ? m->max_rows : d.rows;
+      m->max_k = m->max_k > d.K ? m->max_k : d.K;
+      ++sn_count;
+    }
+  }
+  V2CE_REQUIRE(sn_count == kNumSn, "expected %d spectral-norm convs, found %d", kNumSn, sn_count);
+  if (int e = dev_alloc(m, &m->sn_descs_dev, kNumSn)) return e;
+  V2CE_CUDA_CHECK(cudaMemcpy(m->sn_descs_dev, m->sn_descs_host, sizeof(SnDesc) * kNumSn, cudaMemcpyHostToDevice));
+  V2CE_CUDA_CHECK(cudaDeviceSynchronize());
+  // fp32 copies of the non-SN GEMM weights are no longer needed on the device side, but they are small
+  // next to the activations; host staging copies are released.
+  m->host.clear();
+  m->finalized = true;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_model_workspace_bytes(const v2ce_model* m, int32_t batch, int32_t depth, int32_t height,
+                                          int32_t width, size_t* bytes) {
+  V2CE_REQUIRE(m && bytes, "NULL argument");
+  V2CE_REQUIRE(batch > 0 && depth > 0 && height > 0 && width > 0, "bad shape");
+  V2CE_REQUIRE((long long)batch * depth * height * width < (1LL << 31), "batch*depth*H*W must be < 2^31");
+  *bytes = carve(nullptr, make_dims(batch, depth, height, width)).bytes;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_dev, int32_t B, int32_t D, int32_t H,
+                                  int32_t W, void* ws_dev, size_t ws_bytes, void* stream) {
+  V2CE_REQUIRE(m && x_dev && y_dev && ws_dev, "NULL argument");
+  V2CE_REQUIRE(m->finalized, "model not finalized");
+  V2CE_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "bad shape");
+  V2CE_REQUIRE((long long)B * D * H * W < (1LL << 31), "batch*depth*H*W must be < 2^31");
+  const Dims d = make_dims(B, D, H, W);
+  const Buffers buf = carve(ws_dev, d);
+  if (buf.bytes > ws_bytes) return set_error(V2CE_ERR_WORKSPACE, "workspace too small: need %zu, got %zu", buf.bytes, ws_bytes);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int launches = 0;
+  if (int e = run_sn_step(m, s)) return e;
+  launches += 4;
+
+  const long long M0 = d.M[0];
+  head_conv_kernel<<<(int)((M0 + 127) / 128), 128, 0, s>>>(x_dev, m->layers[0].w32, m->layers[0].bias, B, D, H, W, buf.head);
+  V2CE_LAUNCH_CHECK("head_conv_kernel");
+  ++launches;
+
+  static const int ch[5] = {32, 64, 128, 256, 512};
+  char name[64];
+  const __nv_bfloat16* x = buf.head;
+  // encoders: stride (1,2,2)
+  for (int i = 0; i < 4; ++i) {
+    snprintf(name, sizeof(name), "UNet.encoders.%d.conv1", i);
+    const int l1 = layer_index(name);
+    if (int e = run_conv(m, l1, x, ch[i], d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 1, buf.tmp_t, s)) return e;
+    if (int e = run_conv(m, l1 + 2, x, ch[i], d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 0, buf.tmp_r, s)) return e;
+    if (int e = run_conv(m, l1 + 1, buf.tmp_t, ch[i + 1], d.H[i + 1], d.W[i + 1], nullptr, 0, B, D, d.H[i + 1], d.W[i + 1], 1,
+                         buf.tmp_r, 1, buf.enc[i], s)) return e;
+    x = buf.enc[i];
+    launches += 3;
+  }
+  // residual blocks at the bottleneck
+  for (int i = 0; i < 2; ++i) {
+    snprintf(name, sizeof(name), "UNet.resblocks.%d.conv1", i);
+    const int l1 = layer_index(name);
+    if (int e = run_conv(m, l1, x, 512, d.H[4], d.W[4], nullptr, 0, B, D, d.H[4], d.W[4], 1, nullptr, 1, buf.tmp_t, s)) return e;
+    if (int e = run_conv(m, l1 + 2, x, 512, d.H[4], d.W[4], nullptr, 0, B, D, d.H[4], d.W[4], 1, nullptr, 0, buf.tmp_r, s)) return e;
+    if (int e = run_conv(m, l1 + 1, buf.tmp_t, 512, d.H[4], d.W[4], nullptr, 0, B, D, d.H[4], d.W[4], 1, buf.tmp_r, 1, buf.res[i], s)) return e;
+    x = buf.res[i];
+    launches += 3;
+  }
+  // decoders: virtual concat [nearest_up(x), skip]; skips are head, enc0, enc1, enc2 in reverse
+  int xc = 512, xl = 4;   // channels / level of x
+  for (int i = 0; i < 4; ++i) {
+    const int lvl = 3 - i;                       // output level
+    const __nv_bfloat16* skip = lvl == 0 ? buf.head : buf.enc[lvl - 1];
+    const int sc = ch[lvl];
+    snprintf(name, sizeof(name), "UNet.decoders.%d.conv1", i);
+    const int l1 = layer_index(name);
+    if (int e = run_conv(m, l1, x, xc, d.H[xl], d.W[xl], skip, sc, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 1, buf.tmp_t, s)) return e;
+    if (int e = run_conv(m, l1 + 2, x, xc, d.H[xl], d.W[xl], skip, sc, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 0, buf.tmp_r, s)) return e;
+    if (int e = run_conv(m, l1 + 1, buf.tmp_t, ch[lvl], d.H[lvl], d.W[lvl], nullptr, 0, B, D, d.H[lvl], d.W[lvl], 1, buf.tmp_r, 1,
+                         buf.dec[i], s)) return e;
+    x = buf.dec[i];
+    xc = ch[lvl];
+    xl = lvl;
+    launches += 3;
+  }
+  const int lp = kNumLayers - 1;
+  pred_conv_kernel<<<(int)((M0 + 127) / 128), 128, 0, s>>>(x, m->layers[lp].w32, m->layers[lp].bias, M0, H * W, y_dev);
+  V2CE_LAUNCH_CHECK("pred_conv_kernel");
+  ++launches;
+  m->last_launches = launches;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_model_last_sigmas(const v2ce_model* m, float* sigma12_host) {
+  V2CE_REQUIRE(m && sigma12_host && m->finalized, "bad argument");
+  V2CE_CUDA_CHECK(cudaMemcpy(sigma12_host, m->sigma_dev, sizeof(float) * kNumSn, cudaMemcpyDeviceToHost));
+  int flag = 0;
+  V2CE_CUDA_CHECK(cudaMemcpy(&flag, m->error_flag_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) return set_error(V2CE_ERR_CUDA, "conv pipeline watchdog fired");
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_model_call_count(const v2ce_model* m, int64_t* calls) {
+  V2CE_REQUIRE(m && calls, "NULL argument");
+  *calls = m->calls;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_model_sn_advance(v2ce_model* m, int32_t n_calls, void* stream) {
+  V2CE_REQUIRE(m && m->finalized && n_calls >= 0, "bad argument");
+  for (int i = 0; i < n_calls; ++i)
+    if (int e = run_sn_step(m, static_cast<cudaStream_t>(stream))) return e;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_model_last_launches(const v2ce_model* m, int32_t* launches) {
+  V2CE_REQUIRE(m && launches, "NULL argument");
+  *launches = m->last_launches;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_conv3d_bf16(const void* src0_dev, int32_t c0, int32_t h0, int32_t w0, const void* src1_dev, int32_t c1,
+                                int32_t batch, int32_t depth, int32_t hin, int32_t win, int32_t ksize, int32_t stride_hw,
+                                const float* weight_host, int32_t cout, const float* scale_host, const float* shift_host,
+                                const void* residual_dev, int32_t act, void* out_dev, void* stream) {
+  V2CE_REQUIRE(src0_dev && weight_host && scale_host && shift_host && out_dev, "NULL argument");
+  V2CE_REQUIRE(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
+  V2CE_REQUIRE(stride_hw == 1 || stride_hw == 2, "stride must be 1 or 2");
+  V2CE_REQUIRE(c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0, "channel counts must be multiples of 8");
+  V2CE_REQUIRE((src1_dev != nullptr) == (c1 > 0), "src1 and c1 must agree");
+  const int bn = conv::pick_bn(cout);
+  V2CE_REQUIRE(bn != 0, "cout must be a multiple of 32");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cin = c0 + c1, taps = ksize * ksize * ksize;
+  const int num_kb = (taps * cin + conv::kBlockK - 1) / conv::kBlockK;
+  float *w_dev = nullptr, *scale_dev = nullptr, *shift_dev = nullptr;
+  __nv_bfloat16* wpack = nullptr;
+  int* flag = nullptr;
+  const size_t wn = (size_t)cout * cin * taps, pn = (size_t)cout * num_kb * conv::kBlockK;
+  V2CE_CUDA_CHECK(cudaMalloc(&w_dev, wn * sizeof(float)));
+  V2CE_CUDA_CHECK(cudaMalloc(&scale_dev, cout * sizeof(float)));
+  V2CE_CUDA_CHECK(cudaMalloc(&shift_dev, cout * sizeof(float)));
+  V2CE_CUDA_CHECK(cudaMalloc(&wpack, pn * sizeof(__nv_bfloat16)));
+  V2CE_CUDA_CHECK(cudaMalloc(&flag, sizeof(int)));
+  V2CE_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  V2CE_CUDA_CHECK(cudaMemcpyAsync(w_dev, weight_host, wn * sizeof(float), cudaMemcpyHostToDevice, s));
+  V2CE_CUDA_CHECK(cudaMemcpyAsync(scale_dev, scale_host, cout * sizeof(float), cudaMemcpyHostToDevice, s));
+  V2CE_CUDA_CHECK(cudaMemcpyAsync(shift_dev, shift_host, cout * sizeof(float), cudaMemcpyHostToDevice, s));
+  conv::pack_weights_kernel<<<(int)((pn + 255) / 256 > 4096 ? 4096 : (pn + 255) / 256), 256, 0, s>>>(w_dev, cout, cin, taps, bn,
+                                                                                                     num_kb, wpack);
+  int rc = V2CE_OK;
+  if (cudaGetLastError() != cudaSuccess) rc = set_error(V2CE_ERR_CUDA, "pack_weights_kernel launch failed");
+  if (rc == V2CE_OK) {
+    ConvArgs a;
+    a.src0 = static_cast<const __nv_bfloat16*>(src0_dev);
+    a.src1 = static_cast<const __nv_bfloat16*>(src1_dev);
+    a.C0 = c0; a.C1 = c1; a.Cin = cin; a.H0 = h0; a.W0 = w0;
+    a.B = batch; a.D = depth; a.Hin = hin; a.Win = win;
+    a.stride = stride_hw; a.ksize = ksize; a.pad = ksize / 2;
+    a.Hout = (hin + 2 * a.pad - ksize) / stride_hw + 1;
+    a.Wout = (win + 2 * a.pad - ksize) / stride_hw + 1;
+    a.taps = taps; a.num_kb = num_kb;
+    a.M = batch * depth * a.Hout * a.Wout;
+    a.Cout = cout; a.wpack = wpack; a.scale = scale_dev; a.shift = shift_dev; a.inv_sigma = nullptr;
+    a.residual = static_cast<const __nv_bfloat16*>(residual_dev);
+    a.out = static_cast<__nv_bfloat16*>(out_dev);
+    a.act = act; a.error_flag = flag;
+    rc = conv::launch_conv(a, bn, s);
+  }
+  cudaError_t se = cudaStreamSynchronize(s);
+  int hflag = 0;
+  if (se == cudaSuccess) cudaMemcpy(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(w_dev); cudaFree(scale_dev); cudaFree(shift_dev); cudaFree(wpack); cudaFree(flag);
+  if (rc != V2CE_OK) return rc;
+  if (se != cudaSuccess) return set_error(V2CE_ERR_CUDA, "conv3d_bf16 failed: %s", cudaGetErrorString(se));
+  if (hflag) return set_error(V2CE_ERR_CUDA, "conv pipeline watchdog fired");
+  return V2CE_OK;
+}
