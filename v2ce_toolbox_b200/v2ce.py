@@ -1,0 +1,306 @@
+"""Drop-in for /root/reference/v2ce.py: same CLI flags, function names, arguments and output
+files, with the device work routed through libv2ce_b200.so.
+
+Two ways in:
+  * the reference's functions, one for one (``get_trained_mode``, ``image_pre_processing``,
+    ``infer_center_image_unit``, ``infer_pano_image_unit``, ``video_to_voxels``, ``merge_voxels``,
+    ``write_event_frame_video``) -- same inputs, same host-side return values;
+  * ``stream_clip`` (what ``main`` uses): the reference's __main__ (v2ce.py:322-372) re-scheduled
+    so voxels never leave the GPU.  Per batch of windows: H2D image units -> UNet -> event-frame
+    sums + LDATI on the device -> packed events D2H.  The clip-global percentile of the preview
+    video (v2ce.py:262-264) is taken at the end over the (N,2,H,W) sums kept on the device.
+    Outputs are identical to running the reference's steps in its own order, because windows,
+    frame pairs and pano tiles are independent and the uniform draws are a counter-based
+    function of the global frame index.
+"""
+import argparse
+import logging
+import os
+import os.path as op
+from functools import partial
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import event_frames as _ef
+from . import ldati as _ldati
+from ._lib import V2ceError
+from .scripts.LDATI import sample_voxel_statistical
+from .scripts.v2ce_3d import V2ce3d
+
+logger = logging.getLogger('V2CE')
+
+
+def SBool(v):
+    if isinstance(v, bool):
+        return v
+    if v.lower() in ('yes', 'true', 't', 'y', '1'):
+        return True
+    if v.lower() in ('no', 'false', 'f', 'n', '0'):
+        return False
+    raise argparse.ArgumentTypeError('Boolean value expected.')
+
+
+def get_trained_mode(model_path='./weights/v2ce_3d.pt'):
+    """v2ce.py:30-43 -- load the checkpoint into the B200 model."""
+    model = V2ce3d()
+    model.load_state_dict(torch.load(model_path, map_location='cpu'))
+    model = model.eval()
+    model = model.to('cuda')
+    return model
+
+
+def image_pre_processing(images, height=260):
+    """v2ce.py:45-64 -- (N,H,W) uint8 gray frames -> (N-1,2,H',W') float32 image units.
+    /255, bilinear resize to `height`, pair stacking, Normalize(0.153, 0.165)."""
+    import cv2
+    images = images.astype(np.float32) / 255
+    images = np.stack([cv2.resize(img, (int(img.shape[1] / img.shape[0] * height), height)) for img in images], axis=0)
+    units = np.stack([images[:-1], images[1:]], axis=1)
+    units = (units - np.float32(0.153)) / np.float32(0.165)
+    return torch.from_numpy(np.ascontiguousarray(units, dtype=np.float32))
+
+
+def window_schedule(frame_count, seq_len=16):
+    """v2ce.py:149-154 -- window starts; the last one is pulled back when (F-1) % seq_len != 0."""
+    sequence_num = int(np.ceil((frame_count - 1) / seq_len))
+    mode = (frame_count - 1) % seq_len
+    starts = np.arange(sequence_num) * seq_len
+    if mode != 0:
+        starts[-1] -= (seq_len - mode)
+    return starts, mode
+
+
+def pano_tiles(total_width, width=346):
+    """v2ce.py:103-111 -- (src_start, src_end, columns kept from the right) per 346-px tile."""
+    n = int(np.ceil(total_width / width))
+    exact = total_width % 346 == 0            # the reference tests the literal 346 here
+    rem = total_width % width
+    tiles = []
+    for i in range(n):
+        if i == n - 1 and not exact:
+            tiles.append((total_width - width, total_width, rem))
+        else:
+            tiles.append((i * width, (i + 1) * width, width))
+    return tiles
+
+
+@torch.no_grad()
+def _center_device(model, image_units, width=346):
+    c = image_units.shape[-1] // 2
+    units = image_units[..., c - width // 2:c + width // 2]
+    return model(units.float().contiguous().cuda(non_blocking=True))
+
+
+@torch.no_grad()
+def _pano_device(model, image_units, width=346):
+    parts = []
+    for (a, b, keep) in pano_tiles(image_units.shape[-1], width):
+        out = model(image_units[..., a:b].float().contiguous().cuda(non_blocking=True))
+        parts.append(out[..., -keep:] if keep != width else out)
+    return torch.cat(parts, dim=-1) if len(parts) > 1 else parts[0]
+
+
+@torch.no_grad()
+def infer_center_image_unit(model, image_units, width=346):
+    """v2ce.py:66-89 -- center crop, model, back to host."""
+    return _center_device(model, image_units, width).cpu()
+
+
+@torch.no_grad()
+def infer_pano_image_unit(model, image_units, width=346):
+    """v2ce.py:91-129 -- 346-px width tiles (one model call each), concatenated on the width."""
+    return _pano_device(model, image_units, width).cpu()
+
+
+def _read_window(image_paths, vidcap, start, seq_len):
+    import cv2
+    idx = range(start, start + seq_len + 1)
+    if vidcap is not None:
+        return vidcap.read_frames_at_indices(idx)
+    return np.stack([cv2.imread(p, cv2.IMREAD_GRAYSCALE) for p in image_paths[start:start + seq_len + 1]], axis=0)
+
+
+def _batches(image_paths, vidcap, seq_len, height, batch_size):
+    """Yield (image_units (b,L,2,H',W') float32 host tensor, is_last) in the reference's batching."""
+    frame_count = vidcap.frame_count if vidcap is not None else len(image_paths)
+    starts, mode = window_schedule(frame_count, seq_len)
+    pending = []
+    for i, st in enumerate(starts):
+        pending.append(image_pre_processing(_read_window(image_paths, vidcap, st, seq_len), height)[None])
+        if len(pending) == batch_size or i == len(starts) - 1:
+            yield (torch.cat(pending, dim=0) if len(pending) > 1 else pending[0]), i == len(starts) - 1
+            pending = []
+
+
+@torch.no_grad()
+def video_to_voxels(model, image_paths=None, vidcap=None, infer_type='center', seq_len=16, width=346, height=260,
+                    batch_size=1):
+    """v2ce.py:131-209 -- returns the host voxel grid (N,2,10,H,W) float32 like the reference."""
+    assert image_paths is not None or vidcap is not None
+    frame_count = vidcap.frame_count if vidcap is not None else len(image_paths)
+    _, mode = window_schedule(frame_count, seq_len)
+    outs = []
+    out_width = width
+    for units, _last in _batches(image_paths, vidcap, seq_len, height, batch_size):
+        if infer_type == 'center':
+            out_width = width
+            pred = infer_center_image_unit(model, units, width)
+        elif infer_type == 'pano':
+            out_width = units.shape[-1]
+            pred = infer_pano_image_unit(model, units, width)
+        else:
+            raise ValueError(f'Invalid infer_type {infer_type}')
+        outs.append(pred.numpy())
+    return merge_voxels(outs, height=height, width=out_width, mode=mode)
+
+
+def merge_voxels(voxel_list, height=260, width=346, mode=0):
+    """v2ce.py:211-239 -- (b,L,20,H,W) batches -> (N,2,10,H,W); the pulled-back last window keeps its last `mode` pairs."""
+    chunks = [v.reshape(-1, 2, 10, height, width) for v in voxel_list[:-1]]
+    last = voxel_list[-1]
+    if last.shape[0] > 1:
+        chunks.append(last[:-1].reshape(-1, 2, 10, height, width))
+    tail = last[-1][-mode:] if mode != 0 else last[-1]
+    chunks.append(tail.reshape(-1, 2, 10, height, width))
+    return np.concatenate(chunks, axis=0)
+
+
+write_event_frame_video = _ef.write_event_frame_video      # v2ce.py:241-280
+
+
+def frame_offset_us(i, fps):
+    """v2ce.py:365 -- Python double arithmetic, then int()."""
+    return int(i * 1 / fps * 1e6)
+
+
+class ClipResult:
+    def __init__(self, event_stream, ef_frames, ef_upper_bound, n_pairs):
+        self.event_stream = event_stream
+        self.ef_frames = ef_frames
+        self.ef_upper_bound = ef_upper_bound
+        self.n_pairs = n_pairs
+
+
+@torch.no_grad()
+def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_len=16, width=346, height=260,
+                batch_size=1, fps=30, ceil=10, upper_bound_percentile=98, keep_polarity=True,
+                write_event_frames=True, seed=0, pair_base=0, device=None):
+    """Device-resident version of v2ce.py:322-372.  Returns ClipResult with the concatenated event
+    stream (timestamps offset per frame, v2ce.py:365) and the uint8 BGR preview frames."""
+    assert image_paths is not None or vidcap is not None
+    device = torch.device(device or 'cuda')
+    frame_count = vidcap.frame_count if vidcap is not None else len(image_paths)
+    starts, mode = window_schedule(frame_count, seq_len)
+    eng = _ldati.engine_for(device)
+    sums_all, event_chunks = [], []
+    pair_idx = pair_base
+    for units, is_last in _batches(image_paths, vidcap, seq_len, height, batch_size):
+        pred = _center_device(model, units, width) if infer_type == 'center' else _pano_device(model, units, width)
+        b, L, _, H, W = pred.shape
+        vox = pred.reshape(b * L, 2, 10, H, W)
+        if is_last and mode != 0:                       # merge_voxels: drop the re-inferred overlap
+            vox = torch.cat([vox[:(b - 1) * L], vox[(b - 1) * L + (L - mode):]], dim=0).contiguous()
+        n = vox.shape[0]
+        if write_event_frames:
+            sums_all.append(_ef.accumulate(vox, keep_polarity))
+        params = _ldati.make_params(n, H, W, fps=fps, seed=seed, frame_base=pair_idx, device=device,
+                                    add_frame_offset=True)
+        offs = torch.tensor([frame_offset_us(pair_idx + i, fps) for i in range(n)], dtype=torch.int64,
+                            device=device)
+        events, seg_counts, status = eng.run(vox, params, frame_offsets=offs)
+        total = int(seg_counts.sum())
+        host = torch.empty(total * 13, dtype=torch.uint8, pin_memory=True)
+        host.copy_(events[:total * 13], non_blocking=True)
+        _ldati.check_status(status.cpu().numpy())       # synchronises
+        event_chunks.append(host.numpy().view(_ldati.EVENT_DTYPE))
+        pair_idx += n
+    frames, ub = None, None
+    if write_event_frames:
+        sums = torch.cat(sums_all, dim=0) if len(sums_all) > 1 else sums_all[0]
+        ub = _ef.upper_bound(sums, upper_bound_percentile, ceil, keep_polarity)
+        frames = _ef.normalize(sums, ub, keep_polarity).cpu().numpy()
+    stream = np.concatenate(event_chunks) if event_chunks else np.empty(0, _ldati.EVENT_DTYPE)
+    return ClipResult(stream, frames, ub, pair_idx - pair_base)
+
+
+def build_parser():
+    """The reference's flags, verbatim (v2ce.py:283-302)."""
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--fps', type=int, default=30, help='FPS of the output video')
+    parser.add_argument('--seq_len', type=int, default=16, help='Sequence length')
+    parser.add_argument('--ceil', type=int, default=10, help='The ceiling of the ef value')
+    parser.add_argument('-u', '--upper_bound_percentile', type=int, default=98,
+                        help='The percentile of the event frame nonzero values to set the upper bound during video writing')
+    parser.add_argument('-f', '--image_folder', type=str, help='The folder containing the images to infer')
+    parser.add_argument('-i', '--input_video_path', type=str, help='The path to the input video')
+    parser.add_argument('-o', '--out_folder', type=str, default='./output', help='The folder to save the output video')
+    parser.add_argument('-t', '--infer_type', type=str, default='center', help='The type of inference, can be center or pano')
+    parser.add_argument('-m', '--model_path', type=str, default='./weights/v2ce_3d.pt', help='The path to the trained model')
+    parser.add_argument('--out_name_suffix', type=str, default='', help='The suffix of the output video name')
+    parser.add_argument('--max_frame_num', type=int, default=1800, help='The maximum number of frames to process')
+    parser.add_argument('--width', type=int, default=346, help='The width of the frame/tensor input to the model')
+    parser.add_argument('--height', type=int, default=260, help='The height of the frame/tensor input to the model')
+    parser.add_argument('--write_event_frame_video', type=SBool, default=True, nargs='?', const=True,
+                        help='Whether to write the event frame video')
+    parser.add_argument('--vis_keep_polarity', type=SBool, default=True, nargs='?', const=True,
+                        help='Whether to keep the polarity of the event frame during visualization')
+    parser.add_argument('-l', '--log_level', type=str, default='info', help='Logging level')
+    parser.add_argument('-b', '--batch_size', type=int, default=1, help='Batch size for inference')
+    parser.add_argument('--stage2_batch_size', type=int, default=24, help='Batch size for inference')
+    parser.add_argument('--seed', type=int, default=None,
+                        help='(B200 extension) Philox key of the LDATI uniform draws; default: drawn from torch\'s RNG')
+    return parser
+
+
+def main(argv=None):
+    import cv2
+    args = build_parser().parse_args(argv)
+    logging.basicConfig(level=getattr(logging, args.log_level.upper()))
+    assert args.image_folder is not None or args.input_video_path is not None
+    assert not (args.image_folder is not None and args.input_video_path is not None)
+    if args.image_folder is not None:
+        assert os.path.exists(args.image_folder), f'{args.image_folder} does not exist'
+    if args.input_video_path is not None:
+        assert os.path.exists(args.input_video_path), f'{args.input_video_path} does not exist'
+    name = Path(args.image_folder).name if args.image_folder is not None else Path(args.input_video_path).stem
+    output_name = f'{name}-ceil_{args.ceil}-fps_{args.fps}' if args.out_name_suffix == '' \
+        else f'{name}-ceil_{args.ceil}-fps_{args.fps}-{args.out_name_suffix}'
+    os.makedirs(args.out_folder, exist_ok=True)
+
+    model = get_trained_mode(model_path=args.model_path)
+    image_paths, vidcap = None, None
+    if args.image_folder is not None:
+        image_paths = sorted([op.join(args.image_folder, f) for f in os.listdir(args.image_folder)
+                              if f.endswith('.png')])[:args.max_frame_num]
+        logger.info(f'Now processing {args.image_folder}, Found {len(image_paths)} images.')
+    else:
+        from .scripts.video_reader import VideoReader
+        vidcap = VideoReader(args.input_video_path, color_mode='GRAY')
+        if args.max_frame_num is not None and 0 < args.max_frame_num < vidcap.frame_count:
+            vidcap.frame_count = args.max_frame_num
+        logger.info(f'Now processing {args.input_video_path}, processing {vidcap.frame_count} frames.')
+    seed = args.seed if args.seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+    res = stream_clip(model, image_paths=image_paths, vidcap=vidcap, infer_type=args.infer_type, seq_len=args.seq_len,
+                      width=args.width, height=args.height, batch_size=args.batch_size, fps=args.fps, ceil=args.ceil,
+                      upper_bound_percentile=args.upper_bound_percentile, keep_polarity=args.vis_keep_polarity,
+                      write_event_frames=args.write_event_frame_video, seed=seed)
+    logger.info(f'Predicted voxel shape: ({res.n_pairs}, 2, 10, ...) (kept on the device)')
+    if args.write_event_frame_video:
+        vis_color = 'rgb' if args.vis_keep_polarity else 'gray'
+        ef_video_path = op.join(args.out_folder, f'{args.infer_type}-{output_name}-pred_ef_{vis_color}.mp4')
+        logger.info(f'Upper bound of the event frame value during video writing: {res.ef_upper_bound}')
+        H, W = res.ef_frames.shape[1:3]
+        video = cv2.VideoWriter(ef_video_path, cv2.VideoWriter_fourcc(*'mp4v'), args.fps, (W, H))
+        for f in res.ef_frames:
+            video.write(f)
+        video.release()
+        logger.info(f'Event frame video written to {ef_video_path}')
+    logger.info(f'Generated event stream shape: , {res.event_stream.shape}')
+    np.savez(op.join(args.out_folder, f'{output_name}-events.npz'), event_stream=res.event_stream)
+    return res
+
+
+if __name__ == '__main__':
+    main()
