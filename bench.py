@@ -222,7 +222,7 @@ class Runner:
             self.ev_host[:total * 13].copy_(events[:total * 13], non_blocking=True)
             self.fr_host.copy_(frames, non_blocking=True)
             st = status.cpu()
-            self.d2h_bytes = total * 13 + frames.numel() + seg.numel() * 8 + 16 + 32
+            self.d2h_bytes = total * 13 + frames.numel() + seg.size * 8 + 16 + 32
         return total
 
     def gather(self, events, total):

@@ -13,7 +13,7 @@
 //   k = (tap, input channel), tap = (kd*3+kh)*3+kw, k-block = 64 bf16 = one 128-byte swizzle row
 //
 // CTA = 192 threads:
-//   warps 0-3  A producers (one output row per thread, 8 x 16-byte cp.async per k-block), then the
+//   warps 0-3  A producers (8 lanes per 128-byte row, 8 x 16-byte cp.async per thread per k-block), then the
 //              epilogue (warp w reads TMEM lanes 32w..32w+31 with tcgen05.ld 32x32b)
 //   warp 4     TMEM allocator; lane 0 issues tcgen05.mma and tcgen05.commit
 //   warp 5     lane 0 issues the weight-tile bulk copies
@@ -153,7 +153,8 @@ struct SmemLayout {
   static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 1) * 8;
   static constexpr int kScaleOff = (kTmemPtrOff + 4 + 15) / 16 * 16;
   static constexpr int kShiftOff = kScaleOff + BN * 4;
-  static constexpr int kTotal = kShiftOff + BN * 4;
+  static constexpr int kRowsOff = kShiftOff + BN * 4;                // 3 x 128 ints: per-row gather descriptors
+  static constexpr int kTotal = kRowsOff + 3 * 128 * 4;
   static constexpr int kDynamicBytes = kTotal + 1024;                // slack for the 1024-byte alignment
 };
 
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + L::kTmemPtrOff);
   float* s_scale = reinterpret_cast<float*>(smem + L::kScaleOff);
   float* s_shift = reinterpret_cast<float*>(smem + L::kShiftOff);
+  int* s_rows = reinterpret_cast<int*>(smem + L::kRowsOff);
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -209,59 +211,107 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
   const uint32_t tmem_acc = *tmem_ptr;
 
   if (warp < 4) {
-    // ================= A producer: one output row per thread =================
+    // ================= A producer =================
     const int m = m_tile * kBlockM + tid;
-    const bool row_ok = m < a.M;
-    int wo = 0, ho = 0, d = 0, b = 0;
-    if (row_ok) {
-      wo = m % a.Wout;
-      int t = m / a.Wout;
-      ho = t % a.Hout;
-      t /= a.Hout;
-      d = t % a.D;
-      b = t / a.D;
-    }
-    const int hb = ho * a.stride - a.pad, wb = wo * a.stride - a.pad, db = d - a.pad;
-    const bool ups = (a.H0 != a.Hin) || (a.W0 != a.Win);
-    const uint32_t row_smem = (uint32_t)tid * 128u;
-    const uint32_t swz = (uint32_t)(tid & 7);
+    const bool row_ok = m < a.M;          // row owned by this thread in the epilogue (TMEM lane = tid)
 
-    int tap = 0, c = 0;
-    bool tap_ok = false;
-    const __nv_bfloat16* p0 = a.src0;
-    const __nv_bfloat16* p1 = a.src1;
-    auto set_tap = [&](int tp) {
-      tap_ok = false;
-      if (!row_ok || tp >= a.taps) return;
-      int kd = 0, kh = 0, kw = 0;
-      if (a.ksize == 3) { kd = tp / 9; kh = (tp / 3) % 3; kw = tp % 3; }
-      const int di = db + kd, hi = hb + kh, wi = wb + kw;
-      if (di < 0 || di >= a.D || hi < 0 || hi >= a.Hin || wi < 0 || wi >= a.Win) return;
-      tap_ok = true;
-      const int hs = ups ? (hi * a.H0) / a.Hin : hi;
-      const int ws = ups ? (wi * a.W0) / a.Win : wi;
-      p0 = a.src0 + ((size_t)((b * a.D + di) * a.H0 + hs) * a.W0 + ws) * a.C0;
-      if (a.src1) p1 = a.src1 + ((size_t)((b * a.D + di) * a.Hin + hi) * a.Win + wi) * a.C1;
-    };
-    set_tap(0);
+    // Gather mapping: 8 consecutive lanes fetch the 8 x 16-byte chunks of one 128-byte k-block row, so a
+    // warp instruction touches 4 full cache lines (not 32 partial ones); a thread serves the same chunk
+    // q of rows  it*16 + (tid>>3), it = 0..7.  Per row it keeps two element offsets (centre tap, one per
+    // source) and a 32-bit word: bits 0-26 = validity of the 27 taps, bits 27-30 = whether the nearest-
+    // upsampled source moves by one pixel for kh/kw = 0 / 2 (always 1 when src0 is not upsampled).
+    const int q = tid & 7, rg = tid >> 3;
+    const bool ups = (a.H0 != a.Hin) || (a.W0 != a.Win);
+    {
+      // each producer thread derives the descriptor of ONE row (its epilogue row) and publishes it
+      int o0 = 0, o1 = 0;
+      uint32_t info = 0u;
+      if (row_ok) {
+        const int wo = m % a.Wout;
+        int t = m / a.Wout;
+        const int ho = t % a.Hout;
+        t /= a.Hout;                       // t = b*D + d
+        const int d = t % a.D;
+        const int hc = ho * a.stride, wc = wo * a.stride;      // centre-tap input coordinates
+        uint32_t vd = 0, vh = 0, vw = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          vd |= (uint32_t)((d + k - 1) >= 0 && (d + k - 1) < a.D) << k;
+          vh |= (uint32_t)((hc + k - 1) >= 0 && (hc + k - 1) < a.Hin) << k;
+          vw |= (uint32_t)((wc + k - 1) >= 0 && (wc + k - 1) < a.Win) << k;
+        }
+        uint32_t m9 = 0, mask = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) m9 |= ((vh >> k) & 1u) ? (vw << (3 * k)) : 0u;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) mask |= ((vd >> k) & 1u) ? (m9 << (9 * k)) : 0u;
+        if (a.ksize == 1) mask &= (1u << 13);
+        int hs1 = hc, ws1 = wc;
+        uint32_t bits = 0xFu;
+        if (ups) {
+          hs1 = (hc * a.H0) / a.Hin;
+          ws1 = (wc * a.W0) / a.Win;
+          bits = 0;
+          if (hc - 1 >= 0 && ((hc - 1) * a.H0) / a.Hin != hs1) bits |= 1u;
+          if (hc + 1 < a.Hin && ((hc + 1) * a.H0) / a.Hin != hs1) bits |= 2u;
+          if (wc - 1 >= 0 && ((wc - 1) * a.W0) / a.Win != ws1) bits |= 4u;
+          if (wc + 1 < a.Win && ((wc + 1) * a.W0) / a.Win != ws1) bits |= 8u;
+        }
+        info = mask | (bits << 27);
+        o0 = ((t * a.H0 + hs1) * a.W0 + ws1) * a.C0;
+        o1 = ((t * a.Hin + hc) * a.Win + wc) * a.C1;
+      }
+      s_rows[tid] = o0;
+      s_rows[128 + tid] = o1;
+      s_rows[256 + tid] = (int)info;
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // producer warps only
+    }
+    int off0[8], off1[8];
+    uint32_t rinfo[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 16 + rg;
+      off0[it] = s_rows[r];
+      off1[it] = s_rows[128 + r];
+      rinfo[it] = (uint32_t)s_rows[256 + r];
+    }
+    const uint32_t dst_thread = (uint32_t)rg * 128u + ((uint32_t)(q ^ (rg & 7)) << 4);
+    const int plane0 = a.H0 * a.W0 * a.C0, row0 = a.W0 * a.C0;
+    const int plane1 = a.Hin * a.Win * a.C1, row1 = a.Win * a.C1;
 
     auto arrive_stage = [&](int kb) {
       fence_proxy_async();              // generic-proxy (cp.async) writes -> visible to the tensor core's async proxy
       mbar_arrive(full_bar(kb % STAGES));
     };
+    int tap = 0, c = q * 8;             // this thread's (tap, channel) inside the current k-block
+    while (c >= a.Cin) { c -= a.Cin; ++tap; }
     for (int kb = 0; kb < a.num_kb; ++kb) {
       const int s = kb % STAGES;
       mbar_wait(empty_bar(s), ((kb / STAGES) & 1) ^ 1, a.error_flag);
-      const uint32_t dst_row = a_base + (uint32_t)s * kAStageBytes + row_smem;
+      const uint32_t dst = a_base + (uint32_t)s * kAStageBytes + dst_thread;
+      const int tap27 = (a.ksize == 3) ? tap : 13;
+      const int kd = tap27 / 9, kh = (tap27 / 3) % 3, kw = tap27 % 3;
+      const bool k_ok = tap < a.taps;
+      const bool from0 = c < a.C0;
+      const __nv_bfloat16* sbase = from0 ? a.src0 + c : a.src1 + (c - a.C0);
+      const int toff = from0 ? (kd - 1) * plane0 : ((kd - 1) * plane1 + (kh - 1) * row1 + (kw - 1) * a.C1);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const __nv_bfloat16* src = (c < a.C0) ? (p0 + c) : (p1 + (c - a.C0));
-        cp_async_16(dst_row + (((uint32_t)q ^ swz) << 4), tap_ok ? (const void*)src : (const void*)a.src0,
-                    tap_ok ? 16u : 0u);
-        c += 8;
-        if (c >= a.Cin) { c = 0; ++tap; set_tap(tap); }
+      for (int it = 0; it < 8; ++it) {
+        const uint32_t ri = rinfo[it];
+        const bool ok = k_ok && ((ri >> tap27) & 1u);
+        int off;
+        if (from0) {
+          const int dh = (kh == 0) ? -(int)((ri >> 27) & 1u) : (kh == 2) ? (int)((ri >> 28) & 1u) : 0;
+          const int dw = (kw == 0) ? -(int)((ri >> 29) & 1u) : (kw == 2) ? (int)((ri >> 30) & 1u) : 0;
+          off = off0[it] + toff + dh * row0 + dw * a.C0;
+        } else {
+          off = off1[it] + toff;
+        }
+        cp_async_16(dst + (uint32_t)it * 2048u, ok ? (const void*)(sbase + off) : (const void*)a.src0, ok ? 16u : 0u);
       }
       cp_async_commit();
+      c += kBlockK;
+      while (c >= a.Cin) { c -= a.Cin; ++tap; }
       if (kb >= kLag) {
         cp_async_wait<kLag>();
         arrive_stage(kb - kLag);
@@ -408,6 +458,10 @@ inline int launch_one(const ConvArgs& a, cudaStream_t s) {
 }
 
 inline int launch_conv(const ConvArgs& a, int bn, cudaStream_t s) {
+  // the gather uses 32-bit element offsets
+  if ((long long)a.B * a.D * a.H0 * a.W0 * a.C0 >= (1LL << 31) || (long long)a.B * a.D * a.Hin * a.Win * a.C1 >= (1LL << 31) ||
+      (long long)a.M * a.Cout >= (1LL << 40))
+    return set_error(V2CE_ERR_RANGE, "activation tensor too large for 32-bit gather offsets; lower the batch size");
   switch (bn) {
     case 32: return launch_one<32, 4>(a, s);
     case 64: return launch_one<64, 4>(a, s);
