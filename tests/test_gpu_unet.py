@@ -13,7 +13,7 @@ from oracle.unet_oracle import UNetOracle
 pytestmark = pytest.mark.gpu
 
 
-def conv_hook(src0, src1, hin, win, w, scale, shift, residual, act, ksize, stride):
+def conv_hook(src0, src1, hin, win, w, scale, shift, residual, act, ksize, stride, impl=0, desc_mode=0):
     """src0 (B,D,H0,W0,C0) bf16, src1 (B,D,Hin,Win,C1) bf16 | None -> out (B,D,Hout,Wout,Cout) bf16."""
     from v2ce_toolbox_b200 import _lib
     lib = _lib.load()
@@ -27,10 +27,10 @@ def conv_hook(src0, src1, hin, win, w, scale, shift, residual, act, ksize, strid
     wh = np.ascontiguousarray(w.cpu().numpy(), dtype=np.float32)
     sh = np.ascontiguousarray(scale.cpu().numpy(), dtype=np.float32)
     th = np.ascontiguousarray(shift.cpu().numpy(), dtype=np.float32)
-    _lib.check(lib.v2ce_conv3d_bf16(_lib.ptr(src0), C0, H0, W0, _lib.ptr(src1), C1, B, D, hin, win, ksize, stride,
-                                    wh.ctypes.data_as(ctypes.c_void_p), cout, sh.ctypes.data_as(ctypes.c_void_p),
-                                    th.ctypes.data_as(ctypes.c_void_p), _lib.ptr(residual), act, _lib.ptr(out),
-                                    _lib.stream_ptr()))
+    _lib.check(lib.v2ce_conv3d_bf16_ex(_lib.ptr(src0), C0, H0, W0, _lib.ptr(src1), C1, B, D, hin, win, ksize, stride,
+                                       wh.ctypes.data_as(ctypes.c_void_p), cout, sh.ctypes.data_as(ctypes.c_void_p),
+                                       th.ctypes.data_as(ctypes.c_void_p), _lib.ptr(residual), act, _lib.ptr(out),
+                                       impl, desc_mode, _lib.stream_ptr()))
     torch.cuda.synchronize()
     return out
 
@@ -79,9 +79,24 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('case', CASES, ids=[c[0] for c in CASES])
+# 3x3x3 stride-1 cases for the halo-tile kernel (channel pitches multiple of 64, no upsample)
+HALO_CASES = [
+    ('halo_64_64', 1, 3, 9, 11, 64, None, 0, 64, 3, 1, False, 1),
+    ('halo_n32', 1, 3, 9, 11, 64, None, 0, 32, 3, 1, False, 0),
+    ('halo_128_res', 1, 4, 10, 12, 128, None, 0, 128, 3, 1, True, 1),
+    ('halo_two_src', 1, 3, 9, 11, 64, None, 64, 32, 3, 1, False, 2),
+    ('halo_512', 1, 4, 6, 7, 512, None, 0, 512, 3, 1, True, 1),
+    ('halo_768', 1, 2, 9, 11, 512, None, 256, 256, 3, 1, False, 1),
+    ('halo_wide', 1, 2, 20, 70, 64, None, 0, 64, 3, 1, False, 1),
+    ('halo_many', 2, 16, 33, 44, 64, None, 0, 64, 3, 1, True, 1),
+    ('halo_fullres_slice', 1, 2, 260, 346, 64, None, 64, 32, 3, 1, False, 1),
+]
+
+
+@pytest.mark.parametrize('case', CASES + HALO_CASES, ids=[c[0] for c in CASES + HALO_CASES])
 def test_conv_layer_vs_torch(case):
     name, B, D, hin, win, C0, up, C1, cout, k, stride, use_res, act = case
+    impl = 1 if name.startswith('halo') else 0
     g = torch.Generator(device='cpu').manual_seed(hash(name) % 1000)
     h0, w0 = up if up else (hin, win)
     src0 = torch.randn(B, D, h0, w0, C0, generator=g).to(torch.bfloat16).cuda()
@@ -93,7 +108,7 @@ def test_conv_layer_vs_torch(case):
     pad = k // 2
     hout, wout = (hin + 2 * pad - k) // stride + 1, (win + 2 * pad - k) // stride + 1
     res = torch.randn(B, D, hout, wout, cout, generator=g).to(torch.bfloat16).cuda() if use_res else None
-    out = conv_hook(src0, src1, hin, win, w, scale, shift, res, act, k, stride)
+    out = conv_hook(src0, src1, hin, win, w, scale, shift, res, act, k, stride, impl=impl)
     ref = torch_ref(src0, src1, hin, win, w, scale, shift, res, act, k, stride)
     assert not torch.isnan(out.float()).any(), 'unwritten outputs'
     err = (out.float() - ref).abs()

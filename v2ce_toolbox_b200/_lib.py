@@ -57,6 +57,10 @@ _SIGNATURES = {
     'v2ce_conv3d_bf16': (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                  c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
                                  c_int32, c_void_p, c_void_p]),
+    'v2ce_conv3d_bf16_ex': (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                    c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                    c_int32, c_void_p, c_int32, c_int32, c_void_p]),
+    'v2ce_model_set_option': (c_int, [c_void_p, c_char_p, c_int64]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

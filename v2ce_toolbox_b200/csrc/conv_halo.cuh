@@ -1,0 +1,388 @@
+// Halo-tile Conv3d (3x3x3, stride 1, pad 1) for sm_100a: the A operand of all nine (kh,kw) taps of a
+// depth slice comes from ONE shared-memory copy of the input patch.
+//
+// Why: with one gather per tap (conv_igemm.cuh) a 128xN tile needs 16 KB of activations per 64-wide
+// k-block; for N <= 64 that is 128-256 B/clk/SM against ~40 B/clk/SM of L2->SM bandwidth, so the
+// tensor pipe idles (measured: 5.6 % active on decoders.3.conv1).  Here TMA (cp.async.bulk.tensor.5d,
+// 128B swizzle, zero fill outside the image = the conv padding) loads a (TH+2) x PW pixel patch of 64
+// channels once per (kd, channel chunk); the tile's M index runs over the patch with pitch PW = TW+2,
+// so tap (kh,kw) is the same buffer read from row kh*PW+kw on: a descriptor whose start address is
+// shifted by whole 128-byte rows.  Rows whose column index falls in the 2 halo columns produce
+// garbage accumulator rows that the epilogue skips (MMA rows are independent).
+//
+// Replaces the same reference calls as conv_igemm.cuh (submodules.py:249-263) for the 20 stride-1
+// 3x3x3 convs, i.e. 91 % of the network's FLOPs.
+//
+// CTA = 224 threads: warp 0 lane 0 TMA patch producer, warp 1 lane 0 weight-tile producer (bulk copy),
+// warp 2 TMEM allocator + lane 0 MMA issuer, warps 3-6 epilogue (TMEM lane quarter = warp % 4).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "conv_igemm.cuh"
+
+namespace v2ce {
+namespace halo {
+
+using namespace conv;
+
+constexpr int kHaloThreads = 224;
+constexpr int kMaxSA = 4, kMaxSB = 8;
+
+struct HaloArgs {
+  int B, D, H, W;
+  int PW, TH, TW;              // patch pitch (TW + 2), output rows and valid columns of a tile; TH*PW <= 128
+  int tiles_w, tiles_h;
+  int ncc0, ncc1;              // 64-channel chunks taken from source 0 / source 1 (virtual concat)
+  int Cout;                    // real output channels (multiple of BN)
+  int out_pitch;               // channel pitch of `out`; columns [Cout, out_pitch) are zero-filled
+  int res_pitch;               // channel pitch of `residual`
+  int SA, SB;                  // pipeline depths (patch ring / weight ring)
+  int a_stage_bytes;           // bytes reserved per patch stage (multiple of 1024)
+  int box_bytes;               // bytes one TMA box delivers: PW * (TH+2) * 128
+  const __nv_bfloat16* wpack;  // [Cout/BN][3 kd][ncc][9 taps][BN][64], rows pre-swizzled
+  const float* scale;
+  const float* shift;
+  const float* inv_sigma;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+  int act;
+  int desc_mode;               // 0: base_offset = 0, 1: base_offset = (addr >> 7) & 7  (bring-up switch)
+  int* error_flag;
+};
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::
+          "r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
+}
+
+__device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t smem_addr, int mode) {
+  uint64_t d = make_smem_desc(smem_addr);
+  if (mode == 1) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_constant__ CUtensorMap tm0,
+                                                                  const __grid_constant__ CUtensorMap tm1,
+                                                                  const HaloArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  constexpr int kBStage = BN * kBlockK * 2;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = a.Cout / BN;
+  int t = blockIdx.x;
+  const int n_tile = t % n_tiles; t /= n_tiles;
+  const int tw_i = t % a.tiles_w; t /= a.tiles_w;
+  const int th_i = t % a.tiles_h; t /= a.tiles_h;
+  const int d = t % a.D;
+  const int b = t / a.D;
+  const int h0 = th_i * a.TH, w0 = tw_i * a.TW;
+  const int ncc = a.ncc0 + a.ncc1;
+  const int groups = 3 * ncc;
+
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + (uint32_t)a.SA * a.a_stage_bytes;
+  const uint32_t bar_base = b_base + (uint32_t)a.SB * kBStage;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (kMaxSA + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxSA + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (2 * kMaxSA + kMaxSB + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxSA + 2 * kMaxSB);
+  const int bar_bytes = (2 * kMaxSA + 2 * kMaxSB + 1) * 8;
+  uint8_t* tail = smem + (bar_base - base) + bar_bytes;
+  volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(tail);
+  float* s_scale = reinterpret_cast<float*>(tail + 16);
+  float* s_shift = s_scale + BN;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < a.SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(const_cast<uint32_t*>(tmem_ptr))),
+                 "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    const float isg = a.inv_sigma ? __ldg(a.inv_sigma) : 1.f;
+    for (int i = tid; i < BN; i += kHaloThreads) {
+      s_scale[i] = __ldg(a.scale + n_tile * BN + i) * isg;
+      s_shift[i] = __ldg(a.shift + n_tile * BN + i);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================= patch producer (TMA) =================
+    if (lane == 0) {
+      for (int g = 0; g < groups; ++g) {
+        const int s = g % a.SA;
+        mbar_wait(a_empty(s), ((g / a.SA) & 1) ^ 1, a.error_flag);
+        mbar_arrive_expect_tx(a_full(s), (uint32_t)a.box_bytes);
+        const int kd = g / ncc, cc = g % ncc;
+        const bool first = cc < a.ncc0;
+        tma_load_5d(a_base + (uint32_t)s * a.a_stage_bytes, first ? &tm0 : &tm1, (first ? cc : cc - a.ncc0) * kBlockK,
+                    w0 - 1, h0 - 1, d + kd - 1, b, a_full(s));
+      }
+    }
+  } else if (warp == 1) {
+    // ================= weight-tile producer (bulk copy) =================
+    if (lane == 0) {
+      const __nv_bfloat16* wt = a.wpack + (size_t)n_tile * groups * 9 * (BN * kBlockK);
+      const int total = groups * 9;
+      for (int it = 0; it < total; ++it) {
+        const int s = it % a.SB;
+        mbar_wait(b_empty(s), ((it / a.SB) & 1) ^ 1, a.error_flag);
+        mbar_arrive_expect_tx(b_full(s), (uint32_t)kBStage);
+        bulk_copy_g2s(b_base + (uint32_t)s * kBStage, wt + (size_t)it * (BN * kBlockK), (uint32_t)kBStage, b_full(s));
+      }
+    }
+  } else if (warp == 2) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int it = 0;
+      for (int g = 0; g < groups; ++g) {
+        const int sa = g % a.SA;
+        mbar_wait(a_full(sa), (g / a.SA) & 1, a.error_flag);
+        tcgen05_fence_after();
+        const uint32_t patch = a_base + (uint32_t)sa * a.a_stage_bytes;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap, ++it) {
+          const int sb = it % a.SB;
+          mbar_wait(b_full(sb), (it / a.SB) & 1, a.error_flag);
+          tcgen05_fence_after();
+          const uint32_t a_addr = patch + (uint32_t)((tap / 3) * a.PW + (tap % 3)) * 128u;
+          const uint32_t b_addr = b_base + (uint32_t)sb * kBStage;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            tcgen05_mma_bf16(tmem_acc, make_smem_desc_shifted(a_addr + k * 32, a.desc_mode), make_smem_desc(b_addr + k * 32),
+                             idesc, (g | tap | k) != 0 ? 1u : 0u);
+          }
+          tcgen05_commit(b_empty(sb));
+        }
+        tcgen05_commit(a_empty(sa));
+      }
+      tcgen05_commit(tmem_full_bar);
+    }
+  } else {
+    // ================= epilogue =================
+    const int quarter = warp & 3;
+    const int i = quarter * 32 + lane;            // accumulator row == TMEM lane
+    const int th = i / a.PW, tw = i % a.PW;
+    const int h = h0 + th, w = w0 + tw;
+    const bool row_ok = (th < a.TH) && (tw < a.TW) && (h < a.H) && (w < a.W);
+    const size_t m = ((size_t)(b * a.D + d) * a.H + h) * a.W + w;
+    mbar_wait(tmem_full_bar, 0, a.error_flag);
+    __syncwarp();
+    tcgen05_fence_after();
+    const uint32_t lane_addr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+    __nv_bfloat16* orow = a.out + m * a.out_pitch + n_tile * BN;
+    const __nv_bfloat16* rrow = a.residual ? a.residual + m * a.res_pitch + n_tile * BN : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(lane_addr + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float r[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = 0.f;
+          if (rrow) {
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + g * 8));
+            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(rp[j]);
+              r[2 * j] = f.x;
+              r[2 * j + 1] = f.y;
+            }
+          }
+          uint4 ov;
+          __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float y[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int n = c0 + g * 8 + 2 * j + hh;
+              float tt = fmaf(__uint_as_float(v[g * 8 + 2 * j + hh]), s_scale[n], s_shift[n]) + r[2 * j + hh];
+              if (a.act == 1) tt = fmaxf(tt, 0.f);
+              else if (a.act == 2) tt = tt > 0.f ? tt : 0.01f * tt;
+              y[hh] = tt;
+            }
+            op[j] = __floats2bfloat162_rn(y[0], y[1]);
+          }
+          *reinterpret_cast<uint4*>(orow + c0 + g * 8) = ov;
+        }
+      }
+    }
+    if (row_ok && n_tile == n_tiles - 1) {        // zero the padding channels so later TMA reads see 0, not garbage
+      for (int c = a.Cout; c < a.out_pitch; c += 8)
+        *reinterpret_cast<uint4*>(a.out + m * a.out_pitch + c) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// fp32 (Cout, Cin_real, 3,3,3) -> bf16 [Cout/BN][kd][cc][kh*3+kw][BN][64] (rows swizzled); padded input
+// channel p maps to a real channel through two segments (pad0/real0 | pad1/real1), zero elsewhere.
+__global__ void pack_weights_halo_kernel(const float* __restrict__ w, int Cout, int cin_real, int BN, int pad0, int real0,
+                                         int pad1, int real1, __nv_bfloat16* __restrict__ out) {
+  const int ncc = (pad0 + pad1) / kBlockK;
+  const size_t total = (size_t)Cout * 27 * ncc * kBlockK;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % 8);
+    const int qs = (int)((i / 8) % 8);
+    const int r = (int)((i / 64) % BN);
+    size_t tile = i / ((size_t)64 * BN);        // ((n_tile*3 + kd)*ncc + cc)*9 + tap9
+    const int tap9 = (int)(tile % 9); tile /= 9;
+    const int cc = (int)(tile % ncc); tile /= ncc;
+    const int kd = (int)(tile % 3);
+    const int n_tile = (int)(tile / 3);
+    const int q = qs ^ (r & 7);
+    const int p = cc * kBlockK + q * 8 + e;      // padded input channel
+    int c = -1;
+    if (p < pad0) { if (p < real0) c = p; }
+    else { const int p1 = p - pad0; if (p1 < real1) c = real0 + p1; }
+    const int n = n_tile * BN + r;
+    float v = 0.f;
+    if (c >= 0) v = w[((size_t)n * cin_real + c) * 27 + kd * 9 + tap9];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// nearest-neighbour upsample (unet_2layer.py:359-362), bf16 NDHWC, src = (dst*in)//out per axis
+__global__ void upsample_nearest_kernel(const __nv_bfloat16* __restrict__ in, int planes, int H0, int W0, int H, int W, int C,
+                                        __nv_bfloat16* __restrict__ out) {
+  const int vec = C / 8;
+  const size_t total = (size_t)planes * H * W * vec;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec);
+    size_t px = i / vec;
+    const int w = (int)(px % W); px /= W;
+    const int h = (int)(px % H);
+    const size_t pl = px / H;
+    const int hs = (h * H0) / H, ws = (w * W0) / W;
+    const uint4 val = __ldg(reinterpret_cast<const uint4*>(in + ((pl * H0 + hs) * W0 + ws) * (size_t)C) + v);
+    reinterpret_cast<uint4*>(out)[i] = val;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// tensor map over a (B, D, H, W, Cpitch) bf16 activation: box = 64 channels x PW x (TH+2) pixels
+inline int make_patch_map(CUtensorMap* map, const void* ptr, int B, int D, int H, int W, int cpitch, int PW, int rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(V2CE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[5] = {(cuuint64_t)cpitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)cpitch * 2, (cuuint64_t)W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2,
+                           (cuuint64_t)D * H * W * cpitch * 2};
+  cuuint32_t box[5] = {64u, (cuuint32_t)PW, (cuuint32_t)rows, 1u, 1u};
+  cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(V2CE_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return V2CE_OK;
+}
+
+struct TileShape { int PW, TH; };
+// pitch / rows per tile for an output plane of H x W (see file header); chosen to maximise the useful
+// fraction of the 128 accumulator rows
+inline TileShape pick_tile(int H, int W) {
+  TileShape best{16, 8};
+  double best_eff = 0.0;
+  for (int pw = 10; pw <= 66; pw += 2) {
+    const int tw = pw - 2, th = 128 / pw;
+    if (th < 1) continue;
+    const long tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+    const double eff = (double)H * W / (tiles * 128.0);
+    // prefer the smaller patch (less halo re-read) unless a wider one is clearly more efficient
+    if (eff > best_eff + 0.01) { best_eff = eff; best = TileShape{pw, th}; }
+  }
+  return best;
+}
+
+struct HaloPlan {
+  TileShape ts;
+  int SA, SB, a_stage_bytes, box_bytes, smem_bytes;
+};
+
+inline HaloPlan plan_for(int bn, int H, int W) {
+  HaloPlan p;
+  p.ts = pick_tile(H, W);
+  const int rows = p.ts.PW * (p.ts.TH + 2);
+  p.box_bytes = rows * 128;
+  p.a_stage_bytes = ((rows + 2 + 7) / 8) * 1024;
+  p.SA = 3;
+  p.SB = bn >= 256 ? 3 : 4;
+  if (bn >= 256) p.SA = 2;
+  const int tail = (2 * kMaxSA + 2 * kMaxSB + 1) * 8 + 16 + 2 * bn * 4;
+  p.smem_bytes = p.SA * p.a_stage_bytes + p.SB * bn * kBlockK * 2 + tail + 1024;
+  return p;
+}
+
+template <int BN>
+inline int launch_halo_one(const CUtensorMap& tm0, const CUtensorMap& tm1, const HaloArgs& a, int smem_bytes, cudaStream_t s) {
+  static int configured = 0;
+  if (configured < smem_bytes) {
+    V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = smem_bytes;
+  }
+  const int grid = a.B * a.D * a.tiles_h * a.tiles_w * (a.Cout / BN);
+  conv_halo_kernel<BN><<<grid, kHaloThreads, smem_bytes, s>>>(tm0, tm1, a);
+  V2CE_LAUNCH_CHECK("conv_halo_kernel");
+  return V2CE_OK;
+}
+
+inline int launch_halo(const CUtensorMap& tm0, const CUtensorMap& tm1, const HaloArgs& a, int bn, int smem_bytes,
+                       cudaStream_t s) {
+  switch (bn) {
+    case 32: return launch_halo_one<32>(tm0, tm1, a, smem_bytes, s);
+    case 64: return launch_halo_one<64>(tm0, tm1, a, smem_bytes, s);
+    case 128: return launch_halo_one<128>(tm0, tm1, a, smem_bytes, s);
+    case 256: return launch_halo_one<256>(tm0, tm1, a, smem_bytes, s);
+  }
+  return set_error(V2CE_ERR_INVALID, "unsupported N tile %d", bn);
+}
+
+}  // namespace halo
+}  // namespace v2ce

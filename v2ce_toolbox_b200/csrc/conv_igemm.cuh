@@ -17,7 +17,7 @@
 //              epilogue (warp w reads TMEM lanes 32w..32w+31 with tcgen05.ld 32x32b)
 //   warp 4     TMEM allocator; lane 0 issues tcgen05.mma and tcgen05.commit
 //   warp 5     lane 0 issues the weight-tile bulk copies
-// Synchronisation: full[s] (128 producer arrivals + 1 expect_tx arrival), empty[s] (tcgen05.commit),
+// Synchronisation: full[s] (128 cp.async.mbarrier.arrive.noinc arrivals + 1 expect_tx arrival), empty[s] (tcgen05.commit),
 // tmem_full (tcgen05.commit after the last k-block).
 #pragma once
 #include <cuda_bf16.h>
@@ -31,7 +31,6 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // bf16 elements = 128 bytes
 constexpr int kThreads = 192;
 constexpr int kProducerThreads = 128;
-constexpr int kLag = 2;                     // cp.async groups a producer keeps in flight
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;
 
 struct ConvArgs {
@@ -93,6 +92,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -279,10 +281,6 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
     const int plane0 = a.H0 * a.W0 * a.C0, row0 = a.W0 * a.C0;
     const int plane1 = a.Hin * a.Win * a.C1, row1 = a.Win * a.C1;
 
-    auto arrive_stage = [&](int kb) {
-      fence_proxy_async();              // generic-proxy (cp.async) writes -> visible to the tensor core's async proxy
-      mbar_arrive(full_bar(kb % STAGES));
-    };
     int tap = 0, c = q * 8;             // this thread's (tap, channel) inside the current k-block
     while (c >= a.Cin) { c -= a.Cin; ++tap; }
     for (int kb = 0; kb < a.num_kb; ++kb) {
@@ -309,18 +307,14 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
         }
         cp_async_16(dst + (uint32_t)it * 2048u, ok ? (const void*)(sbase + off) : (const void*)a.src0, ok ? 16u : 0u);
       }
-      cp_async_commit();
+      // The arrival on full[s] is performed by the copy unit when this thread's copies have landed
+      // (no wait in the producer: a proxy fence here would drain every cp.async in flight and
+      // serialise the pipeline -- measured: 2400 cycles per k-block).  The MMA thread orders the
+      // generic-proxy writes before its async-proxy reads with one fence after the barrier wait.
+      cp_async_mbar_arrive_noinc(full_bar(s));
       c += kBlockK;
       while (c >= a.Cin) { c -= a.Cin; ++tap; }
-      if (kb >= kLag) {
-        cp_async_wait<kLag>();
-        arrive_stage(kb - kLag);
-      }
     }
-    // drain the last kLag groups
-    if (a.num_kb >= 2) { cp_async_wait<1>(); arrive_stage(a.num_kb - 2); }
-    cp_async_wait<0>();
-    arrive_stage(a.num_kb - 1);
 
     // ================= epilogue: TMEM -> registers -> bf16 global =================
     mbar_wait(tmem_full_bar, 0, a.error_flag);
@@ -376,6 +370,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
       for (int kb = 0; kb < a.num_kb; ++kb) {
         const int s = kb % STAGES;
         mbar_wait(full_bar(s), (kb / STAGES) & 1, a.error_flag);
+        fence_proxy_async();
         tcgen05_fence_after();
         const uint32_t a_addr = a_base + (uint32_t)s * kAStageBytes;
         const uint32_t b_addr = b_base + (uint32_t)s * L::kBStageBytes;
@@ -409,10 +404,13 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
   }
 }
 
-// Weight repack: fp32 (Cout, Cin, k,k,k) -> bf16 tiles [Cout/BN][num_kb][BN][64] with the 128B swizzle
-// applied per row (16-byte chunk q of row r is stored at chunk q ^ (r & 7)); k = tap*Cin + c, zero padded.
-__global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int BN, int num_kb,
-                                    __nv_bfloat16* __restrict__ out) {
+// Weight repack: fp32 (Cout, Cin_real, k,k,k) -> bf16 tiles [Cout/BN][num_kb][BN][64] with the 128B swizzle
+// applied per row (16-byte chunk q of row r is stored at chunk q ^ (r & 7)); k = tap*Cin_pad + p, zero padded.
+// Padded input channel p maps to a real channel through two segments (pad0/real0 | pad1/real1): activations
+// with fewer than 64 channels are stored with a 64-channel pitch so every TMA box is one 128-byte row.
+__global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int cin_real, int taps, int BN, int num_kb,
+                                    int pad0, int real0, int pad1, int real1, __nv_bfloat16* __restrict__ out) {
+  const int cin_pad = pad0 + pad1;
   const size_t total = (size_t)Cout * num_kb * kBlockK;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int e = (int)(i % 8);
@@ -425,9 +423,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int C
     const int kk = kb * kBlockK + q * 8 + e;
     const int n = n_tile * BN + r;
     float v = 0.f;
-    if (kk < taps * Cin) {
-      const int tap = kk / Cin, c = kk % Cin;
-      v = w[((size_t)n * Cin + c) * taps + tap];
+    if (kk < taps * cin_pad) {
+      const int tap = kk / cin_pad, p = kk % cin_pad;
+      int c = -1;
+      if (p < pad0) { if (p < real0) c = p; }
+      else { const int p1 = p - pad0; if (p1 < real1) c = real0 + p1; }
+      if (c >= 0) v = w[((size_t)n * cin_real + c) * taps + tap];
     }
     out[i] = __float2bfloat16_rn(v);
   }

@@ -3,10 +3,11 @@
 // scripts/submodules.py:85-124,216-264 and scripts/spectral_norm.py:9-64.
 //
 // Activation layout in HBM: NDHWC bf16, (B, D=16, H, W, C), row m = ((b*D+d)*H+h)*W+w.
-// Schedule per forward (36 launches):
+// Schedule per forward (40 launches):
 //   4  spectral-norm power-iteration kernels (fp32; 12 convs batched per launch)
 //   1  head conv 2->32 (direct fp32 CUDA-core kernel, K=54 is HBM-bound) + LeakyReLU
-//   30 tcgen05 implicit-GEMM convs (conv_igemm.cuh): per residual block
+//   30 tcgen05 convs: 3x3x3 stride-1 layers on the halo-tile kernel (conv_halo.cuh), stride-2 convs and the
+//      1x1x1 shortcuts on the gather kernel (conv_igemm.cuh); 4 nearest-upsample launches; per residual block
 //        t = relu(bn1(conv1(x)))            x may be the virtual concat [nearest_up(prev), skip]
 //        r = bn_d(conv_d(x) + bias_d)       1x1x1 shortcut, present on every block
 //        y = relu(bn2(conv2(t)) + r)
@@ -15,7 +16,9 @@
 #include <string>
 #include <vector>
 
-#include "conv_igemm.cuh"
+#include <tuple>
+
+#include "conv_halo.cuh"
 
 namespace v2ce {
 namespace unet {
@@ -69,7 +72,7 @@ static const LayerSpec kLayers[] = {
 constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
 
 // ------------------------------------------------------------------------------------------
-// head: Conv3d(2->32, k3, p1, bias) + LeakyReLU(0.01), fp32 in (B,L,2,H,W) -> bf16 NDHWC
+// head: Conv3d(2->32, k3, p1, bias) + LeakyReLU(0.01), fp32 in (B,L,2,H,W) -> bf16 NDHWC (pitch 64)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, int B, int D, int H, int W,
@@ -122,9 +125,11 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict_
     a1 = a1 > 0.f ? a1 : 0.01f * a1;
     op[i] = __floats2bfloat162_rn(a0, a1);
   }
-  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m * 32);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m * 64);     // 64-channel pitch, upper half zero (TMA rows)
 #pragma unroll
   for (int i = 0; i < 4; ++i) dst[i] = o[i];
+#pragma unroll
+  for (int i = 4; i < 8; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -262,7 +267,18 @@ __global__ void __launch_bounds__(256) sn_finish_kernel(const SnDesc* __restrict
 // ------------------------------------------------------------------------------------------
 // model
 // ------------------------------------------------------------------------------------------
+// Which kernel runs a layer and how its (virtual-concat) input channels are laid out in memory:
+// activations with fewer than 64 channels are stored with a 64-channel pitch (zeros above), so that
+// every TMA box row is a full 128-byte swizzle row; the packed weights carry zeros for the padding.
+struct LayerCfg {
+  int kind;                 // 0 direct fp32 (head, pred), 1 gather implicit GEMM (conv_igemm), 2 halo-tile (conv_halo)
+  int pad0, real0, pad1, real1;
+};
+
+static inline int pitch_of(int c) { return c < 64 ? 64 : c; }
+
 struct DevLayer {
+  LayerCfg cfg{0, 0, 0, 0, 0};
   __nv_bfloat16* wpack = nullptr;
   float* scale = nullptr;
   float* shift = nullptr;
@@ -289,6 +305,8 @@ struct v2ce_model {
   int max_rows = 0, max_k = 0;
   int64_t calls = 0;
   int last_launches = 0;
+  int desc_mode = 0;
+  std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> tmaps;
 };
 
 namespace v2ce {
@@ -363,7 +381,7 @@ static Dims make_dims(int B, int D, int H, int W) {
 }
 
 struct Buffers {
-  __nv_bfloat16 *head, *enc[4], *res[2], *dec[4], *tmp_t, *tmp_r;
+  __nv_bfloat16 *head, *enc[4], *res[2], *dec[4], *tmp_t, *tmp_r, *up;
   size_t bytes;
 };
 
@@ -371,14 +389,16 @@ static Buffers carve(void* ws, const Dims& d) {
   Arena a(ws, (size_t)-1);
   Buffers b;
   static const int ch[5] = {32, 64, 128, 256, 512};
-  b.head = a.take<__nv_bfloat16>((size_t)d.M[0] * 32);
+  b.head = a.take<__nv_bfloat16>((size_t)d.M[0] * 64);                 // 32 channels, 64-channel pitch
   for (int i = 0; i < 4; ++i) b.enc[i] = a.take<__nv_bfloat16>((size_t)d.M[i + 1] * ch[i + 1]);
   for (int i = 0; i < 2; ++i) b.res[i] = a.take<__nv_bfloat16>((size_t)d.M[4] * 512);
   for (int i = 0; i < 4; ++i) b.dec[i] = a.take<__nv_bfloat16>((size_t)d.M[3 - i] * ch[3 - i]);
-  size_t tmax = 0;
-  for (int i = 0; i < 5; ++i) tmax = tmax > (size_t)d.M[i] * ch[i] ? tmax : (size_t)d.M[i] * ch[i];
+  size_t tmax = 0, umax = 0;
+  for (int i = 0; i < 5; ++i) tmax = tmax > (size_t)d.M[i] * pitch_of(ch[i]) ? tmax : (size_t)d.M[i] * pitch_of(ch[i]);
+  for (int i = 0; i < 4; ++i) umax = umax > (size_t)d.M[i] * ch[i + 1] ? umax : (size_t)d.M[i] * ch[i + 1];
   b.tmp_t = a.take<__nv_bfloat16>(tmax);
   b.tmp_r = a.take<__nv_bfloat16>(tmax);
+  b.up = a.take<__nv_bfloat16>(umax);                                  // materialised nearest-upsample of the decoder input
   b.bytes = align_up(a.off, 256);
   return b;
 }
@@ -389,7 +409,43 @@ static int layer_index(const char* name) {
   return -1;
 }
 
-// one fused conv launch of layer `li`
+// kernel choice and channel padding per layer (see LayerCfg)
+static LayerCfg layer_cfg(int li) {
+  const LayerSpec& L = kLayers[li];
+  const std::string n = L.name;
+  if (li == 0 || li == kNumLayers - 1) return LayerCfg{0, 0, 0, 0, 0};
+  const bool is_conv2 = n.find(".conv2") != std::string::npos;
+  const bool is_dec = n.find("decoders") != std::string::npos;
+  const bool is_enc = n.find("encoders") != std::string::npos;
+  LayerCfg c{1, 0, 0, 0, 0};
+  if (is_conv2) {
+    c.kind = 2;
+    c.real0 = L.cin; c.pad0 = pitch_of(L.cin);
+  } else if (is_dec) {                       // conv1 / shortcut of a decoder: [up (2/3 of Cin) | skip (1/3)]
+    c.kind = (L.k == 3) ? 2 : 1;
+    c.real0 = L.cin / 3 * 2; c.pad0 = c.real0;
+    c.real1 = L.cin / 3; c.pad1 = pitch_of(c.real1);
+  } else {                                   // conv1 / shortcut of an encoder (stride 2) or bottleneck block
+    c.kind = (L.k == 3 && !is_enc) ? 2 : 1;
+    c.real0 = L.cin; c.pad0 = pitch_of(L.cin);
+  }
+  return c;
+}
+
+static int get_tmap(v2ce_model* m, const void* ptr, int B, int D, int H, int W, int cpitch, int PW, int rows,
+                    CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, B, D, H, W, cpitch, PW, rows);
+  auto it = m->tmaps.find(key);
+  if (it == m->tmaps.end()) {
+    CUtensorMap tm;
+    if (int e = halo::make_patch_map(&tm, ptr, B, D, H, W, cpitch, PW, rows)) return e;
+    it = m->tmaps.emplace(key, tm).first;
+  }
+  *out = it->second;
+  return V2CE_OK;
+}
+
+// gather implicit-GEMM launch of layer `li` (stride-2 convs, 1x1x1 shortcuts); c0/c1 are channel PITCHES
 static int run_conv(v2ce_model* m, int li, const __nv_bfloat16* src0, int c0, int h0, int w0, const __nv_bfloat16* src1,
                     int c1, int B, int D, int hin, int win, int stride, const __nv_bfloat16* residual, int act,
                     __nv_bfloat16* out, cudaStream_t s) {
@@ -409,21 +465,76 @@ static int run_conv(v2ce_model* m, int li, const __nv_bfloat16* src0, int c0, in
   a.inv_sigma = dl.sn_index >= 0 ? m->inv_sigma_dev + dl.sn_index : nullptr;
   a.residual = residual; a.out = out; a.act = act;
   a.error_flag = m->error_flag_dev;
-  if (a.Cin != L.cin) return set_error(V2CE_ERR_STATE, "layer %s: Cin %d != %d", L.name, a.Cin, L.cin);
+  if (dl.cfg.kind != 1 || c0 != dl.cfg.pad0 || c1 != dl.cfg.pad1)
+    return set_error(V2CE_ERR_STATE, "layer %s: gather launch with pitches %d+%d, packed for %d+%d", L.name, c0, c1,
+                     dl.cfg.pad0, dl.cfg.pad1);
   return conv::launch_conv(a, dl.bn_tile, s);
+}
+
+// halo-tile launch of layer `li` (3x3x3, stride 1); sources are full-resolution (B,D,H,W,pitch) tensors
+static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, const __nv_bfloat16* src1, int p1, int B, int D,
+                    int H, int W, const __nv_bfloat16* residual, int res_pitch, int act, __nv_bfloat16* out, int out_pitch,
+                    cudaStream_t s) {
+  const LayerSpec& L = kLayers[li];
+  const DevLayer& dl = m->layers[li];
+  if (dl.cfg.kind != 2 || p0 != dl.cfg.pad0 || p1 != dl.cfg.pad1)
+    return set_error(V2CE_ERR_STATE, "layer %s: halo launch with pitches %d+%d, packed for %d+%d", L.name, p0, p1,
+                     dl.cfg.pad0, dl.cfg.pad1);
+  const halo::HaloPlan plan = halo::plan_for(dl.bn_tile, H, W);
+  halo::HaloArgs a;
+  a.B = B; a.D = D; a.H = H; a.W = W;
+  a.PW = plan.ts.PW; a.TH = plan.ts.TH; a.TW = plan.ts.PW - 2;
+  a.tiles_w = (W + a.TW - 1) / a.TW;
+  a.tiles_h = (H + a.TH - 1) / a.TH;
+  a.ncc0 = p0 / 64; a.ncc1 = p1 / 64;
+  a.Cout = L.cout; a.out_pitch = out_pitch; a.res_pitch = res_pitch;
+  a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
+  a.wpack = dl.wpack; a.scale = dl.scale; a.shift = dl.shift;
+  a.inv_sigma = dl.sn_index >= 0 ? m->inv_sigma_dev + dl.sn_index : nullptr;
+  a.residual = residual; a.out = out; a.act = act;
+  a.desc_mode = m->desc_mode;
+  a.error_flag = m->error_flag_dev;
+  CUtensorMap tm0, tm1;
+  if (int e = get_tmap(m, src0, B, D, H, W, p0, a.PW, a.TH + 2, &tm0)) return e;
+  tm1 = tm0;
+  if (src1)
+    if (int e = get_tmap(m, src1, B, D, H, W, p1, a.PW, a.TH + 2, &tm1)) return e;
+  return halo::launch_halo(tm0, tm1, a, dl.bn_tile, plan.smem_bytes, s);
 }
 
 static int pack_layer(v2ce_model* m, int li, const float* w_dev, cudaStream_t s) {
   const LayerSpec& L = kLayers[li];
   DevLayer& dl = m->layers[li];
+  const LayerCfg c = layer_cfg(li);
+  dl.cfg = c;
   const int taps = L.k * L.k * L.k;
+  const int cin_pad = c.pad0 + c.pad1;
   dl.bn_tile = conv::pick_bn(L.cout);
-  dl.num_kb = (taps * L.cin + conv::kBlockK - 1) / conv::kBlockK;
+  if (c.real0 + c.real1 != L.cin) return set_error(V2CE_ERR_STATE, "layer %s: channel split mismatch", L.name);
+  if (c.kind == 2) {
+    const size_t n = (size_t)L.cout * 27 * cin_pad;
+    dl.num_kb = 27 * cin_pad / conv::kBlockK;
+    if (int e = dev_alloc(m, &dl.wpack, n)) return e;
+    halo::pack_weights_halo_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(
+        w_dev, L.cout, L.cin, dl.bn_tile, c.pad0, c.real0, c.pad1, c.real1, dl.wpack);
+    V2CE_LAUNCH_CHECK("pack_weights_halo_kernel");
+    return V2CE_OK;
+  }
+  dl.num_kb = (taps * cin_pad + conv::kBlockK - 1) / conv::kBlockK;
   const size_t n = (size_t)L.cout * dl.num_kb * conv::kBlockK;
   if (int e = dev_alloc(m, &dl.wpack, n)) return e;
   conv::pack_weights_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(
-      w_dev, L.cout, L.cin, taps, dl.bn_tile, dl.num_kb, dl.wpack);
+      w_dev, L.cout, L.cin, taps, dl.bn_tile, dl.num_kb, c.pad0, c.real0, c.pad1, c.real1, dl.wpack);
   V2CE_LAUNCH_CHECK("pack_weights_kernel");
+  return V2CE_OK;
+}
+
+static int run_upsample(const __nv_bfloat16* in, int planes, int H0, int W0, int H, int W, int C, __nv_bfloat16* out,
+                        cudaStream_t s) {
+  const size_t total = (size_t)planes * H * W * (C / 8);
+  const int grid = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+  halo::upsample_nearest_kernel<<<grid, 256, 0, s>>>(in, planes, H0, W0, H, W, C, out);
+  V2CE_LAUNCH_CHECK("upsample_nearest_kernel");
   return V2CE_OK;
 }
 
@@ -570,14 +681,14 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
   static const int ch[5] = {32, 64, 128, 256, 512};
   char name[64];
   const __nv_bfloat16* x = buf.head;
-  // encoders: stride (1,2,2)
+  // encoders: conv1 and the shortcut are stride (1,2,2) -> gather kernel; conv2 -> halo kernel
   for (int i = 0; i < 4; ++i) {
     snprintf(name, sizeof(name), "UNet.encoders.%d.conv1", i);
     const int l1 = layer_index(name);
-    if (int e = run_conv(m, l1, x, ch[i], d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 1, buf.tmp_t, s)) return e;
-    if (int e = run_conv(m, l1 + 2, x, ch[i], d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 0, buf.tmp_r, s)) return e;
-    if (int e = run_conv(m, l1 + 1, buf.tmp_t, ch[i + 1], d.H[i + 1], d.W[i + 1], nullptr, 0, B, D, d.H[i + 1], d.W[i + 1], 1,
-                         buf.tmp_r, 1, buf.enc[i], s)) return e;
+    const int pin = pitch_of(ch[i]), co = ch[i + 1];
+    if (int e = run_conv(m, l1, x, pin, d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 1, buf.tmp_t, s)) return e;
+    if (int e = run_conv(m, l1 + 2, x, pin, d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 0, buf.tmp_r, s)) return e;
+    if (int e = run_halo(m, l1 + 1, buf.tmp_t, co, nullptr, 0, B, D, d.H[i + 1], d.W[i + 1], buf.tmp_r, co, 1, buf.enc[i], co, s)) return e;
     x = buf.enc[i];
     launches += 3;
   }
@@ -585,28 +696,28 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
   for (int i = 0; i < 2; ++i) {
     snprintf(name, sizeof(name), "UNet.resblocks.%d.conv1", i);
     const int l1 = layer_index(name);
-    if (int e = run_conv(m, l1, x, 512, d.H[4], d.W[4], nullptr, 0, B, D, d.H[4], d.W[4], 1, nullptr, 1, buf.tmp_t, s)) return e;
+    if (int e = run_halo(m, l1, x, 512, nullptr, 0, B, D, d.H[4], d.W[4], nullptr, 0, 1, buf.tmp_t, 512, s)) return e;
     if (int e = run_conv(m, l1 + 2, x, 512, d.H[4], d.W[4], nullptr, 0, B, D, d.H[4], d.W[4], 1, nullptr, 0, buf.tmp_r, s)) return e;
-    if (int e = run_conv(m, l1 + 1, buf.tmp_t, 512, d.H[4], d.W[4], nullptr, 0, B, D, d.H[4], d.W[4], 1, buf.tmp_r, 1, buf.res[i], s)) return e;
+    if (int e = run_halo(m, l1 + 1, buf.tmp_t, 512, nullptr, 0, B, D, d.H[4], d.W[4], buf.tmp_r, 512, 1, buf.res[i], 512, s)) return e;
     x = buf.res[i];
     launches += 3;
   }
-  // decoders: virtual concat [nearest_up(x), skip]; skips are head, enc0, enc1, enc2 in reverse
+  // decoders: virtual concat [nearest_up(x), skip]; skips are enc2, enc1, enc0, head
   int xc = 512, xl = 4;   // channels / level of x
   for (int i = 0; i < 4; ++i) {
     const int lvl = 3 - i;                       // output level
     const __nv_bfloat16* skip = lvl == 0 ? buf.head : buf.enc[lvl - 1];
-    const int sc = ch[lvl];
+    const int sp = pitch_of(ch[lvl]), co = ch[lvl], tp = pitch_of(co);
     snprintf(name, sizeof(name), "UNet.decoders.%d.conv1", i);
     const int l1 = layer_index(name);
-    if (int e = run_conv(m, l1, x, xc, d.H[xl], d.W[xl], skip, sc, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 1, buf.tmp_t, s)) return e;
-    if (int e = run_conv(m, l1 + 2, x, xc, d.H[xl], d.W[xl], skip, sc, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 0, buf.tmp_r, s)) return e;
-    if (int e = run_conv(m, l1 + 1, buf.tmp_t, ch[lvl], d.H[lvl], d.W[lvl], nullptr, 0, B, D, d.H[lvl], d.W[lvl], 1, buf.tmp_r, 1,
-                         buf.dec[i], s)) return e;
+    if (int e = run_upsample(x, B * D, d.H[xl], d.W[xl], d.H[lvl], d.W[lvl], xc, buf.up, s)) return e;
+    if (int e = run_halo(m, l1, buf.up, xc, skip, sp, B, D, d.H[lvl], d.W[lvl], nullptr, 0, 1, buf.tmp_t, tp, s)) return e;
+    if (int e = run_conv(m, l1 + 2, buf.up, xc, d.H[lvl], d.W[lvl], skip, sp, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 0, buf.tmp_r, s)) return e;
+    if (int e = run_halo(m, l1 + 1, buf.tmp_t, tp, nullptr, 0, B, D, d.H[lvl], d.W[lvl], buf.tmp_r, co, 1, buf.dec[i], co, s)) return e;
     x = buf.dec[i];
-    xc = ch[lvl];
+    xc = co;
     xl = lvl;
-    launches += 3;
+    launches += 4;
   }
   const int lp = kNumLayers - 1;
   pred_conv_kernel<<<(int)((M0 + 127) / 128), 128, 0, s>>>(x, m->layers[lp].w32, m->layers[lp].bias, M0, H * W, y_dev);
@@ -644,10 +755,17 @@ extern "C" int v2ce_model_last_launches(const v2ce_model* m, int32_t* launches) 
   return V2CE_OK;
 }
 
-extern "C" int v2ce_conv3d_bf16(const void* src0_dev, int32_t c0, int32_t h0, int32_t w0, const void* src1_dev, int32_t c1,
-                                int32_t batch, int32_t depth, int32_t hin, int32_t win, int32_t ksize, int32_t stride_hw,
-                                const float* weight_host, int32_t cout, const float* scale_host, const float* shift_host,
-                                const void* residual_dev, int32_t act, void* out_dev, void* stream) {
+extern "C" int v2ce_model_set_option(v2ce_model* m, const char* key, int64_t value) {
+  V2CE_REQUIRE(m && key, "NULL argument");
+  if (std::string(key) == "desc_mode") { m->desc_mode = (int)value; return V2CE_OK; }
+  return set_error(V2CE_ERR_INVALID, "unknown option '%s'", key);
+}
+
+extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0, int32_t w0, const void* src1_dev, int32_t c1,
+                                   int32_t batch, int32_t depth, int32_t hin, int32_t win, int32_t ksize, int32_t stride_hw,
+                                   const float* weight_host, int32_t cout, const float* scale_host, const float* shift_host,
+                                   const void* residual_dev, int32_t act, void* out_dev, int32_t impl, int32_t desc_mode,
+                                   void* stream) {
   V2CE_REQUIRE(src0_dev && weight_host && scale_host && shift_host && out_dev, "NULL argument");
   V2CE_REQUIRE(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
   V2CE_REQUIRE(stride_hw == 1 || stride_hw == 2, "stride must be 1 or 2");
@@ -655,6 +773,9 @@ extern "C" int v2ce_conv3d_bf16(const void* src0_dev, int32_t c0, int32_t h0, in
   V2CE_REQUIRE((src1_dev != nullptr) == (c1 > 0), "src1 and c1 must agree");
   const int bn = conv::pick_bn(cout);
   V2CE_REQUIRE(bn != 0, "cout must be a multiple of 32");
+  if (impl == 1)
+    V2CE_REQUIRE(ksize == 3 && stride_hw == 1 && h0 == hin && w0 == win && c0 % 64 == 0 && c1 % 64 == 0,
+                 "halo kernel: 3x3x3, stride 1, no upsample, channel pitches multiple of 64");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int cin = c0 + c1, taps = ksize * ksize * ksize;
   const int num_kb = (taps * cin + conv::kBlockK - 1) / conv::kBlockK;
@@ -671,21 +792,43 @@ extern "C" int v2ce_conv3d_bf16(const void* src0_dev, int32_t c0, int32_t h0, in
   V2CE_CUDA_CHECK(cudaMemcpyAsync(w_dev, weight_host, wn * sizeof(float), cudaMemcpyHostToDevice, s));
   V2CE_CUDA_CHECK(cudaMemcpyAsync(scale_dev, scale_host, cout * sizeof(float), cudaMemcpyHostToDevice, s));
   V2CE_CUDA_CHECK(cudaMemcpyAsync(shift_dev, shift_host, cout * sizeof(float), cudaMemcpyHostToDevice, s));
-  conv::pack_weights_kernel<<<(int)((pn + 255) / 256 > 4096 ? 4096 : (pn + 255) / 256), 256, 0, s>>>(w_dev, cout, cin, taps, bn,
-                                                                                                     num_kb, wpack);
+  const int pgrid = (int)((pn + 255) / 256 > 4096 ? 4096 : (pn + 255) / 256);
+  if (impl == 1)
+    halo::pack_weights_halo_kernel<<<pgrid, 256, 0, s>>>(w_dev, cout, cin, bn, c0, c0, c1, c1, wpack);
+  else
+    conv::pack_weights_kernel<<<pgrid, 256, 0, s>>>(w_dev, cout, cin, taps, bn, num_kb, c0, c0, c1, c1, wpack);
   int rc = V2CE_OK;
-  if (cudaGetLastError() != cudaSuccess) rc = set_error(V2CE_ERR_CUDA, "pack_weights_kernel launch failed");
-  if (rc == V2CE_OK) {
+  if (cudaGetLastError() != cudaSuccess) rc = set_error(V2CE_ERR_CUDA, "weight pack launch failed");
+  const int pad = ksize / 2;
+  const int hout = (hin + 2 * pad - ksize) / stride_hw + 1, wout = (win + 2 * pad - ksize) / stride_hw + 1;
+  if (rc == V2CE_OK && impl == 1) {
+    const halo::HaloPlan plan = halo::plan_for(bn, hin, win);
+    halo::HaloArgs a;
+    a.B = batch; a.D = depth; a.H = hin; a.W = win;
+    a.PW = plan.ts.PW; a.TH = plan.ts.TH; a.TW = plan.ts.PW - 2;
+    a.tiles_w = (win + a.TW - 1) / a.TW; a.tiles_h = (hin + a.TH - 1) / a.TH;
+    a.ncc0 = c0 / 64; a.ncc1 = c1 / 64;
+    a.Cout = cout; a.out_pitch = cout; a.res_pitch = cout;
+    a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
+    a.wpack = wpack; a.scale = scale_dev; a.shift = shift_dev; a.inv_sigma = nullptr;
+    a.residual = static_cast<const __nv_bfloat16*>(residual_dev);
+    a.out = static_cast<__nv_bfloat16*>(out_dev);
+    a.act = act; a.desc_mode = desc_mode; a.error_flag = flag;
+    CUtensorMap tm0, tm1;
+    rc = halo::make_patch_map(&tm0, src0_dev, batch, depth, hin, win, c0, a.PW, a.TH + 2);
+    tm1 = tm0;
+    if (rc == V2CE_OK && src1_dev) rc = halo::make_patch_map(&tm1, src1_dev, batch, depth, hin, win, c1, a.PW, a.TH + 2);
+    if (rc == V2CE_OK) rc = halo::launch_halo(tm0, tm1, a, bn, plan.smem_bytes, s);
+  } else if (rc == V2CE_OK) {
     ConvArgs a;
     a.src0 = static_cast<const __nv_bfloat16*>(src0_dev);
     a.src1 = static_cast<const __nv_bfloat16*>(src1_dev);
     a.C0 = c0; a.C1 = c1; a.Cin = cin; a.H0 = h0; a.W0 = w0;
     a.B = batch; a.D = depth; a.Hin = hin; a.Win = win;
-    a.stride = stride_hw; a.ksize = ksize; a.pad = ksize / 2;
-    a.Hout = (hin + 2 * a.pad - ksize) / stride_hw + 1;
-    a.Wout = (win + 2 * a.pad - ksize) / stride_hw + 1;
+    a.stride = stride_hw; a.ksize = ksize; a.pad = pad;
+    a.Hout = hout; a.Wout = wout;
     a.taps = taps; a.num_kb = num_kb;
-    a.M = batch * depth * a.Hout * a.Wout;
+    a.M = batch * depth * hout * wout;
     a.Cout = cout; a.wpack = wpack; a.scale = scale_dev; a.shift = shift_dev; a.inv_sigma = nullptr;
     a.residual = static_cast<const __nv_bfloat16*>(residual_dev);
     a.out = static_cast<__nv_bfloat16*>(out_dev);
@@ -700,4 +843,12 @@ extern "C" int v2ce_conv3d_bf16(const void* src0_dev, int32_t c0, int32_t h0, in
   if (se != cudaSuccess) return set_error(V2CE_ERR_CUDA, "conv3d_bf16 failed: %s", cudaGetErrorString(se));
   if (hflag) return set_error(V2CE_ERR_CUDA, "conv pipeline watchdog fired");
   return V2CE_OK;
+}
+
+extern "C" int v2ce_conv3d_bf16(const void* src0_dev, int32_t c0, int32_t h0, int32_t w0, const void* src1_dev, int32_t c1,
+                                int32_t batch, int32_t depth, int32_t hin, int32_t win, int32_t ksize, int32_t stride_hw,
+                                const float* weight_host, int32_t cout, const float* scale_host, const float* shift_host,
+                                const void* residual_dev, int32_t act, void* out_dev, void* stream) {
+  return v2ce_conv3d_bf16_ex(src0_dev, c0, h0, w0, src1_dev, c1, batch, depth, hin, win, ksize, stride_hw, weight_host, cout,
+                             scale_host, shift_host, residual_dev, act, out_dev, 0, 0, stream);
 }
