@@ -10,6 +10,13 @@
 // shifted by whole 128-byte rows.  Rows whose column index falls in the 2 halo columns produce
 // garbage accumulator rows that the epilogue skips (MMA rows are independent).
 //
+// Depth blocking: a CTA computes T consecutive depth slices of the same (h,w) tile (T accumulators of
+// BN TMEM columns).  Slice d+t under tap kd reads input slice d+t+kd-1, so the T+2 patches d-1..d+T
+// serve all 3*T (kd, t) pairs, and every weight tile (cc, kd, tap) fetched from L2 is used for T*128
+// output rows instead of 128.  With M = 128 rows per weight tile the L2->SM weight stream alone needs
+// 64 B/clk/SM (more than the fabric delivers: measured 12-25 % tensor-pipe activity); T = 4 cuts it to
+// 16 B/clk and the patch traffic by a further (T+2)/(3T).
+//
 // Replaces the same reference calls as conv_igemm.cuh (submodules.py:249-263) for the 20 stride-1
 // 3x3x3 convs, i.e. 91 % of the network's FLOPs.
 //
@@ -27,7 +34,7 @@ namespace halo {
 using namespace conv;
 
 constexpr int kHaloThreads = 224;
-constexpr int kMaxSA = 4, kMaxSB = 8;
+constexpr int kMaxSA = 6, kMaxSB = 8;
 
 struct HaloArgs {
   int B, D, H, W;
@@ -37,17 +44,17 @@ struct HaloArgs {
   int Cout;                    // real output channels (multiple of BN)
   int out_pitch;               // channel pitch of `out`; columns [Cout, out_pitch) are zero-filled
   int res_pitch;               // channel pitch of `residual`
+  int T;                       // depth slices per CTA (T accumulators); D % T == 0
   int SA, SB;                  // pipeline depths (patch ring / weight ring)
   int a_stage_bytes;           // bytes reserved per patch stage (multiple of 1024)
   int box_bytes;               // bytes one TMA box delivers: PW * (TH+2) * 128
-  const __nv_bfloat16* wpack;  // [Cout/BN][3 kd][ncc][9 taps][BN][64], rows pre-swizzled
+  const __nv_bfloat16* wpack;  // [Cout/BN][ncc][3 kd][9 taps][BN][64], rows pre-swizzled
   const float* scale;
   const float* shift;
   const float* inv_sigma;
   const __nv_bfloat16* residual;
   __nv_bfloat16* out;
   int act;
-  int desc_mode;               // 0: base_offset = 0, 1: base_offset = (addr >> 7) & 7  (bring-up switch)
   int* error_flag;
 };
 
@@ -60,13 +67,11 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-__device__ __forceinline__ uint64_t make_smem_desc_shifted(uint32_t smem_addr, int mode) {
-  uint64_t d = make_smem_desc(smem_addr);
-  if (mode == 1) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
-  return d;
-}
+// Measured on B200 (tools/run_halo_cases.sh): the UMMA 128B swizzle is a function of the absolute shared-
+// memory address, so a descriptor whose start is shifted by whole 128-byte rows reads a TMA-written patch
+// correctly with base_offset = 0; setting base_offset = (addr >> 7) & 7 gives wrong results.
 
-template <int BN>
+template <int BN, int T>
 __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_constant__ CUtensorMap tm0,
                                                                   const __grid_constant__ CUtensorMap tm1,
                                                                   const HaloArgs a) {
@@ -76,18 +81,18 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
   uint8_t* smem = smem_raw + (base - raw);
   constexpr int kBStage = BN * kBlockK * 2;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
   const int n_tiles = a.Cout / BN;
   int t = blockIdx.x;
   const int n_tile = t % n_tiles; t /= n_tiles;
   const int tw_i = t % a.tiles_w; t /= a.tiles_w;
   const int th_i = t % a.tiles_h; t /= a.tiles_h;
-  const int d = t % a.D;
-  const int b = t / a.D;
+  const int dgroups = a.D / T;
+  const int d0 = (t % dgroups) * T;              // first of the T output depth slices
+  const int b = t / dgroups;
   const int h0 = th_i * a.TH, w0 = tw_i * a.TW;
   const int ncc = a.ncc0 + a.ncc1;
-  const int groups = 3 * ncc;
-
+  
   const uint32_t a_base = base;
   const uint32_t b_base = base + (uint32_t)a.SA * a.a_stage_bytes;
   const uint32_t bar_base = b_base + (uint32_t)a.SB * kBStage;
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(const_cast<uint32_t*>(tmem_ptr))),
-                 "r"((uint32_t)BN)
+                 "r"((uint32_t)(BN * T))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -127,59 +132,95 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
   tcgen05_fence_after();
   const uint32_t tmem_acc = *tmem_ptr;
 
+  // The three feeding roles run warp-converged (uniform registers for addresses/descriptors); the single
+  // issuing lane is chosen by elect.sync.
   if (warp == 0) {
     // ================= patch producer (TMA) =================
-    if (lane == 0) {
-      for (int g = 0; g < groups; ++g) {
-        const int s = g % a.SA;
-        mbar_wait(a_empty(s), ((g / a.SA) & 1) ^ 1, a.error_flag);
-        mbar_arrive_expect_tx(a_full(s), (uint32_t)a.box_bytes);
-        const int kd = g / ncc, cc = g % ncc;
-        const bool first = cc < a.ncc0;
-        tma_load_5d(a_base + (uint32_t)s * a.a_stage_bytes, first ? &tm0 : &tm1, (first ? cc : cc - a.ncc0) * kBlockK,
-                    w0 - 1, h0 - 1, d + kd - 1, b, a_full(s));
+    int s = 0, ph = 1;                              // stage / parity of the empty barrier to wait on
+    for (int cc = 0; cc < ncc; ++cc) {
+      const bool first = cc < a.ncc0;
+      const CUtensorMap* map = first ? &tm0 : &tm1;
+      const int c0 = (first ? cc : cc - a.ncc0) * kBlockK;
+      for (int z = 0; z < T + 2; ++z) {
+        mbar_wait(a_empty(s), (uint32_t)ph, a.error_flag);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(a_full(s), (uint32_t)a.box_bytes);
+          tma_load_5d(a_base + (uint32_t)s * a.a_stage_bytes, map, c0, w0 - 1, h0 - 1, d0 - 1 + z, b, a_full(s));
+        }
+        __syncwarp();
+        if (++s == a.SA) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================= weight-tile producer (bulk copy) =================
-    if (lane == 0) {
-      const __nv_bfloat16* wt = a.wpack + (size_t)n_tile * groups * 9 * (BN * kBlockK);
-      const int total = groups * 9;
-      for (int it = 0; it < total; ++it) {
-        const int s = it % a.SB;
-        mbar_wait(b_empty(s), ((it / a.SB) & 1) ^ 1, a.error_flag);
+    const int total = ncc * 27;
+    const __nv_bfloat16* wt = a.wpack + (size_t)n_tile * total * (BN * kBlockK);
+    int s = 0, ph = 1;
+    for (int it = 0; it < total; ++it) {
+      mbar_wait(b_empty(s), (uint32_t)ph, a.error_flag);
+      if (elect_one()) {
         mbar_arrive_expect_tx(b_full(s), (uint32_t)kBStage);
         bulk_copy_g2s(b_base + (uint32_t)s * kBStage, wt + (size_t)it * (BN * kBlockK), (uint32_t)kBStage, b_full(s));
       }
+      __syncwarp();
+      if (++s == a.SB) { s = 0; ph ^= 1; }
     }
   } else if (warp == 2) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
-      int it = 0;
-      for (int g = 0; g < groups; ++g) {
-        const int sa = g % a.SA;
-        mbar_wait(a_full(sa), (g / a.SA) & 1, a.error_flag);
-        tcgen05_fence_after();
-        const uint32_t patch = a_base + (uint32_t)sa * a.a_stage_bytes;
+    constexpr uint32_t idesc = make_idesc(BN);
+    int sb = 0, pb = 0;                             // weight ring position / parity
+    int sw = 0, pw = 0;                             // next patch stage to wait for / its parity
+    int arrived = 0;
+    int s_first = 0;                                // stage of slice kd of the current chunk
+    for (int cc = 0; cc < ncc; ++cc) {
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap, ++it) {
-          const int sb = it % a.SB;
-          mbar_wait(b_full(sb), (it / a.SB) & 1, a.error_flag);
-          tcgen05_fence_after();
-          const uint32_t a_addr = patch + (uint32_t)((tap / 3) * a.PW + (tap % 3)) * 128u;
-          const uint32_t b_addr = b_base + (uint32_t)sb * kBStage;
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            tcgen05_mma_bf16(tmem_acc, make_smem_desc_shifted(a_addr + k * 32, a.desc_mode), make_smem_desc(b_addr + k * 32),
-                             idesc, (g | tap | k) != 0 ? 1u : 0u);
-          }
-          tcgen05_commit(b_empty(sb));
+      for (int kd = 0; kd < 3; ++kd) {
+        const int need = cc * (T + 2) + kd + T;     // slices kd .. kd+T-1 of this chunk must have landed
+        while (arrived < need) {
+          mbar_wait(a_full(sw), (uint32_t)pw, a.error_flag);
+          ++arrived;
+          if (++sw == a.SA) { sw = 0; pw ^= 1; }
         }
-        tcgen05_commit(a_empty(sa));
+        tcgen05_fence_after();
+        uint32_t patch[T];
+#pragma unroll
+        for (int tt = 0; tt < T; ++tt) {
+          int st = s_first + tt;
+          if (st >= a.SA) st -= a.SA;
+          patch[tt] = a_base + (uint32_t)st * a.a_stage_bytes;
+        }
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(b_full(sb), (uint32_t)pb, a.error_flag);
+          tcgen05_fence_after();
+          const uint32_t b_addr = b_base + (uint32_t)sb * kBStage;
+          const uint32_t shift = (uint32_t)((tap / 3) * a.PW + (tap % 3)) * 128u;
+          const uint32_t acc0 = (cc | kd | tap) == 0 ? 0u : 1u;
+#pragma unroll
+          for (int tt = 0; tt < T; ++tt) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              tcgen05_mma_bf16_elect(tmem_acc + (uint32_t)(tt * BN), make_smem_desc(patch[tt] + shift + k * 32),
+                                     make_smem_desc(b_addr + k * 32), idesc, k == 0 ? acc0 : 1u);
+            }
+          }
+          tcgen05_commit_elect(b_empty(sb));
+          if (++sb == a.SB) { sb = 0; pb ^= 1; }
+        }
+        // input slice kd is done after tap block kd; the last block frees the remaining T slices
+        if (kd < 2) {
+          tcgen05_commit_elect(a_empty(s_first));
+          if (++s_first == a.SA) s_first = 0;
+        } else {
+#pragma unroll
+          for (int z = 0; z < T; ++z) {
+            tcgen05_commit_elect(a_empty(s_first));
+            if (++s_first == a.SA) s_first = 0;
+          }
+        }
       }
-      tcgen05_commit(tmem_full_bar);
     }
+    tcgen05_commit_elect(tmem_full_bar);
   } else {
     // ================= epilogue =================
     const int quarter = warp & 3;
@@ -187,67 +228,69 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
     const int th = i / a.PW, tw = i % a.PW;
     const int h = h0 + th, w = w0 + tw;
     const bool row_ok = (th < a.TH) && (tw < a.TW) && (h < a.H) && (w < a.W);
-    const size_t m = ((size_t)(b * a.D + d) * a.H + h) * a.W + w;
     mbar_wait(tmem_full_bar, 0, a.error_flag);
     __syncwarp();
     tcgen05_fence_after();
-    const uint32_t lane_addr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-    __nv_bfloat16* orow = a.out + m * a.out_pitch + n_tile * BN;
-    const __nv_bfloat16* rrow = a.residual ? a.residual + m * a.res_pitch + n_tile * BN : nullptr;
+    for (int tt = 0; tt < T; ++tt) {
+      const size_t m = ((size_t)(b * a.D + d0 + tt) * a.H + h) * a.W + w;
+      const uint32_t lane_addr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tt * BN);
+      __nv_bfloat16* orow = a.out + m * a.out_pitch + n_tile * BN;
+      const __nv_bfloat16* rrow = a.residual ? a.residual + m * a.res_pitch + n_tile * BN : nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(lane_addr + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (row_ok) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(lane_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float r[8];
+          for (int g = 0; g < 4; ++g) {
+            float r[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[j] = 0.f;
-          if (rrow) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + g * 8));
-            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+            for (int j = 0; j < 8; ++j) r[j] = 0.f;
+            if (rrow) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + g * 8));
+              const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(rp[j]);
+                r[2 * j] = f.x;
+                r[2 * j + 1] = f.y;
+              }
+            }
+            uint4 ov;
+            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(rp[j]);
-              r[2 * j] = f.x;
-              r[2 * j + 1] = f.y;
-            }
-          }
-          uint4 ov;
-          __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+              float y[2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float y[2];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int n = c0 + g * 8 + 2 * j + hh;
-              float tt = fmaf(__uint_as_float(v[g * 8 + 2 * j + hh]), s_scale[n], s_shift[n]) + r[2 * j + hh];
-              if (a.act == 1) tt = fmaxf(tt, 0.f);
-              else if (a.act == 2) tt = tt > 0.f ? tt : 0.01f * tt;
-              y[hh] = tt;
+              for (int hh = 0; hh < 2; ++hh) {
+                const int n = c0 + g * 8 + 2 * j + hh;
+                float tv = fmaf(__uint_as_float(v[g * 8 + 2 * j + hh]), s_scale[n], s_shift[n]) + r[2 * j + hh];
+                if (a.act == 1) tv = fmaxf(tv, 0.f);
+                else if (a.act == 2) tv = tv > 0.f ? tv : 0.01f * tv;
+                y[hh] = tv;
+              }
+              op[j] = __floats2bfloat162_rn(y[0], y[1]);
             }
-            op[j] = __floats2bfloat162_rn(y[0], y[1]);
+            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = ov;
           }
-          *reinterpret_cast<uint4*>(orow + c0 + g * 8) = ov;
         }
       }
-    }
-    if (row_ok && n_tile == n_tiles - 1) {        // zero the padding channels so later TMA reads see 0, not garbage
-      for (int c = a.Cout; c < a.out_pitch; c += 8)
-        *reinterpret_cast<uint4*>(a.out + m * a.out_pitch + c) = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok && n_tile == n_tiles - 1) {      // zero the padding channels so later TMA reads see 0, not garbage
+        for (int c = a.Cout; c < a.out_pitch; c += 8)
+          *reinterpret_cast<uint4*>(a.out + m * a.out_pitch + c) = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)(BN * T)) : "memory");
   }
 }
 
-// fp32 (Cout, Cin_real, 3,3,3) -> bf16 [Cout/BN][kd][cc][kh*3+kw][BN][64] (rows swizzled); padded input
+// fp32 (Cout, Cin_real, 3,3,3) -> bf16 [Cout/BN][cc][kd][kh*3+kw][BN][64] (rows swizzled); padded input
 // channel p maps to a real channel through two segments (pad0/real0 | pad1/real1), zero elsewhere.
 __global__ void pack_weights_halo_kernel(const float* __restrict__ w, int Cout, int cin_real, int BN, int pad0, int real0,
                                          int pad1, int real1, __nv_bfloat16* __restrict__ out) {
@@ -257,11 +300,11 @@ __global__ void pack_weights_halo_kernel(const float* __restrict__ w, int Cout, 
     const int e = (int)(i % 8);
     const int qs = (int)((i / 8) % 8);
     const int r = (int)((i / 64) % BN);
-    size_t tile = i / ((size_t)64 * BN);        // ((n_tile*3 + kd)*ncc + cc)*9 + tap9
+    size_t tile = i / ((size_t)64 * BN);        // ((n_tile*ncc + cc)*3 + kd)*9 + tap9
     const int tap9 = (int)(tile % 9); tile /= 9;
-    const int cc = (int)(tile % ncc); tile /= ncc;
-    const int kd = (int)(tile % 3);
-    const int n_tile = (int)(tile / 3);
+    const int kd = (int)(tile % 3); tile /= 3;
+    const int cc = (int)(tile % ncc);
+    const int n_tile = (int)(tile / ncc);
     const int q = qs ^ (r & 7);
     const int p = cc * kBlockK + q * 8 + e;      // padded input channel
     int c = -1;
@@ -343,43 +386,63 @@ inline TileShape pick_tile(int H, int W) {
 
 struct HaloPlan {
   TileShape ts;
-  int SA, SB, a_stage_bytes, box_bytes, smem_bytes;
+  int T, SA, SB, a_stage_bytes, box_bytes, smem_bytes;
 };
 
-inline HaloPlan plan_for(int bn, int H, int W) {
+inline HaloPlan plan_for(int bn, int D, int H, int W) {
   HaloPlan p;
   p.ts = pick_tile(H, W);
   const int rows = p.ts.PW * (p.ts.TH + 2);
   p.box_bytes = rows * 128;
   p.a_stage_bytes = ((rows + 2 + 7) / 8) * 1024;
-  p.SA = 3;
-  p.SB = bn >= 256 ? 3 : 4;
-  if (bn >= 256) p.SA = 2;
   const int tail = (2 * kMaxSA + 2 * kMaxSB + 1) * 8 + 16 + 2 * bn * 4;
-  p.smem_bytes = p.SA * p.a_stage_bytes + p.SB * bn * kBlockK * 2 + tail + 1024;
+  const int budget = 227 * 1024 - 1024 - tail;
+  const int b_stage = bn * kBlockK * 2;
+  // depth blocking: as many slices as TMEM (512 columns) and D allow
+  p.T = (bn <= 128) ? 4 : 2;
+  while (p.T > 1 && (D % p.T != 0)) p.T /= 2;
+  for (;; p.T /= 2) {
+    p.SB = bn <= 32 ? 8 : bn <= 64 ? 6 : bn <= 128 ? 5 : 3;
+    p.SA = p.T + 2;
+    while (p.SA > p.T + 1 && p.SA * p.a_stage_bytes + p.SB * b_stage > budget) --p.SA;
+    while (p.SB > 2 && p.SA * p.a_stage_bytes + p.SB * b_stage > budget) --p.SB;
+    if (p.SA * p.a_stage_bytes + p.SB * b_stage <= budget || p.T == 1) break;
+  }
+  if (p.SA > kMaxSA) p.SA = kMaxSA;
+  p.smem_bytes = p.SA * p.a_stage_bytes + p.SB * b_stage + tail + 1024;
   return p;
 }
 
-template <int BN>
+template <int BN, int T>
 inline int launch_halo_one(const CUtensorMap& tm0, const CUtensorMap& tm1, const HaloArgs& a, int smem_bytes, cudaStream_t s) {
   static int configured = 0;
   if (configured < smem_bytes) {
-    V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = smem_bytes;
   }
-  const int grid = a.B * a.D * a.tiles_h * a.tiles_w * (a.Cout / BN);
-  conv_halo_kernel<BN><<<grid, kHaloThreads, smem_bytes, s>>>(tm0, tm1, a);
+  const int grid = a.B * (a.D / T) * a.tiles_h * a.tiles_w * (a.Cout / BN);
+  conv_halo_kernel<BN, T><<<grid, kHaloThreads, smem_bytes, s>>>(tm0, tm1, a);
   V2CE_LAUNCH_CHECK("conv_halo_kernel");
   return V2CE_OK;
+}
+
+template <int BN>
+inline int launch_halo_bn(const CUtensorMap& tm0, const CUtensorMap& tm1, const HaloArgs& a, int smem_bytes, cudaStream_t s) {
+  if constexpr (BN <= 128) {
+    if (a.T == 4) return launch_halo_one<BN, 4>(tm0, tm1, a, smem_bytes, s);
+  }
+  if (a.T == 2) return launch_halo_one<BN, 2>(tm0, tm1, a, smem_bytes, s);
+  if (a.T == 1) return launch_halo_one<BN, 1>(tm0, tm1, a, smem_bytes, s);
+  return set_error(V2CE_ERR_INVALID, "unsupported depth blocking T=%d for N tile %d", a.T, BN);
 }
 
 inline int launch_halo(const CUtensorMap& tm0, const CUtensorMap& tm1, const HaloArgs& a, int bn, int smem_bytes,
                        cudaStream_t s) {
   switch (bn) {
-    case 32: return launch_halo_one<32>(tm0, tm1, a, smem_bytes, s);
-    case 64: return launch_halo_one<64>(tm0, tm1, a, smem_bytes, s);
-    case 128: return launch_halo_one<128>(tm0, tm1, a, smem_bytes, s);
-    case 256: return launch_halo_one<256>(tm0, tm1, a, smem_bytes, s);
+    case 32: return launch_halo_bn<32>(tm0, tm1, a, smem_bytes, s);
+    case 64: return launch_halo_bn<64>(tm0, tm1, a, smem_bytes, s);
+    case 128: return launch_halo_bn<128>(tm0, tm1, a, smem_bytes, s);
+    case 256: return launch_halo_bn<256>(tm0, tm1, a, smem_bytes, s);
   }
   return set_error(V2CE_ERR_INVALID, "unsupported N tile %d", bn);
 }

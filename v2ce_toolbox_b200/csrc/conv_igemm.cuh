@@ -116,6 +116,38 @@ __device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-converged issue helpers.  The loops that feed the tensor core run with all 32 lanes converged so
+// that nvcc keeps addresses and descriptors in uniform registers; the instruction that must execute
+// once is predicated on elect.sync inside the asm block.  (Running those loops under `if (lane == 0)`
+// cost ~150 cycles per tcgen05.mma in R2UR/ELECT round trips -- measured with ncu source counters.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, e;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tcgen05_mma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -169,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
   uint8_t* smem = smem_raw + (base - raw);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  const int warp = uniform_warp_id(), lane = tid & 31;
   const int n_tiles = a.Cout / BN;
   const int n_tile = blockIdx.x % n_tiles;
   const int m_tile = blockIdx.x / n_tiles;
@@ -364,36 +396,36 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
       }
     }
   } else if (warp == 4) {
-    // ================= MMA issuer (single thread) =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
-      for (int kb = 0; kb < a.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(full_bar(s), (kb / STAGES) & 1, a.error_flag);
-        fence_proxy_async();
-        tcgen05_fence_after();
-        const uint32_t a_addr = a_base + (uint32_t)s * kAStageBytes;
-        const uint32_t b_addr = b_base + (uint32_t)s * L::kBStageBytes;
+    // ================= MMA issuer (warp converged, one elected lane issues) =================
+    constexpr uint32_t idesc = make_idesc(BN);
+    for (int kb = 0; kb < a.num_kb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(full_bar(s), (kb / STAGES) & 1, a.error_flag);
+      fence_proxy_async();
+      tcgen05_fence_after();
+      const uint32_t a_addr = a_base + (uint32_t)s * kAStageBytes;
+      const uint32_t b_addr = b_base + (uint32_t)s * L::kBStageBytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          tcgen05_mma_bf16(tmem_acc, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc,
-                           (kb | k) != 0 ? 1u : 0u);
-        }
-        tcgen05_commit(empty_bar(s));       // frees the stage once these MMAs have read it
+      for (int k = 0; k < kBlockK / 16; ++k) {
+        tcgen05_mma_bf16_elect(tmem_acc, make_smem_desc(a_addr + k * 32), make_smem_desc(b_addr + k * 32), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
       }
-      tcgen05_commit(tmem_full_bar);        // accumulator complete
+      tcgen05_commit_elect(empty_bar(s));   // frees the stage once these MMAs have read it
     }
+    tcgen05_commit_elect(tmem_full_bar);    // accumulator complete
+    (void)lane;
   } else {
     // ================= weight-tile producer (bulk copy engine) =================
-    if (lane == 0) {
-      const __nv_bfloat16* wt = a.wpack + (size_t)n_tile * a.num_kb * (BN * kBlockK);
-      for (int kb = 0; kb < a.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(empty_bar(s), ((kb / STAGES) & 1) ^ 1, a.error_flag);
+    const __nv_bfloat16* wt = a.wpack + (size_t)n_tile * a.num_kb * (BN * kBlockK);
+    for (int kb = 0; kb < a.num_kb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(empty_bar(s), ((kb / STAGES) & 1) ^ 1, a.error_flag);
+      if (elect_one()) {
         mbar_arrive_expect_tx(full_bar(s), (uint32_t)L::kBStageBytes);
         bulk_copy_g2s(b_base + (uint32_t)s * L::kBStageBytes, wt + (size_t)kb * (BN * kBlockK),
                       (uint32_t)L::kBStageBytes, full_bar(s));
       }
+      __syncwarp();
     }
   }
 

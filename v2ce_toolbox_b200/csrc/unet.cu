@@ -480,7 +480,7 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
   if (dl.cfg.kind != 2 || p0 != dl.cfg.pad0 || p1 != dl.cfg.pad1)
     return set_error(V2CE_ERR_STATE, "layer %s: halo launch with pitches %d+%d, packed for %d+%d", L.name, p0, p1,
                      dl.cfg.pad0, dl.cfg.pad1);
-  const halo::HaloPlan plan = halo::plan_for(dl.bn_tile, H, W);
+  const halo::HaloPlan plan = halo::plan_for(dl.bn_tile, D, H, W);
   halo::HaloArgs a;
   a.B = B; a.D = D; a.H = H; a.W = W;
   a.PW = plan.ts.PW; a.TH = plan.ts.TH; a.TW = plan.ts.PW - 2;
@@ -488,11 +488,10 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
   a.tiles_h = (H + a.TH - 1) / a.TH;
   a.ncc0 = p0 / 64; a.ncc1 = p1 / 64;
   a.Cout = L.cout; a.out_pitch = out_pitch; a.res_pitch = res_pitch;
-  a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
+  a.T = plan.T; a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
   a.wpack = dl.wpack; a.scale = dl.scale; a.shift = dl.shift;
   a.inv_sigma = dl.sn_index >= 0 ? m->inv_sigma_dev + dl.sn_index : nullptr;
   a.residual = residual; a.out = out; a.act = act;
-  a.desc_mode = m->desc_mode;
   a.error_flag = m->error_flag_dev;
   CUtensorMap tm0, tm1;
   if (int e = get_tmap(m, src0, B, D, H, W, p0, a.PW, a.TH + 2, &tm0)) return e;
@@ -802,18 +801,18 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
   const int pad = ksize / 2;
   const int hout = (hin + 2 * pad - ksize) / stride_hw + 1, wout = (win + 2 * pad - ksize) / stride_hw + 1;
   if (rc == V2CE_OK && impl == 1) {
-    const halo::HaloPlan plan = halo::plan_for(bn, hin, win);
+    const halo::HaloPlan plan = halo::plan_for(bn, depth, hin, win);
     halo::HaloArgs a;
     a.B = batch; a.D = depth; a.H = hin; a.W = win;
     a.PW = plan.ts.PW; a.TH = plan.ts.TH; a.TW = plan.ts.PW - 2;
     a.tiles_w = (win + a.TW - 1) / a.TW; a.tiles_h = (hin + a.TH - 1) / a.TH;
     a.ncc0 = c0 / 64; a.ncc1 = c1 / 64;
     a.Cout = cout; a.out_pitch = cout; a.res_pitch = cout;
-    a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
+    a.T = plan.T; a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
     a.wpack = wpack; a.scale = scale_dev; a.shift = shift_dev; a.inv_sigma = nullptr;
     a.residual = static_cast<const __nv_bfloat16*>(residual_dev);
     a.out = static_cast<__nv_bfloat16*>(out_dev);
-    a.act = act; a.desc_mode = desc_mode; a.error_flag = flag;
+    a.act = act; a.error_flag = flag;
     CUtensorMap tm0, tm1;
     rc = halo::make_patch_map(&tm0, src0_dev, batch, depth, hin, win, c0, a.PW, a.TH + 2);
     tm1 = tm0;
