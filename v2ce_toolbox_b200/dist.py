@@ -1,0 +1,86 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), windows sharded by contiguous ranges, NCCL only
+for the final gather of the per-rank event shards.  No data-path collective: windows,
+frame pairs and pano tiles are independent; the spectral-norm schedule is input-independent, so a rank
+replays (``V2ce3d.sn_advance``) the power-iteration steps of the model calls it does not own.
+
+The same functions run on CPU tensors over the ``gloo`` backend (tests/test_dist_cpu.py).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+EVENT_BYTES = 13
+
+
+def shard_range(n_items, world, rank):
+    """Contiguous [start, end) of `n_items` owned by `rank`: rank r gets items [r*ceil(n/R), ...)."""
+    per = -(-n_items // world)
+    start = min(rank * per, n_items)
+    return start, min(start + per, n_items)
+
+
+def model_calls_before(first_batch, infer_type='center', tiles=1):
+    """Number of V2ce3d forwards the single-process schedule has executed before batch `first_batch`
+    (v2ce.py:181-198: one call per batch in center mode, one per tile per batch in pano mode)."""
+    return first_batch * (1 if infer_type == 'center' else tiles)
+
+
+def gather_event_shards(events_u8, n_events, group=None, dst=0):
+    """events_u8: 1-D uint8 tensor holding n_events*13 bytes (device for NCCL, CPU for gloo).
+    Returns on `dst` the concatenation of all shards in rank order (a uint8 tensor), None elsewhere.
+    Ranks own contiguous, increasing frame ranges, so concatenation by rank IS the time-ordered merge."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = events_u8.device
+    cnt = torch.tensor([n_events], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    pad = torch.zeros(mx * EVENT_BYTES, dtype=torch.uint8, device=dev)
+    pad[:n_events * EVENT_BYTES] = events_u8[:n_events * EVENT_BYTES]
+    if rank == dst:
+        bufs = [torch.empty(mx * EVENT_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.gather(pad, bufs, dst=dst, group=group)
+        return torch.cat([b[:c * EVENT_BYTES] for b, c in zip(bufs, counts)]), counts
+    dist.gather(pad, None, dst=dst, group=group)
+    return None, counts
+
+
+def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=16, batch_size=1, **kw):
+    """Run v2ce.stream_clip on this rank's contiguous share of the batches of a clip and gather the
+    event shards on rank 0.  `frames_reader` duck-types VideoReader.  Returns (event_stream | None, n_pairs)."""
+    from . import v2ce as drv
+    starts, mode = drv.window_schedule(frame_count, seq_len)
+    n_batches = -(-len(starts) // batch_size)
+    b0, b1 = shard_range(n_batches, world, rank)
+    model.sn_advance(model_calls_before(b0) - model.call_count())
+
+    class _Shard:
+        """Presents windows [b0*bs, b1*bs) of the clip as a clip of its own."""
+
+        def __init__(self):
+            w0, w1 = b0 * batch_size, min(b1 * batch_size, len(starts))
+            self.first = int(starts[w0]) if w1 > w0 else 0
+            last_start = int(starts[w1 - 1]) if w1 > w0 else 0
+            self.frame_count = (last_start + seq_len + 1 - self.first) if w1 > w0 else 0
+            self.is_tail = (w1 == len(starts))
+
+        def read_frames_at_indices(self, idxs):
+            return frames_reader.read_frames_at_indices([self.first + i for i in idxs])
+
+    shard = _Shard()
+    dev = kw.pop('device', torch.device('cuda', torch.cuda.current_device()))
+    if shard.frame_count > 1:
+        # a pulled-back last window only exists in the tail shard; there the local schedule reproduces it
+        res = drv.stream_clip(model, vidcap=shard, seq_len=seq_len, batch_size=batch_size,
+                              pair_base=shard.first, device=dev, write_event_frames=False, **kw)
+        ev = torch.from_numpy(res.event_stream.view(np.uint8).copy()).to(dev)
+        n = res.event_stream.shape[0]
+    else:
+        ev, n = torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev), 0
+    out, counts = gather_event_shards(ev, n)
+    if out is not None:
+        from .ldati import EVENT_DTYPE
+        return out.cpu().numpy().view(EVENT_DTYPE), sum(counts)
+    return None, sum(counts)
