@@ -96,3 +96,29 @@ def test_sn_replay_makes_sharded_ranks_match_single_process():
     m_shard.sn_advance(2)
     y2 = m_shard(x[2])
     assert torch.equal(ys[2], y2)
+
+
+def test_batch_runner_overlapped_results_match_oracle():
+    """runner.BatchRunner (side-stream transfers, double-buffered outputs) returns, for every batch,
+    exactly the oracle's events / frames for the voxels the model produced."""
+    from v2ce_toolbox_b200.runner import BatchRunner
+    from oracle import ldati_oracle as lo
+    H, W = 24, 32
+    g = torch.Generator().manual_seed(3)
+    units = [torch.randn(2, 16, 2, H, W, generator=g).pin_memory() for _ in range(3)]
+    m_run, m_ref = _model(12), _model(12)
+    runner = BatchRunner(m_run, 'cuda', fps=30, seed=21)
+    tickets = [runner.submit(u, pair_base=32 * i) for i, u in enumerate(units)][:2]
+    # slots=2: the third submit reuses slot 0 only after its copy-out finished
+    results = [runner.wait(t) for t in tickets]
+    for i, (ev, fr) in enumerate(results):
+        vox = (m_ref(units[i].cuda()).cpu().numpy()).reshape(32, 2, 10, H, W)
+        want_fr, _, _ = ef_oracle.event_frames_oracle(vox, 10, 98, True)
+        assert np.array_equal(fr, want_fr)
+        want = lo.sample_voxel_statistical_oracle(vox, fps=30, seed=21, frame_base=32 * i, flavor='cuda')
+        for k, r in enumerate(want):
+            r['timestamp'] += pipeline_oracle.frame_offset_us(32 * i + k, 30)
+        want = np.concatenate(want)
+        assert len(ev) == len(want)
+        for f in ('timestamp', 'x', 'y', 'polarity'):
+            assert np.array_equal(ev[f], want[f]), (i, f)
