@@ -108,9 +108,12 @@ def test_batch_runner_overlapped_results_match_oracle():
     units = [torch.randn(2, 16, 2, H, W, generator=g).pin_memory() for _ in range(3)]
     m_run, m_ref = _model(12), _model(12)
     runner = BatchRunner(m_run, 'cuda', fps=30, seed=21)
-    tickets = [runner.submit(u, pair_base=32 * i) for i, u in enumerate(units)][:2]
-    # slots=2: the third submit reuses slot 0 only after its copy-out finished
-    results = [runner.wait(t) for t in tickets]
+    # slots=2: a batch must be collected before the submit that reuses its slot
+    t0 = runner.submit(units[0], pair_base=0)
+    t1 = runner.submit(units[1], pair_base=32)
+    r0 = runner.wait(t0)
+    t2 = runner.submit(units[2], pair_base=64)
+    results = [r0, runner.wait(t1), runner.wait(t2)]
     for i, (ev, fr) in enumerate(results):
         vox = (m_ref(units[i].cuda()).cpu().numpy()).reshape(32, 2, 10, H, W)
         want_fr, _, _ = ef_oracle.event_frames_oracle(vox, 10, 98, True)

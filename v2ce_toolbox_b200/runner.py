@@ -3,8 +3,8 @@
     image units (pinned host or device) ─H2D→ V2ce3d ─→ voxels ─→ event-frame sums [+ frames]
                                                          └─→ LDATI count ─(counts D2H)→ emit/sort/pack ─D2H→ host events
 
-Two CUDA streams: the caller's current stream computes, a side stream moves results to pinned host
-buffers while the next batch computes.  Output buffers are double-buffered, so ``submit`` may be
+Three CUDA streams: the caller's current stream computes, one side stream uploads the next inputs and
+another moves results to pinned host buffers while the next batch computes.  Output buffers are double-buffered, so ``submit`` may be
 called for batch i+1 before ``wait`` is called for batch i.  This is what ``v2ce.stream_clip`` and
 ``bench.py`` (e2e) use; it composes the same public calls a user would make one by one
 (``V2ce3d.__call__``, ``event_frames.*``, ``LdatiEngine.count/emit``).
@@ -29,13 +29,15 @@ class BatchRunner:
         self.seed = seed
         self.per_batch_frames = per_batch_frames
         self.eng = _ldati.engine_for(self.device)
-        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)      # D2H of results
+        self.h2d_stream = torch.cuda.Stream(device=self.device)       # H2D of inputs (PCIe is full duplex)
         self.slots = slots
         self._ev_dev = [None] * slots
         self._ev_host = [None] * slots
         self._fr_dev = [None] * slots
         self._fr_host = [None] * slots
         self._x_dev = [None] * slots
+        self._st_host = [torch.empty(4, dtype=torch.int32, pin_memory=True) for _ in range(slots)]
         self._free = [None] * slots            # event: the side stream has finished reading slot buffers
         self._next = 0
         self.launches = 0
@@ -62,10 +64,10 @@ class BatchRunner:
         t.h2d_bytes = 0
         if not units.is_cuda:
             t.h2d_bytes = units.numel() * units.element_size()
-            with torch.cuda.stream(self.copy_stream):
+            with torch.cuda.stream(self.h2d_stream):
                 x = units.to(self.device, non_blocking=True)
                 ready = torch.cuda.Event()
-                ready.record(self.copy_stream)
+                ready.record(self.h2d_stream)
             cur.wait_event(ready)
             self._x_dev[slot] = x               # keep alive until the forward has consumed it
         else:
@@ -109,7 +111,8 @@ class BatchRunner:
                 frh = self._buf(self._fr_host, slot, frames.numel(), pinned=True)
                 frh[:frames.numel()].copy_(frames.reshape(-1), non_blocking=True)
                 t.d2h_bytes += frames.numel() + 32
-            t.status = status.to('cpu', non_blocking=True)
+            t.status = self._st_host[slot]
+            t.status.copy_(status, non_blocking=True)   # pinned: a pageable target would block the host here
             t.done = torch.cuda.Event()
             t.done.record(self.copy_stream)
         self._free[slot] = t.done
