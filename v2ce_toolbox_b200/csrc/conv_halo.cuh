@@ -20,8 +20,11 @@
 // Replaces the same reference calls as conv_igemm.cuh (submodules.py:249-263) for the 20 stride-1
 // 3x3x3 convs, i.e. 91 % of the network's FLOPs.
 //
-// CTA = 224 threads: warp 0 lane 0 TMA patch producer, warp 1 lane 0 weight-tile producer (bulk copy),
-// warp 2 TMEM allocator + lane 0 MMA issuer, warps 3-6 epilogue (TMEM lane quarter = warp % 4).
+// Persistent CTAs (one per SM) walk a strided tile sequence; the smem rings run on across tiles and, where
+// 2*T*BN <= 512 TMEM columns, two accumulator sets let the epilogue of tile i overlap the MMAs of tile i+1.
+// CTA = 224 threads: warp 0 TMA patch producer, warp 1 weight-tile producer (bulk copy), warp 2 TMEM
+// allocator + MMA issuer (all three warp-converged, one elected lane issues), warps 3-6 epilogue (TMEM lane
+// quarter = warp % 4).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -71,10 +74,37 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
 // memory address, so a descriptor whose start is shifted by whole 128-byte rows reads a TMA-written patch
 // correctly with base_offset = 0; setting base_offset = (addr >> 7) & 7 gives wrong results.
 
+// NBUF = number of TMEM accumulator sets (T*BN columns each): 2 when 2*T*BN <= 512, so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
+template <int BN, int T>
+struct HaloCfg {
+  static constexpr int kNBuf = (2 * T * BN <= 512) ? 2 : 1;
+  static constexpr int kTmemCols = kNBuf * T * BN;
+};
+
+struct TileCoord { int n_tile, b, d0, h0, w0; };
+
+__device__ __forceinline__ TileCoord decode_tile(int tile, const HaloArgs& a, int T, int n_tiles_unused) {
+  // spatial tiles fastest, then depth group, batch, and the output-channel tile slowest: CTAs that run
+  // at the same time read neighbouring patches and the same weights
+  TileCoord c;
+  const int tw_i = tile % a.tiles_w; tile /= a.tiles_w;
+  const int th_i = tile % a.tiles_h; tile /= a.tiles_h;
+  const int dgroups = a.D / T;
+  c.d0 = (tile % dgroups) * T; tile /= dgroups;
+  c.b = tile % a.B;
+  c.n_tile = tile / a.B;
+  c.h0 = th_i * a.TH;
+  c.w0 = tw_i * a.TW;
+  return c;
+}
+
 template <int BN, int T>
 __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_constant__ CUtensorMap tm0,
                                                                   const __grid_constant__ CUtensorMap tm1,
                                                                   const HaloArgs a) {
+  using Cfg = HaloCfg<BN, T>;
+  constexpr int NBUF = Cfg::kNBuf;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -83,16 +113,9 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
 
   const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
   const int n_tiles = a.Cout / BN;
-  int t = blockIdx.x;
-  const int n_tile = t % n_tiles; t /= n_tiles;
-  const int tw_i = t % a.tiles_w; t /= a.tiles_w;
-  const int th_i = t % a.tiles_h; t /= a.tiles_h;
-  const int dgroups = a.D / T;
-  const int d0 = (t % dgroups) * T;              // first of the T output depth slices
-  const int b = t / dgroups;
-  const int h0 = th_i * a.TH, w0 = tw_i * a.TW;
+  const int total_tiles = a.B * (a.D / T) * a.tiles_h * a.tiles_w * n_tiles;
   const int ncc = a.ncc0 + a.ncc1;
-  
+
   const uint32_t a_base = base;
   const uint32_t b_base = base + (uint32_t)a.SA * a.a_stage_bytes;
   const uint32_t bar_base = b_base + (uint32_t)a.SB * kBStage;
@@ -100,8 +123,9 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
   auto a_empty = [&](int s) { return bar_base + 8u * (kMaxSA + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (2 * kMaxSA + s); };
   auto b_empty = [&](int s) { return bar_base + 8u * (2 * kMaxSA + kMaxSB + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kMaxSA + 2 * kMaxSB);
-  const int bar_bytes = (2 * kMaxSA + 2 * kMaxSB + 1) * 8;
+  auto tmem_full = [&](int s) { return bar_base + 8u * (2 * kMaxSA + 2 * kMaxSB + s); };
+  auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * kMaxSA + 2 * kMaxSB + 2 + s); };
+  const int bar_bytes = (2 * kMaxSA + 2 * kMaxSB + 4) * 8;
   uint8_t* tail = smem + (bar_base - base) + bar_bytes;
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(tail);
   float* s_scale = reinterpret_cast<float*>(tail + 16);
@@ -110,183 +134,214 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
   if (tid == 0) {
     for (int s = 0; s < a.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < a.SB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(const_cast<uint32_t*>(tmem_ptr))),
-                 "r"((uint32_t)(BN * T))
+                 "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  {
-    const float isg = a.inv_sigma ? __ldg(a.inv_sigma) : 1.f;
-    for (int i = tid; i < BN; i += kHaloThreads) {
-      s_scale[i] = __ldg(a.scale + n_tile * BN + i) * isg;
-      s_shift[i] = __ldg(a.shift + n_tile * BN + i);
-    }
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_acc = *tmem_ptr;
 
+  // Persistent CTA: every role walks the same tile sequence; the smem rings and their phases run on
+  // across tiles, so the producers prefetch the next tile while the current one is multiplied/stored.
   // The three feeding roles run warp-converged (uniform registers for addresses/descriptors); the single
   // issuing lane is chosen by elect.sync.
   if (warp == 0) {
     // ================= patch producer (TMA) =================
     int s = 0, ph = 1;                              // stage / parity of the empty barrier to wait on
-    for (int cc = 0; cc < ncc; ++cc) {
-      const bool first = cc < a.ncc0;
-      const CUtensorMap* map = first ? &tm0 : &tm1;
-      const int c0 = (first ? cc : cc - a.ncc0) * kBlockK;
-      for (int z = 0; z < T + 2; ++z) {
-        mbar_wait(a_empty(s), (uint32_t)ph, a.error_flag);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(a_full(s), (uint32_t)a.box_bytes);
-          tma_load_5d(a_base + (uint32_t)s * a.a_stage_bytes, map, c0, w0 - 1, h0 - 1, d0 - 1 + z, b, a_full(s));
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(tile, a, T, n_tiles);
+      for (int cc = 0; cc < ncc; ++cc) {
+        const bool first = cc < a.ncc0;
+        const CUtensorMap* map = first ? &tm0 : &tm1;
+        const int c0 = (first ? cc : cc - a.ncc0) * kBlockK;
+        for (int z = 0; z < T + 2; ++z) {
+          mbar_wait(a_empty(s), (uint32_t)ph, a.error_flag);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(a_full(s), (uint32_t)a.box_bytes);
+            tma_load_5d(a_base + (uint32_t)s * a.a_stage_bytes, map, c0, tc.w0 - 1, tc.h0 - 1, tc.d0 - 1 + z, tc.b, a_full(s));
+          }
+          __syncwarp();
+          if (++s == a.SA) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++s == a.SA) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================= weight-tile producer (bulk copy) =================
-    const int total = ncc * 27;
-    const __nv_bfloat16* wt = a.wpack + (size_t)n_tile * total * (BN * kBlockK);
+    const int per_tile = ncc * 27;
     int s = 0, ph = 1;
-    for (int it = 0; it < total; ++it) {
-      mbar_wait(b_empty(s), (uint32_t)ph, a.error_flag);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(b_full(s), (uint32_t)kBStage);
-        bulk_copy_g2s(b_base + (uint32_t)s * kBStage, wt + (size_t)it * (BN * kBlockK), (uint32_t)kBStage, b_full(s));
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(tile, a, T, n_tiles);
+      const __nv_bfloat16* wt = a.wpack + (size_t)tc.n_tile * per_tile * (BN * kBlockK);
+      for (int it = 0; it < per_tile; ++it) {
+        mbar_wait(b_empty(s), (uint32_t)ph, a.error_flag);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(b_full(s), (uint32_t)kBStage);
+          bulk_copy_g2s(b_base + (uint32_t)s * kBStage, wt + (size_t)it * (BN * kBlockK), (uint32_t)kBStage, b_full(s));
+        }
+        __syncwarp();
+        if (++s == a.SB) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++s == a.SB) { s = 0; ph ^= 1; }
     }
   } else if (warp == 2) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = make_idesc(BN);
     int sb = 0, pb = 0;                             // weight ring position / parity
     int sw = 0, pw = 0;                             // next patch stage to wait for / its parity
-    int arrived = 0;
+    int arrived = 0, loads_base = 0;
     int s_first = 0;                                // stage of slice kd of the current chunk
-    for (int cc = 0; cc < ncc; ++cc) {
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const int ab = (NBUF == 2) ? (iter & 1) : 0;
+      const int use = (NBUF == 2) ? (iter >> 1) : iter;
+      mbar_wait(tmem_empty(ab), (uint32_t)((use & 1) ^ 1), a.error_flag);     // epilogue has drained this accumulator set
+      tcgen05_fence_after();
+      const uint32_t acc_base = tmem_acc + (uint32_t)(ab * T * BN);
+      for (int cc = 0; cc < ncc; ++cc) {
 #pragma unroll 1
-      for (int kd = 0; kd < 3; ++kd) {
-        const int need = cc * (T + 2) + kd + T;     // slices kd .. kd+T-1 of this chunk must have landed
-        while (arrived < need) {
-          mbar_wait(a_full(sw), (uint32_t)pw, a.error_flag);
-          ++arrived;
-          if (++sw == a.SA) { sw = 0; pw ^= 1; }
-        }
-        tcgen05_fence_after();
-        uint32_t patch[T];
-#pragma unroll
-        for (int tt = 0; tt < T; ++tt) {
-          int st = s_first + tt;
-          if (st >= a.SA) st -= a.SA;
-          patch[tt] = a_base + (uint32_t)st * a.a_stage_bytes;
-        }
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(b_full(sb), (uint32_t)pb, a.error_flag);
+        for (int kd = 0; kd < 3; ++kd) {
+          const int need = loads_base + cc * (T + 2) + kd + T;   // slices kd .. kd+T-1 of this chunk must have landed
+          while (arrived < need) {
+            mbar_wait(a_full(sw), (uint32_t)pw, a.error_flag);
+            ++arrived;
+            if (++sw == a.SA) { sw = 0; pw ^= 1; }
+          }
           tcgen05_fence_after();
-          const uint32_t b_addr = b_base + (uint32_t)sb * kBStage;
-          const uint32_t shift = (uint32_t)((tap / 3) * a.PW + (tap % 3)) * 128u;
-          const uint32_t acc0 = (cc | kd | tap) == 0 ? 0u : 1u;
+          uint32_t patch[T];
 #pragma unroll
           for (int tt = 0; tt < T; ++tt) {
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              tcgen05_mma_bf16_elect(tmem_acc + (uint32_t)(tt * BN), make_smem_desc(patch[tt] + shift + k * 32),
-                                     make_smem_desc(b_addr + k * 32), idesc, k == 0 ? acc0 : 1u);
-            }
+            int st = s_first + tt;
+            if (st >= a.SA) st -= a.SA;
+            patch[tt] = a_base + (uint32_t)st * a.a_stage_bytes;
           }
-          tcgen05_commit_elect(b_empty(sb));
-          if (++sb == a.SB) { sb = 0; pb ^= 1; }
-        }
-        // input slice kd is done after tap block kd; the last block frees the remaining T slices
-        if (kd < 2) {
-          tcgen05_commit_elect(a_empty(s_first));
-          if (++s_first == a.SA) s_first = 0;
-        } else {
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(b_full(sb), (uint32_t)pb, a.error_flag);
+            tcgen05_fence_after();
+            const uint32_t b_addr = b_base + (uint32_t)sb * kBStage;
+            const uint32_t shift = (uint32_t)((tap / 3) * a.PW + (tap % 3)) * 128u;
+            const uint32_t acc0 = (cc | kd | tap) == 0 ? 0u : 1u;
 #pragma unroll
-          for (int z = 0; z < T; ++z) {
+            for (int tt = 0; tt < T; ++tt) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                tcgen05_mma_bf16_elect(acc_base + (uint32_t)(tt * BN), make_smem_desc(patch[tt] + shift + k * 32),
+                                       make_smem_desc(b_addr + k * 32), idesc, k == 0 ? acc0 : 1u);
+              }
+            }
+            tcgen05_commit_elect(b_empty(sb));
+            if (++sb == a.SB) { sb = 0; pb ^= 1; }
+          }
+          // input slice kd is done after tap block kd; the last block frees the remaining T slices
+          if (kd < 2) {
             tcgen05_commit_elect(a_empty(s_first));
             if (++s_first == a.SA) s_first = 0;
+          } else {
+#pragma unroll
+            for (int z = 0; z < T; ++z) {
+              tcgen05_commit_elect(a_empty(s_first));
+              if (++s_first == a.SA) s_first = 0;
+            }
           }
         }
       }
+      tcgen05_commit_elect(tmem_full(ab));
+      loads_base += ncc * (T + 2);
     }
-    tcgen05_commit_elect(tmem_full_bar);
   } else {
-    // ================= epilogue =================
+    // ================= epilogue (warps 3-6) =================
     const int quarter = warp & 3;
     const int i = quarter * 32 + lane;            // accumulator row == TMEM lane
     const int th = i / a.PW, tw = i % a.PW;
-    const int h = h0 + th, w = w0 + tw;
-    const bool row_ok = (th < a.TH) && (tw < a.TW) && (h < a.H) && (w < a.W);
-    mbar_wait(tmem_full_bar, 0, a.error_flag);
-    __syncwarp();
-    tcgen05_fence_after();
-    for (int tt = 0; tt < T; ++tt) {
-      const size_t m = ((size_t)(b * a.D + d0 + tt) * a.H + h) * a.W + w;
-      const uint32_t lane_addr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tt * BN);
-      __nv_bfloat16* orow = a.out + m * a.out_pitch + n_tile * BN;
-      const __nv_bfloat16* rrow = a.residual ? a.residual + m * a.res_pitch + n_tile * BN : nullptr;
+    const int etid = tid - 96;                    // 0..127 inside the epilogue group
+    const float isg = a.inv_sigma ? __ldg(a.inv_sigma) : 1.f;
+    int cur_n_tile = -1;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const TileCoord tc = decode_tile(tile, a, T, n_tiles);
+      if (tc.n_tile != cur_n_tile) {              // (re)stage the folded BatchNorm scale/shift of this channel tile
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int j = etid; j < BN; j += 128) {
+          s_scale[j] = __ldg(a.scale + tc.n_tile * BN + j) * isg;
+          s_shift[j] = __ldg(a.shift + tc.n_tile * BN + j);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_n_tile = tc.n_tile;
+      }
+      const int h = tc.h0 + th, w = tc.w0 + tw;
+      const bool row_ok = (th < a.TH) && (tw < a.TW) && (h < a.H) && (w < a.W);
+      const int ab = (NBUF == 2) ? (iter & 1) : 0;
+      const int use = (NBUF == 2) ? (iter >> 1) : iter;
+      mbar_wait(tmem_full(ab), (uint32_t)(use & 1), a.error_flag);
+      __syncwarp();
+      tcgen05_fence_after();
+      for (int tt = 0; tt < T; ++tt) {
+        const size_t m = ((size_t)(tc.b * a.D + tc.d0 + tt) * a.H + h) * a.W + w;
+        const uint32_t lane_addr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((ab * T + tt) * BN);
+        __nv_bfloat16* orow = a.out + m * a.out_pitch + tc.n_tile * BN;
+        const __nv_bfloat16* rrow = a.residual ? a.residual + m * a.res_pitch + tc.n_tile * BN : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(lane_addr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (row_ok) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(lane_addr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (row_ok) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float r[8];
+            for (int g = 0; g < 4; ++g) {
+              float r[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = 0.f;
-            if (rrow) {
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + g * 8));
-              const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+              for (int j = 0; j < 8; ++j) r[j] = 0.f;
+              if (rrow) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + g * 8));
+                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(rp[j]);
+                  r[2 * j] = f.x;
+                  r[2 * j + 1] = f.y;
+                }
+              }
+              uint4 ov;
+              __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(rp[j]);
-                r[2 * j] = f.x;
-                r[2 * j + 1] = f.y;
-              }
-            }
-            uint4 ov;
-            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
+                float y[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float y[2];
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                const int n = c0 + g * 8 + 2 * j + hh;
-                float tv = fmaf(__uint_as_float(v[g * 8 + 2 * j + hh]), s_scale[n], s_shift[n]) + r[2 * j + hh];
-                if (a.act == 1) tv = fmaxf(tv, 0.f);
-                else if (a.act == 2) tv = tv > 0.f ? tv : 0.01f * tv;
-                y[hh] = tv;
+                for (int hh = 0; hh < 2; ++hh) {
+                  const int n = c0 + g * 8 + 2 * j + hh;
+                  float tv = fmaf(__uint_as_float(v[g * 8 + 2 * j + hh]), s_scale[n], s_shift[n]) + r[2 * j + hh];
+                  if (a.act == 1) tv = fmaxf(tv, 0.f);
+                  else if (a.act == 2) tv = tv > 0.f ? tv : 0.01f * tv;
+                  y[hh] = tv;
+                }
+                op[j] = __floats2bfloat162_rn(y[0], y[1]);
               }
-              op[j] = __floats2bfloat162_rn(y[0], y[1]);
+              *reinterpret_cast<uint4*>(orow + c0 + g * 8) = ov;
             }
-            *reinterpret_cast<uint4*>(orow + c0 + g * 8) = ov;
           }
         }
+        if (row_ok && tc.n_tile == n_tiles - 1) {   // zero the padding channels so later TMA reads see 0, not garbage
+          for (int c = a.Cout; c < a.out_pitch; c += 8)
+            *reinterpret_cast<uint4*>(a.out + m * a.out_pitch + c) = make_uint4(0u, 0u, 0u, 0u);
+        }
       }
-      if (row_ok && n_tile == n_tiles - 1) {      // zero the padding channels so later TMA reads see 0, not garbage
-        for (int c = a.Cout; c < a.out_pitch; c += 8)
-          *reinterpret_cast<uint4*>(a.out + m * a.out_pitch + c) = make_uint4(0u, 0u, 0u, 0u);
-      }
+      // this accumulator set may be overwritten by the MMAs of a later tile
+      tcgen05_fence_before();
+      mbar_arrive(tmem_empty(ab));
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)(BN * T)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)Cfg::kTmemCols) : "memory");
   }
 }
 
@@ -395,7 +450,7 @@ inline HaloPlan plan_for(int bn, int D, int H, int W) {
   const int rows = p.ts.PW * (p.ts.TH + 2);
   p.box_bytes = rows * 128;
   p.a_stage_bytes = ((rows + 2 + 7) / 8) * 1024;
-  const int tail = (2 * kMaxSA + 2 * kMaxSB + 1) * 8 + 16 + 2 * bn * 4;
+  const int tail = (2 * kMaxSA + 2 * kMaxSB + 4) * 8 + 16 + 2 * bn * 4;
   const int budget = 227 * 1024 - 1024 - tail;
   const int b_stage = bn * kBlockK * 2;
   // depth blocking: as many slices as TMEM (512 columns) and D allow
@@ -420,7 +475,10 @@ inline int launch_halo_one(const CUtensorMap& tm0, const CUtensorMap& tm1, const
     V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = smem_bytes;
   }
-  const int grid = a.B * (a.D / T) * a.tiles_h * a.tiles_w * (a.Cout / BN);
+  const int total = a.B * (a.D / T) * a.tiles_h * a.tiles_w * (a.Cout / BN);
+  int per_sm = 1;                                   // resident CTAs per SM (shared memory bound)
+  if (2 * (smem_bytes + 1024) <= 227 * 1024 && 2 * HaloCfg<BN, T>::kTmemCols <= 512) per_sm = 2;
+  const int grid = total < sm_count_cached() * per_sm ? total : sm_count_cached() * per_sm;
   conv_halo_kernel<BN, T><<<grid, kHaloThreads, smem_bytes, s>>>(tm0, tm1, a);
   V2CE_LAUNCH_CHECK("conv_halo_kernel");
   return V2CE_OK;
