@@ -161,6 +161,9 @@ int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0, int32_t w0
                         const float* weight_host, int32_t cout, const float* scale_host, const float* shift_host,
                         const void* residual_dev, int32_t act, void* out_dev, int32_t impl, int32_t desc_mode,
                         void* stream);
+/* Bring-up microbenchmark: cycles per back-to-back tcgen05.mma (M=128, N=bn, K=16, both operands in shared
+ * memory) with `naccs` accumulators in rotation on `ctas` CTAs. */
+int v2ce_debug_mma_rate(int32_t bn, int32_t iters, int32_t naccs, int32_t ctas, double* cycles_per_mma);
 /* Tuning / bring-up options of a model handle: "desc_mode". */
 int v2ce_model_set_option(v2ce_model* m, const char* key, int64_t value);
 

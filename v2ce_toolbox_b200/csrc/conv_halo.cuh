@@ -28,6 +28,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "conv_igemm.cuh"
 
@@ -58,6 +59,11 @@ struct HaloArgs {
   const __nv_bfloat16* residual;
   __nv_bfloat16* out;
   int act;
+  int up_H, up_W;              // > 0: write the output nearest-upsampled to (up_H, up_W) (unet_2layer.py:359-362),
+                               //      i.e. every source pixel is stored to all dst with (dst*H)//up_H == h
+  const float* pred_w;         // != nullptr (BN == 32 only): fuse pred = relu(W[20][32] . y + b) and write the
+  const float* pred_b;         //      float32 (B,L,20,H,W) network output instead of `out` (v2ce_3d.py:29)
+  float* pred_out;
   int* error_flag;
 };
 
@@ -130,6 +136,7 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(tail);
   float* s_scale = reinterpret_cast<float*>(tail + 16);
   float* s_shift = s_scale + BN;
+  float* s_pred = s_shift + BN;                   // [20][32] weights + [20] bias (used when a.pred_w != nullptr)
 
   if (tid == 0) {
     for (int s = 0; s < a.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
@@ -262,6 +269,9 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
     const int th = i / a.PW, tw = i % a.PW;
     const int etid = tid - 96;                    // 0..127 inside the epilogue group
     const float isg = a.inv_sigma ? __ldg(a.inv_sigma) : 1.f;
+    if (a.pred_w != nullptr) {
+      for (int j = etid; j < 660; j += 128) s_pred[j] = j < 640 ? __ldg(a.pred_w + j) : __ldg(a.pred_b + (j - 640));
+    }
     int cur_n_tile = -1;
     int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -282,55 +292,107 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
       mbar_wait(tmem_full(ab), (uint32_t)(use & 1), a.error_flag);
       __syncwarp();
       tcgen05_fence_after();
-      for (int tt = 0; tt < T; ++tt) {
-        const size_t m = ((size_t)(tc.b * a.D + tc.d0 + tt) * a.H + h) * a.W + w;
-        const uint32_t lane_addr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((ab * T + tt) * BN);
-        __nv_bfloat16* orow = a.out + m * a.out_pitch + tc.n_tile * BN;
-        const __nv_bfloat16* rrow = a.residual ? a.residual + m * a.res_pitch + tc.n_tile * BN : nullptr;
+      // destination rows/columns of this source pixel when the output is written nearest-upsampled
+      int uh0 = 0, uh1 = 0, uw0 = 0, uw1 = 0;
+      if (a.up_H > 0 && row_ok) {
+        uh0 = (h * a.up_H + a.H - 1) / a.H;  uh1 = ((h + 1) * a.up_H + a.H - 1) / a.H;
+        uw0 = (w * a.up_W + a.W - 1) / a.W;  uw1 = ((w + 1) * a.up_W + a.W - 1) / a.W;
+      }
+      // Chunks of 32 accumulator columns, flattened over (slice, column block).  The residual of chunk q+1 is
+      // requested before chunk q is processed: one exposed global-load latency per tile instead of one per
+      // 16-byte piece (the epilogue was as long as the MMA phase -- ncu: 50 % of samples in long_scoreboard).
+      constexpr int kChunksPerSlice = BN / 32;
+      constexpr int kChunks = T * kChunksPerSlice;
+      const size_t plane0 = (size_t)(tc.b * a.D + tc.d0);
+      const size_t pix = (size_t)h * a.W + w;
+      const size_t HWp = (size_t)a.H * a.W;
+      uint4 rv[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      auto res_ptr = [&](int q) {
+        const int tt = q / kChunksPerSlice, c0 = (q % kChunksPerSlice) * 32;
+        return reinterpret_cast<const uint4*>(a.residual + ((plane0 + tt) * HWp + pix) * a.res_pitch + tc.n_tile * BN + c0);
+      };
+      const bool has_res = (a.residual != nullptr) && row_ok;
+      if (has_res) {
+        const uint4* rp = res_ptr(0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);
+      }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(lane_addr + (uint32_t)c0, v);
-          tmem_ld_wait();
-          if (row_ok) {
+      for (int q = 0; q < kChunks; ++q) {
+        const int tt = q / kChunksPerSlice, c0 = (q % kChunksPerSlice) * 32;
+        const size_t plane = plane0 + tt;
+        const size_t m = plane * HWp + pix;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((ab * T + tt) * BN + c0), v);
+        uint4 rn[4] = {rv[0], rv[1], rv[2], rv[3]};
+        if (has_res && q + 1 < kChunks) {
+          const uint4* rp = res_ptr(q + 1);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float r[8];
+          for (int g = 0; g < 4; ++g) rn[g] = __ldg(rp + g);
+        }
+        tmem_ld_wait();
+        if (row_ok) {
+          float yv[32];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) r[j] = 0.f;
-              if (rrow) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + g * 8));
-                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+          for (int g = 0; g < 4; ++g) {
+            const __nv_bfloat162* rp2 = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = __bfloat1622float2(rp[j]);
-                  r[2 * j] = f.x;
-                  r[2 * j + 1] = f.y;
-                }
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(rp2[j]);      // zeros when there is no residual
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int n = c0 + g * 8 + 2 * j + hh;
+                float tv = fmaf(__uint_as_float(v[g * 8 + 2 * j + hh]), s_scale[n], s_shift[n]) + (hh ? f.y : f.x);
+                if (a.act == 1) tv = fmaxf(tv, 0.f);
+                else if (a.act == 2) tv = tv > 0.f ? tv : 0.01f * tv;
+                yv[g * 8 + 2 * j + hh] = tv;
               }
-              uint4 ov;
-              __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float y[2];
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  const int n = c0 + g * 8 + 2 * j + hh;
-                  float tv = fmaf(__uint_as_float(v[g * 8 + 2 * j + hh]), s_scale[n], s_shift[n]) + r[2 * j + hh];
-                  if (a.act == 1) tv = fmaxf(tv, 0.f);
-                  else if (a.act == 2) tv = tv > 0.f ? tv : 0.01f * tv;
-                  y[hh] = tv;
-                }
-                op[j] = __floats2bfloat162_rn(y[0], y[1]);
-              }
-              *reinterpret_cast<uint4*>(orow + c0 + g * 8) = ov;
             }
           }
+          if (BN == 32 && a.pred_w != nullptr) {
+            // fused prediction layer: 20 dot products over the 32 channels of this pixel, ReLU, planar fp32 store
+            float* dst = a.pred_out + plane * 20 * HWp + pix;
+            const float4* pw4 = reinterpret_cast<const float4*>(s_pred);
+#pragma unroll 2
+            for (int n = 0; n < 20; ++n) {
+              float acc = s_pred[640 + n];
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 wv = pw4[n * 8 + c4];
+                acc = fmaf(yv[c4 * 4 + 0], wv.x, acc);
+                acc = fmaf(yv[c4 * 4 + 1], wv.y, acc);
+                acc = fmaf(yv[c4 * 4 + 2], wv.z, acc);
+                acc = fmaf(yv[c4 * 4 + 3], wv.w, acc);
+              }
+              dst[(size_t)n * HWp] = fmaxf(acc, 0.f);
+            }
+          } else {
+            uint4 ov[4];
+            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(ov);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) op[j] = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]);
+            if (a.up_H > 0) {
+              for (int hh = uh0; hh < uh1; ++hh)
+                for (int ww = uw0; ww < uw1; ++ww) {
+                  uint4* d4 = reinterpret_cast<uint4*>(a.out + ((plane * a.up_H + hh) * a.up_W + ww) * a.out_pitch +
+                                                       tc.n_tile * BN + c0);
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) d4[g] = ov[g];
+                }
+            } else {
+              uint4* d4 = reinterpret_cast<uint4*>(a.out + m * a.out_pitch + tc.n_tile * BN + c0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) d4[g] = ov[g];
+            }
+          }
+          if (c0 + 32 == BN && tc.n_tile == n_tiles - 1 && a.up_H == 0 && a.pred_w == nullptr) {
+            // zero the padding channels so later TMA reads see 0, not garbage
+            for (int c = a.Cout; c < a.out_pitch; c += 8)
+              *reinterpret_cast<uint4*>(a.out + m * a.out_pitch + c) = make_uint4(0u, 0u, 0u, 0u);
+          }
         }
-        if (row_ok && tc.n_tile == n_tiles - 1) {   // zero the padding channels so later TMA reads see 0, not garbage
-          for (int c = a.Cout; c < a.out_pitch; c += 8)
-            *reinterpret_cast<uint4*>(a.out + m * a.out_pitch + c) = make_uint4(0u, 0u, 0u, 0u);
-        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rv[g] = rn[g];
       }
       // this accumulator set may be overwritten by the MMAs of a later tile
       tcgen05_fence_before();
@@ -450,15 +512,23 @@ inline HaloPlan plan_for(int bn, int D, int H, int W) {
   const int rows = p.ts.PW * (p.ts.TH + 2);
   p.box_bytes = rows * 128;
   p.a_stage_bytes = ((rows + 2 + 7) / 8) * 1024;
-  const int tail = (2 * kMaxSA + 2 * kMaxSB + 4) * 8 + 16 + 2 * bn * 4;
+  const int tail = (2 * kMaxSA + 2 * kMaxSB + 4) * 8 + 16 + 2 * bn * 4 + 660 * 4;
   const int budget = 227 * 1024 - 1024 - tail;
   const int b_stage = bn * kBlockK * 2;
-  // depth blocking: as many slices as TMEM (512 columns) and D allow
-  p.T = (bn <= 128) ? 4 : 2;
+  // depth blocking T and ring depths.  A chunk needs T patches before its first tap and holds T+2 over its
+  // lifetime; the ring must be deep enough to prefetch the next chunk's first patches (SA >= T + 2 + T/2 would
+  // be ideal), which T = 2 allows within 227 KB while T = 4 does not.  Tuning knobs: V2CE_HALO_T / _SA / _SB.
+  const char* et = getenv("V2CE_HALO_T");
+  const char* esa = getenv("V2CE_HALO_SA");
+  const char* esb = getenv("V2CE_HALO_SB");
+  p.T = et ? atoi(et) : 2;
+  if (bn > 128 && p.T > 2) p.T = 2;
   while (p.T > 1 && (D % p.T != 0)) p.T /= 2;
   for (;; p.T /= 2) {
-    p.SB = bn <= 32 ? 8 : bn <= 64 ? 6 : bn <= 128 ? 5 : 3;
-    p.SA = p.T + 2;
+    p.SB = esb ? atoi(esb) : (bn <= 32 ? 8 : bn <= 64 ? 6 : bn <= 128 ? 4 : 3);
+    p.SA = esa ? atoi(esa) : kMaxSA;
+    if (p.SA > kMaxSA) p.SA = kMaxSA;
+    if (p.SB > kMaxSB) p.SB = kMaxSB;
     while (p.SA > p.T + 1 && p.SA * p.a_stage_bytes + p.SB * b_stage > budget) --p.SA;
     while (p.SB > 2 && p.SA * p.a_stage_bytes + p.SB * b_stage > budget) --p.SB;
     if (p.SA * p.a_stage_bytes + p.SB * b_stage <= budget || p.T == 1) break;

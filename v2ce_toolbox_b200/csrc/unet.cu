@@ -3,7 +3,7 @@
 // scripts/submodules.py:85-124,216-264 and scripts/spectral_norm.py:9-64.
 //
 // Activation layout in HBM: NDHWC bf16, (B, D=16, H, W, C), row m = ((b*D+d)*H+h)*W+w.
-// Schedule per forward (40 launches):
+// Schedule per forward (35 launches):
 //   4  spectral-norm power-iteration kernels (fp32; 12 convs batched per launch)
 //   1  head conv 2->32 (direct fp32 CUDA-core kernel, K=54 is HBM-bound) + LeakyReLU
 //   30 tcgen05 convs: 3x3x3 stride-1 layers on the halo-tile kernel (conv_halo.cuh), stride-2 convs and the
@@ -77,8 +77,8 @@ constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
 __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, int B, int D, int H, int W,
                                                          __nv_bfloat16* __restrict__ out) {
-  __shared__ float sw[27 * 2 * 32];     // [tap][cin][cout]
-  __shared__ float sb[32];
+  __shared__ __align__(16) float sw[27 * 2 * 32];     // [tap][cin][cout]: 16-byte reads give 4 output channels
+  __shared__ __align__(16) float sb[32];
   for (int i = threadIdx.x; i < 27 * 2 * 32; i += blockDim.x) {
     const int n = i % 32, ci = (i / 32) % 2, tap = i / 64;
     sw[i] = w[((size_t)n * 2 + ci) * 27 + tap];
@@ -94,9 +94,9 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict_
   t /= H;
   const int d = (int)(t % D);
   const int b = (int)(t / D);
-  float acc[32];
+  float4 acc[8];
 #pragma unroll
-  for (int n = 0; n < 32; ++n) acc[n] = sb[n];
+  for (int n = 0; n < 8; ++n) acc[n] = reinterpret_cast<const float4*>(sb)[n];
   const size_t HW = (size_t)H * W;
   for (int kd = 0; kd < 3; ++kd) {
     const int di = d + kd - 1;
@@ -110,20 +110,29 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict_
         if (wi < 0 || wi >= W) continue;
         const size_t base = ((size_t)(b * D + di) * 2) * HW + (size_t)hi * W + wi;
         const float x0 = __ldg(x + base), x1 = __ldg(x + base + HW);
-        const float* wt = sw + ((kd * 3 + kh) * 3 + kw) * 64;
+        const float4* wt = reinterpret_cast<const float4*>(sw + ((kd * 3 + kh) * 3 + kw) * 64);
 #pragma unroll
-        for (int n = 0; n < 32; ++n) acc[n] = fmaf(x0, wt[n], fmaf(x1, wt[32 + n], acc[n]));
+        for (int n = 0; n < 8; ++n) {
+          const float4 w0 = wt[n], w1 = wt[8 + n];
+          acc[n].x = fmaf(x0, w0.x, fmaf(x1, w1.x, acc[n].x));
+          acc[n].y = fmaf(x0, w0.y, fmaf(x1, w1.y, acc[n].y));
+          acc[n].z = fmaf(x0, w0.z, fmaf(x1, w1.z, acc[n].z));
+          acc[n].w = fmaf(x0, w0.w, fmaf(x1, w1.w, acc[n].w));
+        }
       }
     }
   }
   uint4 o[4];
   __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float a0 = acc[2 * i], a1 = acc[2 * i + 1];
-    a0 = a0 > 0.f ? a0 : 0.01f * a0;
-    a1 = a1 > 0.f ? a1 : 0.01f * a1;
-    op[i] = __floats2bfloat162_rn(a0, a1);
+  for (int i = 0; i < 8; ++i) {
+    float4 v = acc[i];
+    v.x = v.x > 0.f ? v.x : 0.01f * v.x;
+    v.y = v.y > 0.f ? v.y : 0.01f * v.y;
+    v.z = v.z > 0.f ? v.z : 0.01f * v.z;
+    v.w = v.w > 0.f ? v.w : 0.01f * v.w;
+    op[2 * i] = __floats2bfloat162_rn(v.x, v.y);
+    op[2 * i + 1] = __floats2bfloat162_rn(v.z, v.w);
   }
   uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m * 64);     // 64-channel pitch, upper half zero (TMA rows)
 #pragma unroll
@@ -306,6 +315,8 @@ struct v2ce_model {
   int64_t calls = 0;
   int last_launches = 0;
   int desc_mode = 0;
+  cudaStream_t sn_stream = nullptr;     // the spectral-norm step overlaps the head / encoder convs
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> tmaps;
 };
 
@@ -381,7 +392,7 @@ static Dims make_dims(int B, int D, int H, int W) {
 }
 
 struct Buffers {
-  __nv_bfloat16 *head, *enc[4], *res[2], *dec[4], *tmp_t, *tmp_r, *up;
+  __nv_bfloat16 *head, *enc[4], *res[2], *dec[4], *tmp_t, *tmp_r, *up, *up2;
   size_t bytes;
 };
 
@@ -398,7 +409,8 @@ static Buffers carve(void* ws, const Dims& d) {
   for (int i = 0; i < 4; ++i) umax = umax > (size_t)d.M[i] * ch[i + 1] ? umax : (size_t)d.M[i] * ch[i + 1];
   b.tmp_t = a.take<__nv_bfloat16>(tmax);
   b.tmp_r = a.take<__nv_bfloat16>(tmax);
-  b.up = a.take<__nv_bfloat16>(umax);                                  // materialised nearest-upsample of the decoder input
+  b.up = a.take<__nv_bfloat16>(umax);                                  // nearest-upsampled decoder inputs (written by the
+  b.up2 = a.take<__nv_bfloat16>(umax);                                 // producing layer's epilogue), double-buffered
   b.bytes = align_up(a.off, 256);
   return b;
 }
@@ -474,7 +486,7 @@ static int run_conv(v2ce_model* m, int li, const __nv_bfloat16* src0, int c0, in
 // halo-tile launch of layer `li` (3x3x3, stride 1); sources are full-resolution (B,D,H,W,pitch) tensors
 static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, const __nv_bfloat16* src1, int p1, int B, int D,
                     int H, int W, const __nv_bfloat16* residual, int res_pitch, int act, __nv_bfloat16* out, int out_pitch,
-                    cudaStream_t s) {
+                    cudaStream_t s, int up_H = 0, int up_W = 0, float* pred_out = nullptr) {
   const LayerSpec& L = kLayers[li];
   const DevLayer& dl = m->layers[li];
   if (dl.cfg.kind != 2 || p0 != dl.cfg.pad0 || p1 != dl.cfg.pad1)
@@ -492,6 +504,10 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
   a.wpack = dl.wpack; a.scale = dl.scale; a.shift = dl.shift;
   a.inv_sigma = dl.sn_index >= 0 ? m->inv_sigma_dev + dl.sn_index : nullptr;
   a.residual = residual; a.out = out; a.act = act;
+  a.up_H = up_H; a.up_W = up_W;
+  a.pred_w = pred_out ? m->layers[kNumLayers - 1].w32 : nullptr;
+  a.pred_b = pred_out ? m->layers[kNumLayers - 1].bias : nullptr;
+  a.pred_out = pred_out;
   a.error_flag = m->error_flag_dev;
   CUtensorMap tm0, tm1;
   if (int e = get_tmap(m, src0, B, D, H, W, p0, a.PW, a.TH + 2, &tm0)) return e;
@@ -555,6 +571,9 @@ extern "C" int v2ce_model_create(v2ce_model** out, int device) {
 extern "C" int v2ce_model_destroy(v2ce_model* m) {
   if (!m) return V2CE_OK;
   for (void* p : m->allocs) cudaFree(p);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->ev_join) cudaEventDestroy(m->ev_join);
+  if (m->sn_stream) cudaStreamDestroy(m->sn_stream);
   delete m;
   return V2CE_OK;
 }
@@ -582,6 +601,9 @@ extern "C" int v2ce_model_finalize(v2ce_model* m) {
   if (int e = dev_alloc(m, &m->inv_sigma_dev, kNumSn)) return e;
   if (int e = dev_alloc(m, &m->error_flag_dev, 1)) return e;
   V2CE_CUDA_CHECK(cudaMemset(m->error_flag_dev, 0, sizeof(int)));
+  V2CE_CUDA_CHECK(cudaStreamCreateWithFlags(&m->sn_stream, cudaStreamNonBlocking));
+  V2CE_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  V2CE_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
   int sn_count = 0;
   for (int li = 0; li < kNumLayers; ++li) {
     const LayerSpec& L = kLayers[li];
@@ -669,7 +691,11 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
   if (buf.bytes > ws_bytes) return set_error(V2CE_ERR_WORKSPACE, "workspace too small: need %zu, got %zu", buf.bytes, ws_bytes);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int launches = 0;
-  if (int e = run_sn_step(m, s)) return e;
+  // spectral-norm power iteration (input independent) on a side stream, joined before the first SN conv
+  V2CE_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
+  V2CE_CUDA_CHECK(cudaStreamWaitEvent(m->sn_stream, m->ev_fork, 0));
+  if (int e = run_sn_step(m, m->sn_stream)) return e;
+  V2CE_CUDA_CHECK(cudaEventRecord(m->ev_join, m->sn_stream));
   launches += 4;
 
   const long long M0 = d.M[0];
@@ -691,43 +717,55 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
     x = buf.enc[i];
     launches += 3;
   }
-  // residual blocks at the bottleneck
+  // residual blocks at the bottleneck (first spectral-norm convs: join the side stream here)
+  V2CE_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join, 0));
   for (int i = 0; i < 2; ++i) {
     snprintf(name, sizeof(name), "UNet.resblocks.%d.conv1", i);
     const int l1 = layer_index(name);
     if (int e = run_halo(m, l1, x, 512, nullptr, 0, B, D, d.H[4], d.W[4], nullptr, 0, 1, buf.tmp_t, 512, s)) return e;
     if (int e = run_conv(m, l1 + 2, x, 512, d.H[4], d.W[4], nullptr, 0, B, D, d.H[4], d.W[4], 1, nullptr, 0, buf.tmp_r, s)) return e;
-    if (int e = run_halo(m, l1 + 1, buf.tmp_t, 512, nullptr, 0, B, D, d.H[4], d.W[4], buf.tmp_r, 512, 1, buf.res[i], 512, s)) return e;
+    // the last block's output is only ever read nearest-upsampled by decoders.0: write it that way
+    if (i == 1) {
+      if (int e = run_halo(m, l1 + 1, buf.tmp_t, 512, nullptr, 0, B, D, d.H[4], d.W[4], buf.tmp_r, 512, 1, buf.up, 512, s,
+                           d.H[3], d.W[3])) return e;
+    } else {
+      if (int e = run_halo(m, l1 + 1, buf.tmp_t, 512, nullptr, 0, B, D, d.H[4], d.W[4], buf.tmp_r, 512, 1, buf.res[i], 512, s)) return e;
+    }
     x = buf.res[i];
     launches += 3;
   }
-  // decoders: virtual concat [nearest_up(x), skip]; skips are enc2, enc1, enc0, head
-  int xc = 512, xl = 4;   // channels / level of x
+  // decoders: virtual concat [nearest_up(x), skip]; skips are enc2, enc1, enc0, head.  `up` is written directly by
+  // the epilogue of the layer that produced x (upsample-on-store); two buffers alternate because a decoder reads
+  // one while its conv2 writes the next.  The last decoder's conv2 also applies the prediction layer.
+  int xc = 512;
+  __nv_bfloat16* up_cur = buf.up;
+  __nv_bfloat16* up_next = buf.up2;
   for (int i = 0; i < 4; ++i) {
     const int lvl = 3 - i;                       // output level
     const __nv_bfloat16* skip = lvl == 0 ? buf.head : buf.enc[lvl - 1];
     const int sp = pitch_of(ch[lvl]), co = ch[lvl], tp = pitch_of(co);
     snprintf(name, sizeof(name), "UNet.decoders.%d.conv1", i);
     const int l1 = layer_index(name);
-    if (int e = run_upsample(x, B * D, d.H[xl], d.W[xl], d.H[lvl], d.W[lvl], xc, buf.up, s)) return e;
-    if (int e = run_halo(m, l1, buf.up, xc, skip, sp, B, D, d.H[lvl], d.W[lvl], nullptr, 0, 1, buf.tmp_t, tp, s)) return e;
-    if (int e = run_conv(m, l1 + 2, buf.up, xc, d.H[lvl], d.W[lvl], skip, sp, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 0, buf.tmp_r, s)) return e;
-    if (int e = run_halo(m, l1 + 1, buf.tmp_t, tp, nullptr, 0, B, D, d.H[lvl], d.W[lvl], buf.tmp_r, co, 1, buf.dec[i], co, s)) return e;
-    x = buf.dec[i];
+    if (int e = run_halo(m, l1, up_cur, xc, skip, sp, B, D, d.H[lvl], d.W[lvl], nullptr, 0, 1, buf.tmp_t, tp, s)) return e;
+    if (int e = run_conv(m, l1 + 2, up_cur, xc, d.H[lvl], d.W[lvl], skip, sp, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 0, buf.tmp_r, s)) return e;
+    if (lvl > 0) {
+      if (int e = run_halo(m, l1 + 1, buf.tmp_t, tp, nullptr, 0, B, D, d.H[lvl], d.W[lvl], buf.tmp_r, co, 1, up_next, co, s,
+                           d.H[lvl - 1], d.W[lvl - 1])) return e;
+    } else {
+      if (int e = run_halo(m, l1 + 1, buf.tmp_t, tp, nullptr, 0, B, D, d.H[lvl], d.W[lvl], buf.tmp_r, co, 1, buf.dec[i], co, s,
+                           0, 0, y_dev)) return e;
+    }
+    __nv_bfloat16* tsw = up_cur; up_cur = up_next; up_next = tsw;
     xc = co;
-    xl = lvl;
-    launches += 4;
+    launches += 3;
   }
-  const int lp = kNumLayers - 1;
-  pred_conv_kernel<<<(int)((M0 + 127) / 128), 128, 0, s>>>(x, m->layers[lp].w32, m->layers[lp].bias, M0, H * W, y_dev);
-  V2CE_LAUNCH_CHECK("pred_conv_kernel");
-  ++launches;
   m->last_launches = launches;
   return V2CE_OK;
 }
 
 extern "C" int v2ce_model_last_sigmas(const v2ce_model* m, float* sigma12_host) {
   V2CE_REQUIRE(m && sigma12_host && m->finalized, "bad argument");
+  V2CE_CUDA_CHECK(cudaDeviceSynchronize());
   V2CE_CUDA_CHECK(cudaMemcpy(sigma12_host, m->sigma_dev, sizeof(float) * kNumSn, cudaMemcpyDeviceToHost));
   int flag = 0;
   V2CE_CUDA_CHECK(cudaMemcpy(&flag, m->error_flag_dev, sizeof(int), cudaMemcpyDeviceToHost));
@@ -813,6 +851,7 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
     a.residual = static_cast<const __nv_bfloat16*>(residual_dev);
     a.out = static_cast<__nv_bfloat16*>(out_dev);
     a.act = act; a.error_flag = flag;
+    a.up_H = 0; a.up_W = 0; a.pred_w = nullptr; a.pred_b = nullptr; a.pred_out = nullptr;
     CUtensorMap tm0, tm1;
     rc = halo::make_patch_map(&tm0, src0_dev, batch, depth, hin, win, c0, a.PW, a.TH + 2);
     tm1 = tm0;
@@ -850,4 +889,72 @@ extern "C" int v2ce_conv3d_bf16(const void* src0_dev, int32_t c0, int32_t h0, in
                                 const void* residual_dev, int32_t act, void* out_dev, void* stream) {
   return v2ce_conv3d_bf16_ex(src0_dev, c0, h0, w0, src1_dev, c1, batch, depth, hin, win, ksize, stride_hw, weight_host, cout,
                              scale_host, shift_host, residual_dev, act, out_dev, 0, 0, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Bring-up microbenchmark: tensor-pipe rate of back-to-back tcgen05.mma (SS operands, M=128, K=16)
+// on resident shared-memory tiles, no loads.  Gives the ceiling the conv kernels can reach with
+// cta_group::1.  Not used by the product path.
+// ------------------------------------------------------------------------------------------
+namespace v2ce {
+namespace unet {
+template <int BN>
+__global__ void __launch_bounds__(128) mma_rate_kernel(int iters, int naccs, long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = conv::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) unsigned long long bar;
+  const int warp = conv::uniform_warp_id();
+  for (int i = threadIdx.x; i < (16384 + BN * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - raw))[i] = 0u;
+  if (threadIdx.x == 0) {
+    conv::mbar_init(conv::smem_u32(&bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(conv::smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  conv::fence_proxy_async();
+  conv::tcgen05_fence_before();
+  __syncthreads();
+  conv::tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp == 1) {
+    const uint32_t idesc = conv::make_idesc(BN);
+    const uint32_t a_addr = base, b_addr = base + 16384;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        conv::tcgen05_mma_bf16_elect(tmem + (uint32_t)((it % naccs) * BN), conv::make_smem_desc(a_addr + k * 32),
+                                     conv::make_smem_desc(b_addr + k * 32), idesc, 1u);
+    }
+    conv::tcgen05_commit_elect(conv::smem_u32(&bar));
+    conv::mbar_wait(conv::smem_u32(&bar), 0, nullptr);
+    long long t1 = clock64();
+    if (threadIdx.x == 32 && blockIdx.x == 0) cycles_out[0] = t1 - t0;
+  }
+  conv::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+}  // namespace unet
+}  // namespace v2ce
+
+extern "C" int v2ce_debug_mma_rate(int32_t bn, int32_t iters, int32_t naccs, int32_t ctas, double* cycles_per_mma) {
+  long long* d = nullptr;
+  V2CE_CUDA_CHECK(cudaMalloc(&d, sizeof(long long)));
+  const int smem = 16384 + 256 * 128 + 2048;
+  #define RUN(N) { V2CE_CUDA_CHECK(cudaFuncSetAttribute(mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+                   mma_rate_kernel<N><<<ctas, 128, smem>>>(iters, naccs, d); }
+  if (bn == 32) RUN(32) else if (bn == 64) RUN(64) else if (bn == 128) RUN(128) else if (bn == 256) RUN(256)
+  else { cudaFree(d); return set_error(V2CE_ERR_INVALID, "bn"); }
+  #undef RUN
+  V2CE_CUDA_CHECK(cudaDeviceSynchronize());
+  long long c = 0;
+  V2CE_CUDA_CHECK(cudaMemcpy(&c, d, sizeof(c), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  *cycles_per_mma = (double)c / ((double)iters * 4.0);
+  return V2CE_OK;
 }
