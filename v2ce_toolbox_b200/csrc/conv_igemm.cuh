@@ -12,11 +12,12 @@
 //   n = output channel                            tile: BN in {32, 64, 128, 256}
 //   k = (tap, input channel), tap = (kd*3+kh)*3+kw, k-block = 64 bf16 = one 128-byte swizzle row
 //
-// CTA = 192 threads:
-//   warps 0-3  A producers (8 lanes per 128-byte row, 8 x 16-byte cp.async per thread per k-block), then the
-//              epilogue (warp w reads TMEM lanes 32w..32w+31 with tcgen05.ld 32x32b)
-//   warp 4     TMEM allocator; lane 0 issues tcgen05.mma and tcgen05.commit
-//   warp 5     lane 0 issues the weight-tile bulk copies
+// CTA = 320 threads:
+//   warps 0-7  A producers (8 lanes per 128-byte row, 4 x 16-byte cp.async per thread per k-block; the gather is
+//              instruction bound, hence 8 warps), then the epilogue (warps w and w+4 read TMEM lanes
+//              32(w%4).. with tcgen05.ld 32x32b and alternate 32-column chunks)
+//   warp 8     TMEM allocator + MMA issuer (warp converged, elect.sync)
+//   warp 9     weight-tile bulk copies
 // Synchronisation: full[s] (128 cp.async.mbarrier.arrive.noinc arrivals + 1 expect_tx arrival), empty[s] (tcgen05.commit),
 // tmem_full (tcgen05.commit after the last k-block).
 #pragma once
@@ -29,8 +30,8 @@ namespace conv {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // bf16 elements = 128 bytes
-constexpr int kThreads = 192;
-constexpr int kProducerThreads = 128;
+constexpr int kThreads = 320;
+constexpr int kProducerThreads = 256;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;
 
 struct ConvArgs {
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(const_cast<uint32_t*>(tmem_ptr))),
                  "r"((uint32_t)BN)
@@ -244,14 +245,14 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
   tcgen05_fence_after();
   const uint32_t tmem_acc = *tmem_ptr;
 
-  if (warp < 4) {
-    // ================= A producer =================
-    const int m = m_tile * kBlockM + tid;
+  if (warp < 8) {
+    // ================= A producer (8 warps) =================
+    const int m = m_tile * kBlockM + (tid & 127);
     const bool row_ok = m < a.M;          // row owned by this thread in the epilogue (TMEM lane = tid)
 
     // Gather mapping: 8 consecutive lanes fetch the 8 x 16-byte chunks of one 128-byte k-block row, so a
     // warp instruction touches 4 full cache lines (not 32 partial ones); a thread serves the same chunk
-    // q of rows  it*16 + (tid>>3), it = 0..7.  Per row it keeps two element offsets (centre tap, one per
+    // q of rows  it*32 + (tid>>3), it = 0..3.  Per row it keeps two element offsets (centre tap, one per
     // source) and a 32-bit word: bits 0-26 = validity of the 27 taps, bits 27-30 = whether the nearest-
     // upsampled source moves by one pixel for kh/kw = 0 / 2 (always 1 when src0 is not upsampled).
     const int q = tid & 7, rg = tid >> 3;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
       // each producer thread derives the descriptor of ONE row (its epilogue row) and publishes it
       int o0 = 0, o1 = 0;
       uint32_t info = 0u;
-      if (row_ok) {
+      if (row_ok && tid < 128) {
         const int wo = m % a.Wout;
         int t = m / a.Wout;
         const int ho = t % a.Hout;
@@ -295,16 +296,18 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
         o0 = ((t * a.H0 + hs1) * a.W0 + ws1) * a.C0;
         o1 = ((t * a.Hin + hc) * a.Win + wc) * a.C1;
       }
-      s_rows[tid] = o0;
-      s_rows[128 + tid] = o1;
-      s_rows[256 + tid] = (int)info;
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // producer warps only
+      if (tid < 128) {
+        s_rows[tid] = o0;
+        s_rows[128 + tid] = o1;
+        s_rows[256 + tid] = (int)info;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // producer warps only
     }
-    int off0[8], off1[8];
-    uint32_t rinfo[8];
+    int off0[4], off1[4];
+    uint32_t rinfo[4];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 16 + rg;
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 32 + rg;
       off0[it] = s_rows[r];
       off1[it] = s_rows[128 + r];
       rinfo[it] = (uint32_t)s_rows[256 + r];
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
       const __nv_bfloat16* sbase = from0 ? a.src0 + c : a.src1 + (c - a.C0);
       const int toff = from0 ? (kd - 1) * plane0 : ((kd - 1) * plane1 + (kh - 1) * row1 + (kw - 1) * a.C1);
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
+      for (int it = 0; it < 4; ++it) {
         const uint32_t ri = rinfo[it];
         const bool ok = k_ok && ((ri >> tap27) & 1u);
         int off;
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
         } else {
           off = off1[it] + toff;
         }
-        cp_async_16(dst + (uint32_t)it * 2048u, ok ? (const void*)(sbase + off) : (const void*)a.src0, ok ? 16u : 0u);
+        cp_async_16(dst + (uint32_t)it * 4096u, ok ? (const void*)(sbase + off) : (const void*)a.src0, ok ? 16u : 0u);
       }
       // The arrival on full[s] is performed by the copy unit when this thread's copies have landed
       // (no wait in the producer: a proxy fence here would drain every cp.async in flight and
@@ -352,11 +355,11 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
     mbar_wait(tmem_full_bar, 0, a.error_flag);
     __syncwarp();                       // tcgen05.ld is .sync.aligned: the warp must be converged
     tcgen05_fence_after();
-    const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem_acc + ((uint32_t)((warp & 3) * 32) << 16);   // warps w and w+4 share a lane quarter
     __nv_bfloat16* orow = a.out + (size_t)m * a.Cout + n_tile * BN;
     const __nv_bfloat16* rrow = a.residual ? a.residual + (size_t)m * a.Cout + n_tile * BN : nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = (warp >> 2) * 32; c0 < BN; c0 += 64) {         // ... and alternate 32-column chunks
       uint32_t v[32];
       tmem_ld_32x32b_x32(lane_addr + (uint32_t)c0, v);
       tmem_ld_wait();
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ================= MMA issuer (warp converged, one elected lane issues) =================
     constexpr uint32_t idesc = make_idesc(BN);
     for (int kb = 0; kb < a.num_kb; ++kb) {
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)BN) : "memory");
   }
 }

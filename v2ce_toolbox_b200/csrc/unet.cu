@@ -74,10 +74,12 @@ constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
 // ------------------------------------------------------------------------------------------
 // head: Conv3d(2->32, k3, p1, bias) + LeakyReLU(0.01), fp32 in (B,L,2,H,W) -> bf16 NDHWC (pitch 64)
 // ------------------------------------------------------------------------------------------
+// One thread = 4 consecutive output pixels of a row x 32 channels: every 16-byte weight read from shared
+// memory feeds 16 FMAs (with 1 pixel per thread the kernel was LDS bound at 3x its FP32 floor).
 __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, int B, int D, int H, int W,
                                                          __nv_bfloat16* __restrict__ out) {
-  __shared__ __align__(16) float sw[27 * 2 * 32];     // [tap][cin][cout]: 16-byte reads give 4 output channels
+  __shared__ __align__(16) float sw[27 * 2 * 32];     // [tap][cin][cout]
   __shared__ __align__(16) float sb[32];
   for (int i = threadIdx.x; i < 27 * 2 * 32; i += blockDim.x) {
     const int n = i % 32, ci = (i / 32) % 2, tap = i / 64;
@@ -85,18 +87,21 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict_
   }
   if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
-  const long long M = (long long)B * D * H * W;
-  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const int wo = (int)(m % W);
-  long long t = m / W;
+  const int G = (W + 3) / 4;
+  const long long total = (long long)B * D * H * G;
+  const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= total) return;
+  const int w0 = (int)(gi % G) * 4;
+  long long t = gi / G;
   const int ho = (int)(t % H);
   t /= H;
   const int d = (int)(t % D);
   const int b = (int)(t / D);
-  float4 acc[8];
+  float4 acc[4][8];
 #pragma unroll
-  for (int n = 0; n < 8; ++n) acc[n] = reinterpret_cast<const float4*>(sb)[n];
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[p][n] = reinterpret_cast<const float4*>(sb)[n];
   const size_t HW = (size_t)H * W;
   for (int kd = 0; kd < 3; ++kd) {
     const int di = d + kd - 1;
@@ -104,41 +109,55 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict_
     for (int kh = 0; kh < 3; ++kh) {
       const int hi = ho + kh - 1;
       if (hi < 0 || hi >= H) continue;
+      const float* r0 = x + ((size_t)(b * D + di) * 2) * HW + (size_t)hi * W;
+      float xa[6], xb[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int wi = w0 - 1 + j;
+        const bool ok = wi >= 0 && wi < W;
+        xa[j] = ok ? __ldg(r0 + wi) : 0.f;
+        xb[j] = ok ? __ldg(r0 + HW + wi) : 0.f;
+      }
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int wi = wo + kw - 1;
-        if (wi < 0 || wi >= W) continue;
-        const size_t base = ((size_t)(b * D + di) * 2) * HW + (size_t)hi * W + wi;
-        const float x0 = __ldg(x + base), x1 = __ldg(x + base + HW);
         const float4* wt = reinterpret_cast<const float4*>(sw + ((kd * 3 + kh) * 3 + kw) * 64);
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-          const float4 w0 = wt[n], w1 = wt[8 + n];
-          acc[n].x = fmaf(x0, w0.x, fmaf(x1, w1.x, acc[n].x));
-          acc[n].y = fmaf(x0, w0.y, fmaf(x1, w1.y, acc[n].y));
-          acc[n].z = fmaf(x0, w0.z, fmaf(x1, w1.z, acc[n].z));
-          acc[n].w = fmaf(x0, w0.w, fmaf(x1, w1.w, acc[n].w));
+          const float4 wa = wt[n], wb = wt[8 + n];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float x0 = xa[p + kw], x1 = xb[p + kw];
+            acc[p][n].x = fmaf(x0, wa.x, fmaf(x1, wb.x, acc[p][n].x));
+            acc[p][n].y = fmaf(x0, wa.y, fmaf(x1, wb.y, acc[p][n].y));
+            acc[p][n].z = fmaf(x0, wa.z, fmaf(x1, wb.z, acc[p][n].z));
+            acc[p][n].w = fmaf(x0, wa.w, fmaf(x1, wb.w, acc[p][n].w));
+          }
         }
       }
     }
   }
-  uint4 o[4];
-  __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(o);
+  const size_t m0 = ((size_t)(b * D + d) * H + ho) * W + w0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4 v = acc[i];
-    v.x = v.x > 0.f ? v.x : 0.01f * v.x;
-    v.y = v.y > 0.f ? v.y : 0.01f * v.y;
-    v.z = v.z > 0.f ? v.z : 0.01f * v.z;
-    v.w = v.w > 0.f ? v.w : 0.01f * v.w;
-    op[2 * i] = __floats2bfloat162_rn(v.x, v.y);
-    op[2 * i + 1] = __floats2bfloat162_rn(v.z, v.w);
+  for (int p = 0; p < 4; ++p) {
+    if (w0 + p >= W) break;
+    uint4 o[4];
+    __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 v = acc[p][i];
+      v.x = v.x > 0.f ? v.x : 0.01f * v.x;
+      v.y = v.y > 0.f ? v.y : 0.01f * v.y;
+      v.z = v.z > 0.f ? v.z : 0.01f * v.z;
+      v.w = v.w > 0.f ? v.w : 0.01f * v.w;
+      op[2 * i] = __floats2bfloat162_rn(v.x, v.y);
+      op[2 * i + 1] = __floats2bfloat162_rn(v.z, v.w);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + (m0 + p) * 64);   // 64-channel pitch, upper half zero (TMA rows)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = o[i];
+#pragma unroll
+    for (int i = 4; i < 8; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m * 64);     // 64-channel pitch, upper half zero (TMA rows)
-#pragma unroll
-  for (int i = 0; i < 4; ++i) dst[i] = o[i];
-#pragma unroll
-  for (int i = 4; i < 8; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -699,7 +718,10 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
   launches += 4;
 
   const long long M0 = d.M[0];
-  head_conv_kernel<<<(int)((M0 + 127) / 128), 128, 0, s>>>(x_dev, m->layers[0].w32, m->layers[0].bias, B, D, H, W, buf.head);
+  {
+    const long long groups = (long long)B * D * H * ((W + 3) / 4);
+    head_conv_kernel<<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, m->layers[0].w32, m->layers[0].bias, B, D, H, W, buf.head);
+  }
   V2CE_LAUNCH_CHECK("head_conv_kernel");
   ++launches;
 
