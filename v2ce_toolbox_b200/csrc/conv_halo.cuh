@@ -45,6 +45,7 @@ struct HaloArgs {
   int PW, TH, TW;              // patch pitch (TW + 2), output rows and valid columns of a tile; TH*PW <= 128
   int tiles_w, tiles_h;
   int ncc0, ncc1;              // 64-channel chunks taken from source 0 / source 1 (virtual concat)
+  int real0, real1;            // real channels per source: a chunk with < 64 of them issues fewer K=16 MMA steps
   int Cout;                    // real output channels (multiple of BN)
   int out_pitch;               // channel pitch of `out`; columns [Cout, out_pitch) are zero-filled
   int res_pitch;               // channel pitch of `residual`
@@ -212,6 +213,9 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
       tcgen05_fence_after();
       const uint32_t acc_base = tmem_acc + (uint32_t)(ab * T * BN);
       for (int cc = 0; cc < ncc; ++cc) {
+        // zero-padded channels (64-channel pitch of a 32-channel tensor) are not multiplied
+        const int rem = (cc < a.ncc0) ? (a.real0 - cc * kBlockK) : (a.real1 - (cc - a.ncc0) * kBlockK);
+        const int ks = rem >= kBlockK ? kBlockK / 16 : (rem + 15) / 16;
 #pragma unroll 1
         for (int kd = 0; kd < 3; ++kd) {
           const int need = loads_base + cc * (T + 2) + kd + T;   // slices kd .. kd+T-1 of this chunk must have landed
@@ -239,8 +243,9 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
             for (int tt = 0; tt < T; ++tt) {
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
-                tcgen05_mma_bf16_elect(acc_base + (uint32_t)(tt * BN), make_smem_desc(patch[tt] + shift + k * 32),
-                                       make_smem_desc(b_addr + k * 32), idesc, k == 0 ? acc0 : 1u);
+                if (k < ks)
+                  tcgen05_mma_bf16_elect(acc_base + (uint32_t)(tt * BN), make_smem_desc(patch[tt] + shift + k * 32),
+                                         make_smem_desc(b_addr + k * 32), idesc, k == 0 ? acc0 : 1u);
               }
             }
             tcgen05_commit_elect(b_empty(sb));
@@ -521,7 +526,7 @@ inline HaloPlan plan_for(int bn, int D, int H, int W) {
   const char* et = getenv("V2CE_HALO_T");
   const char* esa = getenv("V2CE_HALO_SA");
   const char* esb = getenv("V2CE_HALO_SB");
-  p.T = et ? atoi(et) : 2;
+  p.T = et ? atoi(et) : (bn <= 64 ? 4 : 2);   // measured: T=4 wins for N<=64, T=2 (double-buffered TMEM) for N=128
   if (bn > 128 && p.T > 2) p.T = 2;
   while (p.T > 1 && (D % p.T != 0)) p.T /= 2;
   for (;; p.T /= 2) {

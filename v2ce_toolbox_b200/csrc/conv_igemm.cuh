@@ -37,7 +37,8 @@ constexpr int kAStageBytes = kBlockM * kBlockK * 2;
 struct ConvArgs {
   const __nv_bfloat16* src0;   // (B,D,H0,W0,C0); nearest-upsampled to (Hin,Win) when H0 != Hin or W0 != Win
   const __nv_bfloat16* src1;   // (B,D,Hin,Win,C1) or nullptr
-  int C0, C1, Cin;
+  int C0, C1, Cin;             // real channels gathered from each source; Cin = C0 + C1
+  int P0, P1;                  // channel pitch (elements per pixel) of each source, >= C0 / C1
   int H0, W0;
   int B, D, Hin, Win, Hout, Wout;
   int stride, ksize, pad;
@@ -293,8 +294,8 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
           if (wc + 1 < a.Win && ((wc + 1) * a.W0) / a.Win != ws1) bits |= 8u;
         }
         info = mask | (bits << 27);
-        o0 = ((t * a.H0 + hs1) * a.W0 + ws1) * a.C0;
-        o1 = ((t * a.Hin + hc) * a.Win + wc) * a.C1;
+        o0 = ((t * a.H0 + hs1) * a.W0 + ws1) * a.P0;
+        o1 = ((t * a.Hin + hc) * a.Win + wc) * a.P1;
       }
       if (tid < 128) {
         s_rows[tid] = o0;
@@ -313,8 +314,8 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
       rinfo[it] = (uint32_t)s_rows[256 + r];
     }
     const uint32_t dst_thread = (uint32_t)rg * 128u + ((uint32_t)(q ^ (rg & 7)) << 4);
-    const int plane0 = a.H0 * a.W0 * a.C0, row0 = a.W0 * a.C0;
-    const int plane1 = a.Hin * a.Win * a.C1, row1 = a.Win * a.C1;
+    const int plane0 = a.H0 * a.W0 * a.P0, row0 = a.W0 * a.P0;
+    const int plane1 = a.Hin * a.Win * a.P1, row1 = a.Win * a.P1;
 
     int tap = 0, c = q * 8;             // this thread's (tap, channel) inside the current k-block
     while (c >= a.Cin) { c -= a.Cin; ++tap; }
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
       const bool k_ok = tap < a.taps;
       const bool from0 = c < a.C0;
       const __nv_bfloat16* sbase = from0 ? a.src0 + c : a.src1 + (c - a.C0);
-      const int toff = from0 ? (kd - 1) * plane0 : ((kd - 1) * plane1 + (kh - 1) * row1 + (kw - 1) * a.C1);
+      const int toff = from0 ? (kd - 1) * plane0 : ((kd - 1) * plane1 + (kh - 1) * row1 + (kw - 1) * a.P1);
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const uint32_t ri = rinfo[it];
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
         if (from0) {
           const int dh = (kh == 0) ? -(int)((ri >> 27) & 1u) : (kh == 2) ? (int)((ri >> 28) & 1u) : 0;
           const int dw = (kw == 0) ? -(int)((ri >> 29) & 1u) : (kw == 2) ? (int)((ri >> 30) & 1u) : 0;
-          off = off0[it] + toff + dh * row0 + dw * a.C0;
+          off = off0[it] + toff + dh * row0 + dw * a.P0;
         } else {
           off = off1[it] + toff;
         }
@@ -495,7 +496,7 @@ inline int launch_one(const ConvArgs& a, cudaStream_t s) {
 
 inline int launch_conv(const ConvArgs& a, int bn, cudaStream_t s) {
   // the gather uses 32-bit element offsets
-  if ((long long)a.B * a.D * a.H0 * a.W0 * a.C0 >= (1LL << 31) || (long long)a.B * a.D * a.Hin * a.Win * a.C1 >= (1LL << 31) ||
+  if ((long long)a.B * a.D * a.H0 * a.W0 * a.P0 >= (1LL << 31) || (long long)a.B * a.D * a.Hin * a.Win * a.P1 >= (1LL << 31) ||
       (long long)a.M * a.Cout >= (1LL << 40))
     return set_error(V2CE_ERR_RANGE, "activation tensor too large for 32-bit gather offsets; lower the batch size");
   switch (bn) {

@@ -300,13 +300,14 @@ __global__ void __launch_bounds__(256) sn_finish_kernel(const SnDesc* __restrict
 // every TMA box row is a full 128-byte swizzle row; the packed weights carry zeros for the padding.
 struct LayerCfg {
   int kind;                 // 0 direct fp32 (head, pred), 1 gather implicit GEMM (conv_igemm), 2 halo-tile (conv_halo)
-  int pad0, real0, pad1, real1;
+  int pad0, real0, pad1, real1;   // channels per source in the packed K dimension (pad) and how many are real
+  int pitch0, pitch1;             // channel pitch of each source in memory
 };
 
 static inline int pitch_of(int c) { return c < 64 ? 64 : c; }
 
 struct DevLayer {
-  LayerCfg cfg{0, 0, 0, 0, 0};
+  LayerCfg cfg{0, 0, 0, 0, 0, 0, 0};
   __nv_bfloat16* wpack = nullptr;
   float* scale = nullptr;
   float* shift = nullptr;
@@ -444,22 +445,28 @@ static int layer_index(const char* name) {
 static LayerCfg layer_cfg(int li) {
   const LayerSpec& L = kLayers[li];
   const std::string n = L.name;
-  if (li == 0 || li == kNumLayers - 1) return LayerCfg{0, 0, 0, 0, 0};
+  if (li == 0 || li == kNumLayers - 1) return LayerCfg{0, 0, 0, 0, 0, 0, 0};
   const bool is_conv2 = n.find(".conv2") != std::string::npos;
   const bool is_dec = n.find("decoders") != std::string::npos;
   const bool is_enc = n.find("encoders") != std::string::npos;
-  LayerCfg c{1, 0, 0, 0, 0};
+  LayerCfg c{1, 0, 0, 0, 0, 0, 0};
   if (is_conv2) {
     c.kind = 2;
-    c.real0 = L.cin; c.pad0 = pitch_of(L.cin);
+    c.real0 = L.cin;
   } else if (is_dec) {                       // conv1 / shortcut of a decoder: [up (2/3 of Cin) | skip (1/3)]
     c.kind = (L.k == 3) ? 2 : 1;
-    c.real0 = L.cin / 3 * 2; c.pad0 = c.real0;
-    c.real1 = L.cin / 3; c.pad1 = pitch_of(c.real1);
+    c.real0 = L.cin / 3 * 2;
+    c.real1 = L.cin / 3;
   } else {                                   // conv1 / shortcut of an encoder (stride 2) or bottleneck block
     c.kind = (L.k == 3 && !is_enc) ? 2 : 1;
-    c.real0 = L.cin; c.pad0 = pitch_of(L.cin);
+    c.real0 = L.cin;
   }
+  c.pitch0 = pitch_of(c.real0);
+  c.pitch1 = c.real1 ? pitch_of(c.real1) : 0;
+  // the halo kernel multiplies whole 64-channel TMA rows (padding channels carry zero weights and are skipped
+  // at K=16 granularity); the gather kernel addresses real channels through the pitch
+  c.pad0 = (c.kind == 2) ? c.pitch0 : c.real0;
+  c.pad1 = (c.kind == 2) ? c.pitch1 : c.real1;
   return c;
 }
 
@@ -483,7 +490,8 @@ static int run_conv(v2ce_model* m, int li, const __nv_bfloat16* src0, int c0, in
   const LayerSpec& L = kLayers[li];
   const DevLayer& dl = m->layers[li];
   ConvArgs a;
-  a.src0 = src0; a.src1 = src1; a.C0 = c0; a.C1 = c1; a.Cin = c0 + c1;
+  a.src0 = src0; a.src1 = src1; a.C0 = dl.cfg.real0; a.C1 = dl.cfg.real1; a.Cin = a.C0 + a.C1;
+  a.P0 = c0; a.P1 = c1;
   a.H0 = h0; a.W0 = w0; a.B = B; a.D = D; a.Hin = hin; a.Win = win;
   a.stride = stride; a.ksize = L.k; a.pad = L.k / 2;
   a.Hout = (hin + 2 * a.pad - L.k) / stride + 1;
@@ -496,9 +504,9 @@ static int run_conv(v2ce_model* m, int li, const __nv_bfloat16* src0, int c0, in
   a.inv_sigma = dl.sn_index >= 0 ? m->inv_sigma_dev + dl.sn_index : nullptr;
   a.residual = residual; a.out = out; a.act = act;
   a.error_flag = m->error_flag_dev;
-  if (dl.cfg.kind != 1 || c0 != dl.cfg.pad0 || c1 != dl.cfg.pad1)
-    return set_error(V2CE_ERR_STATE, "layer %s: gather launch with pitches %d+%d, packed for %d+%d", L.name, c0, c1,
-                     dl.cfg.pad0, dl.cfg.pad1);
+  if (dl.cfg.kind != 1 || c0 != dl.cfg.pitch0 || c1 != dl.cfg.pitch1)
+    return set_error(V2CE_ERR_STATE, "layer %s: gather launch with pitches %d+%d, expected %d+%d", L.name, c0, c1,
+                     dl.cfg.pitch0, dl.cfg.pitch1);
   return conv::launch_conv(a, dl.bn_tile, s);
 }
 
@@ -518,6 +526,7 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
   a.tiles_w = (W + a.TW - 1) / a.TW;
   a.tiles_h = (H + a.TH - 1) / a.TH;
   a.ncc0 = p0 / 64; a.ncc1 = p1 / 64;
+  a.real0 = dl.cfg.real0; a.real1 = dl.cfg.real1;
   a.Cout = L.cout; a.out_pitch = out_pitch; a.res_pitch = res_pitch;
   a.T = plan.T; a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
   a.wpack = dl.wpack; a.scale = dl.scale; a.shift = dl.shift;
@@ -867,6 +876,7 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
     a.PW = plan.ts.PW; a.TH = plan.ts.TH; a.TW = plan.ts.PW - 2;
     a.tiles_w = (win + a.TW - 1) / a.TW; a.tiles_h = (hin + a.TH - 1) / a.TH;
     a.ncc0 = c0 / 64; a.ncc1 = c1 / 64;
+    a.real0 = c0; a.real1 = c1;
     a.Cout = cout; a.out_pitch = cout; a.res_pitch = cout;
     a.T = plan.T; a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
     a.wpack = wpack; a.scale = scale_dev; a.shift = shift_dev; a.inv_sigma = nullptr;
@@ -883,7 +893,7 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
     ConvArgs a;
     a.src0 = static_cast<const __nv_bfloat16*>(src0_dev);
     a.src1 = static_cast<const __nv_bfloat16*>(src1_dev);
-    a.C0 = c0; a.C1 = c1; a.Cin = cin; a.H0 = h0; a.W0 = w0;
+    a.C0 = c0; a.C1 = c1; a.Cin = cin; a.P0 = c0; a.P1 = c1; a.H0 = h0; a.W0 = w0;
     a.B = batch; a.D = depth; a.Hin = hin; a.Win = win;
     a.stride = stride_hw; a.ksize = ksize; a.pad = pad;
     a.Hout = hout; a.Wout = wout;
