@@ -164,7 +164,10 @@ int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0, int32_t w0
 /* Bring-up microbenchmark: cycles per back-to-back tcgen05.mma (M=128, N=bn, K=16, both operands in shared
  * memory) with `naccs` accumulators in rotation on `ctas` CTAs. */
 int v2ce_debug_mma_rate(int32_t bn, int32_t iters, int32_t naccs, int32_t ctas, double* cycles_per_mma);
-/* Tuning / bring-up options of a model handle: "desc_mode". */
+/* Per-launch device times of the last forward, measured with CUDA events on the launch stream when the option
+ * "layer_timing" is 1: ms_out[i] and the layer name (48 bytes each, NUL terminated) of launch i. */
+int v2ce_model_layer_times(v2ce_model* m, int32_t cap, float* ms_out, char* names_out, int32_t* count);
+/* Tuning / bring-up options of a model handle: "desc_mode", "layer_timing". */
 int v2ce_model_set_option(v2ce_model* m, const char* key, int64_t value);
 
 #ifdef __cplusplus

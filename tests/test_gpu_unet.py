@@ -92,11 +92,21 @@ HALO_CASES = [
     ('halo_fullres_slice', 1, 2, 260, 346, 64, None, 64, 32, 3, 1, False, 1),
 ]
 
+# same, through the depth-merged variant (Cout <= 64, depth % 8 == 0): one and two depth blocks, two sources,
+# two N tiles, residual, full-resolution tile shape
+KDM_CASES = [
+    ('kdm_n32', 1, 8, 9, 11, 64, None, 0, 32, 3, 1, False, 0),
+    ('kdm_two_src_d16', 1, 16, 9, 11, 64, None, 64, 32, 3, 1, True, 1),
+    ('kdm_n64_many', 2, 16, 33, 44, 64, None, 0, 64, 3, 1, True, 1),
+    ('kdm_128_in', 1, 8, 20, 70, 128, None, 64, 64, 3, 1, False, 2),
+    ('kdm_fullres', 1, 8, 260, 346, 64, None, 64, 32, 3, 1, True, 1),
+]
 
-@pytest.mark.parametrize('case', CASES + HALO_CASES, ids=[c[0] for c in CASES + HALO_CASES])
+
+@pytest.mark.parametrize('case', CASES + HALO_CASES + KDM_CASES, ids=[c[0] for c in CASES + HALO_CASES + KDM_CASES])
 def test_conv_layer_vs_torch(case):
     name, B, D, hin, win, C0, up, C1, cout, k, stride, use_res, act = case
-    impl = 1 if name.startswith('halo') else 0
+    impl = 2 if name.startswith('kdm') else 1 if name.startswith('halo') else 0
     g = torch.Generator(device='cpu').manual_seed(hash(name) % 1000)
     h0, w0 = up if up else (hin, win)
     src0 = torch.randn(B, D, h0, w0, C0, generator=g).to(torch.bfloat16).cuda()

@@ -9,7 +9,7 @@ import test_gpu_unet as T
 
 
 def main(name, impl=0, desc_mode=0):
-    case = [c for c in T.CASES + T.HALO_CASES if c[0] == name][0]
+    case = [c for c in T.CASES + T.HALO_CASES + T.KDM_CASES if c[0] == name][0]
     _, B, D, hin, win, C0, up, C1, cout, k, stride, use_res, act = case
     g = torch.Generator(device='cpu').manual_seed(hash(name) % 1000)
     h0, w0 = up if up else (hin, win)

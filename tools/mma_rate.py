@@ -5,7 +5,7 @@ from v2ce_toolbox_b200 import _lib
 lib = _lib.load()
 torch.cuda.init(); torch.zeros(1, device='cuda')
 for ctas in (1, 148):
-    for bn in (32, 64, 128, 256):
+    for bn in (32, 64, 96, 128, 192, 256):
         for naccs in (1, 2):
             if naccs * bn > 512: continue
             c = ctypes.c_double()

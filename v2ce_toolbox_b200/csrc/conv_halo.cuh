@@ -91,6 +91,10 @@ struct HaloCfg {
 
 struct TileCoord { int n_tile, b, d0, h0, w0; };
 
+// prediction layer (v2ce_3d.py:29, 32 -> 20 channels, 1x1x1, bias, ReLU) fused into the last decoder conv:
+// [20][32] weights followed by [20] biases.  Loaded by load_pred_constants() before the launch that uses them.
+__constant__ float c_pred[660];
+
 __device__ __forceinline__ TileCoord decode_tile(int tile, const HaloArgs& a, int T, int n_tiles_unused) {
   // spatial tiles fastest, then depth group, batch, and the output-channel tile slowest: CTAs that run
   // at the same time read neighbouring patches and the same weights
@@ -105,6 +109,122 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const HaloArgs& a, in
   c.w0 = tw_i * a.TW;
   return c;
 }
+
+// Epilogue of one tile for the accumulator rows of one TMEM lane quarter: slices tt0, tt0+tt_step, ... < tt_end of
+// the tile (accumulator of slice tt at TMEM columns `tmem_cols + tt*BN`, lane offset already in `tmem_cols`).
+//   y = act(acc*scale(+1/sigma) + shift (+ residual)) -> bf16 NDHWC, optionally stored nearest-upsampled, or fed to
+//   the fused prediction layer.  Chunks of 32 accumulator columns, flattened over (slice, column block); the residual
+//   of chunk q+1 is requested before chunk q is processed: one exposed global-load latency per tile instead of one
+//   per 16-byte piece (the epilogue was as long as the MMA phase -- ncu: 50 % of samples in long_scoreboard).
+template <int BN>
+__device__ __forceinline__ void halo_epilogue_slices(const HaloArgs& a, const TileCoord& tc, int n_tiles, uint32_t tmem_cols,
+                                                     int tt0, int tt_step, int tt_end, int th, int tw,
+                                                     const float* s_scale, const float* s_shift, const float* s_pred) {
+  const int h = tc.h0 + th, w = tc.w0 + tw;
+  const bool row_ok = (th < a.TH) && (tw < a.TW) && (h < a.H) && (w < a.W);
+  // destination rows/columns of this source pixel when the output is written nearest-upsampled
+  int uh0 = 0, uh1 = 0, uw0 = 0, uw1 = 0;
+  if (a.up_H > 0 && row_ok) {
+    uh0 = (h * a.up_H + a.H - 1) / a.H;  uh1 = ((h + 1) * a.up_H + a.H - 1) / a.H;
+    uw0 = (w * a.up_W + a.W - 1) / a.W;  uw1 = ((w + 1) * a.up_W + a.W - 1) / a.W;
+  }
+  constexpr int kChunksPerSlice = BN / 32;
+  const int n_slices = (tt_end - tt0 + tt_step - 1) / tt_step;
+  const int n_chunks = n_slices * kChunksPerSlice;
+  const size_t plane0 = (size_t)(tc.b * a.D + tc.d0);
+  const size_t pix = (size_t)h * a.W + w;
+  const size_t HWp = (size_t)a.H * a.W;
+  uint4 rv[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+  auto res_ptr = [&](int q) {
+    const int tt = tt0 + (q / kChunksPerSlice) * tt_step, c0 = (q % kChunksPerSlice) * 32;
+    return reinterpret_cast<const uint4*>(a.residual + ((plane0 + tt) * HWp + pix) * a.res_pitch + tc.n_tile * BN + c0);
+  };
+  const bool has_res = (a.residual != nullptr) && row_ok;
+  if (has_res && n_chunks > 0) {
+    const uint4* rp = res_ptr(0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);
+  }
+#pragma unroll 1
+  for (int q = 0; q < n_chunks; ++q) {
+    const int tt = tt0 + (q / kChunksPerSlice) * tt_step, c0 = (q % kChunksPerSlice) * 32;
+    const size_t plane = plane0 + tt;
+    const size_t m = plane * HWp + pix;
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_cols + (uint32_t)(tt * BN + c0), v);
+    uint4 rn[4] = {rv[0], rv[1], rv[2], rv[3]};
+    if (has_res && q + 1 < n_chunks) {
+      const uint4* rp = res_ptr(q + 1);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) rn[g] = __ldg(rp + g);
+    }
+    tmem_ld_wait();
+    if (row_ok) {
+      float yv[32];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const __nv_bfloat162* rp2 = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(rp2[j]);      // zeros when there is no residual
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int n = c0 + g * 8 + 2 * j + hh;
+            float tv = fmaf(__uint_as_float(v[g * 8 + 2 * j + hh]), s_scale[n], s_shift[n]) + (hh ? f.y : f.x);
+            if (a.act == 1) tv = fmaxf(tv, 0.f);
+            else if (a.act == 2) tv = tv > 0.f ? tv : 0.01f * tv;
+            yv[g * 8 + 2 * j + hh] = tv;
+          }
+        }
+      }
+      if (BN == 32 && a.pred_w != nullptr) {
+        // fused prediction layer: 20 dot products over the 32 channels of this pixel (four independent
+        // accumulation chains at a time), ReLU, planar fp32 store.  The weights are FFMA constant-bank operands
+        // (c_pred): no shared-memory loads in the loop.
+        float* dst = a.pred_out + plane * 20 * HWp + pix;
+#pragma unroll
+        for (int n0 = 0; n0 < 20; n0 += 4) {
+          float acc[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = c_pred[640 + n0 + u];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fmaf(yv[c], c_pred[(n0 + u) * 32 + c], acc[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dst[(size_t)(n0 + u) * HWp] = fmaxf(acc[u], 0.f);
+        }
+      } else {
+        uint4 ov[4];
+        __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(ov);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) op[j] = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]);
+        if (a.up_H > 0) {
+          for (int hh = uh0; hh < uh1; ++hh)
+            for (int ww = uw0; ww < uw1; ++ww) {
+              uint4* d4 = reinterpret_cast<uint4*>(a.out + ((plane * a.up_H + hh) * a.up_W + ww) * a.out_pitch +
+                                                   tc.n_tile * BN + c0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) d4[g] = ov[g];
+            }
+        } else {
+          uint4* d4 = reinterpret_cast<uint4*>(a.out + m * a.out_pitch + tc.n_tile * BN + c0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) d4[g] = ov[g];
+        }
+      }
+      if (c0 + 32 == BN && tc.n_tile == n_tiles - 1 && a.up_H == 0 && a.pred_w == nullptr) {
+        // zero the padding channels so later TMA reads see 0, not garbage
+        for (int c = a.Cout; c < a.out_pitch; c += 8)
+          *reinterpret_cast<uint4*>(a.out + m * a.out_pitch + c) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) rv[g] = rn[g];
+  }
+}
+
 
 template <int BN, int T>
 __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_constant__ CUtensorMap tm0,
@@ -290,115 +410,13 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
         asm volatile("bar.sync 1, 128;" ::: "memory");
         cur_n_tile = tc.n_tile;
       }
-      const int h = tc.h0 + th, w = tc.w0 + tw;
-      const bool row_ok = (th < a.TH) && (tw < a.TW) && (h < a.H) && (w < a.W);
       const int ab = (NBUF == 2) ? (iter & 1) : 0;
       const int use = (NBUF == 2) ? (iter >> 1) : iter;
       mbar_wait(tmem_full(ab), (uint32_t)(use & 1), a.error_flag);
       __syncwarp();
       tcgen05_fence_after();
-      // destination rows/columns of this source pixel when the output is written nearest-upsampled
-      int uh0 = 0, uh1 = 0, uw0 = 0, uw1 = 0;
-      if (a.up_H > 0 && row_ok) {
-        uh0 = (h * a.up_H + a.H - 1) / a.H;  uh1 = ((h + 1) * a.up_H + a.H - 1) / a.H;
-        uw0 = (w * a.up_W + a.W - 1) / a.W;  uw1 = ((w + 1) * a.up_W + a.W - 1) / a.W;
-      }
-      // Chunks of 32 accumulator columns, flattened over (slice, column block).  The residual of chunk q+1 is
-      // requested before chunk q is processed: one exposed global-load latency per tile instead of one per
-      // 16-byte piece (the epilogue was as long as the MMA phase -- ncu: 50 % of samples in long_scoreboard).
-      constexpr int kChunksPerSlice = BN / 32;
-      constexpr int kChunks = T * kChunksPerSlice;
-      const size_t plane0 = (size_t)(tc.b * a.D + tc.d0);
-      const size_t pix = (size_t)h * a.W + w;
-      const size_t HWp = (size_t)a.H * a.W;
-      uint4 rv[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-      auto res_ptr = [&](int q) {
-        const int tt = q / kChunksPerSlice, c0 = (q % kChunksPerSlice) * 32;
-        return reinterpret_cast<const uint4*>(a.residual + ((plane0 + tt) * HWp + pix) * a.res_pitch + tc.n_tile * BN + c0);
-      };
-      const bool has_res = (a.residual != nullptr) && row_ok;
-      if (has_res) {
-        const uint4* rp = res_ptr(0);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);
-      }
-#pragma unroll 1
-      for (int q = 0; q < kChunks; ++q) {
-        const int tt = q / kChunksPerSlice, c0 = (q % kChunksPerSlice) * 32;
-        const size_t plane = plane0 + tt;
-        const size_t m = plane * HWp + pix;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((ab * T + tt) * BN + c0), v);
-        uint4 rn[4] = {rv[0], rv[1], rv[2], rv[3]};
-        if (has_res && q + 1 < kChunks) {
-          const uint4* rp = res_ptr(q + 1);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) rn[g] = __ldg(rp + g);
-        }
-        tmem_ld_wait();
-        if (row_ok) {
-          float yv[32];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const __nv_bfloat162* rp2 = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(rp2[j]);      // zeros when there is no residual
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                const int n = c0 + g * 8 + 2 * j + hh;
-                float tv = fmaf(__uint_as_float(v[g * 8 + 2 * j + hh]), s_scale[n], s_shift[n]) + (hh ? f.y : f.x);
-                if (a.act == 1) tv = fmaxf(tv, 0.f);
-                else if (a.act == 2) tv = tv > 0.f ? tv : 0.01f * tv;
-                yv[g * 8 + 2 * j + hh] = tv;
-              }
-            }
-          }
-          if (BN == 32 && a.pred_w != nullptr) {
-            // fused prediction layer: 20 dot products over the 32 channels of this pixel, ReLU, planar fp32 store
-            float* dst = a.pred_out + plane * 20 * HWp + pix;
-            const float4* pw4 = reinterpret_cast<const float4*>(s_pred);
-#pragma unroll 2
-            for (int n = 0; n < 20; ++n) {
-              float acc = s_pred[640 + n];
-#pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4) {
-                const float4 wv = pw4[n * 8 + c4];
-                acc = fmaf(yv[c4 * 4 + 0], wv.x, acc);
-                acc = fmaf(yv[c4 * 4 + 1], wv.y, acc);
-                acc = fmaf(yv[c4 * 4 + 2], wv.z, acc);
-                acc = fmaf(yv[c4 * 4 + 3], wv.w, acc);
-              }
-              dst[(size_t)n * HWp] = fmaxf(acc, 0.f);
-            }
-          } else {
-            uint4 ov[4];
-            __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(ov);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) op[j] = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]);
-            if (a.up_H > 0) {
-              for (int hh = uh0; hh < uh1; ++hh)
-                for (int ww = uw0; ww < uw1; ++ww) {
-                  uint4* d4 = reinterpret_cast<uint4*>(a.out + ((plane * a.up_H + hh) * a.up_W + ww) * a.out_pitch +
-                                                       tc.n_tile * BN + c0);
-#pragma unroll
-                  for (int g = 0; g < 4; ++g) d4[g] = ov[g];
-                }
-            } else {
-              uint4* d4 = reinterpret_cast<uint4*>(a.out + m * a.out_pitch + tc.n_tile * BN + c0);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) d4[g] = ov[g];
-            }
-          }
-          if (c0 + 32 == BN && tc.n_tile == n_tiles - 1 && a.up_H == 0 && a.pred_w == nullptr) {
-            // zero the padding channels so later TMA reads see 0, not garbage
-            for (int c = a.Cout; c < a.out_pitch; c += 8)
-              *reinterpret_cast<uint4*>(a.out + m * a.out_pitch + c) = make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) rv[g] = rn[g];
-      }
+      halo_epilogue_slices<BN>(a, tc, n_tiles, tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * T * BN), 0, 1, T,
+                               th, tw, s_scale, s_shift, s_pred);
       // this accumulator set may be overwritten by the MMAs of a later tile
       tcgen05_fence_before();
       mbar_arrive(tmem_empty(ab));
@@ -460,6 +478,13 @@ __global__ void upsample_nearest_kernel(const __nv_bfloat16* __restrict__ in, in
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// stream-ordered upload of the prediction layer into constant memory (device pointers, fp32)
+inline int load_pred_constants(const float* w_dev, const float* b_dev, cudaStream_t s) {
+  V2CE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_pred, w_dev, 640 * sizeof(float), 0, cudaMemcpyDeviceToDevice, s));
+  V2CE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_pred, b_dev, 20 * sizeof(float), 640 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return V2CE_OK;
+}
 
 inline EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;

@@ -141,6 +141,23 @@ __device__ __forceinline__ void tcgen05_mma_bf16_elect(uint32_t tmem_d, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the descriptors given by their low words only (start address >> 4 | LBO field): the high word of a
+// K-major SWIZZLE_128B descriptor is the constant 0x40004040 (SBO = 1024 B, version 1, layout type 2), so an issue
+// loop advances a descriptor with one 32-bit add instead of rebuilding 64 bits (the MMA warp of the N=32 kernels was
+// instruction bound: ~100 uniform-datapath instructions per tap, ncu source counters).
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void tcgen05_mma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"

@@ -18,7 +18,7 @@
 
 #include <tuple>
 
-#include "conv_halo.cuh"
+#include "conv_halo_kdm.cuh"
 
 namespace v2ce {
 namespace unet {
@@ -309,6 +309,7 @@ static inline int pitch_of(int c) { return c < 64 ? 64 : c; }
 struct DevLayer {
   LayerCfg cfg{0, 0, 0, 0, 0, 0, 0};
   __nv_bfloat16* wpack = nullptr;
+  __nv_bfloat16* wpack_kdm = nullptr;   // depth-merged packing (conv_halo_kdm.cuh) for halo layers with Cout <= 64
   float* scale = nullptr;
   float* shift = nullptr;
   float* w32 = nullptr;     // head / pred fp32 weights, SN weight_bar
@@ -321,6 +322,7 @@ struct DevLayer {
 
 struct v2ce_model {
   int device = 0;
+  unsigned long long uid = 0;           // unique per handle (constant-memory ownership)
   bool finalized = false;
   std::map<std::string, std::vector<float>> host;
   std::map<std::string, std::vector<int64_t>> shapes;
@@ -335,6 +337,8 @@ struct v2ce_model {
   int64_t calls = 0;
   int last_launches = 0;
   int desc_mode = 0;
+  int layer_timing = 0;                 // option "layer_timing": CUDA events around every launch of forward()
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
   cudaStream_t sn_stream = nullptr;     // the spectral-norm step overlaps the head / encoder convs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> tmaps;
@@ -520,6 +524,10 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
     return set_error(V2CE_ERR_STATE, "layer %s: halo launch with pitches %d+%d, packed for %d+%d", L.name, p0, p1,
                      dl.cfg.pad0, dl.cfg.pad1);
   const halo::HaloPlan plan = halo::plan_for(dl.bn_tile, D, H, W);
+  // layers with few output channels: depth taps merged into the MMA N dimension (conv_halo_kdm.cuh)
+  const halo::KdmPlan kplan = halo::plan_kdm(D, H, W);
+  static const int kdm_max_cout = getenv("V2CE_KDM_MAX_COUT") ? atoi(getenv("V2CE_KDM_MAX_COUT")) : 64;
+  const bool kdm = dl.wpack_kdm != nullptr && kplan.ok && L.cout <= kdm_max_cout;
   halo::HaloArgs a;
   a.B = B; a.D = D; a.H = H; a.W = W;
   a.PW = plan.ts.PW; a.TH = plan.ts.TH; a.TW = plan.ts.PW - 2;
@@ -530,6 +538,7 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
   a.Cout = L.cout; a.out_pitch = out_pitch; a.res_pitch = res_pitch;
   a.T = plan.T; a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
   a.wpack = dl.wpack; a.scale = dl.scale; a.shift = dl.shift;
+  if (kdm) { a.T = halo::kKdmT; a.SA = kplan.SA; a.SB = 9; a.wpack = dl.wpack_kdm; }
   a.inv_sigma = dl.sn_index >= 0 ? m->inv_sigma_dev + dl.sn_index : nullptr;
   a.residual = residual; a.out = out; a.act = act;
   a.up_H = up_H; a.up_W = up_W;
@@ -537,11 +546,20 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
   a.pred_b = pred_out ? m->layers[kNumLayers - 1].bias : nullptr;
   a.pred_out = pred_out;
   a.error_flag = m->error_flag_dev;
+  if (pred_out) {
+    // constant memory is per device, not per handle: reload when another handle ran last (stream ordered)
+    static unsigned long long pred_owner[64] = {0};
+    if (pred_owner[m->device & 63] != m->uid) {
+      if (int e = halo::load_pred_constants(a.pred_w, a.pred_b, s)) return e;
+      pred_owner[m->device & 63] = m->uid;
+    }
+  }
   CUtensorMap tm0, tm1;
   if (int e = get_tmap(m, src0, B, D, H, W, p0, a.PW, a.TH + 2, &tm0)) return e;
   tm1 = tm0;
   if (src1)
     if (int e = get_tmap(m, src1, B, D, H, W, p1, a.PW, a.TH + 2, &tm1)) return e;
+  if (kdm) return halo::launch_halo_kdm(tm0, tm1, a, kplan.smem_bytes, s);
   return halo::launch_halo(tm0, tm1, a, dl.bn_tile, plan.smem_bytes, s);
 }
 
@@ -561,6 +579,12 @@ static int pack_layer(v2ce_model* m, int li, const float* w_dev, cudaStream_t s)
     halo::pack_weights_halo_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(
         w_dev, L.cout, L.cin, dl.bn_tile, c.pad0, c.real0, c.pad1, c.real1, dl.wpack);
     V2CE_LAUNCH_CHECK("pack_weights_halo_kernel");
+    if (L.cout <= 64) {
+      if (int e = dev_alloc(m, &dl.wpack_kdm, n)) return e;
+      halo::pack_weights_kdm_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(
+          w_dev, L.cout, L.cin, c.pad0, c.real0, c.pad1, c.real1, dl.wpack_kdm);
+      V2CE_LAUNCH_CHECK("pack_weights_kdm_kernel");
+    }
     return V2CE_OK;
   }
   dl.num_kb = (taps * cin_pad + conv::kBlockK - 1) / conv::kBlockK;
@@ -590,8 +614,10 @@ using namespace v2ce::unet;
 extern "C" int v2ce_model_create(v2ce_model** out, int device) {
   V2CE_REQUIRE(out != nullptr, "out is NULL");
   if (int e = v2ce_device_check(device, nullptr, nullptr, nullptr)) return e;
+  static unsigned long long next_uid = 0;
   v2ce_model* m = new v2ce_model();
   m->device = device;
+  m->uid = ++next_uid;
   *out = m;
   return V2CE_OK;
 }
@@ -599,6 +625,7 @@ extern "C" int v2ce_model_create(v2ce_model** out, int device) {
 extern "C" int v2ce_model_destroy(v2ce_model* m) {
   if (!m) return V2CE_OK;
   for (void* p : m->allocs) cudaFree(p);
+  for (auto& mk : m->marks) cudaEventDestroy(mk.second);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
   if (m->sn_stream) cudaStreamDestroy(m->sn_stream);
@@ -719,6 +746,19 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
   if (buf.bytes > ws_bytes) return set_error(V2CE_ERR_WORKSPACE, "workspace too small: need %zu, got %zu", buf.bytes, ws_bytes);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int launches = 0;
+  size_t n_marks = 0;
+  auto mark = [&](const char* what) {             // per-launch timing (tools/layer_times.py); off by default
+    if (!m->layer_timing) return;
+    if (n_marks == m->marks.size()) {
+      cudaEvent_t ev;
+      cudaEventCreate(&ev);
+      m->marks.emplace_back(std::string(), ev);
+    }
+    m->marks[n_marks].first = what;
+    cudaEventRecord(m->marks[n_marks].second, s);
+    ++n_marks;
+  };
+  mark("start");
   // spectral-norm power iteration (input independent) on a side stream, joined before the first SN conv
   V2CE_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
   V2CE_CUDA_CHECK(cudaStreamWaitEvent(m->sn_stream, m->ev_fork, 0));
@@ -733,6 +773,7 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
   }
   V2CE_LAUNCH_CHECK("head_conv_kernel");
   ++launches;
+  mark("UNet.head.conv3d");
 
   static const int ch[5] = {32, 64, 128, 256, 512};
   char name[64];
@@ -743,8 +784,11 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
     const int l1 = layer_index(name);
     const int pin = pitch_of(ch[i]), co = ch[i + 1];
     if (int e = run_conv(m, l1, x, pin, d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 1, buf.tmp_t, s)) return e;
+    mark(kLayers[l1].name);
     if (int e = run_conv(m, l1 + 2, x, pin, d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 0, buf.tmp_r, s)) return e;
+    mark(kLayers[l1 + 2].name);
     if (int e = run_halo(m, l1 + 1, buf.tmp_t, co, nullptr, 0, B, D, d.H[i + 1], d.W[i + 1], buf.tmp_r, co, 1, buf.enc[i], co, s)) return e;
+    mark(kLayers[l1 + 1].name);
     x = buf.enc[i];
     launches += 3;
   }
@@ -754,7 +798,9 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
     snprintf(name, sizeof(name), "UNet.resblocks.%d.conv1", i);
     const int l1 = layer_index(name);
     if (int e = run_halo(m, l1, x, 512, nullptr, 0, B, D, d.H[4], d.W[4], nullptr, 0, 1, buf.tmp_t, 512, s)) return e;
+    mark(kLayers[l1].name);
     if (int e = run_conv(m, l1 + 2, x, 512, d.H[4], d.W[4], nullptr, 0, B, D, d.H[4], d.W[4], 1, nullptr, 0, buf.tmp_r, s)) return e;
+    mark(kLayers[l1 + 2].name);
     // the last block's output is only ever read nearest-upsampled by decoders.0: write it that way
     if (i == 1) {
       if (int e = run_halo(m, l1 + 1, buf.tmp_t, 512, nullptr, 0, B, D, d.H[4], d.W[4], buf.tmp_r, 512, 1, buf.up, 512, s,
@@ -762,6 +808,7 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
     } else {
       if (int e = run_halo(m, l1 + 1, buf.tmp_t, 512, nullptr, 0, B, D, d.H[4], d.W[4], buf.tmp_r, 512, 1, buf.res[i], 512, s)) return e;
     }
+    mark(kLayers[l1 + 1].name);
     x = buf.res[i];
     launches += 3;
   }
@@ -778,7 +825,9 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
     snprintf(name, sizeof(name), "UNet.decoders.%d.conv1", i);
     const int l1 = layer_index(name);
     if (int e = run_halo(m, l1, up_cur, xc, skip, sp, B, D, d.H[lvl], d.W[lvl], nullptr, 0, 1, buf.tmp_t, tp, s)) return e;
+    mark(kLayers[l1].name);
     if (int e = run_conv(m, l1 + 2, up_cur, xc, d.H[lvl], d.W[lvl], skip, sp, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 0, buf.tmp_r, s)) return e;
+    mark(kLayers[l1 + 2].name);
     if (lvl > 0) {
       if (int e = run_halo(m, l1 + 1, buf.tmp_t, tp, nullptr, 0, B, D, d.H[lvl], d.W[lvl], buf.tmp_r, co, 1, up_next, co, s,
                            d.H[lvl - 1], d.W[lvl - 1])) return e;
@@ -786,6 +835,7 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
       if (int e = run_halo(m, l1 + 1, buf.tmp_t, tp, nullptr, 0, B, D, d.H[lvl], d.W[lvl], buf.tmp_r, co, 1, buf.dec[i], co, s,
                            0, 0, y_dev)) return e;
     }
+    mark(kLayers[l1 + 1].name);
     __nv_bfloat16* tsw = up_cur; up_cur = up_next; up_next = tsw;
     xc = co;
     launches += 3;
@@ -823,9 +873,26 @@ extern "C" int v2ce_model_last_launches(const v2ce_model* m, int32_t* launches) 
   return V2CE_OK;
 }
 
+extern "C" int v2ce_model_layer_times(v2ce_model* m, int32_t cap, float* ms_out, char* names_out, int32_t* count) {
+  V2CE_REQUIRE(m && ms_out && names_out && count && cap > 0, "bad argument");
+  V2CE_CUDA_CHECK(cudaDeviceSynchronize());
+  int n = 0;
+  for (size_t i = 1; i < m->marks.size() && n < cap; ++i) {
+    if (m->marks[i].first == "start") break;     // marks of an earlier, longer forward
+    float ms = 0.f;
+    V2CE_CUDA_CHECK(cudaEventElapsedTime(&ms, m->marks[i - 1].second, m->marks[i].second));
+    ms_out[n] = ms;
+    snprintf(names_out + (size_t)n * 48, 48, "%s", m->marks[i].first.c_str());
+    ++n;
+  }
+  *count = n;
+  return V2CE_OK;
+}
+
 extern "C" int v2ce_model_set_option(v2ce_model* m, const char* key, int64_t value) {
   V2CE_REQUIRE(m && key, "NULL argument");
   if (std::string(key) == "desc_mode") { m->desc_mode = (int)value; return V2CE_OK; }
+  if (std::string(key) == "layer_timing") { m->layer_timing = (int)value; return V2CE_OK; }
   return set_error(V2CE_ERR_INVALID, "unknown option '%s'", key);
 }
 
@@ -841,7 +908,8 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
   V2CE_REQUIRE((src1_dev != nullptr) == (c1 > 0), "src1 and c1 must agree");
   const int bn = conv::pick_bn(cout);
   V2CE_REQUIRE(bn != 0, "cout must be a multiple of 32");
-  if (impl == 1)
+  if (impl == 2) V2CE_REQUIRE(cout <= 64 && halo::plan_kdm(depth, hin, win).ok, "depth-merged halo kernel: Cout <= 64, depth % 8 == 0");
+  if (impl >= 1)
     V2CE_REQUIRE(ksize == 3 && stride_hw == 1 && h0 == hin && w0 == win && c0 % 64 == 0 && c1 % 64 == 0,
                  "halo kernel: 3x3x3, stride 1, no upsample, channel pitches multiple of 64");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -863,14 +931,17 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
   const int pgrid = (int)((pn + 255) / 256 > 4096 ? 4096 : (pn + 255) / 256);
   if (impl == 1)
     halo::pack_weights_halo_kernel<<<pgrid, 256, 0, s>>>(w_dev, cout, cin, bn, c0, c0, c1, c1, wpack);
+  else if (impl == 2)
+    halo::pack_weights_kdm_kernel<<<pgrid, 256, 0, s>>>(w_dev, cout, cin, c0, c0, c1, c1, wpack);
   else
     conv::pack_weights_kernel<<<pgrid, 256, 0, s>>>(w_dev, cout, cin, taps, bn, num_kb, c0, c0, c1, c1, wpack);
   int rc = V2CE_OK;
   if (cudaGetLastError() != cudaSuccess) rc = set_error(V2CE_ERR_CUDA, "weight pack launch failed");
   const int pad = ksize / 2;
   const int hout = (hin + 2 * pad - ksize) / stride_hw + 1, wout = (win + 2 * pad - ksize) / stride_hw + 1;
-  if (rc == V2CE_OK && impl == 1) {
+  if (rc == V2CE_OK && impl >= 1) {
     const halo::HaloPlan plan = halo::plan_for(bn, depth, hin, win);
+    const halo::KdmPlan kplan = halo::plan_kdm(depth, hin, win);
     halo::HaloArgs a;
     a.B = batch; a.D = depth; a.H = hin; a.W = win;
     a.PW = plan.ts.PW; a.TH = plan.ts.TH; a.TW = plan.ts.PW - 2;
@@ -880,6 +951,7 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
     a.Cout = cout; a.out_pitch = cout; a.res_pitch = cout;
     a.T = plan.T; a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
     a.wpack = wpack; a.scale = scale_dev; a.shift = shift_dev; a.inv_sigma = nullptr;
+    if (impl == 2) { a.T = halo::kKdmT; a.SA = kplan.SA; a.SB = 9; }
     a.residual = static_cast<const __nv_bfloat16*>(residual_dev);
     a.out = static_cast<__nv_bfloat16*>(out_dev);
     a.act = act; a.error_flag = flag;
@@ -888,7 +960,8 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
     rc = halo::make_patch_map(&tm0, src0_dev, batch, depth, hin, win, c0, a.PW, a.TH + 2);
     tm1 = tm0;
     if (rc == V2CE_OK && src1_dev) rc = halo::make_patch_map(&tm1, src1_dev, batch, depth, hin, win, c1, a.PW, a.TH + 2);
-    if (rc == V2CE_OK) rc = halo::launch_halo(tm0, tm1, a, bn, plan.smem_bytes, s);
+    if (rc == V2CE_OK) rc = impl == 2 ? halo::launch_halo_kdm(tm0, tm1, a, kplan.smem_bytes, s)
+                                      : halo::launch_halo(tm0, tm1, a, bn, plan.smem_bytes, s);
   } else if (rc == V2CE_OK) {
     ConvArgs a;
     a.src0 = static_cast<const __nv_bfloat16*>(src0_dev);
@@ -980,7 +1053,8 @@ extern "C" int v2ce_debug_mma_rate(int32_t bn, int32_t iters, int32_t naccs, int
   const int smem = 16384 + 256 * 128 + 2048;
   #define RUN(N) { V2CE_CUDA_CHECK(cudaFuncSetAttribute(mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
                    mma_rate_kernel<N><<<ctas, 128, smem>>>(iters, naccs, d); }
-  if (bn == 32) RUN(32) else if (bn == 64) RUN(64) else if (bn == 128) RUN(128) else if (bn == 256) RUN(256)
+  if (bn == 32) RUN(32) else if (bn == 64) RUN(64) else if (bn == 96) RUN(96) else if (bn == 128) RUN(128)
+  else if (bn == 192) RUN(192) else if (bn == 256) RUN(256)
   else { cudaFree(d); return set_error(V2CE_ERR_INVALID, "bn"); }
   #undef RUN
   V2CE_CUDA_CHECK(cudaDeviceSynchronize());

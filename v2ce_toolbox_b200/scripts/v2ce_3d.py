@@ -125,3 +125,15 @@ class V2ce3d(nn.Module):
         n = ctypes.c_int32()
         check(self._lib.v2ce_model_last_launches(self._handle, ctypes.byref(n)))
         return n.value
+
+    def set_option(self, key, value):
+        check(self._lib.v2ce_model_set_option(self._handle, key.encode(), int(value)))
+
+    def layer_times(self):
+        """[(layer name, ms)] of the last forward (after set_option('layer_timing', 1))."""
+        cap = 64
+        ms = (ctypes.c_float * cap)()
+        names = ctypes.create_string_buffer(cap * 48)
+        n = ctypes.c_int32()
+        check(self._lib.v2ce_model_layer_times(self._handle, cap, ms, names, ctypes.byref(n)))
+        return [(names.raw[i * 48:(i + 1) * 48].split(b'\0', 1)[0].decode(), float(ms[i])) for i in range(n.value)]
