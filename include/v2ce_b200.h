@@ -154,8 +154,10 @@ int v2ce_conv3d_bf16(const void* src0_dev, int32_t c0, int32_t h0, int32_t w0, c
                      const void* residual_dev, int32_t act, void* out_dev, void* stream);
 
 /* Same hook with the kernel made explicit: impl 0 = gather implicit GEMM (csrc/conv_igemm.cuh), 1 = halo-tile
- * kernel (csrc/conv_halo.cuh; 3x3x3, stride 1, h0==hin, channel pitches multiple of 64).  desc_mode is a
- * bring-up switch of the shifted shared-memory descriptor (0 or 1). */
+ * kernel (csrc/conv_halo.cuh; 3x3x3, stride 1, h0==hin, channel pitches multiple of 64), 2 = its depth-merged
+ * variant (csrc/conv_halo_kdm.cuh; additionally Cout <= 64, depth % 8 == 0), 3 = the same with the fused 1x1x1
+ * shortcut: residual_dev is then an OUTPUT (B,D,H,W,Cout) bf16 receiving scale*conv1x1(x, weight[:,:,1,1,1])+shift.
+ * desc_mode is a bring-up switch of the shifted shared-memory descriptor (0 or 1). */
 int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0, int32_t w0, const void* src1_dev, int32_t c1,
                         int32_t batch, int32_t depth, int32_t hin, int32_t win, int32_t ksize, int32_t stride_hw,
                         const float* weight_host, int32_t cout, const float* scale_host, const float* shift_host,

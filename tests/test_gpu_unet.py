@@ -127,6 +127,30 @@ def test_conv_layer_vs_torch(case):
     assert bad == 0, f'{name}: {bad} of {err.numel()} outside tolerance, max err {err.max().item():.4g}'
 
 
+@pytest.mark.parametrize('case', KDM_CASES, ids=[c[0] + '_shortcut' for c in KDM_CASES])
+def test_conv_with_fused_shortcut_vs_torch(case):
+    """Depth-merged kernel with the block's 1x1x1 shortcut conv fused in (impl 3 of the hook): both outputs."""
+    name, B, D, hin, win, C0, up, C1, cout, k, stride, use_res, act = case
+    g = torch.Generator(device='cpu').manual_seed(hash(name) % 1000 + 1)
+    src0 = torch.randn(B, D, hin, win, C0, generator=g).to(torch.bfloat16).cuda()
+    src1 = torch.randn(B, D, hin, win, C1, generator=g).to(torch.bfloat16).cuda() if C1 else None
+    cin = C0 + C1
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / np.sqrt(cin * 27)
+    w[:, :, 1, 1, 1] *= 4.0                      # the shortcut weights: make them count
+    scale = 0.5 + torch.rand(cout, generator=g)
+    shift = 0.2 * torch.randn(cout, generator=g)
+    out2 = torch.full((B, D, hin, win, cout), float('nan'), dtype=torch.bfloat16, device='cuda')
+    out = conv_hook(src0, src1, hin, win, w, scale, shift, out2, act, 3, 1, impl=3)
+    ref = torch_ref(src0, src1, hin, win, w, scale, shift, None, act, 3, 1)
+    ref2 = torch_ref(src0, src1, hin, win, w[:, :, 1:2, 1:2, 1:2].contiguous(), scale, shift, None, 0, 1, 1)
+    for got, want, what in ((out, ref, 'conv'), (out2, ref2, 'shortcut')):
+        assert not torch.isnan(got.float()).any(), f'{what}: unwritten outputs'
+        err = (got.float() - want).abs()
+        tol = 2.0 ** -8 * want.abs() + 2e-3
+        bad = (err > tol).sum().item()
+        assert bad == 0, f'{name} {what}: {bad} of {err.numel()} outside tolerance, max err {err.max().item():.4g}'
+
+
 def _model(seed, init):
     from v2ce_toolbox_b200.scripts.v2ce_3d import V2ce3d
     sd = synth.make_state_dict(seed, init)

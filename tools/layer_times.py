@@ -57,6 +57,11 @@ def main():
         if r >= 2:
             acc = [(n, a + ms) for (n, ms), (_, a) in zip(t, acc)] if acc else t
     gf = layer_gflop(B)
+    seen = {n for n, _ in acc}
+    for i in range(4):                              # shortcut fused into conv1: count its FLOPs there
+        sc = f'UNet.decoders.{i}.downsample.0'
+        if sc not in seen:
+            gf[f'UNet.decoders.{i}.conv1'] += gf.pop(sc)
     tot = sum(ms for _, ms in acc) / reps
     print(f'batch {B}, {reps} reps, forward {tot:.3f} ms = {sum(gf.values()) / tot:.1f} TFLOP/s')
     print(f'{"layer":34s} {"ms":>8s} {"GFLOP":>9s} {"TFLOP/s":>9s} {"share":>6s}')

@@ -1,24 +1,33 @@
 // Halo-tile Conv3d (3x3x3, stride 1, pad 1) with the three depth taps merged into the MMA's N dimension, for
-// layers with few output channels (N tile = 32).
+// layers with few output channels (N tile = 32), optionally with the block's 1x1x1 shortcut conv fused in.
 //
 // Why: tcgen05.mma with both operands in shared memory reads 128 rows of A and N rows of B (32 bytes each) per
 // K=16 step; the shared-memory port moves 128 B/clk, so one step costs max(N/2, (128+N)/4) cycles
-// (tools/mma_rate.py on B200: N=32 44.7, N=64 50.2, N=128 64, N=256 128).  At N=32 the tensor pipe is therefore
-// busy 36 % of the time at best: the A operand is re-read for every 32 output channels.
+// (tools/mma_rate.py on B200: N=32 44.7, N=64 50.2, N=96 56.3, N=128 64, N=256 128).  At N=32 the tensor pipe is
+// therefore busy 36 % of the time at best: the A operand is re-read for every 32 output channels.
 //
 // Input slice z under depth tap kd contributes to output slice z-kd+1 AT THE SAME accumulator rows.  With the
 // accumulators of consecutive output slices in consecutive TMEM column blocks, ONE instruction of N = 3*32 = 96
 //     D[:, (z-1 .. z+1) * 32 ..] += A_z(tap kh,kw) x [W(kd=2); W(kd=1); W(kd=0)]^T
-// does the work of three, for one read of A: 57 cycles instead of 134.  Slices outside the CTA's depth block
+// does the work of three, for one read of A: 56 cycles instead of 134.  Slices outside the CTA's depth block
 // are dropped by shrinking N and offsetting the B descriptor by whole 32-row blocks; the first touch of an
 // accumulator block (output slice z+1 at input slice z) is one extra N=32 instruction without the accumulate flag.
 //
 // Loop order per tile (spatial tile x T=8 output slices x 32 channels): channel chunk -> input slice -> 9 taps.
 // The nine [3 kd][32][64] weight tiles of a chunk stay resident in shared memory (108 KB) while the T+2 input
 // patches stream through a TMA ring; every patch is multiplied exactly once.  Depth slices -1 and D are zero
-// padding and are skipped.  Two accumulator sets (2 x 8 x 32 = 512 TMEM columns): the epilogue of tile i
-// overlaps the MMAs of tile i+1, and runs on 8 warps (two per TMEM lane quarter, alternate slices) because at
-// this MMA rate the epilogue would otherwise set the pace.
+// padding and are skipped.
+//
+// Accumulator hand-off is per output slice: TMEM holds R slots of 32 columns, each with its own full/empty
+// mbarrier.  Slice o is complete after input slice o+1 of the last chunk, so the epilogue (8 warps: two per TMEM
+// lane quarter, alternate slices) drains it while later slices are still being multiplied, and frees the slot as
+// soon as the values are in registers.  R = 16 (two tiles in flight) without the shortcut; with it, R = 8 and the
+// other 256 columns hold the shortcut accumulators.
+//
+// Fused shortcut (SHORT): ResidualBlock3D's downsample branch bn_d(conv_d(x)) (submodules.py:244-247,259) is a
+// 1x1x1 conv of the SAME input, i.e. the centre tap's A operand times a second weight tile: one extra N=32
+// instruction per K step of the centre tap (+9 % tensor time) replaces a separate pass over the input
+// (1.5 GB of reads at 346x260).  The epilogue writes both outputs.
 //
 // Layers with 64 output channels run as two N tiles of 32 (112 cycles per three taps instead of 150).
 // Replaces the same reference calls as conv_halo.cuh (submodules.py:249-263).
@@ -32,11 +41,95 @@ constexpr int kKdmThreads = 384;      // warp 0 TMA patches, warp 1 weight tiles
 constexpr int kKdmBN = 32;
 constexpr int kKdmT = 8;
 constexpr int kKdmWTile = 3 * kKdmBN * kBlockK * 2;   // bytes of one (chunk, tap) weight tile: [3][32][64] bf16
+constexpr int kKdmSTile = kKdmBN * kBlockK * 2;       // bytes of one (chunk) shortcut weight tile: [32][64] bf16
+constexpr int kKdmWSlots = 10;                        // 9 taps + shortcut
+constexpr int kKdmBars = 2 * kMaxSA + 2 * kKdmWSlots + 32;
 
+// second output of the fused kernel (the block's shortcut branch)
+struct KdmShort {
+  const __nv_bfloat16* wpack;  // [Cout/32][ncc][32][64], rows pre-swizzled
+  const float* scale;          // folded BatchNorm of the shortcut (bias included in shift)
+  const float* shift;
+  __nv_bfloat16* out;          // (B,D,H,W,out_pitch)
+  int out_pitch;
+};
+
+// One 32-column accumulator chunk of one pixel row: y = act(acc*scale + shift (+ residual)) -> bf16 store (plain or
+// nearest-upsampled) or the fused prediction layer.  `v` holds the raw accumulators.
+struct KdmRow {
+  size_t pix, HWp;
+  int uh0, uh1, uw0, uw1;
+  bool ok;
+};
+
+__device__ __forceinline__ void kdm_store_chunk(const HaloArgs& a, const KdmRow& r, const uint32_t (&v)[32], const uint4 (&rv)[4],
+                                                const float* s_scale, const float* s_shift, int act, size_t plane, int n0,
+                                                __nv_bfloat16* out, int out_pitch, int cout, bool main_out) {
+  float yv[32];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const __nv_bfloat162* rp2 = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(rp2[j]);      // zeros when there is no residual
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int n = g * 8 + 2 * j + hh;
+        float tv = fmaf(__uint_as_float(v[n]), s_scale[n], s_shift[n]) + (hh ? f.y : f.x);
+        if (act == 1) tv = fmaxf(tv, 0.f);
+        else if (act == 2) tv = tv > 0.f ? tv : 0.01f * tv;
+        yv[n] = tv;
+      }
+    }
+  }
+  if (main_out && a.pred_w != nullptr) {
+    // fused prediction layer (see conv_halo.cuh): weights are FFMA constant-bank operands
+    float* dst = a.pred_out + plane * 20 * r.HWp + r.pix;
+#pragma unroll
+    for (int m0 = 0; m0 < 20; m0 += 4) {
+      float acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = c_pred[640 + m0 + u];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fmaf(yv[c], c_pred[(m0 + u) * 32 + c], acc[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dst[(size_t)(m0 + u) * r.HWp] = fmaxf(acc[u], 0.f);
+    }
+    return;
+  }
+  uint4 ov[4];
+  __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(ov);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) op[j] = __floats2bfloat162_rn(yv[2 * j], yv[2 * j + 1]);
+  if (main_out && a.up_H > 0) {
+    for (int hh = r.uh0; hh < r.uh1; ++hh)
+      for (int ww = r.uw0; ww < r.uw1; ++ww) {
+        uint4* d4 = reinterpret_cast<uint4*>(out + ((plane * a.up_H + hh) * a.up_W + ww) * out_pitch + n0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) d4[g] = ov[g];
+      }
+    return;
+  }
+  __nv_bfloat16* row = out + (plane * r.HWp + r.pix) * out_pitch;
+  uint4* d4 = reinterpret_cast<uint4*>(row + n0);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) d4[g] = ov[g];
+  if (n0 + 32 == cout) {
+    // zero the padding channels so later TMA reads see 0, not garbage
+    for (int c = cout; c < out_pitch; c += 8) *reinterpret_cast<uint4*>(row + c) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+template <bool SHORT>
 __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1,
-                                                                     const HaloArgs a) {
+                                                                     const HaloArgs a, const KdmShort sc) {
   constexpr int BN = kKdmBN, T = kKdmT;
+  constexpr int G = SHORT ? 1 : 2;                  // tiles whose accumulators fit in TMEM at once
+  constexpr uint32_t kShortCols = 256;              // shortcut accumulator of slot s: column 256 + 32 s
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -47,26 +140,27 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
   const int total_tiles = a.B * (a.D / T) * a.tiles_h * a.tiles_w * n_tiles;
   const int ncc = a.ncc0 + a.ncc1;
 
-  const uint32_t w_base = base;                                   // 9 resident weight tiles
-  const uint32_t a_base = base + 9u * kKdmWTile;                  // patch ring
+  const uint32_t w_base = base;                                   // 9 resident tap tiles + the shortcut tile
+  const uint32_t ws_base = base + 9u * kKdmWTile;
+  const uint32_t a_base = ws_base + kKdmSTile;                    // patch ring
   const uint32_t bar_base = a_base + (uint32_t)a.SA * a.a_stage_bytes;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (kMaxSA + s); };
   auto w_full = [&](int s) { return bar_base + 8u * (2 * kMaxSA + s); };
-  auto w_empty = [&](int s) { return bar_base + 8u * (2 * kMaxSA + 9 + s); };
-  auto tmem_full = [&](int s) { return bar_base + 8u * (2 * kMaxSA + 18 + s); };
-  auto tmem_empty = [&](int s) { return bar_base + 8u * (2 * kMaxSA + 20 + s); };
-  const int bar_bytes = (2 * kMaxSA + 22) * 8;
-  uint8_t* tail = smem + (bar_base - base) + bar_bytes;
+  auto w_empty = [&](int s) { return bar_base + 8u * (2 * kMaxSA + kKdmWSlots + s); };
+  auto s_full = [&](int s) { return bar_base + 8u * (2 * kMaxSA + 2 * kKdmWSlots + s); };
+  auto s_empty = [&](int s) { return bar_base + 8u * (2 * kMaxSA + 2 * kKdmWSlots + 16 + s); };
+  uint8_t* tail = smem + (bar_base - base) + kKdmBars * 8;
   volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(tail);
-  float* s_scale = reinterpret_cast<float*>(tail + 16);
+  float* s_scale = reinterpret_cast<float*>(tail + 16);           // main scale | main shift | shortcut scale | shortcut shift
   float* s_shift = s_scale + BN;
-  float* s_pred = s_shift + BN;                   // [20][32] weights + [20] bias (used when a.pred_w != nullptr)
+  float* s_scale2 = s_shift + BN;
+  float* s_shift2 = s_scale2 + BN;
 
   if (tid == 0) {
     for (int s = 0; s < a.SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < 9; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full(s), 1); mbar_init(tmem_empty(s), 256); }
+    for (int s = 0; s < kKdmWSlots; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int s = 0; s < 16; ++s) { mbar_init(s_full(s), 1); mbar_init(s_empty(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -107,7 +201,7 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    // ================= weight-tile producer: slot = tap, refilled once per (tile, chunk) =================
+    // ================= weight-tile producer: slot = tap (9 = shortcut), refilled once per (tile, chunk) =================
     uint32_t ph = 1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, a, T, n_tiles);
@@ -121,6 +215,14 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
           }
           __syncwarp();
         }
+        if (SHORT) {
+          mbar_wait(w_empty(9), ph, a.error_flag);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(w_full(9), (uint32_t)kKdmSTile);
+            bulk_copy_g2s(ws_base, sc.wpack + (size_t)(tc.n_tile * ncc + cc) * (kKdmSTile / 2), (uint32_t)kKdmSTile, w_full(9));
+          }
+          __syncwarp();
+        }
         ph ^= 1u;
       }
     }
@@ -129,27 +231,35 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
     int sa = 0, pa = 0;                             // patch ring position / parity
     uint32_t pw = 0;                                // parity of the weight slots for the current (tile, chunk)
     const uint32_t pw8 = (uint32_t)a.PW * 8u;       // one patch row of pixels in descriptor units (16 B)
+    const uint32_t idesc32 = make_idesc(BN);
     int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const TileCoord tc = decode_tile(tile, a, T, n_tiles);
       const int zl = z_lo(tc.d0), zh = z_hi(tc.d0);
-      const int ab = iter & 1, use = iter >> 1;
-      mbar_wait(tmem_empty(ab), (uint32_t)((use & 1) ^ 1), a.error_flag);     // epilogue has drained this accumulator set
-      tcgen05_fence_after();
-      const uint32_t acc_base = tmem_acc + (uint32_t)(ab * T * BN);
+      const int slot0 = (iter % G) * T;
+      const uint32_t par_empty = (uint32_t)(((iter / G) & 1) ^ 1);
+      const uint32_t acc_base = tmem_acc + (uint32_t)(slot0 * BN);
       for (int cc = 0; cc < ncc; ++cc) {
         // zero-padded channels (64-channel pitch of a 32-channel tensor) are not multiplied
         const int rem = (cc < a.ncc0) ? (a.real0 - cc * kBlockK) : (a.real1 - (cc - a.ncc0) * kBlockK);
         const int ks = rem >= kBlockK ? kBlockK / 16 : (rem + 15) / 16;
+        const bool last_cc = (cc == ncc - 1);
 #pragma unroll 1
         for (int z = zl; z <= zh; ++z) {
-          mbar_wait(a_full(sa), (uint32_t)pa, a.error_flag);
-          tcgen05_fence_after();
-          const uint32_t patch = a_base + (uint32_t)sa * a.a_stage_bytes;
           // output slices z-1+j, j = 0..2 (depth tap kd = 2-j), clipped to the block [d0, d0+T)
           const int jlo = (z - 1 >= tc.d0) ? 0 : (tc.d0 - z + 1);
           const int jhi = (z + 1 <= tc.d0 + T - 1) ? 2 : (tc.d0 + T - z);
-          const uint32_t col = acc_base + (uint32_t)((z - 1 + jlo - tc.d0) * BN);
+          const int o_lo = z - 1 + jlo - tc.d0;     // first covered slice, relative to the block
+          const bool first_z = (z == zl), last_z = (z == zh);
+          if (cc == 0) {
+            // slices this input touches first must have been drained by the epilogue (slot reuse)
+            const int f_lo = first_z ? o_lo : o_lo + (jhi - jlo), f_hi = (first_z || jhi == 2) ? o_lo + (jhi - jlo) : -1;
+            for (int o = f_lo; o <= f_hi; ++o) mbar_wait(s_empty(slot0 + o), par_empty, a.error_flag);
+          }
+          mbar_wait(a_full(sa), (uint32_t)pa, a.error_flag);
+          tcgen05_fence_after();
+          const uint32_t patch = a_base + (uint32_t)sa * a.a_stage_bytes;
+          const uint32_t col = acc_base + (uint32_t)(o_lo * BN);
           const uint32_t n_all = (uint32_t)((jhi - jlo + 1) * BN);
           const uint32_t idesc_all = make_idesc((int)n_all);
           // descriptor low words of (tap 0, k 0); a tap adds (kh*PW + kw) rows of 128 B to A and one weight tile to
@@ -157,7 +267,6 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
           // one N=96 instruction occupies the tensor pipe)
           const uint32_t a_lo = smem_desc_lo(patch);
           const uint32_t b_lo = smem_desc_lo(w_base + (uint32_t)jlo * (BN * 128));
-          const bool first_z = (z == zl), last_z = (z == zh);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             if (first_z) {
@@ -179,18 +288,35 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
                   const int j_old_hi = jhi < 1 ? jhi : 1;
                   const uint32_t n_old = (uint32_t)((j_old_hi - jlo + 1) * BN);
                   tcgen05_mma_bf16_lo(col, a_t, b_t, make_idesc((int)n_old), 1u);
-                  if (jhi == 2) tcgen05_mma_bf16_lo(col + n_old, a_t, b_t + n_old * 8u, make_idesc(BN), 0u);
+                  if (jhi == 2) tcgen05_mma_bf16_lo(col + n_old, a_t, b_t + n_old * 8u, idesc32, 0u);
                 }
               }
             }
+            if (SHORT && tap == 4 && z >= tc.d0 && z < tc.d0 + T) {
+              // shortcut conv of output slice z: centre tap of input slice z times the 1x1x1 weights
+              if (first_z || z == tc.d0) {           // first use of the shortcut tile in this chunk
+                mbar_wait(w_full(9), pw, a.error_flag);
+                tcgen05_fence_after();
+              }
+              const uint32_t scol = tmem_acc + kShortCols + (uint32_t)((slot0 + z - tc.d0) * BN);
+              const uint32_t bs_lo = smem_desc_lo(ws_base);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                if (k < ks) tcgen05_mma_bf16_lo(scol, a_t + 2 * k, bs_lo + 2 * k, idesc32, (cc != 0 || k != 0) ? 1u : 0u);
+            }
             if (last_z) tcgen05_commit_elect(w_empty(tap));     // last use of this chunk's tap tile
           }
+          if (SHORT && last_z) tcgen05_commit_elect(w_empty(9));
           tcgen05_commit_elect(a_empty(sa));
           if (++sa == a.SA) { sa = 0; pa ^= 1; }
+          if (last_cc) {
+            // output slice z-1 has received its last contribution; at the end of the depth range so has slice z
+            if (z - 1 >= tc.d0) tcgen05_commit_elect(s_full(slot0 + z - 1 - tc.d0));
+            if (last_z && z < tc.d0 + T) tcgen05_commit_elect(s_full(slot0 + z - tc.d0));
+          }
         }
         pw ^= 1u;
       }
-      tcgen05_commit_elect(tmem_full(ab));
     }
   } else if (warp >= 4) {
     // ================= epilogue (warps 4-11) =================
@@ -200,9 +326,7 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
     const int th = i / a.PW, tw = i % a.PW;
     const int etid = tid - 128;                   // 0..255 inside the epilogue group
     const float isg = a.inv_sigma ? __ldg(a.inv_sigma) : 1.f;
-    if (a.pred_w != nullptr) {
-      for (int j = etid; j < 660; j += 256) s_pred[j] = j < 640 ? __ldg(a.pred_w + j) : __ldg(a.pred_b + (j - 640));
-    }
+    const uint32_t lane_base = tmem_acc + ((uint32_t)(quarter * 32) << 16);
     int cur_n_tile = -1;
     int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -212,19 +336,70 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
         for (int j = etid; j < BN; j += 256) {
           s_scale[j] = __ldg(a.scale + tc.n_tile * BN + j) * isg;
           s_shift[j] = __ldg(a.shift + tc.n_tile * BN + j);
+          if (SHORT) {
+            s_scale2[j] = __ldg(sc.scale + tc.n_tile * BN + j);
+            s_shift2[j] = __ldg(sc.shift + tc.n_tile * BN + j);
+          }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         cur_n_tile = tc.n_tile;
       }
-      const int ab = iter & 1, use = iter >> 1;
-      mbar_wait(tmem_full(ab), (uint32_t)(use & 1), a.error_flag);
-      __syncwarp();
-      tcgen05_fence_after();
-      halo_epilogue_slices<BN>(a, tc, n_tiles, tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * T * BN), half, 2, T,
-                               th, tw, s_scale, s_shift, s_pred);
-      // this accumulator set may be overwritten by the MMAs of a later tile
-      tcgen05_fence_before();
-      mbar_arrive(tmem_empty(ab));
+      const int slot0 = (iter % G) * T;
+      const uint32_t par_full = (uint32_t)((iter / G) & 1);
+      const int h = tc.h0 + th, w = tc.w0 + tw;
+      KdmRow r;
+      r.ok = (th < a.TH) && (tw < a.TW) && (h < a.H) && (w < a.W);
+      r.pix = (size_t)h * a.W + w;
+      r.HWp = (size_t)a.H * a.W;
+      r.uh0 = r.uh1 = r.uw0 = r.uw1 = 0;
+      if (a.up_H > 0 && r.ok) {                   // destination rows/columns when the output is written nearest-upsampled
+        r.uh0 = (h * a.up_H + a.H - 1) / a.H;  r.uh1 = ((h + 1) * a.up_H + a.H - 1) / a.H;
+        r.uw0 = (w * a.up_W + a.W - 1) / a.W;  r.uw1 = ((w + 1) * a.up_W + a.W - 1) / a.W;
+      }
+      const size_t plane0 = (size_t)(tc.b * a.D + tc.d0);
+      const int n0 = tc.n_tile * BN;
+      const bool has_res = (a.residual != nullptr) && r.ok;
+      auto res_ptr = [&](int tt) {
+        return reinterpret_cast<const uint4*>(a.residual + ((plane0 + tt) * r.HWp + r.pix) * a.res_pitch + n0);
+      };
+      // the residual of the next slice is requested before the current one is processed
+      uint4 rv[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      if (has_res) {
+        const uint4* rp = res_ptr(half);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);
+      }
+#pragma unroll 1
+      for (int tt = half; tt < T; tt += 2) {
+        const int slot = slot0 + tt;
+        uint4 rn[4] = {rv[0], rv[1], rv[2], rv[3]};
+        if (has_res && tt + 2 < T) {
+          const uint4* rp = res_ptr(tt + 2);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) rn[g] = __ldg(rp + g);
+        }
+        mbar_wait(s_full(slot), par_full, a.error_flag);
+        __syncwarp();
+        tcgen05_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(lane_base + (uint32_t)(slot * BN), v);
+        tmem_ld_wait();
+        if (!SHORT) {                              // values are in registers: the slot may be overwritten
+          tcgen05_fence_before();
+          mbar_arrive(s_empty(slot));
+        }
+        if (r.ok) kdm_store_chunk(a, r, v, rv, s_scale, s_shift, a.act, plane0 + tt, n0, a.out, a.out_pitch, a.Cout, true);
+        if (SHORT) {
+          tmem_ld_32x32b_x32(lane_base + kShortCols + (uint32_t)(slot * BN), v);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          mbar_arrive(s_empty(slot));
+          const uint4 zero[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+          if (r.ok) kdm_store_chunk(a, r, v, zero, s_scale2, s_shift2, 0, plane0 + tt, n0, sc.out, sc.out_pitch, a.Cout, false);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) rv[g] = rn[g];
+      }
     }
   }
 
@@ -264,6 +439,29 @@ __global__ void pack_weights_kdm_kernel(const float* __restrict__ w, int Cout, i
   }
 }
 
+// fp32 (Cout, Cin_real) 1x1x1 weights -> bf16 [Cout/32][cc][32][64] (rows swizzled), same channel padding
+__global__ void pack_weights_kdm_short_kernel(const float* __restrict__ w, int Cout, int cin_real, int pad0, int real0, int pad1,
+                                              int real1, __nv_bfloat16* __restrict__ out) {
+  constexpr int BN = kKdmBN;
+  const int ncc = (pad0 + pad1) / kBlockK;
+  const size_t total = (size_t)Cout * ncc * kBlockK;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % 8);
+    const int qs = (int)((i / 8) % 8);
+    const int r = (int)((i / 64) % BN);
+    const size_t tile = i / ((size_t)64 * BN);   // n_tile*ncc + cc
+    const int cc = (int)(tile % ncc);
+    const int n_tile = (int)(tile / ncc);
+    const int q = qs ^ (r & 7);
+    const int p = cc * kBlockK + q * 8 + e;      // padded input channel
+    int c = -1;
+    if (p < pad0) { if (p < real0) c = p; }
+    else { const int p1 = p - pad0; if (p1 < real1) c = real0 + p1; }
+    const int n = n_tile * BN + r;
+    out[i] = __float2bfloat16_rn(c >= 0 ? w[(size_t)n * cin_real + c] : 0.f);
+  }
+}
+
 struct KdmPlan {
   TileShape ts;
   int SA, a_stage_bytes, box_bytes, smem_bytes;
@@ -277,26 +475,39 @@ inline KdmPlan plan_kdm(int D, int H, int W) {
   const int rows = p.ts.PW * (p.ts.TH + 2);
   p.box_bytes = rows * 128;
   p.a_stage_bytes = ((rows + 2 + 7) / 8) * 1024;
-  const int tail = (2 * kMaxSA + 22) * 8 + 16 + 2 * kKdmBN * 4 + 660 * 4;
-  const int budget = 227 * 1024 - 1024 - tail - 9 * kKdmWTile;
+  const int tail = kKdmBars * 8 + 16 + 4 * kKdmBN * 4;
+  const int budget = 227 * 1024 - 1024 - tail - 9 * kKdmWTile - kKdmSTile;
   p.SA = budget / p.a_stage_bytes;
   if (p.SA > kMaxSA) p.SA = kMaxSA;
   p.ok = (D % kKdmT == 0) && p.SA >= 3;
-  p.smem_bytes = 9 * kKdmWTile + p.SA * p.a_stage_bytes + tail + 1024;
+  p.smem_bytes = 9 * kKdmWTile + kKdmSTile + p.SA * p.a_stage_bytes + tail + 1024;
   return p;
 }
 
-inline int launch_halo_kdm(const CUtensorMap& tm0, const CUtensorMap& tm1, const HaloArgs& a, int smem_bytes, cudaStream_t s) {
-  static int configured = 0;
-  if (configured < smem_bytes) {
-    V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = smem_bytes;
+// `sc` != nullptr: also compute the block's 1x1x1 shortcut conv of the same input (second output)
+inline int launch_halo_kdm(const CUtensorMap& tm0, const CUtensorMap& tm1, const HaloArgs& a, const KdmShort* sc, int smem_bytes,
+                           cudaStream_t s) {
+  static int configured[2] = {0, 0};
+  const int which = sc ? 1 : 0;
+  if (configured[which] < smem_bytes) {
+    if (sc)
+      V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    else
+      V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured[which] = smem_bytes;
   }
   if (a.T != kKdmT || a.D % kKdmT != 0 || a.Cout % kKdmBN != 0)
     return set_error(V2CE_ERR_INVALID, "depth-merged halo kernel: depth %d / Cout %d not supported", a.D, a.Cout);
+  if (sc && (a.up_H > 0 || a.pred_w != nullptr || a.residual != nullptr))
+    return set_error(V2CE_ERR_INVALID, "depth-merged halo kernel: the fused shortcut goes with a plain first conv");
   const int total = a.B * (a.D / kKdmT) * a.tiles_h * a.tiles_w * (a.Cout / kKdmBN);
   const int grid = total < sm_count_cached() ? total : sm_count_cached();
-  conv_halo_kdm_kernel<<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, a);
+  if (sc) {
+    conv_halo_kdm_kernel<true><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, a, *sc);
+  } else {
+    KdmShort none{nullptr, nullptr, nullptr, nullptr, 0};
+    conv_halo_kdm_kernel<false><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, a, none);
+  }
   V2CE_LAUNCH_CHECK("conv_halo_kdm_kernel");
   return V2CE_OK;
 }

@@ -517,7 +517,8 @@ static int run_conv(v2ce_model* m, int li, const __nv_bfloat16* src0, int c0, in
 // halo-tile launch of layer `li` (3x3x3, stride 1); sources are full-resolution (B,D,H,W,pitch) tensors
 static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, const __nv_bfloat16* src1, int p1, int B, int D,
                     int H, int W, const __nv_bfloat16* residual, int res_pitch, int act, __nv_bfloat16* out, int out_pitch,
-                    cudaStream_t s, int up_H = 0, int up_W = 0, float* pred_out = nullptr) {
+                    cudaStream_t s, int up_H = 0, int up_W = 0, float* pred_out = nullptr, int short_li = -1,
+                    __nv_bfloat16* short_out = nullptr, int short_pitch = 0, bool* short_done = nullptr) {
   const LayerSpec& L = kLayers[li];
   const DevLayer& dl = m->layers[li];
   if (dl.cfg.kind != 2 || p0 != dl.cfg.pad0 || p1 != dl.cfg.pad1)
@@ -559,7 +560,18 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
   tm1 = tm0;
   if (src1)
     if (int e = get_tmap(m, src1, B, D, H, W, p1, a.PW, a.TH + 2, &tm1)) return e;
-  if (kdm) return halo::launch_halo_kdm(tm0, tm1, a, kplan.smem_bytes, s);
+  if (short_done) *short_done = false;
+  if (kdm) {
+    // fuse the block's 1x1x1 shortcut conv (layer short_li) when asked for and packed
+    static const bool fuse = !(getenv("V2CE_NO_FUSED_SHORTCUT") && atoi(getenv("V2CE_NO_FUSED_SHORTCUT")));
+    if (short_li >= 0 && fuse && m->layers[short_li].wpack_kdm != nullptr) {
+      const DevLayer& sl = m->layers[short_li];
+      halo::KdmShort sc{sl.wpack_kdm, sl.scale, sl.shift, short_out, short_pitch};
+      if (short_done) *short_done = true;
+      return halo::launch_halo_kdm(tm0, tm1, a, &sc, kplan.smem_bytes, s);
+    }
+    return halo::launch_halo_kdm(tm0, tm1, a, nullptr, kplan.smem_bytes, s);
+  }
   return halo::launch_halo(tm0, tm1, a, dl.bn_tile, plan.smem_bytes, s);
 }
 
@@ -586,6 +598,14 @@ static int pack_layer(v2ce_model* m, int li, const float* w_dev, cudaStream_t s)
       V2CE_LAUNCH_CHECK("pack_weights_kdm_kernel");
     }
     return V2CE_OK;
+  }
+  if (L.k == 1 && L.cout <= 64 && std::string(L.name).find("decoders") != std::string::npos) {
+    // the shortcut of a decoder block can ride in its conv1 launch (conv_halo_kdm.cuh): [Cout/32][cc][32][64]
+    const size_t ns = (size_t)L.cout * (c.pitch0 + c.pitch1);
+    if (int e = dev_alloc(m, &dl.wpack_kdm, ns)) return e;
+    halo::pack_weights_kdm_short_kernel<<<(int)((ns + 255) / 256), 256, 0, s>>>(w_dev, L.cout, L.cin, c.pitch0, c.real0,
+                                                                                c.pitch1, c.real1, dl.wpack_kdm);
+    V2CE_LAUNCH_CHECK("pack_weights_kdm_short_kernel");
   }
   dl.num_kb = (taps * cin_pad + conv::kBlockK - 1) / conv::kBlockK;
   const size_t n = (size_t)L.cout * dl.num_kb * conv::kBlockK;
@@ -824,10 +844,15 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
     const int sp = pitch_of(ch[lvl]), co = ch[lvl], tp = pitch_of(co);
     snprintf(name, sizeof(name), "UNet.decoders.%d.conv1", i);
     const int l1 = layer_index(name);
-    if (int e = run_halo(m, l1, up_cur, xc, skip, sp, B, D, d.H[lvl], d.W[lvl], nullptr, 0, 1, buf.tmp_t, tp, s)) return e;
+    bool short_done = false;
+    if (int e = run_halo(m, l1, up_cur, xc, skip, sp, B, D, d.H[lvl], d.W[lvl], nullptr, 0, 1, buf.tmp_t, tp, s, 0, 0, nullptr,
+                         l1 + 2, buf.tmp_r, co, &short_done)) return e;
     mark(kLayers[l1].name);
-    if (int e = run_conv(m, l1 + 2, up_cur, xc, d.H[lvl], d.W[lvl], skip, sp, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 0, buf.tmp_r, s)) return e;
-    mark(kLayers[l1 + 2].name);
+    if (!short_done) {
+      if (int e = run_conv(m, l1 + 2, up_cur, xc, d.H[lvl], d.W[lvl], skip, sp, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 0, buf.tmp_r, s)) return e;
+      mark(kLayers[l1 + 2].name);
+      ++launches;
+    }
     if (lvl > 0) {
       if (int e = run_halo(m, l1 + 1, buf.tmp_t, tp, nullptr, 0, B, D, d.H[lvl], d.W[lvl], buf.tmp_r, co, 1, up_next, co, s,
                            d.H[lvl - 1], d.W[lvl - 1])) return e;
@@ -838,7 +863,7 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
     mark(kLayers[l1 + 1].name);
     __nv_bfloat16* tsw = up_cur; up_cur = up_next; up_next = tsw;
     xc = co;
-    launches += 3;
+    launches += 2;
   }
   m->last_launches = launches;
   return V2CE_OK;
@@ -908,7 +933,8 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
   V2CE_REQUIRE((src1_dev != nullptr) == (c1 > 0), "src1 and c1 must agree");
   const int bn = conv::pick_bn(cout);
   V2CE_REQUIRE(bn != 0, "cout must be a multiple of 32");
-  if (impl == 2) V2CE_REQUIRE(cout <= 64 && halo::plan_kdm(depth, hin, win).ok, "depth-merged halo kernel: Cout <= 64, depth % 8 == 0");
+  if (impl >= 2) V2CE_REQUIRE(cout <= 64 && halo::plan_kdm(depth, hin, win).ok, "depth-merged halo kernel: Cout <= 64, depth % 8 == 0");
+  if (impl == 3) V2CE_REQUIRE(residual_dev != nullptr, "impl 3: residual_dev receives the fused shortcut output");
   if (impl >= 1)
     V2CE_REQUIRE(ksize == 3 && stride_hw == 1 && h0 == hin && w0 == win && c0 % 64 == 0 && c1 % 64 == 0,
                  "halo kernel: 3x3x3, stride 1, no upsample, channel pitches multiple of 64");
@@ -916,7 +942,7 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
   const int cin = c0 + c1, taps = ksize * ksize * ksize;
   const int num_kb = (taps * cin + conv::kBlockK - 1) / conv::kBlockK;
   float *w_dev = nullptr, *scale_dev = nullptr, *shift_dev = nullptr;
-  __nv_bfloat16* wpack = nullptr;
+  __nv_bfloat16 *wpack = nullptr, *wshort = nullptr;
   int* flag = nullptr;
   const size_t wn = (size_t)cout * cin * taps, pn = (size_t)cout * num_kb * conv::kBlockK;
   V2CE_CUDA_CHECK(cudaMalloc(&w_dev, wn * sizeof(float)));
@@ -931,7 +957,7 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
   const int pgrid = (int)((pn + 255) / 256 > 4096 ? 4096 : (pn + 255) / 256);
   if (impl == 1)
     halo::pack_weights_halo_kernel<<<pgrid, 256, 0, s>>>(w_dev, cout, cin, bn, c0, c0, c1, c1, wpack);
-  else if (impl == 2)
+  else if (impl >= 2)
     halo::pack_weights_kdm_kernel<<<pgrid, 256, 0, s>>>(w_dev, cout, cin, c0, c0, c1, c1, wpack);
   else
     conv::pack_weights_kernel<<<pgrid, 256, 0, s>>>(w_dev, cout, cin, taps, bn, num_kb, c0, c0, c1, c1, wpack);
@@ -951,8 +977,8 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
     a.Cout = cout; a.out_pitch = cout; a.res_pitch = cout;
     a.T = plan.T; a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
     a.wpack = wpack; a.scale = scale_dev; a.shift = shift_dev; a.inv_sigma = nullptr;
-    if (impl == 2) { a.T = halo::kKdmT; a.SA = kplan.SA; a.SB = 9; }
-    a.residual = static_cast<const __nv_bfloat16*>(residual_dev);
+    if (impl >= 2) { a.T = halo::kKdmT; a.SA = kplan.SA; a.SB = 9; }
+    a.residual = impl == 3 ? nullptr : static_cast<const __nv_bfloat16*>(residual_dev);
     a.out = static_cast<__nv_bfloat16*>(out_dev);
     a.act = act; a.error_flag = flag;
     a.up_H = 0; a.up_W = 0; a.pred_w = nullptr; a.pred_b = nullptr; a.pred_out = nullptr;
@@ -960,8 +986,27 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
     rc = halo::make_patch_map(&tm0, src0_dev, batch, depth, hin, win, c0, a.PW, a.TH + 2);
     tm1 = tm0;
     if (rc == V2CE_OK && src1_dev) rc = halo::make_patch_map(&tm1, src1_dev, batch, depth, hin, win, c1, a.PW, a.TH + 2);
-    if (rc == V2CE_OK) rc = impl == 2 ? halo::launch_halo_kdm(tm0, tm1, a, kplan.smem_bytes, s)
-                                      : halo::launch_halo(tm0, tm1, a, bn, plan.smem_bytes, s);
+    if (rc == V2CE_OK && impl == 3) {
+      // fused shortcut: 1x1x1 weights = centre tap of `weight`, same scale/shift, no activation -> residual_dev
+      std::vector<float> wd((size_t)cout * cin);
+      for (size_t i = 0; i < wd.size(); ++i) wd[i] = weight_host[i * 27 + 13];
+      float* wd_dev = nullptr;
+      if (cudaMalloc(&wd_dev, wd.size() * sizeof(float)) != cudaSuccess ||
+          cudaMalloc(&wshort, wd.size() * sizeof(__nv_bfloat16)) != cudaSuccess)
+        rc = set_error(V2CE_ERR_CUDA, "cudaMalloc failed");
+      if (rc == V2CE_OK) {
+        cudaMemcpyAsync(wd_dev, wd.data(), wd.size() * sizeof(float), cudaMemcpyHostToDevice, s);
+        halo::pack_weights_kdm_short_kernel<<<(int)((wd.size() + 255) / 256), 256, 0, s>>>(wd_dev, cout, cin, c0, c0, c1, c1, wshort);
+        cudaStreamSynchronize(s);
+        halo::KdmShort sc{wshort, scale_dev, shift_dev, static_cast<__nv_bfloat16*>(const_cast<void*>(residual_dev)), cout};
+        rc = halo::launch_halo_kdm(tm0, tm1, a, &sc, kplan.smem_bytes, s);
+      }
+      cudaStreamSynchronize(s);
+      cudaFree(wd_dev);
+    } else if (rc == V2CE_OK) {
+      rc = impl == 2 ? halo::launch_halo_kdm(tm0, tm1, a, nullptr, kplan.smem_bytes, s)
+                     : halo::launch_halo(tm0, tm1, a, bn, plan.smem_bytes, s);
+    }
   } else if (rc == V2CE_OK) {
     ConvArgs a;
     a.src0 = static_cast<const __nv_bfloat16*>(src0_dev);
@@ -981,7 +1026,7 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
   cudaError_t se = cudaStreamSynchronize(s);
   int hflag = 0;
   if (se == cudaSuccess) cudaMemcpy(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost);
-  cudaFree(w_dev); cudaFree(scale_dev); cudaFree(shift_dev); cudaFree(wpack); cudaFree(flag);
+  cudaFree(w_dev); cudaFree(scale_dev); cudaFree(shift_dev); cudaFree(wpack); cudaFree(wshort); cudaFree(flag);
   if (rc != V2CE_OK) return rc;
   if (se != cudaSuccess) return set_error(V2CE_ERR_CUDA, "conv3d_bf16 failed: %s", cudaGetErrorString(se));
   if (hflag) return set_error(V2CE_ERR_CUDA, "conv pipeline watchdog fired");
