@@ -74,19 +74,21 @@ constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
 // ------------------------------------------------------------------------------------------
 // head: Conv3d(2->32, k3, p1, bias) + LeakyReLU(0.01), fp32 in (B,L,2,H,W) -> bf16 NDHWC (pitch 64)
 // ------------------------------------------------------------------------------------------
-// One thread = 4 consecutive output pixels of a row x 32 channels: every 16-byte weight read from shared
-// memory feeds 16 FMAs (with 1 pixel per thread the kernel was LDS bound at 3x its FP32 floor).
-__global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                         const float* __restrict__ bias, int B, int D, int H, int W,
+// One thread = 4 consecutive output pixels of a row x 32 channels (128 accumulators).  The weights are FFMA
+// constant-bank operands: with shared-memory weights the kernel ran at 36 % of its FP32 floor (two LDS.128 per
+// 32 FMAs at 2 warps per scheduler).
+__constant__ float c_head_w[27 * 2 * 32];     // [tap][cin][cout]
+__constant__ float c_head_b[32];
+
+__global__ void pack_head_kernel(const float* __restrict__ w, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 27 * 2 * 32) return;
+  const int n = i % 32, ci = (i / 32) % 2, tap = i / 64;
+  out[i] = w[((size_t)n * 2 + ci) * 27 + tap];
+}
+
+__global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ x, int B, int D, int H, int W,
                                                          __nv_bfloat16* __restrict__ out) {
-  __shared__ __align__(16) float sw[27 * 2 * 32];     // [tap][cin][cout]
-  __shared__ __align__(16) float sb[32];
-  for (int i = threadIdx.x; i < 27 * 2 * 32; i += blockDim.x) {
-    const int n = i % 32, ci = (i / 32) % 2, tap = i / 64;
-    sw[i] = w[((size_t)n * 2 + ci) * 27 + tap];
-  }
-  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
   const int G = (W + 3) / 4;
   const long long total = (long long)B * D * H * G;
   const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,42 +99,34 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict_
   t /= H;
   const int d = (int)(t % D);
   const int b = (int)(t / D);
-  float4 acc[4][8];
+  float acc[4][32];
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int n = 0; n < 8; ++n) acc[p][n] = reinterpret_cast<const float4*>(sb)[n];
+    for (int n = 0; n < 32; ++n) acc[p][n] = c_head_b[n];
   const size_t HW = (size_t)H * W;
-  for (int kd = 0; kd < 3; ++kd) {
-    const int di = d + kd - 1;
-    if (di < 0 || di >= D) continue;
-    for (int kh = 0; kh < 3; ++kh) {
-      const int hi = ho + kh - 1;
-      if (hi < 0 || hi >= H) continue;
-      const float* r0 = x + ((size_t)(b * D + di) * 2) * HW + (size_t)hi * W;
-      float xa[6], xb[6];
+#pragma unroll 1
+  for (int kdh = 0; kdh < 9; ++kdh) {
+    const int kd = kdh / 3, kh = kdh - kd * 3;
+    const int di = d + kd - 1, hi = ho + kh - 1;
+    if (di < 0 || di >= D || hi < 0 || hi >= H) continue;
+    const float* r0 = x + ((size_t)(b * D + di) * 2) * HW + (size_t)hi * W;
+    float xa[6], xb[6];
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        const int wi = w0 - 1 + j;
-        const bool ok = wi >= 0 && wi < W;
-        xa[j] = ok ? __ldg(r0 + wi) : 0.f;
-        xb[j] = ok ? __ldg(r0 + HW + wi) : 0.f;
-      }
+    for (int j = 0; j < 6; ++j) {
+      const int wi = w0 - 1 + j;
+      const bool ok = wi >= 0 && wi < W;
+      xa[j] = ok ? __ldg(r0 + wi) : 0.f;
+      xb[j] = ok ? __ldg(r0 + HW + wi) : 0.f;
+    }
+    const float* wt = c_head_w + kdh * (3 * 64);
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const float4* wt = reinterpret_cast<const float4*>(sw + ((kd * 3 + kh) * 3 + kw) * 64);
+    for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-          const float4 wa = wt[n], wb = wt[8 + n];
+      for (int n = 0; n < 32; ++n) {
+        const float wa = wt[kw * 64 + n], wb = wt[kw * 64 + 32 + n];
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float x0 = xa[p + kw], x1 = xb[p + kw];
-            acc[p][n].x = fmaf(x0, wa.x, fmaf(x1, wb.x, acc[p][n].x));
-            acc[p][n].y = fmaf(x0, wa.y, fmaf(x1, wb.y, acc[p][n].y));
-            acc[p][n].z = fmaf(x0, wa.z, fmaf(x1, wb.z, acc[p][n].z));
-            acc[p][n].w = fmaf(x0, wa.w, fmaf(x1, wb.w, acc[p][n].w));
-          }
-        }
+        for (int p = 0; p < 4; ++p) acc[p][n] = fmaf(xa[p + kw], wa, fmaf(xb[p + kw], wb, acc[p][n]));
       }
     }
   }
@@ -143,14 +137,11 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict_
     uint4 o[4];
     __nv_bfloat162* op = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 v = acc[p][i];
-      v.x = v.x > 0.f ? v.x : 0.01f * v.x;
-      v.y = v.y > 0.f ? v.y : 0.01f * v.y;
-      v.z = v.z > 0.f ? v.z : 0.01f * v.z;
-      v.w = v.w > 0.f ? v.w : 0.01f * v.w;
-      op[2 * i] = __floats2bfloat162_rn(v.x, v.y);
-      op[2 * i + 1] = __floats2bfloat162_rn(v.z, v.w);
+    for (int i = 0; i < 16; ++i) {
+      float v0 = acc[p][2 * i], v1 = acc[p][2 * i + 1];
+      v0 = v0 > 0.f ? v0 : 0.01f * v0;
+      v1 = v1 > 0.f ? v1 : 0.01f * v1;
+      op[i] = __floats2bfloat162_rn(v0, v1);
     }
     uint4* dst = reinterpret_cast<uint4*>(out + (m0 + p) * 64);   // 64-channel pitch, upper half zero (TMA rows)
 #pragma unroll
@@ -332,6 +323,7 @@ struct v2ce_model {
   v2ce::unet::SnDesc sn_descs_host[v2ce::unet::kNumSn];
   float* sigma_dev = nullptr;
   float* inv_sigma_dev = nullptr;
+  float* head_wpack = nullptr;          // head weights as [tap][cin][cout] (constant-memory image)
   int* error_flag_dev = nullptr;
   int max_rows = 0, max_k = 0;
   int64_t calls = 0;
@@ -694,6 +686,11 @@ extern "C" int v2ce_model_finalize(v2ce_model* m) {
     const bool direct = (li == 0 || li == kNumLayers - 1);   // head and pred run on CUDA cores in fp32
     if (direct) {
       if (int e = upload(m, &dl.bias, *bias)) return e;
+      if (li == 0) {
+        if (int e = dev_alloc(m, &m->head_wpack, (size_t)27 * 2 * 32)) return e;
+        pack_head_kernel<<<(27 * 2 * 32 + 255) / 256, 256, 0, s>>>(dl.w32, m->head_wpack);
+        V2CE_LAUNCH_CHECK("pack_head_kernel");
+      }
       continue;
     }
     // eval-mode BatchNorm folded into y = acc*scale + shift (scale *= 1/sigma at run time for SN convs)
@@ -789,7 +786,14 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
   const long long M0 = d.M[0];
   {
     const long long groups = (long long)B * D * H * ((W + 3) / 4);
-    head_conv_kernel<<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, m->layers[0].w32, m->layers[0].bias, B, D, H, W, buf.head);
+    // constant memory is per device, not per handle: reload when another handle ran last (stream ordered)
+    static unsigned long long head_owner[64] = {0};
+    if (head_owner[m->device & 63] != m->uid) {
+      V2CE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_head_w, m->head_wpack, sizeof(float) * 27 * 2 * 32, 0, cudaMemcpyDeviceToDevice, s));
+      V2CE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_head_b, m->layers[0].bias, sizeof(float) * 32, 0, cudaMemcpyDeviceToDevice, s));
+      head_owner[m->device & 63] = m->uid;
+    }
+    head_conv_kernel<<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, B, D, H, W, buf.head);
   }
   V2CE_LAUNCH_CHECK("head_conv_kernel");
   ++launches;
