@@ -303,6 +303,29 @@ __device__ __forceinline__ Elem make_elem(long long ts, bool is_nan, long long b
                 (unsigned long long)pix);
 }
 
+// y_relocate one bin at a time (same operations as relocate_pixel): the emit pass walks the bins with a
+// three-bin window (the slope needs the counts of both neighbours) instead of holding all 9 x V counts and
+// debts in registers.  Fully unrolled over bins the kernel was 18 k instructions at 190 registers: one block
+// per SM, most stall samples on instruction fetch (ncu, profiles/).
+__device__ __forceinline__ void relocate_step(float y, float y_last, bool last_bin, float eps6, float& debt, int& n, float& tend) {
+  const float x = __fsub_rn(y, debt);
+  const float nc = ceilf(__fsub_rn(x, eps6));
+  debt = __fsub_rn(nc, x);
+  n = __float2int_rz(nc);
+  tend = debt;
+  if (last_bin) n += __float2int_rz(__fsub_rn(y_last, debt));     // `.int()` truncation, LDATI.py:106
+}
+
+template <int V>
+__device__ __forceinline__ void load_bin(const float* __restrict__ plane0, int HW, int pix, int c, float (&y)[V]) {
+  if (V == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(plane0 + (size_t)c * HW + pix));
+    y[0] = t.x; y[1 % V] = t.y; y[2 % V] = t.z; y[3 % V] = t.w;
+  } else {
+    y[0] = __ldg(plane0 + (size_t)c * HW + pix);
+  }
+}
+
 template <int V, typename Elem>
 __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict__ vox, DevParams P,
                                                          const int32_t* __restrict__ block_base,
@@ -312,99 +335,135 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
                                                          int32_t* __restrict__ status) {
   const int blk = blockIdx.x, p = blockIdx.y, f = blockIdx.z;
   const int pix0 = (blk * kThreads + threadIdx.x) * V;
-  int n[V][kBins];
-  float tend[V][kBins];
-  int tot[kQ];
-#pragma unroll
-  for (int q = 0; q < kQ; ++q) tot[q] = 0;
   const bool active = pix0 < P.HW;
-  if (active) {
-    float y[V][10];
-    load_pixels<V>(vox + ((size_t)(f * 2 + p) * 10) * P.HW, P.HW, pix0, y);
+  const float* plane0 = vox + ((size_t)(f * 2 + p) * 10) * P.HW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- pass A: per-warp totals of the 18 quantities (singles / multi-event totals per bin) ----
+  __shared__ int wtot[kThreads / 32][kQ];
+  {
+    int tot[kQ];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      relocate_pixel(y[v], P.eps6, n[v], tend[v]);
+    for (int q = 0; q < kQ; ++q) tot[q] = 0;
+    if (active) {
+      float y[V][10];
+      load_pixels<V>(plane0, P.HW, pix0, y);
 #pragma unroll
-      for (int c = 0; c < kBins; ++c) {
-        tot[c] += (n[v][c] == 1);
-        tot[kBins + c] += (n[v][c] >= 2) ? n[v][c] : 0;
+      for (int v = 0; v < V; ++v) {
+        int n[kBins];
+        float tend[kBins];
+        relocate_pixel(y[v], P.eps6, n, tend);
+#pragma unroll
+        for (int c = 0; c < kBins; ++c) {
+          tot[c] += (n[c] == 1);
+          tot[kBins + c] += (n[c] >= 2) ? n[c] : 0;
+        }
       }
     }
-  }
-  // block-exclusive scan of the 18 per-thread totals
-  __shared__ int wtot[kThreads / 32][kQ];
-  int excl[kQ];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int q = 0; q < kQ; ++q) {
-    int inc = warp_incl_scan(tot[q]);
-    excl[q] = inc - tot[q];
-    if (lane == 31) wtot[warp][q] = inc;
+    for (int q = 0; q < kQ; ++q) {
+      int v = tot[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) wtot[warp][q] = v;
+    }
   }
   __syncthreads();
-  if (!active) return;
+  // ---- pass B: bins in order, three-bin window of counts; voxels re-read (L1/L2 hits) ----
   const int pol = 1 - p;                         // p-index 0 = positive plane -> polarity 1
   const int grp = (p == 1) ? 0 : 2;              // negative plane is emitted first
   const size_t bb = (((size_t)f * 2 + p) * P.NB + blk) * kQ;
   const unsigned long long frame = (unsigned long long)(P.frame_base + f);
+  float debt[V], tend_cur[V], tend_next[V], y9[V];
+  int n_prev[V], n_cur[V], n_next[V];
 #pragma unroll
-  for (int c = 0; c < kBins; ++c) {
-    int ws = 0, wm = 0;
-    for (int w = 0; w < warp; ++w) { ws += wtot[w][c]; wm += wtot[w][kBins + c]; }
-    const int32_t* gb = group_base + ((size_t)f * kBins + c) * 4;
-    const long long seg = seg_start[(size_t)f * kBins + c];
-    long long slot_s = seg + gb[grp] + block_base[bb + c] + ws + excl[c];
-    long long slot_m = seg + gb[grp + 1] + block_base[bb + kBins + c] + wm + excl[kBins + c];
-    const long long bin_base = P.bin_base[c];
-    const float bstart = P.binstart[c];
+  for (int v = 0; v < V; ++v) { debt[v] = 0.f; n_prev[v] = n_cur[v] = n_next[v] = 0; tend_cur[v] = tend_next[v] = 0.f; y9[v] = 0.f; }
+  if (active) {
+    float y0[V], y1[V];
+    load_bin<V>(plane0, P.HW, pix0, 0, y0);
+    load_bin<V>(plane0, P.HW, pix0, 1, y1);
+    load_bin<V>(plane0, P.HW, pix0, 9, y9);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const int nc = n[v][c];
-      const int pix = pix0 + v;
-      if (nc == 1) {
-        // single event (LDATI.py:156-165): float64 path
-        double t = (double)tend[v][c];
-        t = P.true_div ? __ddiv_rn(__ddiv_rn(t, P.fps64), P.nbins64)
-                       : __dmul_rn(__dmul_rn(t, P.r_fps64), P.r_nbins64);
-        t = __dadd_rn(t, (double)bstart);
-        t = __dmul_rn(t, 1e6);
-        const long long ts = (long long)t;
-        elems[slot_s++] = make_elem<Elem>(ts, false, bin_base, pol, pix, P.pix_bits, P.key_bits, status);
-      } else if (nc >= 2) {
-        // slope-distributed events (LDATI.py:184-196,209-212): float32 path
-        float S = 0.f;
-        if (c > 0 && c < kBins - 1) S = __fsub_rn((float)n[v][c + 1 < kBins ? c + 1 : c], (float)n[v][c > 0 ? c - 1 : c]);
-        const float num = __fsub_rn(__fmul_rn(3.f, S), 0.f);
-        float kk = P.true_div ? __fdiv_rn(__fdiv_rn(num, P.six32), P.vs2_32)
-                              : __fmul_rn(__fmul_rn(num, P.r6_32), P.r_vs2_32);
-        kk = __fdiv_rn(kk, __fadd_rn((float)nc, P.eps8));
-        const float b = __fsub_rn(P.inv_vs32, __fmul_rn(__fmul_rn(P.vs32, kk), 0.5f));
-        const float bb2 = __fmul_rn(b, b);
-        const float k2 = __fmul_rn(2.f, kk);
-        const unsigned long long idx = ((frame * 2ull + (unsigned)p) * 9ull + (unsigned)c) * (unsigned long long)P.HW + (unsigned)pix;
-        for (int j = 0; j < nc; ++j) {
-          float u;
-          if (draws != nullptr) {
-            const size_t di = ((((size_t)f * 2 + p) * kBins + c) * P.HW + pix) * (size_t)P.draws_m + j;
-            u = (j < P.draws_m) ? __ldg(draws + di) : 0.f;
-          } else {
-            u = philox_uniform(idx, (unsigned)j, P.seed);
+      relocate_step(y0[v], 0.f, false, P.eps6, debt[v], n_cur[v], tend_cur[v]);
+      relocate_step(y1[v], 0.f, false, P.eps6, debt[v], n_next[v], tend_next[v]);
+    }
+  }
+#pragma unroll 1
+  for (int c = 0; c < kBins; ++c) {
+    // slots: [segment start] + [group base] + [blocks before] + [warps before] + [lanes before]
+    int ts1 = 0, tsm = 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) { ts1 += (n_cur[v] == 1); tsm += (n_cur[v] >= 2) ? n_cur[v] : 0; }
+    const int ex1 = warp_incl_scan(ts1) - ts1, exm = warp_incl_scan(tsm) - tsm;
+    int ws = 0, wm = 0;
+    for (int w = 0; w < warp; ++w) { ws += wtot[w][c]; wm += wtot[w][kBins + c]; }
+    if (active) {
+      const int32_t* gb = group_base + ((size_t)f * kBins + c) * 4;
+      const long long seg = seg_start[(size_t)f * kBins + c];
+      long long slot_s = seg + gb[grp] + block_base[bb + c] + ws + ex1;
+      long long slot_m = seg + gb[grp + 1] + block_base[bb + kBins + c] + wm + exm;
+      const long long bin_base = P.bin_base[c];
+      const float bstart = P.binstart[c];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int nc = n_cur[v];
+        const int pix = pix0 + v;
+        if (nc == 1) {
+          // single event (LDATI.py:156-165): float64 path
+          double t = (double)tend_cur[v];
+          t = P.true_div ? __ddiv_rn(__ddiv_rn(t, P.fps64), P.nbins64)
+                         : __dmul_rn(__dmul_rn(t, P.r_fps64), P.r_nbins64);
+          t = __dadd_rn(t, (double)bstart);
+          t = __dmul_rn(t, 1e6);
+          const long long ts = (long long)t;
+          elems[slot_s++] = make_elem<Elem>(ts, false, bin_base, pol, pix, P.pix_bits, P.key_bits, status);
+        } else if (nc >= 2) {
+          // slope-distributed events (LDATI.py:184-196,209-212): float32 path
+          float S = 0.f;
+          if (c > 0 && c < kBins - 1) S = __fsub_rn((float)n_next[v], (float)n_prev[v]);
+          const float num = __fsub_rn(__fmul_rn(3.f, S), 0.f);
+          float kk = P.true_div ? __fdiv_rn(__fdiv_rn(num, P.six32), P.vs2_32)
+                                : __fmul_rn(__fmul_rn(num, P.r6_32), P.r_vs2_32);
+          kk = __fdiv_rn(kk, __fadd_rn((float)nc, P.eps8));
+          const float b = __fsub_rn(P.inv_vs32, __fmul_rn(__fmul_rn(P.vs32, kk), 0.5f));
+          const float bb2 = __fmul_rn(b, b);
+          const float k2 = __fmul_rn(2.f, kk);
+          const unsigned long long idx = ((frame * 2ull + (unsigned)p) * 9ull + (unsigned)c) * (unsigned long long)P.HW + (unsigned)pix;
+#pragma unroll 1
+          for (int j = 0; j < nc; ++j) {
+            float u;
+            if (draws != nullptr) {
+              const size_t di = ((((size_t)f * 2 + p) * kBins + c) * P.HW + pix) * (size_t)P.draws_m + j;
+              u = (j < P.draws_m) ? __ldg(draws + di) : 0.f;
+            } else {
+              u = philox_uniform(idx, (unsigned)j, P.seed);
+            }
+            float t;
+            if (kk == 0.f) {
+              t = P.true_div ? __fdiv_rn(__fdiv_rn(u, P.fps32), P.nbins32)
+                             : __fmul_rn(__fmul_rn(u, P.r_fps32), P.r_nbins32);
+            } else {
+              const float disc = __fadd_rn(bb2, __fmul_rn(k2, u));
+              t = __fdiv_rn(__fadd_rn(-b, __fsqrt_rn(disc)), kk);
+            }
+            t = __fadd_rn(t, bstart);
+            t = __fmul_rn(t, 1e6f);
+            const bool is_nan = (t != t);
+            const long long ts = is_nan ? P.nan_ts : (long long)t;
+            elems[slot_m++] = make_elem<Elem>(ts, is_nan, bin_base, pol, pix, P.pix_bits, P.key_bits, status);
           }
-          float t;
-          if (kk == 0.f) {
-            t = P.true_div ? __fdiv_rn(__fdiv_rn(u, P.fps32), P.nbins32)
-                           : __fmul_rn(__fmul_rn(u, P.r_fps32), P.r_nbins32);
-          } else {
-            const float disc = __fadd_rn(bb2, __fmul_rn(k2, u));
-            t = __fdiv_rn(__fadd_rn(-b, __fsqrt_rn(disc)), kk);
-          }
-          t = __fadd_rn(t, bstart);
-          t = __fmul_rn(t, 1e6f);
-          const bool is_nan = (t != t);
-          const long long ts = is_nan ? P.nan_ts : (long long)t;
-          elems[slot_m++] = make_elem<Elem>(ts, is_nan, bin_base, pol, pix, P.pix_bits, P.key_bits, status);
         }
       }
+    }
+    // advance the window: bin c+2 becomes `next`
+#pragma unroll
+    for (int v = 0; v < V; ++v) { n_prev[v] = n_cur[v]; n_cur[v] = n_next[v]; tend_cur[v] = tend_next[v]; n_next[v] = 0; }
+    if (active && c + 2 < kBins) {
+      float yn[V];
+      load_bin<V>(plane0, P.HW, pix0, c + 2, yn);
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        relocate_step(yn[v], y9[v], c + 2 == kBins - 1, P.eps6, debt[v], n_next[v], tend_next[v]);
     }
   }
 }
