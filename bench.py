@@ -40,6 +40,12 @@ N_FRAMES = 321
 BATCH = 4
 GFLOP_PER_WINDOW = 2169.336
 METRIC = '346x260 frame-pairs/s (center, 321 frames, batch 4, voxel+LDATI+event-frame)'
+# dram__bytes_read.sum + dram__bytes_write.sum of one V2ce3d forward (batch 4), summed over its launches from the
+# ncu --set full capture summarised in profiles/ (None until that capture exists for the current kernels)
+TRAFFIC_BYTES = None
+KERNEL_NOTE = ('V2ce3d forward (29 launches): conv_halo_kdm_kernel x6 (N<=64, two with the fused shortcut), '
+               'conv_halo_kernel x14, conv_igemm_kernel x12 (stride-2 convs, remaining 1x1x1 shortcuts), head conv, '
+               '4 spectral-norm launches on a side stream')
 
 
 def peaks():
@@ -165,82 +171,45 @@ def run_reference_arm(args, rank, world):
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 class Runner:
+    """Model + two BatchRunners (v2ce_toolbox_b200.runner): device-resident inputs / results for `value`,
+    pinned host inputs and host results for `e2e`."""
+
     def __init__(self, device, units_host, rank, world):
         from oracle import synth
-        from v2ce_toolbox_b200 import event_frames, ldati
+        from v2ce_toolbox_b200.runner import BatchRunner
         from v2ce_toolbox_b200.scripts.v2ce_3d import V2ce3d
-        self.ef = event_frames
-        self.ldati = ldati
         self.device = device
         self.rank, self.world = rank, world
         self.model = V2ce3d()
         self.model.load_state_dict(synth.make_state_dict(0, 'reference'))
         self.model.eval().to(device)
-        self.eng = ldati.engine_for(device)
-        from v2ce_toolbox_b200.runner import BatchRunner
-        self.batch_runner = BatchRunner(self.model, device, fps=30, seed=0)
+        self.dev_runner = BatchRunner(self.model, device, fps=30, seed=0, copy_out=False)
+        self.host_runner = BatchRunner(self.model, device, fps=30, seed=0, copy_out=True)
+        self.dev_runner.time_forward = True
         self.units_pinned = [units_host[i:i + BATCH].contiguous().pin_memory() for i in range(0, 20, BATCH)]
         self.units_dev = [u.to(device) for u in self.units_pinned]
         self.n_pairs = BATCH * L
-        self.offs = [torch.tensor([int((b * self.n_pairs + i) * 1 / 30 * 1e6) for i in range(self.n_pairs)],
-                                  dtype=torch.int64, device=device) for b in range(5)]
-        self.fwd_events = []
-        self.events_total = 0
-        self.launches = 0
-        self.ev_host = None
-        self.fr_host = torch.empty((self.n_pairs, H, W, 3), dtype=torch.uint8).pin_memory()
-        self.d2h_bytes = 0
-        self.h2d_bytes = 0
 
-    def step(self, i, host_io, timed=False):
-        b = i % 5
-        if host_io:
-            x = self.units_pinned[b].to(self.device, non_blocking=True)
-            self.h2d_bytes = x.numel() * 4
-        else:
-            x = self.units_dev[b]
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        y = self.model(x)
-        if timed:
-            e1.record()
-            self.fwd_events.append((e0, e1))
-        vox = y.view(self.n_pairs, 2, 10, H, W)
-        frames, ub = self.ef.event_frames(vox, 10, 98, True)
-        params = self.ldati.make_params(self.n_pairs, H, W, fps=30, seed=0,
-                                        frame_base=(self.rank * 5 + b) * self.n_pairs, device=self.device,
-                                        add_frame_offset=True)
-        l0 = self.eng.launches
-        events, seg, status = self.eng.run(vox, params, frame_offsets=self.offs[b])
-        total = int(seg.sum())
-        self.events_total += total
-        self.launches += self.model.last_launches() + 11 + (self.eng.launches - l0)
-        if self.world > 1:
-            self.gather(events, total)
-        if host_io:
-            if self.ev_host is None or self.ev_host.numel() < total * 13:
-                self.ev_host = torch.empty(int(total * 13 * 1.2), dtype=torch.uint8).pin_memory()
-            self.ev_host[:total * 13].copy_(events[:total * 13], non_blocking=True)
-            self.fr_host.copy_(frames, non_blocking=True)
-            st = status.cpu()
-            self.d2h_bytes = total * 13 + frames.numel() + seg.size * 8 + 16 + 32
-        return total
-
-    def gather(self, events, total):
-        """Final gather of the per-rank event shards to rank 0 (NCCL over NVLink)."""
+    def gather(self, br, t):
+        """Final gather of the per-rank event shards to rank 0 (NCCL over NVLink), on the post stream, behind
+        the pack kernel of batch t."""
         import torch.distributed as dist
-        cnt = torch.tensor([total], dtype=torch.int64, device=self.device)
-        counts = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
-        dist.all_gather(counts, cnt)
-        mx = int(max(int(c.item()) for c in counts))
-        pad = torch.zeros(mx * 13, dtype=torch.uint8, device=self.device)
-        pad[:total * 13] = events[:total * 13]
-        if self.rank == 0:
-            bufs = [torch.empty(mx * 13, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
-            dist.gather(pad, bufs, dst=0)
-        else:
-            dist.gather(pad, None, dst=0)
+        with torch.cuda.stream(br.post_stream):
+            total = t.total
+            cnt = torch.tensor([total], dtype=torch.int64, device=self.device)
+            counts = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
+            dist.all_gather(counts, cnt)
+            mx = int(max(int(c.item()) for c in counts))
+            pad = torch.zeros(mx * 13, dtype=torch.uint8, device=self.device)
+            pad[:total * 13] = t.events_dev[:total * 13]
+            if self.rank == 0:
+                bufs = [torch.empty(mx * 13, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+                dist.gather(pad, bufs, dst=0)
+            else:
+                dist.gather(pad, None, dst=0)
+            fin = torch.cuda.Event()
+            fin.record(br.post_stream)
+        return fin
 
 
 def run_ours(args, rank, world, local_rank):
@@ -255,58 +224,69 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def e2e_step(i, prev):
-        # public API path: pinned host image units in, host events + preview frames out, transfers
-        # overlapped with the next batch by v2ce_toolbox_b200.runner.BatchRunner
-        b = i % 5
-        t = r.batch_runner.submit(r.units_pinned[b], (rank * 5 + b) * r.n_pairs)
-        if world > 1:
-            r.gather(r.batch_runner._ev_dev[t.slot], t.total)
-        if prev is not None:
-            r.batch_runner.wait(prev, copy=False)
-        r.h2d_bytes, r.d2h_bytes = t.h2d_bytes, t.d2h_bytes
-        return t
-
     def timed_loop(host_io):
-        prev = None
-        for i in range(args.warmup):
-            if host_io:
-                prev = e2e_step(i, prev)
-            else:
-                r.step(i, host_io)
-        if prev is not None:
-            r.batch_runner.wait(prev, copy=False)
+        """One step = one batch of 4 windows through BatchRunner.submit; the results of step i are collected
+        (and, at N > 1, gathered to rank 0) while step i+1 computes."""
+        br = r.host_runner if host_io else r.dev_runner
+        src = r.units_pinned if host_io else r.units_dev
+        stats = {'events': 0, 'fwd': [], 'h2d': 0, 'd2h': 0}
+
+        def collect(t, timed):
+            br.wait(t, copy=False)
+            if world > 1:
+                r.gather(br, t).synchronize()
+            if timed:
+                stats['events'] += t.total
+                stats['h2d'], stats['d2h'] = t.h2d_bytes, t.d2h_bytes
+                if t.fwd_events is not None:
+                    stats['fwd'].append(t.fwd_events[0].elapsed_time(t.fwd_events[1]))
+
+        def run(n, timed):
             prev = None
-        r.fwd_events, r.events_total, r.launches = [], 0, 0
+            for i in range(n):
+                b = i % 5
+                t = br.submit(src[b], (rank * 5 + b) * r.n_pairs)
+                if prev is not None:
+                    collect(prev, timed)
+                prev = t
+            if prev is not None:
+                collect(prev, timed)
+
+        run(args.warmup, False)
+        br.launches = 0
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         s.record()
-        for i in range(args.steps):
-            if host_io:
-                prev = e2e_step(i, prev)
-            else:
-                r.step(i, host_io, timed=True)
-        if prev is not None:
-            r.batch_runner.wait(prev, copy=False)
+        run(args.steps, True)
+        torch.cuda.synchronize()
         e.record()
         barrier()
         wall = time.perf_counter() - t0
-        ms = s.elapsed_time(e)
-        if host_io:
-            ms = max(ms, wall * 1e3)        # end-to-end: the host clock also counts
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        ms = max(s.elapsed_time(e), wall * 1e3) if host_io else s.elapsed_time(e)
+        if not host_io:
+            # results are left on the device; the loop still ends with every stream drained
+            ms = max(ms, 0.0)
+        tt = torch.tensor([ms], dtype=torch.float64, device=device)
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), stats, br.launches
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev = timed_loop(False)
-    fwd_ms = [a.elapsed_time(b) for a, b in r.fwd_events]
-    events_dev, launches = r.events_total, r.launches
-    ms_e2e = timed_loop(True)
+    ms_dev, st_dev, launches = timed_loop(False)
+    ms_e2e, st_e2e, _ = timed_loop(True)
+    # the network alone (no event-frame / LDATI kernels sharing the SMs): what the roofline fraction describes
+    fwd_ms = []
+    for i in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r.model(r.units_dev[i % 5])
+        e1.record()
+        fwd_ms.append((e0, e1))
+    torch.cuda.synchronize()
+    fwd_alone = float(np.mean([a.elapsed_time(b) for a, b in fwd_ms]))
     clocks = sampler.stop() if rank == 0 else None
 
     pairs_per_step = r.n_pairs * world
@@ -315,7 +295,8 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     tf_peak, hbm_peak, how = peaks()
-    fwd = float(np.mean(fwd_ms)) if fwd_ms else float('nan')
+    fwd_in_step = float(np.mean(st_dev['fwd'])) if st_dev['fwd'] else float('nan')
+    fwd = fwd_alone
     achieved = GFLOP_PER_WINDOW * BATCH / fwd            # GFLOP / ms = TFLOP/s
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -330,16 +311,22 @@ def run_ours(args, rank, world, local_rank):
         'config': {'workload': 'center 346x260, 321 frames, batch 4, voxel+LDATI+event-frame video',
                    'pairs_per_step_per_gpu': r.n_pairs, 'weights': 'random-init V2ce3d (seed 0)',
                    'l2': 'inputs+activations per step (2.6 GB) exceed the 126 MB L2',
+                   'pipeline': 'event frames + LDATI of step i run on a second stream under the UNet of step i+1',
                    'multi_gpu': 'windows sharded per rank, NCCL gather of event shards to rank 0'},
-        'e2e': {'value': e2e, 'unit': 'frame-pairs/s', 'h2d_bytes_per_step': r.h2d_bytes,
-                'd2h_bytes_per_step': r.d2h_bytes, 'ms_per_step': ms_e2e / args.steps},
+        'e2e': {'value': e2e, 'unit': 'frame-pairs/s', 'h2d_bytes_per_step': st_e2e['h2d'],
+                'd2h_bytes_per_step': st_e2e['d2h'], 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'ldati_mevents_per_s': events_dev * world / (ms_dev / 1e3) / 1e6,
-        'events_per_pair': events_dev / (r.n_pairs * args.steps),
+        'ldati_mevents_per_s': st_dev['events'] * world / (ms_dev / 1e3) / 1e6,
+        'events_per_pair': st_dev['events'] / (r.n_pairs * args.steps),
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
-                     'frac': achieved / tf_peak, 'traffic': None, 'peak_source': how,
-                     'kernel': 'V2ce3d forward: conv_halo_kernel x16 + conv_igemm_kernel x14 (+head, pred, 4 upsample, 4 spectral-norm launches)',
-                     'forward_ms': fwd, 'forward_share_of_step': fwd / (ms_dev / args.steps)},
+                     'frac': achieved / tf_peak, 'traffic': TRAFFIC_BYTES, 'peak_source': how,
+                     'kernel': KERNEL_NOTE,
+                     'forward_ms': fwd, 'forward_ms_in_step': fwd_in_step,
+                     'frac_in_step': GFLOP_PER_WINDOW * BATCH / fwd_in_step / tf_peak,
+                     'forward_share_of_step': fwd / (ms_dev / args.steps),
+                     'note': 'forward_ms: CUDA events around the network run alone over the same K steps; '
+                             'forward_ms_in_step: the same events inside the timed steps, where the previous '
+                             'batch\'s event-frame / LDATI kernels share the SMs'},
         'cpu_baseline': cpu,
         'clocks': clocks,
     }

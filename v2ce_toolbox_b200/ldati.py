@@ -21,7 +21,19 @@ NBINS = 9
 KEY_BIAS = 8
 
 
+_bin_starts_cache = {}
+
+
 def bin_starts(fps, device, flavor='cuda'):
+    """Cached per (fps, device, flavour): evaluating it reads a device tensor back, i.e. synchronises the
+    current stream, which a pipelined caller (runner.BatchRunner) must not do per batch."""
+    key = (fps, str(device), flavor)
+    if key not in _bin_starts_cache:
+        _bin_starts_cache[key] = _bin_starts(fps, device, flavor)
+    return _bin_starts_cache[key]
+
+
+def _bin_starts(fps, device, flavor='cuda'):
     """`torch.arange(0, frame_step, voxel_step)` exactly as the reference evaluates it
     (LDATI.py:164,209): on the CUDA device for the torch-CUDA flavour, on CPU otherwise."""
     frame_step = 1 / fps
@@ -81,12 +93,12 @@ class LdatiEngine:
             setattr(self, attr, buf)
         return buf
 
-    def count(self, voxels, params):
-        """voxels (F,2,10,H,W) float32 CUDA contiguous -> seg_counts int64 (F,9) on device."""
+    def count(self, voxels, params, out=None):
+        """voxels (F,2,10,H,W) float32 CUDA contiguous -> seg_counts int64 (F,9) on device (`out` if given)."""
         n = ctypes.c_size_t()
         check(self.lib.v2ce_ldati_count_workspace_bytes(ctypes.byref(params), ctypes.byref(n)))
         ws = self._ws('_count_ws', n.value)
-        seg = torch.empty((params.n_frames, NBINS), dtype=torch.int64, device=self.device)
+        seg = out if out is not None else torch.empty((params.n_frames, NBINS), dtype=torch.int64, device=self.device)
         check(self.lib.v2ce_ldati_count(ptr(voxels), ctypes.byref(params), ptr(ws), ws.numel(), ptr(seg),
                                         stream_ptr()))
         self.launches += 3

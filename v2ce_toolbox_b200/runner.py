@@ -1,66 +1,96 @@
-"""BatchRunner: the hot path for one batch of windows, with host transfers overlapped.
+"""BatchRunner: the hot path for one batch of windows, software-pipelined over three CUDA streams.
 
-    image units (pinned host or device) ─H2D→ V2ce3d ─→ voxels ─→ event-frame sums [+ frames]
+    image units (pinned host or device) ─H2D→ V2ce3d ─→ voxels ─→ event-frame sums, order statistics
                                                          └─→ LDATI count ─(counts D2H)→ emit/sort/pack ─D2H→ host events
 
-Three CUDA streams: the caller's current stream computes, one side stream uploads the next inputs and
-another moves results to pinned host buffers while the next batch computes.  Output buffers are double-buffered, so ``submit`` may be
-called for batch i+1 before ``wait`` is called for batch i.  This is what ``v2ce.stream_clip`` and
-``bench.py`` (e2e) use; it composes the same public calls a user would make one by one
+The conv kernels of V2ce3d are persistent CTAs that leave most of an SM's registers, threads and HBM
+bandwidth unused, while event frames and LDATI are short bandwidth/latency-bound launches with one
+data-dependent host read in the middle (the counts size the output, as ``torch.max(y)`` does at
+LDATI.py:169).  Run back to back they cost 1.1 ms of an 11.3 ms step and leave the GPU idle during the host
+read.  Here they run on a second stream, one batch behind the network:
+
+    submit(i):  main stream   UNet(i)                                   (enqueued first, asynchronously)
+                host          wait for counts / order statistics of batch i-1   (the GPU is busy with UNet(i))
+                post stream   stage B(i-1): event-frame normalise, LDATI emit/sort/pack
+                copy stream   D2H of events / frames of batch i-1
+                post stream   stage A(i):   after UNet(i): event-frame sums + radix select, LDATI count, small D2H
+
+``wait(t)`` flushes stage B of ``t`` if no later submit has done so.  Buffers are per slot (``slots`` >= 2), so
+``submit`` may be called for batch i+1 before ``wait`` is called for batch i.  ``bench.py`` (value and e2e)
+and the tests drive it; it composes the same C-ABI calls as the one-by-one public functions
 (``V2ce3d.__call__``, ``event_frames.*``, ``LdatiEngine.count/emit``).
 """
+import ctypes
+import math
+
 import numpy as np
 import torch
 
+from . import _lib
 from . import event_frames as _ef
 from . import ldati as _ldati
+from ._lib import check, ptr, stream_ptr
 
 
 class Ticket:
-    __slots__ = ('slot', 'n_pairs', 'total', 'seg_counts', 'done', 'status', 'ub', 'h2d_bytes', 'd2h_bytes', 'hw')
+    __slots__ = ('slot', 'n_pairs', 'total', 'seg_counts', 'done', 'status', 'ub', 'h2d_bytes', 'd2h_bytes', 'hw',
+                 'pair_base', 'vox', 'sums', 'small_host', 'counts_ready', 'staged', 'params', 'offs', 'fwd_events',
+                 'events_dev', 'packed')
 
 
 class BatchRunner:
     def __init__(self, model, device, fps=30, ceil=10, percentile=98, keep_polarity=True, seed=0,
-                 per_batch_frames=True, slots=2):
+                 per_batch_frames=True, slots=3, copy_out=True):
         self.model = model
         self.device = torch.device(device)
         self.fps, self.ceil, self.percentile, self.keep = fps, ceil, percentile, keep_polarity
         self.seed = seed
         self.per_batch_frames = per_batch_frames
-        self.eng = _ldati.engine_for(self.device)
+        self.copy_out = copy_out                  # False: results stay on the device (device-timed bench)
+        self.lib = _lib.load()
+        self.post_stream = torch.cuda.Stream(device=self.device)      # event frames + LDATI, one batch behind
         self.copy_stream = torch.cuda.Stream(device=self.device)      # D2H of results
         self.h2d_stream = torch.cuda.Stream(device=self.device)       # H2D of inputs (PCIe is full duplex)
         self.slots = slots
+        self.engines = [_ldati.LdatiEngine(self.device) for _ in range(slots)]    # count workspace per slot
         self._ev_dev = [None] * slots
         self._ev_host = [None] * slots
         self._fr_dev = [None] * slots
         self._fr_host = [None] * slots
         self._x_dev = [None] * slots
+        self._sel_ws = [None] * slots
+        self._small_dev = [None] * slots
+        self._small_host = [None] * slots
+        self._offs_host = [None] * slots
+        self._offs_dev = [None] * slots
         self._st_host = [torch.empty(4, dtype=torch.int32, pin_memory=True) for _ in range(slots)]
-        self._free = [None] * slots            # event: the side stream has finished reading slot buffers
+        self._free = [None] * slots            # event: every stream has finished with the slot's buffers
         self._next = 0
+        self._pending = None                   # ticket whose stage B has not been enqueued yet
         self.launches = 0
-        self.sums = []                          # per-batch event-frame sums (kept for a clip-global percentile)
+        self.time_forward = False              # True: CUDA events around every forward (bench roofline)
+        self.sums = []                         # per-batch event-frame sums (kept for a clip-global percentile)
 
     def _buf(self, lst, slot, nbytes, pinned=False):
         b = lst[slot]
         if b is None or b.numel() < nbytes:
-            n = int(nbytes * 1.25) + 256
+            n = (int(nbytes * 1.25) + 256 + 63) // 64 * 64
             b = torch.empty(n, dtype=torch.uint8, pin_memory=True) if pinned else \
                 torch.empty(n, dtype=torch.uint8, device=self.device)
             lst[slot] = b
         return b
 
+    # ------------------------------------------------------------------------------------------
     def submit(self, units, pair_base, keep_sums=False):
         """units: (b,L,2,H,W) float32, pinned host (copied on the side stream) or already on the device."""
         t = Ticket()
         slot = self._next
         self._next = (self._next + 1) % self.slots
-        t.slot = slot
+        t.slot, t.pair_base = slot, pair_base
+        t.staged = False
         cur = torch.cuda.current_stream(self.device)
         if self._free[slot] is not None:
-            cur.wait_event(self._free[slot])    # the previous user of this slot has been copied out
+            cur.wait_event(self._free[slot])    # the previous user of this slot has left the device
         t.h2d_bytes = 0
         if not units.is_cuda:
             t.h2d_bytes = units.numel() * units.element_size()
@@ -69,59 +99,135 @@ class BatchRunner:
                 ready = torch.cuda.Event()
                 ready.record(self.h2d_stream)
             cur.wait_event(ready)
+            x.record_stream(cur)
             self._x_dev[slot] = x               # keep alive until the forward has consumed it
         else:
             x = units
+        t.fwd_events = None
+        if self.time_forward:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
         y = self.model(x)
+        if self.time_forward:
+            e1.record(cur)
+            t.fwd_events = (e0, e1)
+        vox_ready = torch.cuda.Event()
+        vox_ready.record(cur)
         b, L, _, H, W = y.shape
         n = b * L
-        t.n_pairs = n
-        t.hw = (H, W)
-        vox = y.view(n, 2, 10, H, W)
-        sums = _ef.accumulate(vox, self.keep)
-        frames = None
+        t.n_pairs, t.hw = n, (H, W)
+        t.vox = y.view(n, 2, 10, H, W)
+        t.vox.record_stream(self.post_stream)
+        self.launches += self.model.last_launches()
+
+        # the batch before this one: its counts are on the host by the time UNet(i) is queued
+        prev = self._pending
+        if prev is not None:
+            self._stage_b(prev)
+
+        # stage A of this batch on the post stream, behind the network
+        with torch.cuda.stream(self.post_stream):
+            self.post_stream.wait_event(vox_ready)
+            eng = self.engines[slot]
+            t.sums = _ef.accumulate(t.vox, self.keep)
+            if keep_sums:
+                self.sums.append(t.sums)
+            small = self._buf(self._small_dev, slot, 8 * (4 + n * _ldati.NBINS)).view(torch.int64)
+            if self.per_batch_frames:
+                nb = ctypes.c_size_t()
+                check(self.lib.v2ce_ef_select_workspace_bytes(ctypes.byref(nb)))
+                ws = self._buf(self._sel_ws, slot, nb.value)
+                mult = 1 if self.keep else 3
+                check(self.lib.v2ce_ef_select(ptr(t.sums), t.sums.numel(), float(self.percentile), mult, ptr(ws),
+                                              ws.numel(), ptr(small), stream_ptr()))
+            t.params = _ldati.make_params(n, H, W, fps=self.fps, seed=self.seed, frame_base=pair_base,
+                                          device=self.device, add_frame_offset=True)
+            l0 = eng.launches
+            seg = eng.count(t.vox, t.params, out=small[4:4 + n * _ldati.NBINS].view(n, _ldati.NBINS))
+            self.launches += (10 if self.per_batch_frames else 1) + (eng.launches - l0)
+            t.small_host = self._buf(self._small_host, slot, 8 * (4 + n * _ldati.NBINS), pinned=True).view(torch.int64)[
+                :4 + n * _ldati.NBINS]
+            t.small_host.copy_(small[:4 + n * _ldati.NBINS], non_blocking=True)
+            offs_host = self._buf(self._offs_host, slot, 8 * n, pinned=True).view(torch.int64)[:n]
+            offs_host.copy_(torch.tensor([int((pair_base + i) * 1 / self.fps * 1e6) for i in range(n)], dtype=torch.int64))
+            t.offs = self._buf(self._offs_dev, slot, 8 * n).view(torch.int64)[:n]
+            t.offs.copy_(offs_host, non_blocking=True)
+            t.counts_ready = torch.cuda.Event()
+            t.counts_ready.record(self.post_stream)
+        self._pending = t
+        return t
+
+    # ------------------------------------------------------------------------------------------
+    def _stage_b(self, t):
+        """Counts / order statistics of batch t are (about to be) on the host: size the outputs, enqueue
+        normalise + emit/sort/pack on the post stream and the D2H of the results on the copy stream."""
+        if t.staged:
+            return
+        t.counts_ready.synchronize()            # the one data-dependent sync: the counts size the output
+        small = t.small_host.numpy()
+        n, (H, W), slot = t.n_pairs, t.hw, t.slot
+        t.seg_counts = small[4:].reshape(n, _ldati.NBINS).copy()
+        total = int(t.seg_counts.sum())
+        t.total = total
         t.ub = None
-        if keep_sums:
-            self.sums.append(sums)
-        if self.per_batch_frames:
-            t.ub = _ef.upper_bound(sums, self.percentile, self.ceil, self.keep)
-            fr = self._buf(self._fr_dev, slot, n * H * W * 3)
-            frames = _ef.normalize(sums, t.ub, self.keep, out=fr[:n * H * W * 3].view(n, H, W, 3))
-        params = _ldati.make_params(n, H, W, fps=self.fps, seed=self.seed, frame_base=pair_base, device=self.device,
-                                    add_frame_offset=True)
-        offs = torch.tensor([int((pair_base + i) * 1 / self.fps * 1e6) for i in range(n)], dtype=torch.int64).to(
-            self.device, non_blocking=True)
-        l0 = self.eng.launches
-        seg = self.eng.count(vox, params)
-        seg_host = seg.cpu().numpy()            # the one data-dependent sync: the counts size the output
-        total = int(seg_host.sum())
-        ev = self._buf(self._ev_dev, slot, max(total, 1) * 13)
-        _, status = self.eng.emit(vox, params, total, frame_offsets=offs, out=ev)
-        self.launches += self.model.last_launches() + (11 if self.per_batch_frames else 1) + (self.eng.launches - l0)
-        t.total, t.seg_counts = total, seg_host
-        # results leave on the side stream while the next batch computes
-        computed = torch.cuda.Event()
-        computed.record(cur)
+        frames = None
+        with torch.cuda.stream(self.post_stream):
+            if self.per_batch_frames:
+                npos, lo, bits_lo, bits_hi = (int(v) for v in small[:4])
+                if npos == 0:
+                    raise ValueError('event frames hold no positive value: np.percentile of an empty array')
+                mult = 1 if self.keep else 3
+                vi = (npos * mult - 1) * (self.percentile / 100.0)
+                a = np.array([bits_lo], dtype=np.uint32).view(np.float32)[0]
+                b = np.array([bits_hi], dtype=np.uint32).view(np.float32)[0]
+                t.ub = min(_ef.numpy_lerp(a, b, vi - math.floor(vi)), self.ceil)
+                fr = self._buf(self._fr_dev, slot, n * H * W * 3)
+                frames = _ef.normalize(t.sums, t.ub, self.keep, out=fr[:n * H * W * 3].view(n, H, W, 3))
+                self.launches += 1
+            eng = self.engines[slot]
+            ev = self._buf(self._ev_dev, slot, max(total, 1) * 13)
+            l0 = eng.launches
+            _, status = eng.emit(t.vox, t.params, total, frame_offsets=t.offs, out=ev)
+            self.launches += eng.launches - l0
+            t.events_dev = ev
+            t.packed = torch.cuda.Event()
+            t.packed.record(self.post_stream)
+        t.d2h_bytes = 0
         with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(computed)
-            evh = self._buf(self._ev_host, slot, max(total, 1) * 13, pinned=True)
-            evh[:total * 13].copy_(ev[:total * 13], non_blocking=True)
-            t.d2h_bytes = total * 13 + seg_host.size * 8 + 16
-            if frames is not None:
-                frh = self._buf(self._fr_host, slot, frames.numel(), pinned=True)
-                frh[:frames.numel()].copy_(frames.reshape(-1), non_blocking=True)
-                t.d2h_bytes += frames.numel() + 32
+            self.copy_stream.wait_event(t.packed)
+            if self.copy_out:
+                evh = self._buf(self._ev_host, slot, max(total, 1) * 13, pinned=True)
+                evh[:total * 13].copy_(ev[:total * 13], non_blocking=True)
+                t.d2h_bytes = total * 13 + (4 + n * _ldati.NBINS) * 8 + 16
+                if frames is not None:
+                    frh = self._buf(self._fr_host, slot, frames.numel(), pinned=True)
+                    frh[:frames.numel()].copy_(frames.reshape(-1), non_blocking=True)
+                    t.d2h_bytes += frames.numel()
             t.status = self._st_host[slot]
             t.status.copy_(status, non_blocking=True)   # pinned: a pageable target would block the host here
             t.done = torch.cuda.Event()
             t.done.record(self.copy_stream)
         self._free[slot] = t.done
-        return t
+        t.staged = True
+        t.vox = None if not self.keep_vox else t.vox
+        if self._pending is t:
+            self._pending = None
+
+    keep_vox = False                            # tests may set this to inspect the voxels a ticket was computed from
+
+    def flush(self):
+        """Enqueue stage B of the batch submitted last (the end of a clip)."""
+        if self._pending is not None:
+            self._stage_b(self._pending)
 
     def wait(self, t, copy=True):
-        """Block until batch `t` is on the host.  Returns (events recarray view, frames uint8 (n,H,W,3) | None)."""
+        """Block until batch `t` is on the host.  Returns (events recarray view, frames uint8 (n,H,W,3) | None);
+        with copy_out=False both are None (results stay in the slot's device buffers)."""
+        self._stage_b(t)
         t.done.synchronize()
         _ldati.check_status(t.status.numpy())
+        if not self.copy_out:
+            return None, None
         ev = self._ev_host[t.slot][:t.total * 13].numpy().view(_ldati.EVENT_DTYPE)
         fr = None
         if self.per_batch_frames:
