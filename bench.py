@@ -189,12 +189,17 @@ class Runner:
         self.units_pinned = [units_host[i:i + BATCH].contiguous().pin_memory() for i in range(0, 20, BATCH)]
         self.units_dev = [u.to(device) for u in self.units_pinned]
         self.n_pairs = BATCH * L
+        self.comm_stream = None
 
     def gather(self, br, t):
         """Final gather of the per-rank event shards to rank 0 (NCCL over NVLink), on the post stream, behind
         the pack kernel of batch t."""
         import torch.distributed as dist
-        with torch.cuda.stream(br.post_stream):
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self.comm_stream):
+            # its own stream: the post stream already holds stage A of the next batch, which waits for the next UNet
+            self.comm_stream.wait_event(t.packed)
             total = t.total
             cnt = torch.tensor([total], dtype=torch.int64, device=self.device)
             counts = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
@@ -208,7 +213,7 @@ class Runner:
             else:
                 dist.gather(pad, None, dst=0)
             fin = torch.cuda.Event()
-            fin.record(br.post_stream)
+            fin.record(self.comm_stream)
         return fin
 
 

@@ -24,6 +24,28 @@ def test_shard_ranges_cover_everything():
     assert vdist.model_calls_before(3, 'pano', tiles=2) == 6
 
 
+def test_shard_schedules_tile_the_clip():
+    """Every frame pair of the clip is emitted by exactly one rank, in order, including the pulled-back last
+    window when it is the only window of the last rank (F8: 40 frames -> starts [0,16,23], mode 7)."""
+    from v2ce_toolbox_b200 import v2ce as drv
+    for n_frames in (17, 18, 40, 70, 100, 321, 600):
+        for bs in (1, 2, 4):
+            starts, mode = drv.window_schedule(n_frames, 16)
+            n_batches = -(-len(starts) // bs)
+            for world in (1, 2, 3, 8):
+                nxt = 0
+                for r in range(world):
+                    b0, b1 = vdist.shard_range(n_batches, world, r)
+                    first, count, tail, pair_base, (rel, m) = vdist.shard_schedule(starts, mode, b0, b1, bs, 16)
+                    if count == 0:
+                        continue
+                    assert pair_base == nxt and first + rel[0] == starts[b0 * bs]
+                    assert count == first + rel[-1] + 17 - first and (m == mode if tail else m == 0)
+                    emitted = 16 * len(rel) - ((16 - m) if (tail and m) else 0)
+                    nxt += emitted
+                assert nxt == n_frames - 1, (n_frames, bs, world)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))

@@ -1,0 +1,75 @@
+"""2-GPU (NCCL) check of the sharded clip path: windows (and the width tiles of a pano window) sharded over
+ranks with the spectral-norm replay, event shards gathered to rank 0 == the single-process event stream,
+bit for bit.  Skips on a box with fewer than 2 GPUs (run it with ``gpurun --gpus 2``)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle.ref_harness import FakeVideoReader
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _model(seed, dev):
+    from v2ce_toolbox_b200.scripts.v2ce_3d import V2ce3d
+    m = V2ce3d()
+    m.load_state_dict(synth.make_state_dict(seed, 'lively'))
+    return m.eval().to(dev)
+
+
+CASES = {
+    # name: (n_frames, H, W of the source video, infer_type, model width, height, batch size)
+    'center': (70, 28, 36, 'center', 36, 28, 1),           # 5 windows (last pulled back), ragged over 2 ranks
+    'center_b2': (100, 28, 36, 'center', 36, 28, 2),
+    'pano': (40, 24, 80, 'pano', 32, 24, 1),                # 3 width tiles per window, 3 windows
+}
+
+
+def _worker(rank, world, port, out_dir, case):
+    import torch.distributed as dist
+    from v2ce_toolbox_b200 import dist as vdist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        n_frames, H, W, infer_type, width, height, bs = CASES[case]
+        frames = synth.make_video(n_frames, H, W, seed=5)
+        ev, n = vdist.stream_clip_sharded(_model(31, dev), FakeVideoReader(frames), n_frames, world, rank, seq_len=16,
+                                          batch_size=bs, infer_type=infer_type, width=width, height=height, fps=30, seed=9,
+                                          device=dev)
+        if rank == 0:
+            np.save(os.path.join(out_dir, f'{case}.npy'), ev)
+            assert len(ev) == n
+        else:
+            assert ev is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('case', list(CASES))
+def test_sharded_clip_equals_single_process(case, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    from v2ce_toolbox_b200 import v2ce as drv
+    n_frames, H, W, infer_type, width, height, bs = CASES[case]
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), case), nprocs=2, join=True)
+    got = np.load(tmp_path / f'{case}.npy')
+    frames = synth.make_video(n_frames, H, W, seed=5)
+    res = drv.stream_clip(_model(31, 'cuda:0'), vidcap=FakeVideoReader(frames), infer_type=infer_type, seq_len=16,
+                          width=width, height=height, batch_size=bs, fps=30, seed=9, write_event_frames=False)
+    want = res.event_stream
+    assert got.dtype.itemsize == 13 and len(got) == len(want) and len(want) > 0
+    for f in ('timestamp', 'x', 'y', 'polarity'):
+        assert np.array_equal(got[f], want[f]), (case, f)

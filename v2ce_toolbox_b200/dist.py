@@ -47,6 +47,20 @@ def gather_event_shards(events_u8, n_events, group=None, dst=0):
     return None, counts
 
 
+def shard_schedule(starts, mode, b0, b1, batch_size, seq_len=16):
+    """Batches [b0, b1) of a clip's window schedule (v2ce.window_schedule) as a clip of their own:
+    (first frame, frame count, is_tail, index of the first frame pair, (window starts relative to `first`, mode)).
+    Only the clip's last window is pulled back and trimmed to its last `mode` pairs (v2ce.py:153-154,227-236),
+    wherever the window before it lives; every window before the shard emits seq_len pairs."""
+    w0, w1 = b0 * batch_size, min(b1 * batch_size, len(starts))
+    if w1 <= w0:
+        return 0, 0, False, w0 * seq_len, (np.zeros(0, dtype=np.int64), 0)
+    first = int(starts[w0])
+    frame_count = int(starts[w1 - 1]) + seq_len + 1 - first
+    is_tail = (w1 == len(starts))
+    return first, frame_count, is_tail, w0 * seq_len, (np.asarray(starts[w0:w1]) - first, mode if is_tail else 0)
+
+
 def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=16, batch_size=1, **kw):
     """Run v2ce.stream_clip on this rank's contiguous share of the batches of a clip and gather the
     event shards on rank 0.  `frames_reader` duck-types VideoReader.  Returns (event_stream | None, n_pairs)."""
@@ -54,17 +68,23 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
     starts, mode = drv.window_schedule(frame_count, seq_len)
     n_batches = -(-len(starts) // batch_size)
     b0, b1 = shard_range(n_batches, world, rank)
-    model.sn_advance(model_calls_before(b0) - model.call_count())
+    # pano: every batch is one model call per 346-px width tile (v2ce.py:103-111); the tiles of a window stay on
+    # the rank that owns the window, so LDATI sees full-width frames and no voxel exchange is needed
+    infer_type = kw.get('infer_type', 'center')
+    tiles = 1
+    if infer_type == 'pano':
+        probe = np.asarray(frames_reader.read_frames_at_indices([0]))
+        h0, w0 = probe.shape[-2], probe.shape[-1]
+        height = kw.get('height', 260)
+        tiles = len(drv.pano_tiles(int(w0 / h0 * height), kw.get('width', 346)))     # width after image_pre_processing
+    model.sn_advance(model_calls_before(b0, infer_type, tiles) - model.call_count())
 
     class _Shard:
         """Presents windows [b0*bs, b1*bs) of the clip as a clip of its own."""
 
         def __init__(self):
-            w0, w1 = b0 * batch_size, min(b1 * batch_size, len(starts))
-            self.first = int(starts[w0]) if w1 > w0 else 0
-            last_start = int(starts[w1 - 1]) if w1 > w0 else 0
-            self.frame_count = (last_start + seq_len + 1 - self.first) if w1 > w0 else 0
-            self.is_tail = (w1 == len(starts))
+            (self.first, self.frame_count, self.is_tail, self.pair_base, self.schedule) = shard_schedule(
+                starts, mode, b0, b1, batch_size, seq_len)
 
         def read_frames_at_indices(self, idxs):
             return frames_reader.read_frames_at_indices([self.first + i for i in idxs])
@@ -72,9 +92,9 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
     shard = _Shard()
     dev = kw.pop('device', torch.device('cuda', torch.cuda.current_device()))
     if shard.frame_count > 1:
-        # a pulled-back last window only exists in the tail shard; there the local schedule reproduces it
         res = drv.stream_clip(model, vidcap=shard, seq_len=seq_len, batch_size=batch_size,
-                              pair_base=shard.first, device=dev, write_event_frames=False, **kw)
+                              pair_base=shard.pair_base, device=dev, write_event_frames=False, schedule=shard.schedule,
+                              **kw)
         ev = torch.from_numpy(res.event_stream.view(np.uint8).copy()).to(dev)
         n = res.event_stream.shape[0]
     else:

@@ -122,10 +122,11 @@ def _read_window(image_paths, vidcap, start, seq_len):
     return np.stack([cv2.imread(p, cv2.IMREAD_GRAYSCALE) for p in image_paths[start:start + seq_len + 1]], axis=0)
 
 
-def _batches(image_paths, vidcap, seq_len, height, batch_size):
-    """Yield (image_units (b,L,2,H',W') float32 host tensor, is_last) in the reference's batching."""
+def _batches(image_paths, vidcap, seq_len, height, batch_size, schedule=None):
+    """Yield (image_units (b,L,2,H',W') float32 host tensor, is_last) in the reference's batching.
+    `schedule` = (window starts, mode) overrides the schedule derived from the frame count (a rank's share of a clip)."""
     frame_count = vidcap.frame_count if vidcap is not None else len(image_paths)
-    starts, mode = window_schedule(frame_count, seq_len)
+    starts, mode = schedule if schedule is not None else window_schedule(frame_count, seq_len)
     pending = []
     for i, st in enumerate(starts):
         pending.append(image_pre_processing(_read_window(image_paths, vidcap, st, seq_len), height)[None])
@@ -186,17 +187,18 @@ class ClipResult:
 @torch.no_grad()
 def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_len=16, width=346, height=260,
                 batch_size=1, fps=30, ceil=10, upper_bound_percentile=98, keep_polarity=True,
-                write_event_frames=True, seed=0, pair_base=0, device=None):
+                write_event_frames=True, seed=0, pair_base=0, device=None, schedule=None):
     """Device-resident version of v2ce.py:322-372.  Returns ClipResult with the concatenated event
     stream (timestamps offset per frame, v2ce.py:365) and the uint8 BGR preview frames."""
     assert image_paths is not None or vidcap is not None
     device = torch.device(device or 'cuda')
     frame_count = vidcap.frame_count if vidcap is not None else len(image_paths)
-    starts, mode = window_schedule(frame_count, seq_len)
+    # `schedule` = (window starts relative to this reader, mode): a rank's share of a longer clip (dist.py)
+    starts, mode = schedule if schedule is not None else window_schedule(frame_count, seq_len)
     eng = _ldati.engine_for(device)
     sums_all, event_chunks = [], []
     pair_idx = pair_base
-    for units, is_last in _batches(image_paths, vidcap, seq_len, height, batch_size):
+    for units, is_last in _batches(image_paths, vidcap, seq_len, height, batch_size, schedule):
         pred = _center_device(model, units, width) if infer_type == 'center' else _pano_device(model, units, width)
         b, L, _, H, W = pred.shape
         vox = pred.reshape(b * L, 2, 10, H, W)
