@@ -123,12 +123,15 @@ __device__ __forceinline__ void kdm_store_chunk(const HaloArgs& a, const KdmRow&
   }
 }
 
-template <bool SHORT>
+template <bool SHORT, int T>
 __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1,
                                                                      const HaloArgs a, const KdmShort sc) {
-  constexpr int BN = kKdmBN, T = kKdmT;
-  constexpr int G = SHORT ? 1 : 2;                  // tiles whose accumulators fit in TMEM at once
+  // T output slices per tile: 8, or the whole depth of a 16-slice window (no depth halo: 16 patch loads per 16
+  // output slices instead of 20, and fewer narrow edge instructions) when the shortcut does not need half of TMEM
+  constexpr int BN = kKdmBN;
+  static_assert(T == 8 || (T == 16 && !SHORT), "slots");
+  constexpr int G = SHORT ? 1 : 16 / T;             // tiles whose accumulators fit in TMEM at once
   constexpr uint32_t kShortCols = 256;              // shortcut accumulator of slot s: column 256 + 32 s
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -487,27 +490,31 @@ inline KdmPlan plan_kdm(int D, int H, int W) {
 // `sc` != nullptr: also compute the block's 1x1x1 shortcut conv of the same input (second output)
 inline int launch_halo_kdm(const CUtensorMap& tm0, const CUtensorMap& tm1, const HaloArgs& a, const KdmShort* sc, int smem_bytes,
                            cudaStream_t s) {
-  static int configured[2] = {0, 0};
-  const int which = sc ? 1 : 0;
-  if (configured[which] < smem_bytes) {
-    if (sc)
-      V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    else
-      V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured[which] = smem_bytes;
-  }
-  if (a.T != kKdmT || a.D % kKdmT != 0 || a.Cout % kKdmBN != 0)
+  static int configured[3] = {0, 0, 0};
+  static const bool t8_only = getenv("V2CE_KDM_T8") && atoi(getenv("V2CE_KDM_T8"));
+  if (a.D % kKdmT != 0 || a.Cout % kKdmBN != 0)
     return set_error(V2CE_ERR_INVALID, "depth-merged halo kernel: depth %d / Cout %d not supported", a.D, a.Cout);
   if (sc && (a.up_H > 0 || a.pred_w != nullptr || a.residual != nullptr))
     return set_error(V2CE_ERR_INVALID, "depth-merged halo kernel: the fused shortcut goes with a plain first conv");
-  const int total = a.B * (a.D / kKdmT) * a.tiles_h * a.tiles_w * (a.Cout / kKdmBN);
-  const int grid = total < sm_count_cached() ? total : sm_count_cached();
-  if (sc) {
-    conv_halo_kdm_kernel<true><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, a, *sc);
-  } else {
-    KdmShort none{nullptr, nullptr, nullptr, nullptr, 0};
-    conv_halo_kdm_kernel<false><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, a, none);
+  const int which = sc ? 1 : (a.D % 16 == 0 && !t8_only) ? 2 : 0;
+  if (configured[which] < smem_bytes) {
+    if (which == 1)
+      V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    else if (which == 2)
+      V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    else
+      V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured[which] = smem_bytes;
   }
+  const int T = which == 2 ? 16 : 8;
+  HaloArgs b = a;
+  b.T = T;
+  const int total = b.B * (b.D / T) * b.tiles_h * b.tiles_w * (b.Cout / kKdmBN);
+  const int grid = total < sm_count_cached() ? total : sm_count_cached();
+  KdmShort none{nullptr, nullptr, nullptr, nullptr, 0};
+  if (which == 1) conv_halo_kdm_kernel<true, 8><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, b, *sc);
+  else if (which == 2) conv_halo_kdm_kernel<false, 16><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, b, none);
+  else conv_halo_kdm_kernel<false, 8><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, b, none);
   V2CE_LAUNCH_CHECK("conv_halo_kdm_kernel");
   return V2CE_OK;
 }
