@@ -41,8 +41,8 @@ BATCH = 4
 GFLOP_PER_WINDOW = 2169.336
 METRIC = '346x260 frame-pairs/s (center, 321 frames, batch 4, voxel+LDATI+event-frame)'
 # dram__bytes_read.sum + dram__bytes_write.sum of one V2ce3d forward (batch 4), summed over its launches from the
-# ncu --set full capture summarised in profiles/ (None until that capture exists for the current kernels)
-TRAFFIC_BYTES = None
+# ncu capture summarised in profiles/forward_traffic_r1.txt
+TRAFFIC_BYTES = 13.56e9        # profiles/forward_traffic_r1.txt: read 9.01 GB + write 4.55 GB (L2: 65.5 GB)
 KERNEL_NOTE = ('V2ce3d forward (29 launches): conv_halo_kdm_kernel x6 (N<=64, two with the fused shortcut), '
                'conv_halo_kernel x14, conv_igemm_kernel x12 (stride-2 convs, remaining 1x1x1 shortcuts), head conv, '
                '4 spectral-norm launches on a side stream')
@@ -109,13 +109,16 @@ class ClockSampler:
 
 
 def make_inputs():
-    """Preprocessed image units of the 20 windows: (20, 16, 2, 260, 346) float32 (host)."""
+    """The 20 windows of the clip: preprocessed image units (20, 16, 2, 260, 346) float32 and the raw gray frames
+    they come from (20, 17, 260, 346) uint8 (both host)."""
     from oracle import synth
     from v2ce_toolbox_b200.v2ce import image_pre_processing, window_schedule
     frames = synth.make_video(N_FRAMES, H, W, seed=0)
     starts, mode = window_schedule(N_FRAMES, L)
     assert mode == 0 and len(starts) == 20
-    return torch.stack([image_pre_processing(frames[s:s + L + 1], H) for s in starts], dim=0)
+    units = torch.stack([image_pre_processing(frames[s:s + L + 1], H) for s in starts], dim=0)
+    windows = torch.from_numpy(np.stack([frames[s:s + L + 1] for s in starts], axis=0))     # (20, 17, H, W) uint8
+    return units, windows
 
 
 # ------------------------------------------------------------------------------------------------
@@ -148,7 +151,7 @@ def time_cpu_port(units, steps, warmup):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    units = make_inputs()
+    units, _ = make_inputs()
     # bounded: one window (16 pairs) per step; cap the step count so the arm ends within minutes
     steps = max(1, min(args.steps, 6))
     warmup = max(1, min(args.warmup, 1))
@@ -174,7 +177,7 @@ class Runner:
     """Model + two BatchRunners (v2ce_toolbox_b200.runner): device-resident inputs / results for `value`,
     pinned host inputs and host results for `e2e`."""
 
-    def __init__(self, device, units_host, rank, world):
+    def __init__(self, device, units_host, windows_host, rank, world):
         from oracle import synth
         from v2ce_toolbox_b200.runner import BatchRunner
         from v2ce_toolbox_b200.scripts.v2ce_3d import V2ce3d
@@ -186,8 +189,10 @@ class Runner:
         self.dev_runner = BatchRunner(self.model, device, fps=30, seed=0, copy_out=False)
         self.host_runner = BatchRunner(self.model, device, fps=30, seed=0, copy_out=True)
         self.dev_runner.time_forward = True
-        self.units_pinned = [units_host[i:i + BATCH].contiguous().pin_memory() for i in range(0, 20, BATCH)]
-        self.units_dev = [u.to(device) for u in self.units_pinned]
+        # value: image units resident in HBM; e2e: the raw uint8 windows in pinned host memory (the pre-processing
+        # of v2ce.py:45-64 runs inside the head conv, V2ce3d.forward_frames)
+        self.units_dev = [units_host[i:i + BATCH].contiguous().to(device) for i in range(0, 20, BATCH)]
+        self.units_pinned = [windows_host[i:i + BATCH].contiguous().pin_memory() for i in range(0, 20, BATCH)]
         self.n_pairs = BATCH * L
         self.comm_stream = None
 
@@ -221,8 +226,8 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     device = torch.device('cuda', local_rank)
     torch.cuda.set_device(device)
-    units = make_inputs()
-    r = Runner(device, units, rank, world)
+    units, windows = make_inputs()
+    r = Runner(device, units, windows, rank, world)
 
     def barrier():
         if world > 1:
@@ -317,6 +322,8 @@ def run_ours(args, rank, world, local_rank):
                    'pairs_per_step_per_gpu': r.n_pairs, 'weights': 'random-init V2ce3d (seed 0)',
                    'l2': 'inputs+activations per step (2.6 GB) exceed the 126 MB L2',
                    'pipeline': 'event frames + LDATI of step i run on a second stream under the UNet of step i+1',
+                   'e2e_input': 'uint8 gray frame windows (4 x 17 x 260 x 346) in pinned host memory; pre-processing '
+                                'fused into the head conv; events + preview frames copied back to pinned host memory',
                    'multi_gpu': 'windows sharded per rank, NCCL gather of event shards to rank 0'},
         'e2e': {'value': e2e, 'unit': 'frame-pairs/s', 'h2d_bytes_per_step': st_e2e['h2d'],
                 'd2h_bytes_per_step': st_e2e['d2h'], 'ms_per_step': ms_e2e / args.steps},

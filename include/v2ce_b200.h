@@ -136,6 +136,11 @@ int v2ce_model_workspace_bytes(const v2ce_model* m, int32_t batch, int32_t depth
  * spectral-norm power iteration by one step, as the reference does on every forward. */
 int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_dev, int32_t batch, int32_t depth,
                        int32_t height, int32_t width, void* ws_dev, size_t ws_bytes, void* stream);
+/* Same forward fed with raw frames: frames_dev (B, L+1, H, W) uint8 gray, window b = L+1 consecutive frames.  The
+ * pre-processing of v2ce.py:45-64 at the model's own resolution (float32 /255, pair stacking, Normalize(0.153, 0.165);
+ * the resize is the identity there) is evaluated inside the head conv, bit-identically to the host path. */
+int v2ce_model_forward_frames(v2ce_model* m, const uint8_t* frames_dev, float* y_dev, int32_t batch, int32_t depth,
+                              int32_t height, int32_t width, void* ws_dev, size_t ws_bytes, void* stream);
 /* Spectral-norm state access (parity tests, multi-GPU replay): 12 sigmas of the last forward;
  * number of forwards so far; advance the iteration n calls without running the network. */
 int v2ce_model_last_sigmas(const v2ce_model* m, float* sigma12_host);

@@ -211,3 +211,18 @@ def test_rejects_cpu_input():
     m, _ = _model(0, 'reference')
     with pytest.raises(V2ceError):
         m(torch.zeros(1, 16, 2, 20, 28))
+
+
+def test_forward_frames_equals_forward_of_preprocessed_units():
+    """uint8 windows through the fused pre-processing == image_pre_processing (host, v2ce.py:45-64) + forward, bit for bit."""
+    from v2ce_toolbox_b200.v2ce import image_pre_processing
+    H, W = 36, 44
+    frames = synth.make_video(35, H, W, seed=4)
+    frames[0, 0, :4] = (0, 1, 254, 255)                      # the ends of the gray range
+    wins = np.stack([frames[0:17], frames[16:33]], axis=0)   # two windows
+    units = torch.stack([image_pre_processing(w, H) for w in wins], dim=0)
+    m1, _ = _model(2, 'lively')
+    m2, _ = _model(2, 'lively')
+    y_units = m1(units.cuda())
+    y_frames = m2.forward_frames(torch.from_numpy(wins).cuda())
+    assert torch.equal(y_units, y_frames)

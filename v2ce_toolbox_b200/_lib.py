@@ -50,6 +50,8 @@ _SIGNATURES = {
     'v2ce_model_workspace_bytes': (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_size_t)]),
     'v2ce_model_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                    c_size_t, c_void_p]),
+    'v2ce_model_forward_frames': (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                          c_size_t, c_void_p]),
     'v2ce_model_last_sigmas': (c_int, [c_void_p, POINTER(c_float)]),
     'v2ce_model_call_count': (c_int, [c_void_p, POINTER(c_int64)]),
     'v2ce_model_sn_advance': (c_int, [c_void_p, c_int32, c_void_p]),

@@ -154,6 +154,27 @@ __device__ __forceinline__ int warp_incl_scan(int v) {
 }
 
 // Philox4x32-10, counter (lo32(idx), hi32(idx), j>>2, 0), key = seed; see oracle/philox.py.
+// One Philox block = the draws of four consecutive events of a pixel-bin: the emit loop evaluates it once per
+// four events (philox_block) and picks word j & 3.
+__device__ __forceinline__ void philox_block(unsigned long long idx, unsigned blk, unsigned long long seed, unsigned (&w)[4]) {
+  unsigned c0 = (unsigned)idx, c1 = (unsigned)(idx >> 32), c2 = blk, c3 = 0u;
+  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
+__device__ __forceinline__ float philox_word_to_uniform(const unsigned (&w)[4], unsigned j) {
+  const unsigned sel = j & 3u;
+  const unsigned v = sel == 0 ? w[0] : sel == 1 ? w[1] : sel == 2 ? w[2] : w[3];
+  return __fmul_rn((float)(v >> 8), 5.9604644775390625e-08f);   // 2^-24
+}
+
 __device__ __forceinline__ float philox_uniform(unsigned long long idx, unsigned j, unsigned long long seed) {
   unsigned c0 = (unsigned)idx, c1 = (unsigned)(idx >> 32), c2 = j >> 2, c3 = 0u;
   unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
@@ -429,6 +450,7 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
           const float bb2 = __fmul_rn(b, b);
           const float k2 = __fmul_rn(2.f, kk);
           const unsigned long long idx = ((frame * 2ull + (unsigned)p) * 9ull + (unsigned)c) * (unsigned long long)P.HW + (unsigned)pix;
+          unsigned pw[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
           for (int j = 0; j < nc; ++j) {
             float u;
@@ -436,7 +458,8 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
               const size_t di = ((((size_t)f * 2 + p) * kBins + c) * P.HW + pix) * (size_t)P.draws_m + j;
               u = (j < P.draws_m) ? __ldg(draws + di) : 0.f;
             } else {
-              u = philox_uniform(idx, (unsigned)j, P.seed);
+              if ((j & 3) == 0) philox_block(idx, (unsigned)j >> 2, P.seed, pw);
+              u = philox_word_to_uniform(pw, (unsigned)j);
             }
             float t;
             if (kk == 0.f) {

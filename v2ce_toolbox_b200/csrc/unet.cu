@@ -87,8 +87,21 @@ __global__ void pack_head_kernel(const float* __restrict__ w, float* __restrict_
   out[i] = w[((size_t)n * 2 + ci) * 27 + tap];
 }
 
-__global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict__ x, int B, int D, int H, int W,
+// U8 = true: x holds raw uint8 gray frames (B, D+1, H, W); image unit (b, l, c) is frame l + c (pair stacking) and
+// every sample goes through the pre-processing of v2ce.py:45-64 -- float32 `/255`, Normalize(0.153, 0.165) as a
+// float32 subtract and IEEE divide -- evaluated once per gray level into a 256-entry table (bit-identical to the
+// host path).  The resize of image_pre_processing is the identity at the model's own resolution.
+template <bool U8>
+__global__ void __launch_bounds__(128) head_conv_kernel(const void* __restrict__ xin, int B, int D, int H, int W,
                                                          __nv_bfloat16* __restrict__ out) {
+  __shared__ float lut[U8 ? 256 : 1];
+  if (U8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+      lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)i, 255.f), 0.153f), 0.165f);
+    __syncthreads();
+  }
+  const float* x = static_cast<const float*>(xin);
+  const unsigned char* xu = static_cast<const unsigned char*>(xin);
   const int G = (W + 3) / 4;
   const long long total = (long long)B * D * H * G;
   const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,14 +123,25 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const float* __restrict_
     const int kd = kdh / 3, kh = kdh - kd * 3;
     const int di = d + kd - 1, hi = ho + kh - 1;
     if (di < 0 || di >= D || hi < 0 || hi >= H) continue;
-    const float* r0 = x + ((size_t)(b * D + di) * 2) * HW + (size_t)hi * W;
     float xa[6], xb[6];
+    if (U8) {
+      const unsigned char* r0 = xu + (size_t)(b * (D + 1) + di) * HW + (size_t)hi * W;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int wi = w0 - 1 + j;
-      const bool ok = wi >= 0 && wi < W;
-      xa[j] = ok ? __ldg(r0 + wi) : 0.f;
-      xb[j] = ok ? __ldg(r0 + HW + wi) : 0.f;
+      for (int j = 0; j < 6; ++j) {
+        const int wi = w0 - 1 + j;
+        const bool ok = wi >= 0 && wi < W;
+        xa[j] = ok ? lut[__ldg(r0 + wi)] : 0.f;
+        xb[j] = ok ? lut[__ldg(r0 + HW + wi)] : 0.f;
+      }
+    } else {
+      const float* r0 = x + ((size_t)(b * D + di) * 2) * HW + (size_t)hi * W;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int wi = w0 - 1 + j;
+        const bool ok = wi >= 0 && wi < W;
+        xa[j] = ok ? __ldg(r0 + wi) : 0.f;
+        xb[j] = ok ? __ldg(r0 + HW + wi) : 0.f;
+      }
     }
     const float* wt = c_head_w + kdh * (3 * 64);
 #pragma unroll
@@ -752,8 +776,8 @@ extern "C" int v2ce_model_workspace_bytes(const v2ce_model* m, int32_t batch, in
   return V2CE_OK;
 }
 
-extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_dev, int32_t B, int32_t D, int32_t H,
-                                  int32_t W, void* ws_dev, size_t ws_bytes, void* stream) {
+static int forward_impl(v2ce_model* m, const void* x_dev, bool frames_u8, float* y_dev, int32_t B, int32_t D, int32_t H,
+                        int32_t W, void* ws_dev, size_t ws_bytes, void* stream) {
   V2CE_REQUIRE(m && x_dev && y_dev && ws_dev, "NULL argument");
   V2CE_REQUIRE(m->finalized, "model not finalized");
   V2CE_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "bad shape");
@@ -793,7 +817,10 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
       V2CE_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_head_b, m->layers[0].bias, sizeof(float) * 32, 0, cudaMemcpyDeviceToDevice, s));
       head_owner[m->device & 63] = m->uid;
     }
-    head_conv_kernel<<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, B, D, H, W, buf.head);
+    if (frames_u8)
+      head_conv_kernel<true><<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, B, D, H, W, buf.head);
+    else
+      head_conv_kernel<false><<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, B, D, H, W, buf.head);
   }
   V2CE_LAUNCH_CHECK("head_conv_kernel");
   ++launches;
@@ -871,6 +898,16 @@ extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_de
   }
   m->last_launches = launches;
   return V2CE_OK;
+}
+
+extern "C" int v2ce_model_forward(v2ce_model* m, const float* x_dev, float* y_dev, int32_t B, int32_t D, int32_t H,
+                                  int32_t W, void* ws_dev, size_t ws_bytes, void* stream) {
+  return forward_impl(m, x_dev, false, y_dev, B, D, H, W, ws_dev, ws_bytes, stream);
+}
+
+extern "C" int v2ce_model_forward_frames(v2ce_model* m, const uint8_t* frames_dev, float* y_dev, int32_t B, int32_t D,
+                                         int32_t H, int32_t W, void* ws_dev, size_t ws_bytes, void* stream) {
+  return forward_impl(m, frames_dev, true, y_dev, B, D, H, W, ws_dev, ws_bytes, stream);
 }
 
 extern "C" int v2ce_model_last_sigmas(const v2ce_model* m, float* sigma12_host) {

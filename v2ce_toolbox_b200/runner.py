@@ -82,7 +82,8 @@ class BatchRunner:
 
     # ------------------------------------------------------------------------------------------
     def submit(self, units, pair_base, keep_sums=False):
-        """units: (b,L,2,H,W) float32, pinned host (copied on the side stream) or already on the device."""
+        """units: image units (b,L,2,H,W) float32, or raw gray windows (b,L+1,H,W) uint8 at the model's resolution;
+        pinned host (copied on the side stream) or already on the device."""
         t = Ticket()
         slot = self._next
         self._next = (self._next + 1) % self.slots
@@ -107,7 +108,8 @@ class BatchRunner:
         if self.time_forward:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(cur)
-        y = self.model(x)
+        # uint8 windows (b, L+1, H, W): pre-processing fused into the head conv (V2ce3d.forward_frames)
+        y = self.model.forward_frames(x) if x.dtype == torch.uint8 else self.model(x)
         if self.time_forward:
             e1.record(cur)
             t.fwd_events = (e0, e1)

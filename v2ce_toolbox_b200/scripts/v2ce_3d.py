@@ -105,6 +105,31 @@ class V2ce3d(nn.Module):
                                                self._ws.numel(), stream_ptr()))
         return y
 
+    def forward_frames(self, frames):
+        """frames (B, L+1, H, W) uint8 CUDA, window b = L+1 consecutive gray frames at the model's resolution ->
+        (B, L, 20, H, W) float32.  Equals ``forward(image_pre_processing(frames))`` bit for bit (v2ce.py:45-64);
+        the pre-processing runs inside the head conv, so a window costs 1/8 of the H2D bytes of its image units."""
+        require_cuda(frames, 'frames')
+        if frames.dtype != torch.uint8 or frames.dim() != 4:
+            raise V2ceError(f'expected uint8 frames of shape (B,L+1,H,W), got {frames.dtype} {tuple(frames.shape)}')
+        if self._handle is None:
+            if self._state is None:
+                raise V2ceError('V2ce3d: load_state_dict() before forward()')
+            self.to(frames.device)
+        B, L1, H, W = frames.shape
+        L = L1 - 1
+        frames = frames.contiguous()
+        with torch.cuda.device(frames.device):
+            n = ctypes.c_size_t()
+            check(self._lib.v2ce_model_workspace_bytes(self._handle, B, L, H, W, ctypes.byref(n)))
+            if self._ws is None or self._ws.numel() < n.value:
+                self._ws = None
+                self._ws = torch.empty(n.value, dtype=torch.uint8, device=frames.device)
+            y = torch.empty((B, L, 20, H, W), dtype=torch.float32, device=frames.device)
+            check(self._lib.v2ce_model_forward_frames(self._handle, ptr(frames), ptr(y), B, L, H, W, ptr(self._ws),
+                                                      self._ws.numel(), stream_ptr()))
+        return y
+
     # -- spectral-norm state (multi-GPU replay, tests) --------------------------------------
     def last_sigmas(self):
         out = (ctypes.c_float * 12)()
