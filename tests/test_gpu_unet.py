@@ -100,6 +100,11 @@ KDM_CASES = [
     ('kdm_n64_many', 2, 16, 33, 44, 64, None, 0, 64, 3, 1, True, 1),
     ('kdm_128_in', 1, 8, 20, 70, 128, None, 64, 64, 3, 1, False, 2),
     ('kdm_fullres', 1, 8, 260, 346, 64, None, 64, 32, 3, 1, True, 1),
+    # stride (1,2,2) through the four parity views (one source): odd and even planes, 1-4 N tiles, 1-2 channel chunks
+    ('kdm_s2_small', 1, 8, 9, 11, 64, None, 0, 32, 3, 2, False, 1),
+    ('kdm_s2_odd', 2, 16, 33, 44, 64, None, 0, 64, 3, 2, False, 1),
+    ('kdm_s2_128', 1, 8, 20, 70, 128, None, 0, 128, 3, 2, False, 2),
+    ('kdm_s2_fullres', 1, 8, 260, 346, 64, None, 0, 64, 3, 2, False, 1),
 ]
 
 
@@ -139,10 +144,11 @@ def test_conv_with_fused_shortcut_vs_torch(case):
     w[:, :, 1, 1, 1] *= 4.0                      # the shortcut weights: make them count
     scale = 0.5 + torch.rand(cout, generator=g)
     shift = 0.2 * torch.randn(cout, generator=g)
-    out2 = torch.full((B, D, hin, win, cout), float('nan'), dtype=torch.bfloat16, device='cuda')
-    out = conv_hook(src0, src1, hin, win, w, scale, shift, out2, act, 3, 1, impl=3)
-    ref = torch_ref(src0, src1, hin, win, w, scale, shift, None, act, 3, 1)
-    ref2 = torch_ref(src0, src1, hin, win, w[:, :, 1:2, 1:2, 1:2].contiguous(), scale, shift, None, 0, 1, 1)
+    hout, wout = (hin - 1) // stride + 1, (win - 1) // stride + 1
+    out2 = torch.full((B, D, hout, wout, cout), float('nan'), dtype=torch.bfloat16, device='cuda')
+    out = conv_hook(src0, src1, hin, win, w, scale, shift, out2, act, 3, stride, impl=3)
+    ref = torch_ref(src0, src1, hin, win, w, scale, shift, None, act, 3, stride)
+    ref2 = torch_ref(src0, src1, hin, win, w[:, :, 1:2, 1:2, 1:2].contiguous(), scale, shift, None, 0, 1, stride)
     for got, want, what in ((out, ref, 'conv'), (out2, ref2, 'shortcut')):
         assert not torch.isnan(got.float()).any(), f'{what}: unwritten outputs'
         err = (got.float() - want).abs()

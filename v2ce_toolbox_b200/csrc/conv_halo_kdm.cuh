@@ -123,9 +123,23 @@ __device__ __forceinline__ void kdm_store_chunk(const HaloArgs& a, const KdmRow&
   }
 }
 
-template <bool SHORT, int T>
+// S = 2: stride (1,2,2).  A stride-2 3x3 conv is the sum of four stride-1 convs on the even/odd sub-images
+// X_pq[i][j] = X[2i+p][2j+q] (2x2, 2x1, 1x2 and 1x1 taps), and TMA addresses each sub-image as a strided view of the
+// same tensor (ParityMaps), zero fill at its borders = the conv padding.  Per input slice the CTA loads four parity
+// patches of (TH+1) x PW pixels (PW = TW+1) and multiplies each by its taps through row-shifted descriptors:
+//   q = 2p+q':  0 (even,even): tap (1,1)        1 (even row, odd col): (1,0), (1,2)+1
+//               2 (odd row, even col): (0,1), (2,1)+PW     3 (odd,odd): (0,0), (0,2)+1, (2,0)+PW, (2,2)+PW+1
+// so the input is read once (plus halo) instead of once per tap (the gather kernel moved 5.3 GB through L2 for
+// encoders.0.conv1).  The block's stride-2 1x1x1 shortcut is the (1,1) tap, fused as in the stride-1 case.
+struct ParityMaps { CUtensorMap m[4]; };
+
+// taps in the order the stride-2 variant multiplies them
+__device__ __constant__ int kS2TapOrder[9] = {4, 3, 5, 1, 7, 0, 2, 6, 8};
+
+template <bool SHORT, int T, int S>
 __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1,
+                                                                     const __grid_constant__ ParityMaps pm,
                                                                      const HaloArgs a, const KdmShort sc) {
   // T output slices per tile: 8, or the whole depth of a 16-slice window (no depth halo: 16 patch loads per 16
   // output slices instead of 20, and fewer narrow edge instructions) when the shortcut does not need half of TMEM
@@ -193,13 +207,27 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
         const CUtensorMap* map = first ? &tm0 : &tm1;
         const int c0 = (first ? cc : cc - a.ncc0) * kBlockK;
         for (int z = zl; z <= zh; ++z) {
-          mbar_wait(a_empty(s), (uint32_t)ph, a.error_flag);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(a_full(s), (uint32_t)a.box_bytes);
-            tma_load_5d(a_base + (uint32_t)s * a.a_stage_bytes, map, c0, tc.w0 - 1, tc.h0 - 1, z, tc.b, a_full(s));
+          if (S == 1) {
+            mbar_wait(a_empty(s), (uint32_t)ph, a.error_flag);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(a_full(s), (uint32_t)a.box_bytes);
+              tma_load_5d(a_base + (uint32_t)s * a.a_stage_bytes, map, c0, tc.w0 - 1, tc.h0 - 1, z, tc.b, a_full(s));
+            }
+            __syncwarp();
+            if (++s == a.SA) { s = 0; ph ^= 1; }
+          } else {
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {           // parity patch q = 2*(row parity) + (column parity)
+              mbar_wait(a_empty(s), (uint32_t)ph, a.error_flag);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(a_full(s), (uint32_t)a.box_bytes);
+                tma_load_5d(a_base + (uint32_t)s * a.a_stage_bytes, &pm.m[q], c0, tc.w0 - (q & 1), tc.h0 - (q >> 1), z, tc.b,
+                            a_full(s));
+              }
+              __syncwarp();
+              if (++s == a.SA) { s = 0; ph ^= 1; }
+            }
           }
-          __syncwarp();
-          if (++s == a.SA) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -210,7 +238,8 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
       const TileCoord tc = decode_tile(tile, a, T, n_tiles);
       for (int cc = 0; cc < ncc; ++cc) {
         const __nv_bfloat16* wt = a.wpack + (size_t)(tc.n_tile * ncc + cc) * 9 * (kKdmWTile / 2);
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int ti = 0; ti < 9; ++ti) {
+          const int tap = (S == 1) ? ti : kS2TapOrder[ti];      // refill in the order the slots are freed
           mbar_wait(w_empty(tap), ph, a.error_flag);
           if (elect_one()) {
             mbar_arrive_expect_tx(w_full(tap), (uint32_t)kKdmWTile);
@@ -259,29 +288,22 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
             const int f_lo = first_z ? o_lo : o_lo + (jhi - jlo), f_hi = (first_z || jhi == 2) ? o_lo + (jhi - jlo) : -1;
             for (int o = f_lo; o <= f_hi; ++o) mbar_wait(s_empty(slot0 + o), par_empty, a.error_flag);
           }
-          mbar_wait(a_full(sa), (uint32_t)pa, a.error_flag);
-          tcgen05_fence_after();
-          const uint32_t patch = a_base + (uint32_t)sa * a.a_stage_bytes;
           const uint32_t col = acc_base + (uint32_t)(o_lo * BN);
           const uint32_t n_all = (uint32_t)((jhi - jlo + 1) * BN);
           const uint32_t idesc_all = make_idesc((int)n_all);
-          // descriptor low words of (tap 0, k 0); a tap adds (kh*PW + kw) rows of 128 B to A and one weight tile to
-          // B, a K=16 step adds 32 B to both (fully unrolled: the issue loop must stay well under the 56 cycles
-          // one N=96 instruction occupies the tensor pipe)
-          const uint32_t a_lo = smem_desc_lo(patch);
           const uint32_t b_lo = smem_desc_lo(w_base + (uint32_t)jlo * (BN * 128));
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
+          // one tap: all K=16 steps of A(rows shifted by a_t) x the tap's [kd-merged] weight tile; `lead` marks the
+          // tile's very first instruction candidates (first tap in issue order)
+          auto issue_tap = [&](const int tap, const uint32_t a_t, const bool lead) {
             if (first_z) {
               mbar_wait(w_full(tap), pw, a.error_flag);
               tcgen05_fence_after();
             }
-            const uint32_t a_t = a_lo + (uint32_t)(tap / 3) * pw8 + (uint32_t)(tap % 3) * 8u;
             const uint32_t b_t = b_lo + (uint32_t)tap * (kKdmWTile >> 4);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
               if (k < ks) {
-                if (tap != 0 || k != 0 || cc != 0) {
+                if (!lead || k != 0 || cc != 0) {
                   tcgen05_mma_bf16_lo(col, a_t + 2 * k, b_t + 2 * k, idesc_all, 1u);
                 } else if (first_z) {
                   // first multiply into this tile's accumulators: nothing covered has been written yet
@@ -308,10 +330,44 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
                 if (k < ks) tcgen05_mma_bf16_lo(scol, a_t + 2 * k, bs_lo + 2 * k, idesc32, (cc != 0 || k != 0) ? 1u : 0u);
             }
             if (last_z) tcgen05_commit_elect(w_empty(tap));     // last use of this chunk's tap tile
+          };
+          if (S == 1) {
+            mbar_wait(a_full(sa), (uint32_t)pa, a.error_flag);
+            tcgen05_fence_after();
+            // descriptor low words of (tap 0, k 0); a tap adds (kh*PW + kw) rows of 128 B to A and one weight tile to
+            // B, a K=16 step adds 32 B to both (fully unrolled: the issue loop must stay well under the 56 cycles
+            // one N=96 instruction occupies the tensor pipe)
+            const uint32_t a_lo = smem_desc_lo(a_base + (uint32_t)sa * a.a_stage_bytes);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap)
+              issue_tap(tap, a_lo + (uint32_t)(tap / 3) * pw8 + (uint32_t)(tap % 3) * 8u, tap == 0);
+            tcgen05_commit_elect(a_empty(sa));
+            if (++sa == a.SA) { sa = 0; pa ^= 1; }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              mbar_wait(a_full(sa), (uint32_t)pa, a.error_flag);
+              tcgen05_fence_after();
+              const uint32_t a_lo = smem_desc_lo(a_base + (uint32_t)sa * a.a_stage_bytes);
+              if (q == 0) {
+                issue_tap(4, a_lo, true);
+              } else if (q == 1) {
+                issue_tap(3, a_lo, false);
+                issue_tap(5, a_lo + 8u, false);
+              } else if (q == 2) {
+                issue_tap(1, a_lo, false);
+                issue_tap(7, a_lo + pw8, false);
+              } else {
+                issue_tap(0, a_lo, false);
+                issue_tap(2, a_lo + 8u, false);
+                issue_tap(6, a_lo + pw8, false);
+                issue_tap(8, a_lo + pw8 + 8u, false);
+              }
+              tcgen05_commit_elect(a_empty(sa));
+              if (++sa == a.SA) { sa = 0; pa ^= 1; }
+            }
           }
           if (SHORT && last_z) tcgen05_commit_elect(w_empty(9));
-          tcgen05_commit_elect(a_empty(sa));
-          if (++sa == a.SA) { sa = 0; pa ^= 1; }
           if (last_cc) {
             // output slice z-1 has received its last contribution; at the end of the depth range so has slice z
             if (z - 1 >= tc.d0) tcgen05_commit_elect(s_full(slot0 + z - 1 - tc.d0));
@@ -466,57 +522,109 @@ __global__ void pack_weights_kdm_short_kernel(const float* __restrict__ w, int C
 }
 
 struct KdmPlan {
-  TileShape ts;
+  TileShape ts;          // PW (patch pitch) and TH (output rows per tile)
+  int TW;                // valid output columns per tile: PW - 2 (stride 1) or PW - 1 (stride 2)
+  int rows;              // rows of one TMA box: (TH+2)*PW or (TH+1)*PW
   int SA, a_stage_bytes, box_bytes, smem_bytes;
   bool ok;
 };
 
-// the kernel applies to depth multiples of 8 and needs room for at least 3 patch stages beside the weights
-inline KdmPlan plan_kdm(int D, int H, int W) {
+// tile shape for the stride-2 variant over an OUTPUT plane of H x W: one halo column (PW = TW+1), TH*PW <= 128
+inline TileShape pick_tile_s2(int H, int W) {
+  TileShape best{16, 8};
+  double best_eff = 0.0;
+  for (int pw = 8; pw <= 64; pw += 1) {
+    const int tw = pw - 1, th = 128 / pw;
+    if (th < 1) continue;
+    const long tiles = (long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+    const double eff = (double)H * W / (tiles * 128.0);
+    if (eff > best_eff + 0.01) { best_eff = eff; best = TileShape{pw, th}; }
+  }
+  return best;
+}
+
+// the kernel applies to depth multiples of 8 and needs room for at least 3 patch stages beside the weights;
+// H, W = output plane
+inline KdmPlan plan_kdm(int D, int H, int W, int stride = 1) {
   KdmPlan p;
-  p.ts = pick_tile(H, W);
-  const int rows = p.ts.PW * (p.ts.TH + 2);
-  p.box_bytes = rows * 128;
-  p.a_stage_bytes = ((rows + 2 + 7) / 8) * 1024;
+  if (stride == 2) {
+    p.ts = pick_tile_s2(H, W);
+    p.TW = p.ts.PW - 1;
+    p.rows = p.ts.PW * (p.ts.TH + 1);
+  } else {
+    p.ts = pick_tile(H, W);
+    p.TW = p.ts.PW - 2;
+    p.rows = p.ts.PW * (p.ts.TH + 2);
+  }
+  p.box_bytes = p.rows * 128;
+  p.a_stage_bytes = ((p.rows + 2 + 7) / 8) * 1024;
   const int tail = kKdmBars * 8 + 16 + 4 * kKdmBN * 4;
   const int budget = 227 * 1024 - 1024 - tail - 9 * kKdmWTile - kKdmSTile;
   p.SA = budget / p.a_stage_bytes;
   if (p.SA > kMaxSA) p.SA = kMaxSA;
-  p.ok = (D % kKdmT == 0) && p.SA >= 3;
+  p.ok = (D % kKdmT == 0) && p.SA >= (stride == 2 ? 4 : 3);
   p.smem_bytes = 9 * kKdmWTile + kKdmSTile + p.SA * p.a_stage_bytes + tail + 1024;
   return p;
 }
 
-// `sc` != nullptr: also compute the block's 1x1x1 shortcut conv of the same input (second output)
+// tensor map over the parity sub-image X[2i+ph][2j+pw] of a (B, D, H, W, Cpitch) bf16 activation: the same memory
+// with doubled row / pixel strides; box = 64 channels x PW x rows pixels
+inline int make_parity_map(CUtensorMap* map, const void* ptr, int B, int D, int H, int W, int cpitch, int ph, int pw, int PW,
+                           int rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(V2CE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const int Hp = (H - ph + 1) / 2, Wq = (W - pw + 1) / 2;
+  if (Hp < 1 || Wq < 1) return set_error(V2CE_ERR_INVALID, "stride-2 conv needs at least 2x2 input pixels");
+  cuuint64_t dims[5] = {(cuuint64_t)cpitch, (cuuint64_t)Wq, (cuuint64_t)Hp, (cuuint64_t)D, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)2 * cpitch * 2, (cuuint64_t)2 * W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2,
+                           (cuuint64_t)D * H * W * cpitch * 2};
+  cuuint32_t box[5] = {64u, (cuuint32_t)PW, (cuuint32_t)rows, 1u, 1u};
+  cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  void* base = const_cast<char*>(static_cast<const char*>(ptr)) + ((size_t)ph * W + pw) * cpitch * 2;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(V2CE_ERR_CUDA, "cuTensorMapEncodeTiled (parity view) failed with CUresult %d", (int)r);
+  return V2CE_OK;
+}
+
+template <bool SHORT, int T, int S>
+inline int launch_kdm_one(const CUtensorMap& tm0, const CUtensorMap& tm1, const ParityMaps& pm, const HaloArgs& a,
+                          const KdmShort& sc, int smem_bytes, cudaStream_t s) {
+  static int configured = 0;
+  if (configured < smem_bytes) {
+    V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<SHORT, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = smem_bytes;
+  }
+  const int total = a.B * (a.D / T) * a.tiles_h * a.tiles_w * (a.Cout / kKdmBN);
+  const int grid = total < sm_count_cached() ? total : sm_count_cached();
+  conv_halo_kdm_kernel<SHORT, T, S><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, pm, a, sc);
+  V2CE_LAUNCH_CHECK("conv_halo_kdm_kernel");
+  return V2CE_OK;
+}
+
+// `sc` != nullptr: also compute the block's 1x1x1 shortcut conv of the same input (second output).
+// `pm` != nullptr: stride (1,2,2); a.H / a.W are the OUTPUT plane and pm the four parity views of the single source.
 inline int launch_halo_kdm(const CUtensorMap& tm0, const CUtensorMap& tm1, const HaloArgs& a, const KdmShort* sc, int smem_bytes,
-                           cudaStream_t s) {
-  static int configured[3] = {0, 0, 0};
+                           cudaStream_t s, const ParityMaps* pm = nullptr) {
   static const bool t8_only = getenv("V2CE_KDM_T8") && atoi(getenv("V2CE_KDM_T8"));
   if (a.D % kKdmT != 0 || a.Cout % kKdmBN != 0)
     return set_error(V2CE_ERR_INVALID, "depth-merged halo kernel: depth %d / Cout %d not supported", a.D, a.Cout);
   if (sc && (a.up_H > 0 || a.pred_w != nullptr || a.residual != nullptr))
     return set_error(V2CE_ERR_INVALID, "depth-merged halo kernel: the fused shortcut goes with a plain first conv");
-  const int which = sc ? 1 : (a.D % 16 == 0 && !t8_only) ? 2 : 0;
-  if (configured[which] < smem_bytes) {
-    if (which == 1)
-      V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    else if (which == 2)
-      V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    else
-      V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured[which] = smem_bytes;
-  }
-  const int T = which == 2 ? 16 : 8;
+  if (pm && a.ncc1 != 0) return set_error(V2CE_ERR_INVALID, "depth-merged halo kernel: stride 2 takes a single source");
+  const bool t16 = !sc && a.D % 16 == 0 && !t8_only;
   HaloArgs b = a;
-  b.T = T;
-  const int total = b.B * (b.D / T) * b.tiles_h * b.tiles_w * (b.Cout / kKdmBN);
-  const int grid = total < sm_count_cached() ? total : sm_count_cached();
-  KdmShort none{nullptr, nullptr, nullptr, nullptr, 0};
-  if (which == 1) conv_halo_kdm_kernel<true, 8><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, b, *sc);
-  else if (which == 2) conv_halo_kdm_kernel<false, 16><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, b, none);
-  else conv_halo_kdm_kernel<false, 8><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, b, none);
-  V2CE_LAUNCH_CHECK("conv_halo_kdm_kernel");
-  return V2CE_OK;
+  b.T = t16 ? 16 : 8;
+  const KdmShort none{nullptr, nullptr, nullptr, nullptr, 0};
+  static const ParityMaps no_pm{};
+  if (pm) {
+    if (sc) return launch_kdm_one<true, 8, 2>(tm0, tm1, *pm, b, *sc, smem_bytes, s);
+    if (t16) return launch_kdm_one<false, 16, 2>(tm0, tm1, *pm, b, none, smem_bytes, s);
+    return launch_kdm_one<false, 8, 2>(tm0, tm1, *pm, b, none, smem_bytes, s);
+  }
+  if (sc) return launch_kdm_one<true, 8, 1>(tm0, tm1, no_pm, b, *sc, smem_bytes, s);
+  if (t16) return launch_kdm_one<false, 16, 1>(tm0, tm1, no_pm, b, none, smem_bytes, s);
+  return launch_kdm_one<false, 8, 1>(tm0, tm1, no_pm, b, none, smem_bytes, s);
 }
 
 }  // namespace halo

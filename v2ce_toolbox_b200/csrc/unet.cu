@@ -555,7 +555,7 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
   a.Cout = L.cout; a.out_pitch = out_pitch; a.res_pitch = res_pitch;
   a.T = plan.T; a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
   a.wpack = dl.wpack; a.scale = dl.scale; a.shift = dl.shift;
-  if (kdm) { a.T = halo::kKdmT; a.SA = kplan.SA; a.SB = 9; a.wpack = dl.wpack_kdm; }
+  if (kdm) { a.T = halo::kKdmT; a.SA = kplan.SA; a.SB = 9; a.wpack = dl.wpack_kdm; a.a_stage_bytes = kplan.a_stage_bytes; }
   a.inv_sigma = dl.sn_index >= 0 ? m->inv_sigma_dev + dl.sn_index : nullptr;
   a.residual = residual; a.out = out; a.act = act;
   a.up_H = up_H; a.up_W = up_W;
@@ -591,6 +591,50 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
   return halo::launch_halo(tm0, tm1, a, dl.bn_tile, plan.smem_bytes, s);
 }
 
+// stride-(1,2,2) first conv of encoder block `li` with the block's stride-2 1x1x1 shortcut (layer li+2) fused:
+// x (B,D,Hin,Win,pin) -> out (B,D,Hout,Wout,Cout) [ReLU(bn1(conv1))] and short_out [bn_d(conv_d)].  Returns false in
+// *done when the depth-merged kernel does not apply (the caller then runs the two gather launches).
+static int run_enc_kdm(v2ce_model* m, int li, const __nv_bfloat16* x, int pin, int B, int D, int Hin, int Win,
+                       __nv_bfloat16* out, __nv_bfloat16* short_out, cudaStream_t s, bool* done) {
+  const LayerSpec& L = kLayers[li];
+  const DevLayer& dl = m->layers[li];
+  const DevLayer& sl = m->layers[li + 2];
+  *done = false;
+  static const bool off = getenv("V2CE_NO_S2_KDM") && atoi(getenv("V2CE_NO_S2_KDM"));
+  const int Hout = (Hin - 1) / 2 + 1, Wout = (Win - 1) / 2 + 1;
+  const halo::KdmPlan kp = halo::plan_kdm(D, Hout, Wout, 2);
+  if (off || !kp.ok || dl.wpack_kdm == nullptr || sl.wpack_kdm == nullptr || pin % 64 != 0 || Hin < 2 || Win < 2) return V2CE_OK;
+  halo::HaloArgs a;
+  a.B = B; a.D = D; a.H = Hout; a.W = Wout;
+  a.PW = kp.ts.PW; a.TH = kp.ts.TH; a.TW = kp.TW;
+  a.tiles_w = (Wout + a.TW - 1) / a.TW;
+  a.tiles_h = (Hout + a.TH - 1) / a.TH;
+  a.ncc0 = pin / 64; a.ncc1 = 0;
+  a.real0 = dl.cfg.real0; a.real1 = 0;
+  a.Cout = L.cout; a.out_pitch = L.cout; a.res_pitch = 0;
+  a.T = halo::kKdmT; a.SA = kp.SA; a.SB = 9; a.a_stage_bytes = kp.a_stage_bytes; a.box_bytes = kp.box_bytes;
+  a.wpack = dl.wpack_kdm; a.scale = dl.scale; a.shift = dl.shift;
+  a.inv_sigma = nullptr;
+  a.residual = nullptr; a.out = out; a.act = 1;
+  a.up_H = 0; a.up_W = 0; a.pred_w = nullptr; a.pred_b = nullptr; a.pred_out = nullptr;
+  a.error_flag = m->error_flag_dev;
+  halo::ParityMaps pm;
+  for (int q = 0; q < 4; ++q) {
+    // cached by (ptr, geometry); the parity rides in the "rows" key slot with an offset that cannot collide
+    auto key = std::make_tuple(static_cast<const void*>(x), B, D, Hin, Win, pin, a.PW, 1000 + q * 100 + a.TH);
+    auto it = m->tmaps.find(key);
+    if (it == m->tmaps.end()) {
+      CUtensorMap tm;
+      if (int e = halo::make_parity_map(&tm, x, B, D, Hin, Win, pin, q >> 1, q & 1, a.PW, a.TH + 1)) return e;
+      it = m->tmaps.emplace(key, tm).first;
+    }
+    pm.m[q] = it->second;
+  }
+  halo::KdmShort sc{sl.wpack_kdm, sl.scale, sl.shift, short_out, L.cout};
+  *done = true;
+  return halo::launch_halo_kdm(pm.m[0], pm.m[0], a, &sc, kp.smem_bytes, s, &pm);
+}
+
 static int pack_layer(v2ce_model* m, int li, const float* w_dev, cudaStream_t s) {
   const LayerSpec& L = kLayers[li];
   DevLayer& dl = m->layers[li];
@@ -615,7 +659,16 @@ static int pack_layer(v2ce_model* m, int li, const float* w_dev, cudaStream_t s)
     }
     return V2CE_OK;
   }
-  if (L.k == 1 && L.cout <= 64 && std::string(L.name).find("decoders") != std::string::npos) {
+  const bool is_encoder = std::string(L.name).find("encoders") != std::string::npos;
+  if (is_encoder && L.k == 3 && std::string(L.name).find(".conv1") != std::string::npos) {
+    // stride-2 first conv of an encoder block: depth-merged packing for the parity-view kernel (conv_halo_kdm.cuh, S = 2)
+    const size_t nk = (size_t)L.cout * 27 * c.pitch0;
+    if (int e = dev_alloc(m, &dl.wpack_kdm, nk)) return e;
+    halo::pack_weights_kdm_kernel<<<(int)((nk + 255) / 256 > 4096 ? 4096 : (nk + 255) / 256), 256, 0, s>>>(
+        w_dev, L.cout, L.cin, c.pitch0, c.real0, 0, 0, dl.wpack_kdm);
+    V2CE_LAUNCH_CHECK("pack_weights_kdm_kernel");
+  }
+  if (L.k == 1 && ((L.cout <= 64 && std::string(L.name).find("decoders") != std::string::npos) || is_encoder)) {
     // the shortcut of a decoder block can ride in its conv1 launch (conv_halo_kdm.cuh): [Cout/32][cc][32][64]
     const size_t ns = (size_t)L.cout * (c.pitch0 + c.pitch1);
     if (int e = dev_alloc(m, &dl.wpack_kdm, ns)) return e;
@@ -834,10 +887,17 @@ static int forward_impl(v2ce_model* m, const void* x_dev, bool frames_u8, float*
     snprintf(name, sizeof(name), "UNet.encoders.%d.conv1", i);
     const int l1 = layer_index(name);
     const int pin = pitch_of(ch[i]), co = ch[i + 1];
-    if (int e = run_conv(m, l1, x, pin, d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 1, buf.tmp_t, s)) return e;
-    mark(kLayers[l1].name);
-    if (int e = run_conv(m, l1 + 2, x, pin, d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 0, buf.tmp_r, s)) return e;
-    mark(kLayers[l1 + 2].name);
+    bool fused = false;
+    if (int e = run_enc_kdm(m, l1, x, pin, B, D, d.H[i], d.W[i], buf.tmp_t, buf.tmp_r, s, &fused)) return e;
+    if (fused) {
+      mark(kLayers[l1].name);
+      launches -= 1;
+    } else {
+      if (int e = run_conv(m, l1, x, pin, d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 1, buf.tmp_t, s)) return e;
+      mark(kLayers[l1].name);
+      if (int e = run_conv(m, l1 + 2, x, pin, d.H[i], d.W[i], nullptr, 0, B, D, d.H[i], d.W[i], 2, nullptr, 0, buf.tmp_r, s)) return e;
+      mark(kLayers[l1 + 2].name);
+    }
     if (int e = run_halo(m, l1 + 1, buf.tmp_t, co, nullptr, 0, B, D, d.H[i + 1], d.W[i + 1], buf.tmp_r, co, 1, buf.enc[i], co, s)) return e;
     mark(kLayers[l1 + 1].name);
     x = buf.enc[i];
@@ -974,11 +1034,14 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
   V2CE_REQUIRE((src1_dev != nullptr) == (c1 > 0), "src1 and c1 must agree");
   const int bn = conv::pick_bn(cout);
   V2CE_REQUIRE(bn != 0, "cout must be a multiple of 32");
-  if (impl >= 2) V2CE_REQUIRE(cout <= 64 && halo::plan_kdm(depth, hin, win).ok, "depth-merged halo kernel: Cout <= 64, depth % 8 == 0");
+  if (impl >= 2)
+    V2CE_REQUIRE(halo::plan_kdm(depth, stride_hw == 2 ? (hin - 1) / 2 + 1 : hin, stride_hw == 2 ? (win - 1) / 2 + 1 : win, stride_hw).ok,
+                 "depth-merged halo kernel: depth % 8 == 0");
   if (impl == 3) V2CE_REQUIRE(residual_dev != nullptr, "impl 3: residual_dev receives the fused shortcut output");
   if (impl >= 1)
-    V2CE_REQUIRE(ksize == 3 && stride_hw == 1 && h0 == hin && w0 == win && c0 % 64 == 0 && c1 % 64 == 0,
-                 "halo kernel: 3x3x3, stride 1, no upsample, channel pitches multiple of 64");
+    V2CE_REQUIRE(ksize == 3 && (stride_hw == 1 || (impl >= 2 && c1 == 0)) && h0 == hin && w0 == win && c0 % 64 == 0 && c1 % 64 == 0,
+                 "halo kernel: 3x3x3, stride 1 (depth-merged variant: also stride 2 with one source), no upsample, "
+                 "channel pitches multiple of 64");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int cin = c0 + c1, taps = ksize * ksize * ksize;
   const int num_kb = (taps * cin + conv::kBlockK - 1) / conv::kBlockK;
@@ -1008,7 +1071,7 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
   const int hout = (hin + 2 * pad - ksize) / stride_hw + 1, wout = (win + 2 * pad - ksize) / stride_hw + 1;
   if (rc == V2CE_OK && impl >= 1) {
     const halo::HaloPlan plan = halo::plan_for(bn, depth, hin, win);
-    const halo::KdmPlan kplan = halo::plan_kdm(depth, hin, win);
+    const halo::KdmPlan kplan = halo::plan_kdm(depth, hout, wout, stride_hw);
     halo::HaloArgs a;
     a.B = batch; a.D = depth; a.H = hin; a.W = win;
     a.PW = plan.ts.PW; a.TH = plan.ts.TH; a.TW = plan.ts.PW - 2;
@@ -1018,13 +1081,26 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
     a.Cout = cout; a.out_pitch = cout; a.res_pitch = cout;
     a.T = plan.T; a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
     a.wpack = wpack; a.scale = scale_dev; a.shift = shift_dev; a.inv_sigma = nullptr;
-    if (impl >= 2) { a.T = halo::kKdmT; a.SA = kplan.SA; a.SB = 9; }
+    halo::ParityMaps pmaps;
+    const bool s2 = impl >= 2 && stride_hw == 2;
+    if (impl >= 2) {
+      a.T = halo::kKdmT; a.SA = kplan.SA; a.SB = 9; a.a_stage_bytes = kplan.a_stage_bytes; a.box_bytes = kplan.box_bytes;
+      a.H = hout; a.W = wout;
+      a.PW = kplan.ts.PW; a.TH = kplan.ts.TH; a.TW = kplan.TW;
+      a.tiles_w = (wout + a.TW - 1) / a.TW; a.tiles_h = (hout + a.TH - 1) / a.TH;
+    }
     a.residual = impl == 3 ? nullptr : static_cast<const __nv_bfloat16*>(residual_dev);
     a.out = static_cast<__nv_bfloat16*>(out_dev);
     a.act = act; a.error_flag = flag;
     a.up_H = 0; a.up_W = 0; a.pred_w = nullptr; a.pred_b = nullptr; a.pred_out = nullptr;
     CUtensorMap tm0, tm1;
-    rc = halo::make_patch_map(&tm0, src0_dev, batch, depth, hin, win, c0, a.PW, a.TH + 2);
+    if (s2) {
+      for (int q = 0; q < 4 && rc == V2CE_OK; ++q)
+        rc = halo::make_parity_map(&pmaps.m[q], src0_dev, batch, depth, hin, win, c0, q >> 1, q & 1, a.PW, a.TH + 1);
+      tm0 = pmaps.m[0];
+    } else {
+      rc = halo::make_patch_map(&tm0, src0_dev, batch, depth, hin, win, c0, a.PW, a.TH + 2);
+    }
     tm1 = tm0;
     if (rc == V2CE_OK && src1_dev) rc = halo::make_patch_map(&tm1, src1_dev, batch, depth, hin, win, c1, a.PW, a.TH + 2);
     if (rc == V2CE_OK && impl == 3) {
@@ -1040,12 +1116,12 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
         halo::pack_weights_kdm_short_kernel<<<(int)((wd.size() + 255) / 256), 256, 0, s>>>(wd_dev, cout, cin, c0, c0, c1, c1, wshort);
         cudaStreamSynchronize(s);
         halo::KdmShort sc{wshort, scale_dev, shift_dev, static_cast<__nv_bfloat16*>(const_cast<void*>(residual_dev)), cout};
-        rc = halo::launch_halo_kdm(tm0, tm1, a, &sc, kplan.smem_bytes, s);
+        rc = halo::launch_halo_kdm(tm0, tm1, a, &sc, kplan.smem_bytes, s, s2 ? &pmaps : nullptr);
       }
       cudaStreamSynchronize(s);
       cudaFree(wd_dev);
     } else if (rc == V2CE_OK) {
-      rc = impl == 2 ? halo::launch_halo_kdm(tm0, tm1, a, nullptr, kplan.smem_bytes, s)
+      rc = impl == 2 ? halo::launch_halo_kdm(tm0, tm1, a, nullptr, kplan.smem_bytes, s, s2 ? &pmaps : nullptr)
                      : halo::launch_halo(tm0, tm1, a, bn, plan.smem_bytes, s);
     }
   } else if (rc == V2CE_OK) {
