@@ -502,7 +502,10 @@ inline EncodeTiledFn encode_fn() {
 inline int make_patch_map(CUtensorMap* map, const void* ptr, int B, int D, int H, int W, int cpitch, int PW, int rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(V2CE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[5] = {(cuuint64_t)cpitch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  // a tensor stored with fewer than 64 channels per pixel is presented as overlapping 64-channel rows (the upper
+  // part of a row is the next pixel): the box row stays a full 128-byte swizzle row, the kernels skip those K steps
+  const int cview = cpitch < 64 ? 64 : cpitch;
+  cuuint64_t dims[5] = {(cuuint64_t)cview, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)cpitch * 2, (cuuint64_t)W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2,
                            (cuuint64_t)D * H * W * cpitch * 2};
   cuuint32_t box[5] = {64u, (cuuint32_t)PW, (cuuint32_t)rows, 1u, 1u};

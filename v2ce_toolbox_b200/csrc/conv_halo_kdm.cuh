@@ -575,7 +575,8 @@ inline int make_parity_map(CUtensorMap* map, const void* ptr, int B, int D, int 
   if (!fn) return set_error(V2CE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const int Hp = (H - ph + 1) / 2, Wq = (W - pw + 1) / 2;
   if (Hp < 1 || Wq < 1) return set_error(V2CE_ERR_INVALID, "stride-2 conv needs at least 2x2 input pixels");
-  cuuint64_t dims[5] = {(cuuint64_t)cpitch, (cuuint64_t)Wq, (cuuint64_t)Hp, (cuuint64_t)D, (cuuint64_t)B};
+  const int cview = cpitch < 64 ? 64 : cpitch;   // overlapping 64-channel rows over a denser tensor, see make_patch_map
+  cuuint64_t dims[5] = {(cuuint64_t)cview, (cuuint64_t)Wq, (cuuint64_t)Hp, (cuuint64_t)D, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)2 * cpitch * 2, (cuuint64_t)2 * W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2,
                            (cuuint64_t)D * H * W * cpitch * 2};
   cuuint32_t box[5] = {64u, (cuuint32_t)PW, (cuuint32_t)rows, 1u, 1u};

@@ -93,7 +93,7 @@ __global__ void pack_head_kernel(const float* __restrict__ w, float* __restrict_
 // host path).  The resize of image_pre_processing is the identity at the model's own resolution.
 template <bool U8>
 __global__ void __launch_bounds__(128) head_conv_kernel(const void* __restrict__ xin, int B, int D, int H, int W,
-                                                         __nv_bfloat16* __restrict__ out) {
+                                                         __nv_bfloat16* __restrict__ out, int out_pitch) {
   __shared__ float lut[U8 ? 256 : 1];
   if (U8) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
@@ -167,11 +167,13 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const void* __restrict__
       v1 = v1 > 0.f ? v1 : 0.01f * v1;
       op[i] = __floats2bfloat162_rn(v0, v1);
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + (m0 + p) * 64);   // 64-channel pitch, upper half zero (TMA rows)
+    uint4* dst = reinterpret_cast<uint4*>(out + (m0 + p) * out_pitch);
 #pragma unroll
     for (int i = 0; i < 4; ++i) dst[i] = o[i];
+    if (out_pitch == 64) {                       // zero-padded pitch: upper half zero
 #pragma unroll
-    for (int i = 4; i < 8; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = 4; i < 8; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
 }
 
@@ -319,7 +321,16 @@ struct LayerCfg {
   int pitch0, pitch1;             // channel pitch of each source in memory
 };
 
-static inline int pitch_of(int c) { return c < 64 ? 64 : c; }
+// K-chunk padding: the halo kernels multiply 64-channel chunks (one 128-byte swizzle row per pixel)
+static inline int chunk_of(int c) { return c < 64 ? 64 : c; }
+// Memory pitch of a c-channel activation.  32-channel tensors are stored densely (64 B per pixel); their TMA maps
+// present them as 64-channel rows whose upper half is the NEXT pixel (conv_halo.cuh make_patch_map), which the
+// kernels never multiply (K=16 steps beyond the real channels are skipped).  Halves the HBM traffic of the
+// full-resolution 32-channel tensors.  V2CE_PITCH64=1 restores the zero-padded 64-channel pitch.
+static inline int pitch_of(int c) {
+  static const bool p64 = getenv("V2CE_PITCH64") && atoi(getenv("V2CE_PITCH64"));
+  return (c < 64 && p64) ? 64 : c;
+}
 
 struct DevLayer {
   LayerCfg cfg{0, 0, 0, 0, 0, 0, 0};
@@ -440,7 +451,7 @@ static Buffers carve(void* ws, const Dims& d) {
   Arena a(ws, (size_t)-1);
   Buffers b;
   static const int ch[5] = {32, 64, 128, 256, 512};
-  b.head = a.take<__nv_bfloat16>((size_t)d.M[0] * 64);                 // 32 channels, 64-channel pitch
+  b.head = a.take<__nv_bfloat16>((size_t)d.M[0] * pitch_of(32) + 64);  // 32 channels (+ the overlapped TMA view's reach)
   for (int i = 0; i < 4; ++i) b.enc[i] = a.take<__nv_bfloat16>((size_t)d.M[i + 1] * ch[i + 1]);
   for (int i = 0; i < 2; ++i) b.res[i] = a.take<__nv_bfloat16>((size_t)d.M[4] * 512);
   for (int i = 0; i < 4; ++i) b.dec[i] = a.take<__nv_bfloat16>((size_t)d.M[3 - i] * ch[3 - i]);
@@ -485,8 +496,8 @@ static LayerCfg layer_cfg(int li) {
   c.pitch1 = c.real1 ? pitch_of(c.real1) : 0;
   // the halo kernel multiplies whole 64-channel TMA rows (padding channels carry zero weights and are skipped
   // at K=16 granularity); the gather kernel addresses real channels through the pitch
-  c.pad0 = (c.kind == 2) ? c.pitch0 : c.real0;
-  c.pad1 = (c.kind == 2) ? c.pitch1 : c.real1;
+  c.pad0 = (c.kind == 2) ? chunk_of(c.real0) : c.real0;
+  c.pad1 = (c.kind == 2) ? (c.real1 ? chunk_of(c.real1) : 0) : c.real1;
   return c;
 }
 
@@ -537,9 +548,9 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
                     __nv_bfloat16* short_out = nullptr, int short_pitch = 0, bool* short_done = nullptr) {
   const LayerSpec& L = kLayers[li];
   const DevLayer& dl = m->layers[li];
-  if (dl.cfg.kind != 2 || p0 != dl.cfg.pad0 || p1 != dl.cfg.pad1)
-    return set_error(V2CE_ERR_STATE, "layer %s: halo launch with pitches %d+%d, packed for %d+%d", L.name, p0, p1,
-                     dl.cfg.pad0, dl.cfg.pad1);
+  if (dl.cfg.kind != 2 || p0 != dl.cfg.pitch0 || p1 != dl.cfg.pitch1)
+    return set_error(V2CE_ERR_STATE, "layer %s: halo launch with pitches %d+%d, expected %d+%d", L.name, p0, p1,
+                     dl.cfg.pitch0, dl.cfg.pitch1);
   const halo::HaloPlan plan = halo::plan_for(dl.bn_tile, D, H, W);
   // layers with few output channels: depth taps merged into the MMA N dimension (conv_halo_kdm.cuh)
   const halo::KdmPlan kplan = halo::plan_kdm(D, H, W);
@@ -550,7 +561,7 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
   a.PW = plan.ts.PW; a.TH = plan.ts.TH; a.TW = plan.ts.PW - 2;
   a.tiles_w = (W + a.TW - 1) / a.TW;
   a.tiles_h = (H + a.TH - 1) / a.TH;
-  a.ncc0 = p0 / 64; a.ncc1 = p1 / 64;
+  a.ncc0 = dl.cfg.pad0 / 64; a.ncc1 = dl.cfg.pad1 / 64;
   a.real0 = dl.cfg.real0; a.real1 = dl.cfg.real1;
   a.Cout = L.cout; a.out_pitch = out_pitch; a.res_pitch = res_pitch;
   a.T = plan.T; a.SA = plan.SA; a.SB = plan.SB; a.a_stage_bytes = plan.a_stage_bytes; a.box_bytes = plan.box_bytes;
@@ -603,13 +614,13 @@ static int run_enc_kdm(v2ce_model* m, int li, const __nv_bfloat16* x, int pin, i
   static const bool off = getenv("V2CE_NO_S2_KDM") && atoi(getenv("V2CE_NO_S2_KDM"));
   const int Hout = (Hin - 1) / 2 + 1, Wout = (Win - 1) / 2 + 1;
   const halo::KdmPlan kp = halo::plan_kdm(D, Hout, Wout, 2);
-  if (off || !kp.ok || dl.wpack_kdm == nullptr || sl.wpack_kdm == nullptr || pin % 64 != 0 || Hin < 2 || Win < 2) return V2CE_OK;
+  if (off || !kp.ok || dl.wpack_kdm == nullptr || sl.wpack_kdm == nullptr || Hin < 2 || Win < 2) return V2CE_OK;
   halo::HaloArgs a;
   a.B = B; a.D = D; a.H = Hout; a.W = Wout;
   a.PW = kp.ts.PW; a.TH = kp.ts.TH; a.TW = kp.TW;
   a.tiles_w = (Wout + a.TW - 1) / a.TW;
   a.tiles_h = (Hout + a.TH - 1) / a.TH;
-  a.ncc0 = pin / 64; a.ncc1 = 0;
+  a.ncc0 = chunk_of(dl.cfg.real0) / 64; a.ncc1 = 0;
   a.real0 = dl.cfg.real0; a.real1 = 0;
   a.Cout = L.cout; a.out_pitch = L.cout; a.res_pitch = 0;
   a.T = halo::kKdmT; a.SA = kp.SA; a.SB = 9; a.a_stage_bytes = kp.a_stage_bytes; a.box_bytes = kp.box_bytes;
@@ -662,18 +673,19 @@ static int pack_layer(v2ce_model* m, int li, const float* w_dev, cudaStream_t s)
   const bool is_encoder = std::string(L.name).find("encoders") != std::string::npos;
   if (is_encoder && L.k == 3 && std::string(L.name).find(".conv1") != std::string::npos) {
     // stride-2 first conv of an encoder block: depth-merged packing for the parity-view kernel (conv_halo_kdm.cuh, S = 2)
-    const size_t nk = (size_t)L.cout * 27 * c.pitch0;
+    const size_t nk = (size_t)L.cout * 27 * chunk_of(c.real0);
     if (int e = dev_alloc(m, &dl.wpack_kdm, nk)) return e;
     halo::pack_weights_kdm_kernel<<<(int)((nk + 255) / 256 > 4096 ? 4096 : (nk + 255) / 256), 256, 0, s>>>(
-        w_dev, L.cout, L.cin, c.pitch0, c.real0, 0, 0, dl.wpack_kdm);
+        w_dev, L.cout, L.cin, chunk_of(c.real0), c.real0, 0, 0, dl.wpack_kdm);
     V2CE_LAUNCH_CHECK("pack_weights_kdm_kernel");
   }
   if (L.k == 1 && ((L.cout <= 64 && std::string(L.name).find("decoders") != std::string::npos) || is_encoder)) {
     // the shortcut of a decoder block can ride in its conv1 launch (conv_halo_kdm.cuh): [Cout/32][cc][32][64]
-    const size_t ns = (size_t)L.cout * (c.pitch0 + c.pitch1);
+    const int k0 = chunk_of(c.real0), k1 = c.real1 ? chunk_of(c.real1) : 0;
+    const size_t ns = (size_t)L.cout * (k0 + k1);
     if (int e = dev_alloc(m, &dl.wpack_kdm, ns)) return e;
-    halo::pack_weights_kdm_short_kernel<<<(int)((ns + 255) / 256), 256, 0, s>>>(w_dev, L.cout, L.cin, c.pitch0, c.real0,
-                                                                                c.pitch1, c.real1, dl.wpack_kdm);
+    halo::pack_weights_kdm_short_kernel<<<(int)((ns + 255) / 256), 256, 0, s>>>(w_dev, L.cout, L.cin, k0, c.real0, k1, c.real1,
+                                                                                dl.wpack_kdm);
     V2CE_LAUNCH_CHECK("pack_weights_kdm_short_kernel");
   }
   dl.num_kb = (taps * cin_pad + conv::kBlockK - 1) / conv::kBlockK;
@@ -871,9 +883,9 @@ static int forward_impl(v2ce_model* m, const void* x_dev, bool frames_u8, float*
       head_owner[m->device & 63] = m->uid;
     }
     if (frames_u8)
-      head_conv_kernel<true><<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, B, D, H, W, buf.head);
+      head_conv_kernel<true><<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, B, D, H, W, buf.head, pitch_of(32));
     else
-      head_conv_kernel<false><<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, B, D, H, W, buf.head);
+      head_conv_kernel<false><<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, B, D, H, W, buf.head, pitch_of(32));
   }
   V2CE_LAUNCH_CHECK("head_conv_kernel");
   ++launches;
