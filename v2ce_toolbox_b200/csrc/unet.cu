@@ -178,6 +178,67 @@ __global__ void __launch_bounds__(128) head_conv_kernel(const void* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// head on the tensor pipe.  The 2-channel fp32 input becomes an 8-channel bf16 pixel
+//     [x0h, x1h, x0l, x1l, x0h, x1h, 0, 0]        (xh = bf16(x), xl = bf16(x - xh))
+// and the weights [w0h, w1h, w0h, w1h, w0l, w1l, 0, 0], so one K=16 MMA step per tap evaluates
+// xh*wh + xl*wh + xh*wl: the fp32 product to ~2^-17, fp32 accumulation (the direct kernel above is pure fp32; both
+// agree to ~1e-5 relative).  The 16-byte pixels are presented to conv_halo_kdm_kernel as overlapping 64-channel
+// rows (make_patch_map); channels 8..15 of the single K step hold the next pixel and meet zero weights.
+// ------------------------------------------------------------------------------------------
+template <bool U8>
+__global__ void __launch_bounds__(256) head_prep_kernel(const void* __restrict__ xin, int B, int D, int H, int W,
+                                                         __nv_bfloat16* __restrict__ out) {
+  __shared__ float lut[U8 ? 256 : 1];
+  if (U8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+      lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)i, 255.f), 0.153f), 0.165f);
+    __syncthreads();
+  }
+  const size_t HW = (size_t)H * W;
+  const size_t total = (size_t)B * D * HW;
+  // the K step of the last pixel reaches 16 bytes past the tensor: they meet zero weights but must be finite
+  if (blockIdx.x == 0 && threadIdx.x < 8) reinterpret_cast<uint4*>(out)[total + threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i % HW;
+    const size_t pl = i / HW;                       // b*D + d
+    float x0, x1;
+    if (U8) {
+      const unsigned char* xu = static_cast<const unsigned char*>(xin);
+      const size_t b = pl / D, d = pl % D;
+      const unsigned char* f0 = xu + (b * (D + 1) + d) * HW + pix;
+      x0 = lut[__ldg(f0)];
+      x1 = lut[__ldg(f0 + HW)];
+    } else {
+      const float* x = static_cast<const float*>(xin);
+      x0 = __ldg(x + (pl * 2) * HW + pix);
+      x1 = __ldg(x + (pl * 2 + 1) * HW + pix);
+    }
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+    __nv_bfloat162 v[4];
+    v[0] = __halves2bfloat162(h0, h1);
+    v[1] = __halves2bfloat162(l0, l1);
+    v[2] = __halves2bfloat162(h0, h1);
+    v[3] = __floats2bfloat162_rn(0.f, 0.f);
+    reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// fp32 head weights (32, 2, 27) -> fp32 (32, 8, 27) holding exactly representable bf16 values [w0h,w1h,w0h,w1h,w0l,w1l,0,0]
+__global__ void head_split_weights_kernel(const float* __restrict__ w, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * 8 * 27) return;
+  const int tap = i % 27, c = (i / 27) % 8, n = i / (27 * 8);
+  float v = 0.f;
+  if (c < 6) {
+    const float wv = w[((size_t)n * 2 + (c & 1)) * 27 + tap];
+    const float hi = __bfloat162float(__float2bfloat16_rn(wv));
+    v = (c < 4) ? hi : __bfloat162float(__float2bfloat16_rn(wv - hi));
+  }
+  out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
 // pred: Conv3d(32->20, k1, bias) + ReLU, bf16 NDHWC -> float32 (B,L,20,H,W)  (v2ce_3d.py:29)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) pred_conv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
@@ -443,7 +504,7 @@ static Dims make_dims(int B, int D, int H, int W) {
 }
 
 struct Buffers {
-  __nv_bfloat16 *head, *enc[4], *res[2], *dec[4], *tmp_t, *tmp_r, *up, *up2;
+  __nv_bfloat16 *head_in, *head, *enc[4], *res[2], *dec[4], *tmp_t, *tmp_r, *up, *up2;
   size_t bytes;
 };
 
@@ -451,6 +512,7 @@ static Buffers carve(void* ws, const Dims& d) {
   Arena a(ws, (size_t)-1);
   Buffers b;
   static const int ch[5] = {32, 64, 128, 256, 512};
+  b.head_in = a.take<__nv_bfloat16>((size_t)d.M[0] * 8 + 64);          // split-bf16 input pixels of the tensor-pipe head conv
   b.head = a.take<__nv_bfloat16>((size_t)d.M[0] * pitch_of(32) + 64);  // 32 channels (+ the overlapped TMA view's reach)
   for (int i = 0; i < 4; ++i) b.enc[i] = a.take<__nv_bfloat16>((size_t)d.M[i + 1] * ch[i + 1]);
   for (int i = 0; i < 2; ++i) b.res[i] = a.take<__nv_bfloat16>((size_t)d.M[4] * 512);
@@ -779,6 +841,16 @@ extern "C" int v2ce_model_finalize(v2ce_model* m) {
         if (int e = dev_alloc(m, &m->head_wpack, (size_t)27 * 2 * 32)) return e;
         pack_head_kernel<<<(27 * 2 * 32 + 255) / 256, 256, 0, s>>>(dl.w32, m->head_wpack);
         V2CE_LAUNCH_CHECK("pack_head_kernel");
+        // tensor-pipe variant: split weights in the depth-merged packing, unit scale, bias as shift
+        float* w8 = nullptr;
+        if (int e = dev_alloc(m, &w8, (size_t)32 * 8 * 27)) return e;
+        head_split_weights_kernel<<<(32 * 8 * 27 + 255) / 256, 256, 0, s>>>(dl.w32, w8);
+        V2CE_LAUNCH_CHECK("head_split_weights_kernel");
+        if (int e = dev_alloc(m, &dl.wpack_kdm, (size_t)32 * 27 * 64)) return e;
+        halo::pack_weights_kdm_kernel<<<(32 * 27 * 64 + 255) / 256, 256, 0, s>>>(w8, 32, 8, 64, 8, 0, 0, dl.wpack_kdm);
+        V2CE_LAUNCH_CHECK("pack_weights_kdm_kernel");
+        if (int e = upload(m, &dl.scale, std::vector<float>(32, 1.f))) return e;
+        dl.shift = dl.bias;
       }
       continue;
     }
@@ -873,7 +945,33 @@ static int forward_impl(v2ce_model* m, const void* x_dev, bool frames_u8, float*
   launches += 4;
 
   const long long M0 = d.M[0];
-  {
+  static const bool head_direct = getenv("V2CE_HEAD_DIRECT") && atoi(getenv("V2CE_HEAD_DIRECT"));
+  const halo::KdmPlan hplan = halo::plan_kdm(D, H, W, 1);
+  if (hplan.ok && !head_direct) {
+    // head conv on the tensor pipe (see head_prep_kernel): split-bf16 pixels -> depth-merged halo kernel, LeakyReLU
+    const size_t total = (size_t)M0;
+    const int pgrid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    if (frames_u8) head_prep_kernel<true><<<pgrid, 256, 0, s>>>(x_dev, B, D, H, W, buf.head_in);
+    else head_prep_kernel<false><<<pgrid, 256, 0, s>>>(x_dev, B, D, H, W, buf.head_in);
+    V2CE_LAUNCH_CHECK("head_prep_kernel");
+    const DevLayer& dl = m->layers[0];
+    halo::HaloArgs a;
+    a.B = B; a.D = D; a.H = H; a.W = W;
+    a.PW = hplan.ts.PW; a.TH = hplan.ts.TH; a.TW = hplan.TW;
+    a.tiles_w = (W + a.TW - 1) / a.TW;
+    a.tiles_h = (H + a.TH - 1) / a.TH;
+    a.ncc0 = 1; a.ncc1 = 0; a.real0 = 8; a.real1 = 0;
+    a.Cout = 32; a.out_pitch = pitch_of(32); a.res_pitch = 0;
+    a.T = halo::kKdmT; a.SA = hplan.SA; a.SB = 9; a.a_stage_bytes = hplan.a_stage_bytes; a.box_bytes = hplan.box_bytes;
+    a.wpack = dl.wpack_kdm; a.scale = dl.scale; a.shift = dl.shift; a.inv_sigma = nullptr;
+    a.residual = nullptr; a.out = buf.head; a.act = 2;
+    a.up_H = 0; a.up_W = 0; a.pred_w = nullptr; a.pred_b = nullptr; a.pred_out = nullptr;
+    a.error_flag = m->error_flag_dev;
+    CUtensorMap tmh;
+    if (int e = get_tmap(m, buf.head_in, B, D, H, W, 8, a.PW, a.TH + 2, &tmh)) return e;
+    if (int e = halo::launch_halo_kdm(tmh, tmh, a, nullptr, hplan.smem_bytes, s)) return e;
+    ++launches;
+  } else {
     const long long groups = (long long)B * D * H * ((W + 3) / 4);
     // constant memory is per device, not per handle: reload when another handle ran last (stream ordered)
     static unsigned long long head_owner[64] = {0};
@@ -886,8 +984,8 @@ static int forward_impl(v2ce_model* m, const void* x_dev, bool frames_u8, float*
       head_conv_kernel<true><<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, B, D, H, W, buf.head, pitch_of(32));
     else
       head_conv_kernel<false><<<(int)((groups + 127) / 128), 128, 0, s>>>(x_dev, B, D, H, W, buf.head, pitch_of(32));
+    V2CE_LAUNCH_CHECK("head_conv_kernel");
   }
-  V2CE_LAUNCH_CHECK("head_conv_kernel");
   ++launches;
   mark("UNet.head.conv3d");
 
