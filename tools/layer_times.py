@@ -68,6 +68,17 @@ def main():
     for n, ms in acc:
         ms /= reps
         print(f'{n:34s} {ms:8.3f} {gf[n]:9.1f} {gf[n] / ms:9.1f} {100 * ms / tot:5.1f}%')
+    # the forward as the product runs it (no per-launch events; shortcut launches may overlap conv tails)
+    model.set_option('layer_timing', 0)
+    model(x)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        model(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f'untimed forward: {ms:.3f} ms = {sum(gf.values()) / ms:.1f} TFLOP/s')
 
 
 if __name__ == '__main__':

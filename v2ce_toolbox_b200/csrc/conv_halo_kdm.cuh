@@ -233,10 +233,16 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
     }
   } else if (warp == 1) {
     // ================= weight-tile producer: slot = tap (9 = shortcut), refilled once per (tile, chunk) =================
+    // With a single channel chunk the resident tiles only change with the N tile (the slowest tile coordinate):
+    // they are then loaded once and reused by every following tile instead of being re-fetched per tile, which left
+    // the MMA warp waiting for a 108 KB reload at every tile start.
     uint32_t ph = 1;
+    int loaded_n_tile = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, a, T, n_tiles);
       for (int cc = 0; cc < ncc; ++cc) {
+        if (ncc == 1 && tc.n_tile == loaded_n_tile) continue;
+        loaded_n_tile = tc.n_tile;
         const __nv_bfloat16* wt = a.wpack + (size_t)(tc.n_tile * ncc + cc) * 9 * (kKdmWTile / 2);
         for (int ti = 0; ti < 9; ++ti) {
           const int tap = (S == 1) ? ti : kS2TapOrder[ti];      // refill in the order the slots are freed
@@ -261,7 +267,9 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
   } else if (warp == 2) {
     // ================= MMA issuer =================
     int sa = 0, pa = 0;                             // patch ring position / parity
-    uint32_t pw = 0;                                // parity of the weight slots for the current (tile, chunk)
+    uint32_t pw = 0;                                // parity of the weight slots for the current load generation
+    uint32_t pw_next = 0;
+    int loaded_n_tile = -1;
     const uint32_t pw8 = (uint32_t)a.PW * 8u;       // one patch row of pixels in descriptor units (16 B)
     const uint32_t idesc32 = make_idesc(BN);
     int iter = 0;
@@ -276,6 +284,15 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
         const int rem = (cc < a.ncc0) ? (a.real0 - cc * kBlockK) : (a.real1 - (cc - a.ncc0) * kBlockK);
         const int ks = rem >= kBlockK ? kBlockK / 16 : (rem + 15) / 16;
         const bool last_cc = (cc == ncc - 1);
+        // weight generations (see the producer): does this (tile, chunk) start a new one, and will the next one?
+        const bool w_new = !(ncc == 1 && tc.n_tile == loaded_n_tile);
+        loaded_n_tile = tc.n_tile;
+        if (w_new) { pw = pw_next; pw_next ^= 1u; }
+        bool w_release = true;
+        if (ncc == 1) {
+          const int nxt = tile + (int)gridDim.x;
+          w_release = nxt < total_tiles && decode_tile(nxt, a, T, n_tiles).n_tile != tc.n_tile;
+        }
 #pragma unroll 1
         for (int z = zl; z <= zh; ++z) {
           // output slices z-1+j, j = 0..2 (depth tap kd = 2-j), clipped to the block [d0, d0+T)
@@ -295,7 +312,7 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
           // one tap: all K=16 steps of A(rows shifted by a_t) x the tap's [kd-merged] weight tile; `lead` marks the
           // tile's very first instruction candidates (first tap in issue order)
           auto issue_tap = [&](const int tap, const uint32_t a_t, const bool lead) {
-            if (first_z) {
+            if (first_z && w_new) {
               mbar_wait(w_full(tap), pw, a.error_flag);
               tcgen05_fence_after();
             }
@@ -319,7 +336,7 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
             }
             if (SHORT && tap == 4 && z >= tc.d0 && z < tc.d0 + T) {
               // shortcut conv of output slice z: centre tap of input slice z times the 1x1x1 weights
-              if (first_z || z == tc.d0) {           // first use of the shortcut tile in this chunk
+              if ((first_z || z == tc.d0) && w_new) {           // first use of the shortcut tile in this chunk
                 mbar_wait(w_full(9), pw, a.error_flag);
                 tcgen05_fence_after();
               }
@@ -329,7 +346,7 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
               for (int k = 0; k < kBlockK / 16; ++k)
                 if (k < ks) tcgen05_mma_bf16_lo(scol, a_t + 2 * k, bs_lo + 2 * k, idesc32, (cc != 0 || k != 0) ? 1u : 0u);
             }
-            if (last_z) tcgen05_commit_elect(w_empty(tap));     // last use of this chunk's tap tile
+            if (last_z && w_release) tcgen05_commit_elect(w_empty(tap));     // last use of this generation's tap tile
           };
           if (S == 1) {
             mbar_wait(a_full(sa), (uint32_t)pa, a.error_flag);
@@ -367,14 +384,13 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
               if (++sa == a.SA) { sa = 0; pa ^= 1; }
             }
           }
-          if (SHORT && last_z) tcgen05_commit_elect(w_empty(9));
+          if (SHORT && last_z && w_release) tcgen05_commit_elect(w_empty(9));
           if (last_cc) {
             // output slice z-1 has received its last contribution; at the end of the depth range so has slice z
             if (z - 1 >= tc.d0) tcgen05_commit_elect(s_full(slot0 + z - 1 - tc.d0));
             if (last_z && z < tc.d0 + T) tcgen05_commit_elect(s_full(slot0 + z - tc.d0));
           }
         }
-        pw ^= 1u;
       }
     }
   } else if (warp >= 4) {

@@ -429,6 +429,7 @@ struct v2ce_model {
   std::vector<std::pair<std::string, cudaEvent_t>> marks;
   cudaStream_t sn_stream = nullptr;     // the spectral-norm step overlaps the head / encoder convs
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_side[16] = {nullptr};  // x-ready / shortcut-done pairs of the blocks whose shortcut runs on the side stream
   std::map<std::tuple<const void*, int, int, int, int, int, int, int>, CUtensorMap> tmaps;
 };
 
@@ -791,6 +792,7 @@ extern "C" int v2ce_model_destroy(v2ce_model* m) {
   for (auto& mk : m->marks) cudaEventDestroy(mk.second);
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->ev_join) cudaEventDestroy(m->ev_join);
+  for (auto ev : m->ev_side) if (ev) cudaEventDestroy(ev);
   if (m->sn_stream) cudaStreamDestroy(m->sn_stream);
   delete m;
   return V2CE_OK;
@@ -822,6 +824,7 @@ extern "C" int v2ce_model_finalize(v2ce_model* m) {
   V2CE_CUDA_CHECK(cudaStreamCreateWithFlags(&m->sn_stream, cudaStreamNonBlocking));
   V2CE_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
   V2CE_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  for (auto& ev : m->ev_side) V2CE_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   int sn_count = 0;
   for (int li = 0; li < kNumLayers; ++li) {
     const LayerSpec& L = kLayers[li];
@@ -1015,13 +1018,29 @@ static int forward_impl(v2ce_model* m, const void* x_dev, bool frames_u8, float*
   }
   // residual blocks at the bottleneck (first spectral-norm convs: join the side stream here)
   V2CE_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join, 0));
+  static const bool side_ok = !(getenv("V2CE_NO_SIDE_SHORTCUT") && atoi(getenv("V2CE_NO_SIDE_SHORTCUT")));
+  int side_ev = 0;
   for (int i = 0; i < 2; ++i) {
     snprintf(name, sizeof(name), "UNet.resblocks.%d.conv1", i);
     const int l1 = layer_index(name);
+    // conv1 (persistent CTAs, a partial last wave) and the block's shortcut both read x: the shortcut goes to the
+    // side stream AFTER conv1 so that its CTAs fill the SMs conv1 frees in its tail; conv2 waits for it.
+    // (With per-launch timing on, everything stays on one stream.)
+    const bool side = !m->layer_timing && side_ok;
+    if (side) {
+      V2CE_CUDA_CHECK(cudaEventRecord(m->ev_side[side_ev], s));
+      V2CE_CUDA_CHECK(cudaStreamWaitEvent(m->sn_stream, m->ev_side[side_ev], 0));
+    }
     if (int e = run_halo(m, l1, x, 512, nullptr, 0, B, D, d.H[4], d.W[4], nullptr, 0, 1, buf.tmp_t, 512, s)) return e;
     mark(kLayers[l1].name);
-    if (int e = run_conv(m, l1 + 2, x, 512, d.H[4], d.W[4], nullptr, 0, B, D, d.H[4], d.W[4], 1, nullptr, 0, buf.tmp_r, s)) return e;
+    if (int e = run_conv(m, l1 + 2, x, 512, d.H[4], d.W[4], nullptr, 0, B, D, d.H[4], d.W[4], 1, nullptr, 0, buf.tmp_r,
+                         side ? m->sn_stream : s)) return e;
     mark(kLayers[l1 + 2].name);
+    if (side) {
+      V2CE_CUDA_CHECK(cudaEventRecord(m->ev_side[side_ev + 1], m->sn_stream));
+      V2CE_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_side[side_ev + 1], 0));
+      side_ev += 2;
+    }
     // the last block's output is only ever read nearest-upsampled by decoders.0: write it that way
     if (i == 1) {
       if (int e = run_halo(m, l1 + 1, buf.tmp_t, 512, nullptr, 0, B, D, d.H[4], d.W[4], buf.tmp_r, 512, 1, buf.up, 512, s,
@@ -1046,14 +1065,25 @@ static int forward_impl(v2ce_model* m, const void* x_dev, bool frames_u8, float*
     snprintf(name, sizeof(name), "UNet.decoders.%d.conv1", i);
     const int l1 = layer_index(name);
     bool short_done = false;
+    const bool side = !m->layer_timing && side_ok && side_ev + 2 <= 16;
+    if (side) {
+      V2CE_CUDA_CHECK(cudaEventRecord(m->ev_side[side_ev], s));
+      V2CE_CUDA_CHECK(cudaStreamWaitEvent(m->sn_stream, m->ev_side[side_ev], 0));
+    }
     if (int e = run_halo(m, l1, up_cur, xc, skip, sp, B, D, d.H[lvl], d.W[lvl], nullptr, 0, 1, buf.tmp_t, tp, s, 0, 0, nullptr,
                          l1 + 2, buf.tmp_r, co, &short_done)) return e;
     mark(kLayers[l1].name);
     if (!short_done) {
-      if (int e = run_conv(m, l1 + 2, up_cur, xc, d.H[lvl], d.W[lvl], skip, sp, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 0, buf.tmp_r, s)) return e;
+      if (int e = run_conv(m, l1 + 2, up_cur, xc, d.H[lvl], d.W[lvl], skip, sp, B, D, d.H[lvl], d.W[lvl], 1, nullptr, 0, buf.tmp_r,
+                           side ? m->sn_stream : s)) return e;
       mark(kLayers[l1 + 2].name);
       ++launches;
+      if (side) {
+        V2CE_CUDA_CHECK(cudaEventRecord(m->ev_side[side_ev + 1], m->sn_stream));
+        V2CE_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_side[side_ev + 1], 0));
+      }
     }
+    if (side) side_ev += 2;
     if (lvl > 0) {
       if (int e = run_halo(m, l1 + 1, buf.tmp_t, tp, nullptr, 0, B, D, d.H[lvl], d.W[lvl], buf.tmp_r, co, 1, up_next, co, s,
                            d.H[lvl - 1], d.W[lvl - 1])) return e;
