@@ -42,7 +42,7 @@ GFLOP_PER_WINDOW = 2169.336
 METRIC = '346x260 frame-pairs/s (center, 321 frames, batch 4, voxel+LDATI+event-frame)'
 # dram__bytes_read.sum + dram__bytes_write.sum of one V2ce3d forward (batch 4), summed over its launches from the
 # ncu capture summarised in profiles/forward_traffic_r1.txt
-TRAFFIC_BYTES = 13.56e9        # profiles/forward_traffic_r1.txt: read 9.01 GB + write 4.55 GB (L2: 65.5 GB)
+TRAFFIC_BYTES = 13.03e9        # profiles/forward_traffic_r1_b.txt: read 8.98 GB + write 4.05 GB (L2: 59.1 GB)
 KERNEL_NOTE = ('V2ce3d forward (26 launches + 4 spectral-norm launches on a side stream): conv_halo_kdm_kernel x11 '
                '(head, stride-2 encoder convs and decoder convs with fused shortcuts, N<=64 convs), conv_halo_kernel x10, '
                'conv_igemm_kernel x4 (remaining 1x1x1 shortcuts, side stream), head prep')
