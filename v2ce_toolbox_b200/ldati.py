@@ -104,14 +104,14 @@ class LdatiEngine:
         self.launches += 3
         return seg
 
-    def emit(self, voxels, params, total_events, draws=None, frame_offsets=None, out=None):
+    def emit(self, voxels, params, total_events, draws=None, frame_offsets=None, out=None, status_out=None):
         """Second phase.  Returns (events uint8 (total*13,) on device, status int32[4] on device)."""
         n = ctypes.c_size_t()
         check(self.lib.v2ce_ldati_emit_workspace_bytes(ctypes.byref(params), total_events, ctypes.byref(n)))
         ws = self._ws('_emit_ws', n.value)
         if out is None:
             out = torch.empty(max(total_events, 1) * EVENT_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
-        status = torch.empty(4, dtype=torch.int32, device=self.device)
+        status = status_out if status_out is not None else torch.empty(4, dtype=torch.int32, device=self.device)
         m = 0
         if draws is not None:
             m = draws.shape[-1]

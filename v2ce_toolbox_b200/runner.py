@@ -40,13 +40,16 @@ class Ticket:
 
 class BatchRunner:
     def __init__(self, model, device, fps=30, ceil=10, percentile=98, keep_polarity=True, seed=0,
-                 per_batch_frames=True, slots=3, copy_out=True):
+                 per_batch_frames=True, slots=3, copy_out=True, infer=None):
         self.model = model
         self.device = torch.device(device)
         self.fps, self.ceil, self.percentile, self.keep = fps, ceil, percentile, keep_polarity
         self.seed = seed
         self.per_batch_frames = per_batch_frames
         self.copy_out = copy_out                  # False: results stay on the device (device-timed bench)
+        # x on the device -> (b,L,20,H,W) voxels; default: the model itself (raw uint8 windows go through forward_frames).
+        # v2ce.stream_clip passes the reference's center-crop / pano-tile wrappers (v2ce.py:66-129).
+        self.infer = infer
         self.lib = _lib.load()
         self.post_stream = torch.cuda.Stream(device=self.device)      # event frames + LDATI, one batch behind
         self.copy_stream = torch.cuda.Stream(device=self.device)      # D2H of results
@@ -60,6 +63,7 @@ class BatchRunner:
         self._x_dev = [None] * slots
         self._sel_ws = [None] * slots
         self._small_dev = [None] * slots
+        self._st_dev = [None] * slots
         self._small_host = [None] * slots
         self._offs_host = [None] * slots
         self._offs_dev = [None] * slots
@@ -81,9 +85,10 @@ class BatchRunner:
         return b
 
     # ------------------------------------------------------------------------------------------
-    def submit(self, units, pair_base, keep_sums=False):
+    def submit(self, units, pair_base, keep_sums=False, trim_last_window_to=0):
         """units: image units (b,L,2,H,W) float32, or raw gray windows (b,L+1,H,W) uint8 at the model's resolution;
-        pinned host (copied on the side stream) or already on the device."""
+        pinned host (copied on the side stream) or already on the device.  trim_last_window_to = m > 0: only the last m
+        pairs of the batch's last window are kept (the clip's pulled-back last window, v2ce.py:227-236)."""
         t = Ticket()
         slot = self._next
         self._next = (self._next + 1) % self.slots
@@ -109,7 +114,10 @@ class BatchRunner:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(cur)
         # uint8 windows (b, L+1, H, W): pre-processing fused into the head conv (V2ce3d.forward_frames)
-        y = self.model.forward_frames(x) if x.dtype == torch.uint8 else self.model(x)
+        if self.infer is not None:
+            y = self.infer(x)
+        else:
+            y = self.model.forward_frames(x) if x.dtype == torch.uint8 else self.model(x)
         if self.time_forward:
             e1.record(cur)
             t.fwd_events = (e0, e1)
@@ -117,10 +125,14 @@ class BatchRunner:
         vox_ready.record(cur)
         b, L, _, H, W = y.shape
         n = b * L
+        t.vox = y.reshape(n, 2, 10, H, W)
+        if trim_last_window_to:                   # merge_voxels: drop the re-inferred overlap of the pulled-back window
+            keep = trim_last_window_to
+            t.vox = torch.cat([t.vox[:(b - 1) * L], t.vox[(b - 1) * L + (L - keep):]], dim=0).contiguous()
+            n = t.vox.shape[0]
         t.n_pairs, t.hw = n, (H, W)
-        t.vox = y.view(n, 2, 10, H, W)
         t.vox.record_stream(self.post_stream)
-        self.launches += self.model.last_launches()
+        self.launches += self.model.last_launches() if hasattr(self.model, 'last_launches') else 0
 
         # the batch before this one: its counts are on the host by the time UNet(i) is queued
         prev = self._pending
@@ -189,7 +201,10 @@ class BatchRunner:
             eng = self.engines[slot]
             ev = self._buf(self._ev_dev, slot, max(total, 1) * 13)
             l0 = eng.launches
-            _, status = eng.emit(t.vox, t.params, total, frame_offsets=t.offs, out=ev)
+            # per-slot status words: a temporary would return to the post stream's pool while the copy stream
+            # still has to read it
+            st_dev = self._buf(self._st_dev, slot, 16).view(torch.int32)[:4]
+            _, status = eng.emit(t.vox, t.params, total, frame_offsets=t.offs, out=ev, status_out=st_dev)
             self.launches += eng.launches - l0
             t.events_dev = ev
             t.packed = torch.cuda.Event()

@@ -184,45 +184,70 @@ class ClipResult:
         self.n_pairs = n_pairs
 
 
+def _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width):
+    """Raw uint8 windows (b, L+1, H, width), center-cropped like v2ce.py:78, in the reference's batching."""
+    frame_count = vidcap.frame_count if vidcap is not None else len(image_paths)
+    starts, _ = schedule if schedule is not None else window_schedule(frame_count, seq_len)
+    pending = []
+    for i, st in enumerate(starts):
+        fr = np.asarray(_read_window(image_paths, vidcap, st, seq_len))
+        c = fr.shape[-1] // 2
+        pending.append(np.ascontiguousarray(fr[..., c - width // 2:c + width // 2])[None])
+        if len(pending) == batch_size or i == len(starts) - 1:
+            yield torch.from_numpy(np.concatenate(pending, axis=0)), i == len(starts) - 1
+            pending = []
+
+
 @torch.no_grad()
 def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_len=16, width=346, height=260,
                 batch_size=1, fps=30, ceil=10, upper_bound_percentile=98, keep_polarity=True,
                 write_event_frames=True, seed=0, pair_base=0, device=None, schedule=None):
-    """Device-resident version of v2ce.py:322-372.  Returns ClipResult with the concatenated event
-    stream (timestamps offset per frame, v2ce.py:365) and the uint8 BGR preview frames."""
+    """Device-resident, pipelined version of v2ce.py:322-372 (runner.BatchRunner: the network of batch i+1 runs over
+    the event frames + LDATI of batch i, results leave on a copy stream).  Returns ClipResult with the concatenated
+    event stream (timestamps offset per frame, v2ce.py:365) and the uint8 BGR preview frames (clip-global percentile,
+    as the reference computes it)."""
+    from .runner import BatchRunner
     assert image_paths is not None or vidcap is not None
     device = torch.device(device or 'cuda')
     frame_count = vidcap.frame_count if vidcap is not None else len(image_paths)
     # `schedule` = (window starts relative to this reader, mode): a rank's share of a longer clip (dist.py)
     starts, mode = schedule if schedule is not None else window_schedule(frame_count, seq_len)
-    eng = _ldati.engine_for(device)
-    sums_all, event_chunks = [], []
-    pair_idx = pair_base
-    for units, is_last in _batches(image_paths, vidcap, seq_len, height, batch_size, schedule):
-        pred = _center_device(model, units, width) if infer_type == 'center' else _pano_device(model, units, width)
-        b, L, _, H, W = pred.shape
-        vox = pred.reshape(b * L, 2, 10, H, W)
-        if is_last and mode != 0:                       # merge_voxels: drop the re-inferred overlap
-            vox = torch.cat([vox[:(b - 1) * L], vox[(b - 1) * L + (L - mode):]], dim=0).contiguous()
-        n = vox.shape[0]
+    if len(starts) == 0:
+        return ClipResult(np.empty(0, _ldati.EVENT_DTYPE), None, None, 0)
+    # raw uint8 windows when the frames already have the model's height (the resize of image_pre_processing is then
+    # the identity and the rest of it runs inside the head conv); float image units otherwise
+    probe = np.asarray(_read_window(image_paths, vidcap, int(starts[0]), 0))
+    native = (infer_type == 'center' and hasattr(model, 'forward_frames') and probe.dtype == np.uint8 and
+              probe.shape[-2] == height and int(probe.shape[-1] / probe.shape[-2] * height) == probe.shape[-1] and
+              probe.shape[-1] >= width and width % 2 == 0)
+    if native:
+        infer = None
+        batches = _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width)
+    else:
+        infer = (lambda u: _center_device(model, u, width)) if infer_type == 'center' else \
+                (lambda u: _pano_device(model, u, width))
+        batches = _batches(image_paths, vidcap, seq_len, height, batch_size, schedule)
+    with torch.cuda.device(device):
+        runner = BatchRunner(model, device, fps=fps, ceil=ceil, percentile=upper_bound_percentile,
+                             keep_polarity=keep_polarity, seed=seed, per_batch_frames=False, infer=infer)
+        event_chunks = []
+        pair_idx = pair_base
+        prev = None
+        for x, is_last in batches:
+            t = runner.submit(x.pin_memory(), pair_idx, keep_sums=write_event_frames,
+                              trim_last_window_to=mode if (is_last and mode != 0) else 0)
+            pair_idx += t.n_pairs
+            if prev is not None:
+                event_chunks.append(runner.wait(prev)[0])
+            prev = t
+        if prev is not None:
+            event_chunks.append(runner.wait(prev)[0])
+        frames, ub = None, None
         if write_event_frames:
-            sums_all.append(_ef.accumulate(vox, keep_polarity))
-        params = _ldati.make_params(n, H, W, fps=fps, seed=seed, frame_base=pair_idx, device=device,
-                                    add_frame_offset=True)
-        offs = torch.tensor([frame_offset_us(pair_idx + i, fps) for i in range(n)], dtype=torch.int64,
-                            device=device)
-        events, seg_counts, status = eng.run(vox, params, frame_offsets=offs)
-        total = int(seg_counts.sum())
-        host = torch.empty(total * 13, dtype=torch.uint8, pin_memory=True)
-        host.copy_(events[:total * 13], non_blocking=True)
-        _ldati.check_status(status.cpu().numpy())       # synchronises
-        event_chunks.append(host.numpy().view(_ldati.EVENT_DTYPE))
-        pair_idx += n
-    frames, ub = None, None
-    if write_event_frames:
-        sums = torch.cat(sums_all, dim=0) if len(sums_all) > 1 else sums_all[0]
-        ub = _ef.upper_bound(sums, upper_bound_percentile, ceil, keep_polarity)
-        frames = _ef.normalize(sums, ub, keep_polarity).cpu().numpy()
+            torch.cuda.current_stream(device).wait_stream(runner.post_stream)
+            sums = torch.cat(runner.sums, dim=0) if len(runner.sums) > 1 else runner.sums[0]
+            ub = _ef.upper_bound(sums, upper_bound_percentile, ceil, keep_polarity)
+            frames = _ef.normalize(sums, ub, keep_polarity).cpu().numpy()
     stream = np.concatenate(event_chunks) if event_chunks else np.empty(0, _ldati.EVENT_DTYPE)
     return ClipResult(stream, frames, ub, pair_idx - pair_base)
 
