@@ -95,8 +95,11 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
         res = drv.stream_clip(model, vidcap=shard, seq_len=seq_len, batch_size=batch_size,
                               pair_base=shard.pair_base, device=dev, write_event_frames=False, schedule=shard.schedule,
                               **kw)
-        ev = torch.from_numpy(res.event_stream.view(np.uint8).copy()).to(dev)
         n = res.event_stream.shape[0]
+        ev = res.event_stream_dev if res.event_stream_dev is not None else \
+            torch.from_numpy(res.event_stream.view(np.uint8).copy()).to(dev)
+        if n == 0:
+            ev = torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev)
     else:
         ev, n = torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev), 0
     out, counts = gather_event_shards(ev, n)

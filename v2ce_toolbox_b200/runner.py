@@ -40,7 +40,7 @@ class Ticket:
 
 class BatchRunner:
     def __init__(self, model, device, fps=30, ceil=10, percentile=98, keep_polarity=True, seed=0,
-                 per_batch_frames=True, slots=3, copy_out=True, infer=None):
+                 per_batch_frames=True, slots=3, copy_out=True, infer=None, collect_on_device=False):
         self.model = model
         self.device = torch.device(device)
         self.fps, self.ceil, self.percentile, self.keep = fps, ceil, percentile, keep_polarity
@@ -50,6 +50,12 @@ class BatchRunner:
         # x on the device -> (b,L,20,H,W) voxels; default: the model itself (raw uint8 windows go through forward_frames).
         # v2ce.stream_clip passes the reference's center-crop / pano-tile wrappers (v2ce.py:66-129).
         self.infer = infer
+        # True: the packed events of every batch are appended to one growing device buffer (copy stream) and read
+        # back once by collected_events(): one D2H and one host array for a whole clip instead of a staging copy,
+        # a pageable copy and a concatenation per batch (v2ce.stream_clip)
+        self.collect_on_device = collect_on_device
+        self._all_ev = None
+        self._all_bytes = 0
         self.lib = _lib.load()
         self.post_stream = torch.cuda.Stream(device=self.device)      # event frames + LDATI, one batch behind
         self.copy_stream = torch.cuda.Stream(device=self.device)      # D2H of results
@@ -212,6 +218,15 @@ class BatchRunner:
         t.d2h_bytes = 0
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(t.packed)
+            if self.collect_on_device and total > 0:
+                need = self._all_bytes + total * 13
+                if self._all_ev is None or self._all_ev.numel() < need:
+                    grown = torch.empty(max(2 * need, 64 << 20), dtype=torch.uint8, device=self.device)
+                    if self._all_bytes:
+                        grown[:self._all_bytes].copy_(self._all_ev[:self._all_bytes])
+                    self._all_ev = grown
+                self._all_ev[self._all_bytes:need].copy_(ev[:total * 13])
+                self._all_bytes = need
             if self.copy_out:
                 evh = self._buf(self._ev_host, slot, max(total, 1) * 13, pinned=True)
                 evh[:total * 13].copy_(ev[:total * 13], non_blocking=True)
@@ -231,6 +246,18 @@ class BatchRunner:
             self._pending = None
 
     keep_vox = False                            # tests may set this to inspect the voxels a ticket was computed from
+
+    def reset_collection(self):
+        self._all_bytes = 0
+
+    def collected_events(self):
+        """All events appended since reset_collection(), as (device uint8 tensor, host recarray view of one D2H)."""
+        self.flush()
+        self.copy_stream.synchronize()
+        if self._all_bytes == 0:
+            return None, np.empty(0, _ldati.EVENT_DTYPE)
+        dev = self._all_ev[:self._all_bytes]
+        return dev, dev.cpu().numpy().view(_ldati.EVENT_DTYPE)
 
     def flush(self):
         """Enqueue stage B of the batch submitted last (the end of a clip)."""

@@ -182,6 +182,7 @@ class ClipResult:
         self.ef_frames = ef_frames
         self.ef_upper_bound = ef_upper_bound
         self.n_pairs = n_pairs
+        self.event_stream_dev = None
 
 
 def _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width):
@@ -228,9 +229,17 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
                 (lambda u: _pano_device(model, u, width))
         batches = _batches(image_paths, vidcap, seq_len, height, batch_size, schedule)
     with torch.cuda.device(device):
-        runner = BatchRunner(model, device, fps=fps, ceil=ceil, percentile=upper_bound_percentile,
-                             keep_polarity=keep_polarity, seed=seed, per_batch_frames=False, infer=infer)
-        event_chunks = []
+        # the runner owns ~0.5 GB of pinned staging buffers whose allocation costs more than a short clip's compute:
+        # one per (model, device), reused across calls
+        cache = model.__dict__.setdefault('_v2ce_runners', {})
+        runner = cache.get(str(device))
+        if runner is None:
+            runner = cache[str(device)] = BatchRunner(model, device, per_batch_frames=False, copy_out=False,
+                                                      collect_on_device=True)
+        runner.fps, runner.ceil, runner.percentile, runner.keep, runner.seed = fps, ceil, upper_bound_percentile, keep_polarity, seed
+        runner.infer = infer
+        runner.sums = []
+        runner.reset_collection()
         pair_idx = pair_base
         prev = None
         for x, is_last in batches:
@@ -238,18 +247,20 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
                               trim_last_window_to=mode if (is_last and mode != 0) else 0)
             pair_idx += t.n_pairs
             if prev is not None:
-                event_chunks.append(runner.wait(prev)[0])
+                runner.wait(prev)                 # status check; the events stay on the device until the end
             prev = t
         if prev is not None:
-            event_chunks.append(runner.wait(prev)[0])
+            runner.wait(prev)
+        events_dev, stream = runner.collected_events()
         frames, ub = None, None
         if write_event_frames:
             torch.cuda.current_stream(device).wait_stream(runner.post_stream)
             sums = torch.cat(runner.sums, dim=0) if len(runner.sums) > 1 else runner.sums[0]
             ub = _ef.upper_bound(sums, upper_bound_percentile, ceil, keep_polarity)
             frames = _ef.normalize(sums, ub, keep_polarity).cpu().numpy()
-    stream = np.concatenate(event_chunks) if event_chunks else np.empty(0, _ldati.EVENT_DTYPE)
-    return ClipResult(stream, frames, ub, pair_idx - pair_base)
+    res = ClipResult(stream, frames, ub, pair_idx - pair_base)
+    res.event_stream_dev = events_dev            # the same bytes on the device (dist.py gathers from here)
+    return res
 
 
 def build_parser():
