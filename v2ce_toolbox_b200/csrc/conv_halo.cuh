@@ -457,23 +457,6 @@ __global__ void pack_weights_halo_kernel(const float* __restrict__ w, int Cout, 
   }
 }
 
-// nearest-neighbour upsample (unet_2layer.py:359-362), bf16 NDHWC, src = (dst*in)//out per axis
-__global__ void upsample_nearest_kernel(const __nv_bfloat16* __restrict__ in, int planes, int H0, int W0, int H, int W, int C,
-                                        __nv_bfloat16* __restrict__ out) {
-  const int vec = C / 8;
-  const size_t total = (size_t)planes * H * W * vec;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vec);
-    size_t px = i / vec;
-    const int w = (int)(px % W); px /= W;
-    const int h = (int)(px % H);
-    const size_t pl = px / H;
-    const int hs = (h * H0) / H, ws = (w * W0) / W;
-    const uint4 val = __ldg(reinterpret_cast<const uint4*>(in + ((pl * H0 + hs) * W0 + ws) * (size_t)C) + v);
-    reinterpret_cast<uint4*>(out)[i] = val;
-  }
-}
-
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -3,15 +3,19 @@
 // scripts/submodules.py:85-124,216-264 and scripts/spectral_norm.py:9-64.
 //
 // Activation layout in HBM: NDHWC bf16, (B, D=16, H, W, C), row m = ((b*D+d)*H+h)*W+w.
-// Schedule per forward (35 launches):
-//   4  spectral-norm power-iteration kernels (fp32; 12 convs batched per launch)
-//   1  head conv 2->32 (direct fp32 CUDA-core kernel, K=54 is HBM-bound) + LeakyReLU
-//   30 tcgen05 convs: 3x3x3 stride-1 layers on the halo-tile kernel (conv_halo.cuh), stride-2 convs and the
-//      1x1x1 shortcuts on the gather kernel (conv_igemm.cuh); 4 nearest-upsample launches; per residual block
+// Schedule per forward at depth % 8 == 0 (30 launches):
+//   4  spectral-norm power-iteration kernels (fp32; 12 convs batched per launch), on a side stream
+//   2  head: split-bf16 prep + the depth-merged halo kernel (2->32, LeakyReLU)
+//   24 tcgen05 convs, per residual block
 //        t = relu(bn1(conv1(x)))            x may be the virtual concat [nearest_up(prev), skip]
 //        r = bn_d(conv_d(x) + bias_d)       1x1x1 shortcut, present on every block
 //        y = relu(bn2(conv2(t)) + r)
-//   1  pred conv 32->20 + ReLU writing the (B,L,20,H,W) float32 output of V2ce3d.forward
+//      conv1 + shortcut in ONE launch of conv_halo_kdm.cuh for the 4 encoders (stride 2, parity views) and
+//      decoders 2/3; conv1 on conv_halo.cuh and the shortcut on the gather kernel (conv_igemm.cuh, side stream) for the
+//      2 resblocks and decoders 0/1; every conv2 on a halo kernel, writing its output nearest-upsampled where the
+//      next decoder reads it that way; the prediction layer (32->20, ReLU, fp32 (B,L,20,H,W) output) rides in the
+//      epilogue of decoders.3.conv2.
+//   Otherwise: direct fp32 head kernel, gather kernel for the stride-2 convs and all shortcuts.
 #include <map>
 #include <string>
 #include <vector>
@@ -238,43 +242,8 @@ __global__ void head_split_weights_kernel(const float* __restrict__ w, float* __
   out[i] = v;
 }
 
-// ------------------------------------------------------------------------------------------
-// pred: Conv3d(32->20, k1, bias) + ReLU, bf16 NDHWC -> float32 (B,L,20,H,W)  (v2ce_3d.py:29)
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) pred_conv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w,
-                                                         const float* __restrict__ bias, long long M, int HW,
-                                                         float* __restrict__ out) {
-  __shared__ float sw[20 * 32];
-  __shared__ float sb[20];
-  for (int i = threadIdx.x; i < 20 * 32; i += blockDim.x) sw[i] = w[i];
-  if (threadIdx.x < 20) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  float xin[32];
-  const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)m * 32);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 v = __ldg(src + i);
-    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(p[j]);
-      xin[i * 8 + 2 * j] = f.x;
-      xin[i * 8 + 2 * j + 1] = f.y;
-    }
-  }
-  const long long plane = m / HW;          // b*L + d
-  const int pix = (int)(m % HW);
-  float* dst = out + (size_t)plane * 20 * HW + pix;
-#pragma unroll
-  for (int n = 0; n < 20; ++n) {
-    float acc = sb[n];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) acc = fmaf(xin[c], sw[n * 32 + c], acc);
-    dst[(size_t)n * HW] = fmaxf(acc, 0.f);
-  }
-}
+// The prediction layer (Conv3d 32->20, k1, bias, ReLU; v2ce_3d.py:29) is fused into the epilogue of
+// decoders.3.conv2 (conv_halo.cuh / conv_halo_kdm.cuh, c_pred).
 
 // ------------------------------------------------------------------------------------------
 // Spectral norm: one power iteration per SN conv per forward (spectral_norm.py:19-31), fp32.
@@ -757,15 +726,6 @@ static int pack_layer(v2ce_model* m, int li, const float* w_dev, cudaStream_t s)
   conv::pack_weights_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(
       w_dev, L.cout, L.cin, taps, dl.bn_tile, dl.num_kb, c.pad0, c.real0, c.pad1, c.real1, dl.wpack);
   V2CE_LAUNCH_CHECK("pack_weights_kernel");
-  return V2CE_OK;
-}
-
-static int run_upsample(const __nv_bfloat16* in, int planes, int H0, int W0, int H, int W, int C, __nv_bfloat16* out,
-                        cudaStream_t s) {
-  const size_t total = (size_t)planes * H * W * (C / 8);
-  const int grid = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
-  halo::upsample_nearest_kernel<<<grid, 256, 0, s>>>(in, planes, H0, W0, H, W, C, out);
-  V2CE_LAUNCH_CHECK("upsample_nearest_kernel");
   return V2CE_OK;
 }
 
