@@ -61,9 +61,11 @@ def shard_schedule(starts, mode, b0, b1, batch_size, seq_len=16):
     return first, frame_count, is_tail, w0 * seq_len, (np.asarray(starts[w0:w1]) - first, mode if is_tail else 0)
 
 
-def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=16, batch_size=1, **kw):
+def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=16, batch_size=1, to_host=True, **kw):
     """Run v2ce.stream_clip on this rank's contiguous share of the batches of a clip and gather the
-    event shards on rank 0.  `frames_reader` duck-types VideoReader.  Returns (event_stream | None, n_pairs)."""
+    event shards on rank 0 (the shards never visit the host on their way).  `frames_reader` duck-types VideoReader.
+    Returns (event_stream | None, total events); with to_host=False rank 0 gets the merged stream as a device uint8
+    tensor instead of a host recarray."""
     from . import v2ce as drv
     starts, mode = drv.window_schedule(frame_count, seq_len)
     n_batches = -(-len(starts) // batch_size)
@@ -94,16 +96,13 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
     if shard.frame_count > 1:
         res = drv.stream_clip(model, vidcap=shard, seq_len=seq_len, batch_size=batch_size,
                               pair_base=shard.pair_base, device=dev, write_event_frames=False, schedule=shard.schedule,
-                              **kw)
-        n = res.event_stream.shape[0]
-        ev = res.event_stream_dev if res.event_stream_dev is not None else \
-            torch.from_numpy(res.event_stream.view(np.uint8).copy()).to(dev)
-        if n == 0:
-            ev = torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev)
+                              events_to_host=False, **kw)
+        n = res.n_events
+        ev = res.event_stream_dev if n else torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev)
     else:
         ev, n = torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev), 0
     out, counts = gather_event_shards(ev, n)
     if out is not None:
         from .ldati import EVENT_DTYPE
-        return out.cpu().numpy().view(EVENT_DTYPE), sum(counts)
+        return (out.cpu().numpy().view(EVENT_DTYPE) if to_host else out), sum(counts)
     return None, sum(counts)

@@ -250,14 +250,15 @@ class BatchRunner:
     def reset_collection(self):
         self._all_bytes = 0
 
-    def collected_events(self):
-        """All events appended since reset_collection(), as (device uint8 tensor, host recarray view of one D2H)."""
+    def collected_events(self, to_host=True):
+        """All events appended since reset_collection(), as (device uint8 tensor, host recarray view of one D2H or
+        None when to_host is False)."""
         self.flush()
         self.copy_stream.synchronize()
         if self._all_bytes == 0:
-            return None, np.empty(0, _ldati.EVENT_DTYPE)
+            return None, (np.empty(0, _ldati.EVENT_DTYPE) if to_host else None)
         dev = self._all_ev[:self._all_bytes]
-        return dev, dev.cpu().numpy().view(_ldati.EVENT_DTYPE)
+        return dev, (dev.cpu().numpy().view(_ldati.EVENT_DTYPE) if to_host else None)
 
     def flush(self):
         """Enqueue stage B of the batch submitted last (the end of a clip)."""

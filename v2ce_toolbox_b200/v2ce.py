@@ -183,6 +183,7 @@ class ClipResult:
         self.ef_upper_bound = ef_upper_bound
         self.n_pairs = n_pairs
         self.event_stream_dev = None
+        self.n_events = 0 if event_stream is None else len(event_stream)
 
 
 def _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width):
@@ -202,7 +203,7 @@ def _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width
 @torch.no_grad()
 def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_len=16, width=346, height=260,
                 batch_size=1, fps=30, ceil=10, upper_bound_percentile=98, keep_polarity=True,
-                write_event_frames=True, seed=0, pair_base=0, device=None, schedule=None):
+                write_event_frames=True, seed=0, pair_base=0, device=None, schedule=None, events_to_host=True):
     """Device-resident, pipelined version of v2ce.py:322-372 (runner.BatchRunner: the network of batch i+1 runs over
     the event frames + LDATI of batch i, results leave on a copy stream).  Returns ClipResult with the concatenated
     event stream (timestamps offset per frame, v2ce.py:365) and the uint8 BGR preview frames (clip-global percentile,
@@ -251,7 +252,7 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
             prev = t
         if prev is not None:
             runner.wait(prev)
-        events_dev, stream = runner.collected_events()
+        events_dev, stream = runner.collected_events(to_host=events_to_host)   # False: ClipResult.event_stream is None
         frames, ub = None, None
         if write_event_frames:
             torch.cuda.current_stream(device).wait_stream(runner.post_stream)
@@ -260,6 +261,7 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
             frames = _ef.normalize(sums, ub, keep_polarity).cpu().numpy()
     res = ClipResult(stream, frames, ub, pair_idx - pair_base)
     res.event_stream_dev = events_dev            # the same bytes on the device (dist.py gathers from here)
+    res.n_events = 0 if events_dev is None else events_dev.numel() // 13
     return res
 
 
