@@ -504,6 +504,9 @@ struct TileShape { int PW, TH; };
 // pitch / rows per tile for an output plane of H x W (see file header); chosen to maximise the useful
 // fraction of the 128 accumulator rows
 inline TileShape pick_tile(int H, int W) {
+  // tuning override for the large planes: V2CE_TILE_PW=<patch pitch>
+  static const int force_pw = getenv("V2CE_TILE_PW") ? atoi(getenv("V2CE_TILE_PW")) : 0;
+  if (force_pw >= 4 && W >= 100) return TileShape{force_pw, 128 / force_pw};
   TileShape best{16, 8};
   double best_eff = 0.0;
   for (int pw = 10; pw <= 66; pw += 2) {
