@@ -125,3 +125,13 @@ def test_batch_runner_overlapped_results_match_oracle():
         assert len(ev) == len(want)
         for f in ('timestamp', 'x', 'y', 'polarity'):
             assert np.array_equal(ev[f], want[f]), (i, f)
+
+
+def test_event_sink_matches_plain_copy():
+    """sink.to_host (pinned double buffer + threaded first-touch copies) returns the same bytes as tensor.cpu()."""
+    from v2ce_toolbox_b200 import sink
+    g = torch.Generator(device='cuda').manual_seed(0)
+    for n in (0, 1000, (3 << 20) + 12345):
+        t = torch.randint(0, 256, (n,), dtype=torch.uint8, device='cuda', generator=g)
+        got = sink.to_host(t, chunk_bytes=1 << 20, workers=4)
+        assert got.dtype == np.uint8 and np.array_equal(got, t.cpu().numpy())

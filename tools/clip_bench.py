@@ -60,7 +60,8 @@ def main():
         dt_dev = time.perf_counter() - t0             # every rank computed, shards merged on rank 0's device
         if rank == 0:
             from v2ce_toolbox_b200.ldati import EVENT_DTYPE
-            ev = ev_dev.cpu().numpy().view(EVENT_DTYPE)  # the event-stream sink: one pageable D2H
+            from v2ce_toolbox_b200.sink import to_host
+            ev = to_host(ev_dev).view(EVENT_DTYPE)       # the event-stream sink: pipelined D2H into one host array
             dt = time.perf_counter() - t0
             ts = ev['timestamp']
             ok = bool((np.diff(ts[::max(1, len(ts) // 2000000)]) >= -40000).all())      # bins restart every 1/fps/9 inside a frame

@@ -104,5 +104,6 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
     out, counts = gather_event_shards(ev, n)
     if out is not None:
         from .ldati import EVENT_DTYPE
-        return (out.cpu().numpy().view(EVENT_DTYPE) if to_host else out), sum(counts)
+        from .sink import to_host as _sink
+        return (_sink(out).view(EVENT_DTYPE) if to_host else out), sum(counts)
     return None, sum(counts)

@@ -258,7 +258,8 @@ class BatchRunner:
         if self._all_bytes == 0:
             return None, (np.empty(0, _ldati.EVENT_DTYPE) if to_host else None)
         dev = self._all_ev[:self._all_bytes]
-        return dev, (dev.cpu().numpy().view(_ldati.EVENT_DTYPE) if to_host else None)
+        from .sink import to_host as _sink
+        return dev, (_sink(dev).view(_ldati.EVENT_DTYPE) if to_host else None)
 
     def flush(self):
         """Enqueue stage B of the batch submitted last (the end of a clip)."""
