@@ -17,6 +17,12 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  return dev & 63;
+}
+
 int sm_count_cached() {
   static int cached = 0;
   if (cached == 0) {

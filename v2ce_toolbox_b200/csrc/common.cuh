@@ -52,5 +52,8 @@ struct Arena {
 };
 
 int sm_count_cached();
+// index (< 64) of the current CUDA device: function attributes and constant memory are per device, so the
+// one-time-setup caches of the launchers are kept per device (one process may drive several GPUs)
+int device_slot();
 
 }  // namespace v2ce

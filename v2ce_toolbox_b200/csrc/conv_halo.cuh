@@ -559,10 +559,11 @@ inline HaloPlan plan_for(int bn, int D, int H, int W) {
 
 template <int BN, int T>
 inline int launch_halo_one(const CUtensorMap& tm0, const CUtensorMap& tm1, const HaloArgs& a, int smem_bytes, cudaStream_t s) {
-  static int configured = 0;
-  if (configured < smem_bytes) {
+  static int configured[64] = {0};
+  const int slot = device_slot();
+  if (configured[slot] < smem_bytes) {
     V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = smem_bytes;
+    configured[slot] = smem_bytes;
   }
   const int total = a.B * (a.D / T) * a.tiles_h * a.tiles_w * (a.Cout / BN);
   int per_sm = 1;                                   // resident CTAs per SM (shared memory bound)

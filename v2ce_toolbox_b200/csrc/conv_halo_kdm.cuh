@@ -607,10 +607,11 @@ inline int make_parity_map(CUtensorMap* map, const void* ptr, int B, int D, int 
 template <bool SHORT, int T, int S>
 inline int launch_kdm_one(const CUtensorMap& tm0, const CUtensorMap& tm1, const ParityMaps& pm, const HaloArgs& a,
                           const KdmShort& sc, int smem_bytes, cudaStream_t s) {
-  static int configured = 0;
-  if (configured < smem_bytes) {
+  static int configured[64] = {0};
+  const int slot = device_slot();
+  if (configured[slot] < smem_bytes) {
     V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<SHORT, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = smem_bytes;
+    configured[slot] = smem_bytes;
   }
   const int total = a.B * (a.D / T) * a.tiles_h * a.tiles_w * (a.Cout / kKdmBN);
   const int grid = total < sm_count_cached() ? total : sm_count_cached();

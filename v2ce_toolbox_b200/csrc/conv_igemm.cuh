@@ -498,11 +498,12 @@ inline int pick_bn(int cout) {
 template <int BN, int STAGES>
 inline int launch_one(const ConvArgs& a, cudaStream_t s) {
   using L = SmemLayout<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};
+  const int slot = device_slot();
+  if (!configured[slot]) {
     V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          L::kDynamicBytes));
-    configured = true;
+    configured[slot] = true;
   }
   const int m_tiles = (a.M + kBlockM - 1) / kBlockM;
   const int grid = m_tiles * (a.Cout / BN);

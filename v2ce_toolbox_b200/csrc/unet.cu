@@ -538,6 +538,7 @@ static int get_tmap(v2ce_model* m, const void* ptr, int B, int D, int H, int W, 
   auto key = std::make_tuple(ptr, B, D, H, W, cpitch, PW, rows);
   auto it = m->tmaps.find(key);
   if (it == m->tmaps.end()) {
+    if (m->tmaps.size() > 512) m->tmaps.clear();      // callers that move their workspace every call must not grow the cache
     CUtensorMap tm;
     if (int e = halo::make_patch_map(&tm, ptr, B, D, H, W, cpitch, PW, rows)) return e;
     it = m->tmaps.emplace(key, tm).first;
