@@ -276,6 +276,9 @@ __global__ void __launch_bounds__(kHaloThreads) conv_halo_kernel(const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_acc = *tmem_ptr;
+  // prologue done: let the next kernel of the stream be launched, then wait for the previous one's results
+  pdl_launch_dependents();
+  pdl_wait();
 
   // Persistent CTA: every role walks the same tile sequence; the smem rings and their phases run on
   // across tiles, so the producers prefetch the next tile while the current one is multiplied/stored.
@@ -569,7 +572,7 @@ inline int launch_halo_one(const CUtensorMap& tm0, const CUtensorMap& tm1, const
   int per_sm = 1;                                   // resident CTAs per SM (shared memory bound)
   if (2 * (smem_bytes + 1024) <= 227 * 1024 && 2 * HaloCfg<BN, T>::kTmemCols <= 512) per_sm = 2;
   const int grid = total < sm_count_cached() * per_sm ? total : sm_count_cached() * per_sm;
-  conv_halo_kernel<BN, T><<<grid, kHaloThreads, smem_bytes, s>>>(tm0, tm1, a);
+  V2CE_CUDA_CHECK(launch_pdl(conv_halo_kernel<BN, T>, grid, kHaloThreads, (size_t)smem_bytes, s, tm0, tm1, a));
   V2CE_LAUNCH_CHECK("conv_halo_kernel");
   return V2CE_OK;
 }

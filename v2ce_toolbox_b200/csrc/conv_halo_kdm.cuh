@@ -191,6 +191,9 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_acc = *tmem_ptr;
+  // prologue done: let the next kernel of the stream be launched, then wait for the previous one's results
+  pdl_launch_dependents();
+  pdl_wait();
 
   // input slices a tile multiplies: d0-1 .. d0+T, minus the zero-padding slices -1 and D
   auto z_lo = [&](int d0) { return d0 > 0 ? d0 - 1 : 0; };
@@ -615,7 +618,7 @@ inline int launch_kdm_one(const CUtensorMap& tm0, const CUtensorMap& tm1, const 
   }
   const int total = a.B * (a.D / T) * a.tiles_h * a.tiles_w * (a.Cout / kKdmBN);
   const int grid = total < sm_count_cached() ? total : sm_count_cached();
-  conv_halo_kdm_kernel<SHORT, T, S><<<grid, kKdmThreads, smem_bytes, s>>>(tm0, tm1, pm, a, sc);
+  V2CE_CUDA_CHECK(launch_pdl(conv_halo_kdm_kernel<SHORT, T, S>, grid, kKdmThreads, (size_t)smem_bytes, s, tm0, tm1, pm, a, sc));
   V2CE_LAUNCH_CHECK("conv_halo_kdm_kernel");
   return V2CE_OK;
 }

@@ -262,6 +262,9 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const ConvArgs a) 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_acc = *tmem_ptr;
+  // prologue done: let the next kernel of the stream be launched, then wait for the previous one's results
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp < 8) {
     // ================= A producer (8 warps) =================
@@ -507,7 +510,7 @@ inline int launch_one(const ConvArgs& a, cudaStream_t s) {
   }
   const int m_tiles = (a.M + kBlockM - 1) / kBlockM;
   const int grid = m_tiles * (a.Cout / BN);
-  conv_igemm_kernel<BN, STAGES><<<grid, kThreads, L::kDynamicBytes, s>>>(a);
+  V2CE_CUDA_CHECK(launch_pdl(conv_igemm_kernel<BN, STAGES>, grid, kThreads, (size_t)L::kDynamicBytes, s, a));
   V2CE_LAUNCH_CHECK("conv_igemm_kernel");
   return V2CE_OK;
 }
