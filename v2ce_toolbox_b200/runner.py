@@ -127,8 +127,6 @@ class BatchRunner:
         if self.time_forward:
             e1.record(cur)
             t.fwd_events = (e0, e1)
-        vox_ready = torch.cuda.Event()
-        vox_ready.record(cur)
         b, L, _, H, W = y.shape
         n = b * L
         t.vox = y.reshape(n, 2, 10, H, W)
@@ -137,6 +135,8 @@ class BatchRunner:
             t.vox = torch.cat([t.vox[:(b - 1) * L], t.vox[(b - 1) * L + (L - keep):]], dim=0).contiguous()
             n = t.vox.shape[0]
         t.n_pairs, t.hw = n, (H, W)
+        vox_ready = torch.cuda.Event()            # after the trim copy: the post stream reads t.vox
+        vox_ready.record(cur)
         t.vox.record_stream(self.post_stream)
         self.launches += self.model.last_launches() if hasattr(self.model, 'last_launches') else 0
 
