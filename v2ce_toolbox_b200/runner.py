@@ -102,7 +102,10 @@ class BatchRunner:
         t.staged = False
         cur = torch.cuda.current_stream(self.device)
         if self._free[slot] is not None:
-            cur.wait_event(self._free[slot])    # the previous user of this slot has left the device
+            # the previous user of this slot has left the device: its per-slot pinned staging (counts, frame offsets)
+            # is about to be rewritten by the host, its device buffers by this batch
+            self._free[slot].synchronize()
+            cur.wait_event(self._free[slot])
         t.h2d_bytes = 0
         if not units.is_cuda:
             t.h2d_bytes = units.numel() * units.element_size()
