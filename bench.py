@@ -5,16 +5,20 @@
 
 Workload (BASELINE.json configs[1]): center 346x260, 321 synthetic gray frames = 20 windows of
 16 frame pairs, batch 4, random-init V2ce3d, voxel + LDATI + event-frame path.  One *step* is one
-batch of 4 windows (64 frame pairs) through UNet -> event-frame accumulate/select/normalise ->
-LDATI count/emit/sort/pack.  Step i uses batch (i mod 5) of the clip; at N GPUs every rank runs its
-own windows (weak scaling, windows are independent) and the per-rank event shards are gathered to
-rank 0 over NCCL inside the timed region.
+batch of 4 windows (64 frame pairs) through v2ce_toolbox_b200.runner.BatchRunner: UNet ->
+event-frame accumulate/select/normalise -> LDATI count/emit/sort/pack, the last two stages on a second
+stream under the UNet of the next step.  Step i uses batch (i mod 5) of the clip; at N GPUs every rank
+runs its own windows (weak scaling, windows are independent) and the per-rank event shards are gathered
+to rank 0 over NCCL inside the timed region.
 
-  value  device-timed throughput, inputs (float32 image units) already resident in HBM
-  e2e    same steps through the public API with HOST buffers: pinned image units H2D, packed
-         events + preview frames D2H, inside the timed region
+  value  device-timed throughput, inputs (float32 image units) already resident in HBM, results left on
+         the device
+  e2e    same steps with HOST buffers: raw uint8 frame windows in pinned memory H2D (the pre-processing
+         runs inside the head conv), packed events + preview frames D2H, inside the timed region
   roofline    tensor roofline of the UNet forward (2169.336 GFLOP per window) against
-              the measured sustained bf16 peak; CUDA events around the forward of every timed step
+              the measured sustained bf16 peak: CUDA events around the forward run alone over the same
+              K steps (`forward_ms`) and inside the timed steps (`forward_ms_in_step`)
+  ldati  LDATI-only microbench on a bounded sample of configs[2] (24 pairs, two voxel distributions)
   cpu_baseline  the CPU oracle (torch-CPU fp32 UNet + numpy LDATI/EF restatement, oracle/) timed on
               the host cores on a bounded sample (1 window = 16 frame pairs)
 
@@ -274,9 +278,6 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         wall = time.perf_counter() - t0
         ms = max(s.elapsed_time(e), wall * 1e3) if host_io else s.elapsed_time(e)
-        if not host_io:
-            # results are left on the device; the loop still ends with every stream drained
-            ms = max(ms, 0.0)
         tt = torch.tensor([ms], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
