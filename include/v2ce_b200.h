@@ -43,8 +43,10 @@ int v2ce_device_check(int device, int* sm_count, int* cc_major, int* cc_minor);
 /* ------------------------------------------------------------------------------------------
  * Stage 2 -- LDATI.  Replaces scripts/LDATI.py:126-214 (sample_voxel_statistical) with its
  * helpers y_relocate (:80-106), calculate_statistical_linear_params_for_stage2 (:13-51),
- * pick_elements (:217-245) and pick_and_sort (:248-310), for the configuration v2ce.py:356
- * uses (bidirectional=False, additional_events_strategy='slope', pooling_type='none').
+ * pick_elements (:217-245) and pick_and_sort (:248-310).  The configuration v2ce.py:356 uses
+ * (bidirectional=False, additional_events_strategy='slope', pooling_type='none') is the tuned path;
+ * bidirectional=True and the 'random' / 'none' strategies are implemented as options of the same
+ * kernels; pooling_type 'avg' / 'weighted' is not implemented (the Python shim raises).
  *
  * The scalar constants are computed by the host with the reference's own Python
  * expressions so the kernel reproduces torch's rounding.
@@ -69,6 +71,12 @@ typedef struct v2ce_ldati_params {
   int64_t bin_base_us[16];   /* sort-key origin per bin: trunc(binstart_t0_32[c]*1e6)        */
   int32_t key_span;          /* max (ts - bin_base_us) expected + slack; key bits derive from it */
   int32_t add_frame_offset;  /* 1: add frame_offset_us[f] to every timestamp (fused CLI path, v2ce.py:365) */
+  int32_t multi_events;      /* additional_events_strategy for pixel-bins holding more than one event:
+                              * 1 = 'slope' (inverse CDF of the linear density, LDATI.py:184-196; the CLI's setting),
+                              * 2 = 'random' (the raw uniform draw is the offset in SECONDS, LDATI.py:173-174),
+                              * 0 = 'none' (such pixel-bins emit nothing, LDATI.py:206-207,241-244)             */
+  int32_t bidirectional;     /* 1: y_relocate(bidirectional=True), LDATI.py:107-122 (bin_base_us / key_span must
+                              * then cover tendencies in (-1, y[9]] bins; see v2ce_toolbox_b200/ldati.py)        */
 } v2ce_ldati_params;
 
 /* Workspace needed by v2ce_ldati_count (also holds the scan results v2ce_ldati_emit reads). */
@@ -93,8 +101,8 @@ int v2ce_ldati_emit(const float* voxels_dev, const v2ce_ldati_params* p, const v
                     const int64_t* frame_offset_us_dev, int64_t total_events, uint8_t* events_out_dev,
                     int32_t* status_dev, void* stream);
 
-/* Debug/parity hook for LDATI.py:80-106 alone: int32 counts (F,2,9,H,W) and float32 debts. */
-int v2ce_ldati_relocate(const float* voxels_dev, int32_t n_frames, int32_t height, int32_t width,
+/* Debug/parity hook for LDATI.py:80-123 alone (y_relocate): int32 counts (F,2,9,H,W) and float32 tendencies. */
+int v2ce_ldati_relocate(const float* voxels_dev, int32_t n_frames, int32_t height, int32_t width, int32_t bidirectional,
                         int32_t* counts_dev, float* tend_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------

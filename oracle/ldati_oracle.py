@@ -4,6 +4,7 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  numpy float32/float64 arithmetic,
 one rounding per operation, in the operation order of the reference:
 
   relocate_counts      <- /root/reference/scripts/LDATI.py:80-106  (y_relocate, non-bidirectional)
+  relocate_counts_bidirectional <- /root/reference/scripts/LDATI.py:91-94,96-104,107-122 (bidirectional=True)
   single_timestamps    <- /root/reference/scripts/LDATI.py:156-165
   slope_params         <- /root/reference/scripts/LDATI.py:13-51,184-192
   multi_timestamps     <- /root/reference/scripts/LDATI.py:194-196,209-212
@@ -105,6 +106,38 @@ def relocate_counts(y):
     return n, tend
 
 
+def relocate_counts_bidirectional(y):
+    """y_relocate(y, bidirectional=True) (LDATI.py:91-94,107-122): bins 0..3 carry a debt from the left as in
+    relocate_counts, bins 8,7,6 carry a `bless` from the right (seeded with the tenth voxel bin), bin 5 settles
+    both, and bin 4 is never written (stays n = 0, tend = 0).  All arithmetic is float32, one rounding per torch op;
+    tend is the value the reference stores into its float64 `tendency` tensor."""
+    y = np.asarray(y, dtype=F32)
+    C = y.shape[-3]
+    n = np.zeros(y.shape[:-3] + (C - 1,) + y.shape[-2:], dtype=np.int64)
+    tend = np.zeros(n.shape, dtype=F32)
+    debt = np.zeros(y.shape[:-3] + y.shape[-2:], dtype=F32)
+    eps6 = F32(1e-6)
+    with np.errstate(invalid='ignore'):
+        for c in range((C - 1) // 2):                       # LDATI.py:96-104
+            x = y[..., c, :, :] - debt
+            nc = np.ceil(x - eps6)
+            debt = (nc - x).astype(F32)
+            n[..., c, :, :] = nc.astype(np.int64)
+            tend[..., c, :, :] = debt
+        bless = y[..., C - 1, :, :]                         # LDATI.py:108
+        for c in range(C - 2, C // 2, -1):                  # LDATI.py:109-118
+            ys = y[..., c, :, :]
+            tend[..., c, :, :] = bless
+            fl = np.floor((ys + bless) + eps6)
+            bless = ((ys - fl) + bless).astype(F32)
+            bless = np.maximum(bless, F32(0))               # torch.clamp(min=0); NaN propagates in both
+            n[..., c, :, :] = fl.astype(np.int64)
+        c = C // 2                                          # LDATI.py:120-122
+        tend[..., c, :, :] = bless - debt
+        n[..., c, :, :] = np.ceil((y[..., c, :, :] + bless) - debt).astype(np.int64)
+    return n, tend
+
+
 def single_timestamps(tend, k: Consts):
     """Timestamp (us, int64) of the only event of a pixel-bin with n == 1."""
     t = tend.astype(np.float64)
@@ -145,16 +178,21 @@ def _sqrt32(x, flavor):
         return np.sqrt(x)
 
 
-def multi_timestamps(kk, b, u, binstart_t0_32, k: Consts):
-    """Inverse-CDF timestamps for events of pixel-bins with n >= 2 (flat arrays)."""
+def multi_timestamps(kk, b, u, binstart_t0_32, k: Consts, strategy='slope'):
+    """Timestamps for events of pixel-bins with n >= 2 (flat arrays): inverse CDF of the linear density
+    ('slope', LDATI.py:194-196) or the raw uniform draw taken as SECONDS ('random', LDATI.py:173-174: the
+    reference does not scale it by the bin width, so these events spread over [bin start, bin start + 1 s))."""
     with np.errstate(invalid='ignore', divide='ignore', over='ignore'):
-        disc = (b * b + (F32(2) * kk) * u).astype(F32)
-        t = ((-b) + _sqrt32(disc, k.flavor)) / kk
-        if k.flavor == 'cpu':
-            t0 = (u / F32(k.fps)) / F32(k.C)
+        if strategy == 'random':
+            t = u.astype(F32)
         else:
-            t0 = (u * k.r_fps32) * k.r_c32
-        t = np.where(kk == 0, t0, t).astype(F32)
+            disc = (b * b + (F32(2) * kk) * u).astype(F32)
+            t = ((-b) + _sqrt32(disc, k.flavor)) / kk
+            if k.flavor == 'cpu':
+                t0 = (u / F32(k.fps)) / F32(k.C)
+            else:
+                t0 = (u * k.r_fps32) * k.r_c32
+            t = np.where(kk == 0, t0, t).astype(F32)
         t = t + binstart_t0_32
         t = t * F32(1e6)
         with warnings.catch_warnings():
@@ -167,7 +205,7 @@ def multi_timestamps(kk, b, u, binstart_t0_32, k: Consts):
     return out
 
 
-def assemble_frame(n_f, ts1_f, kk_f, b_f, frame_index, H, W, k: Consts, draw_fn):
+def assemble_frame(n_f, ts1_f, kk_f, b_f, frame_index, H, W, k: Consts, draw_fn, strategy='slope'):
     """Events of one frame pair in canonical order.  n_f etc.: (2, 9, H, W)."""
     hw = H * W
     segs = []
@@ -180,7 +218,8 @@ def assemble_frame(n_f, ts1_f, kk_f, b_f, frame_index, H, W, k: Consts, draw_fn)
             parts_ts.append(ts1_f[p, c].reshape(hw)[single])
             parts_pix.append(single)
             parts_pol.append(np.full(single.shape, 1 - p, dtype=np.int8))
-            multi = np.nonzero(nn >= 2)[0]
+            # additional_events_strategy='none' drops every multi-event pixel-bin (LDATI.py:241-244)
+            multi = np.nonzero(nn >= 2)[0] if strategy != 'none' else np.zeros(0, dtype=np.int64)
             cnt = nn[multi]
             pix = np.repeat(multi, cnt)
             start = np.cumsum(cnt) - cnt
@@ -188,7 +227,7 @@ def assemble_frame(n_f, ts1_f, kk_f, b_f, frame_index, H, W, k: Consts, draw_fn)
             idx = philox.event_index(frame_index, p, c, pix, hw)
             u = draw_fn(idx, j, frame_index, p, c, pix)
             ts_m = multi_timestamps(kk_f[p, c].reshape(hw)[pix], b_f[p, c].reshape(hw)[pix],
-                                    u, k.binstart_t0_32[c], k)
+                                    u, k.binstart_t0_32[c], k, strategy)
             parts_ts.append(ts_m)
             parts_pix.append(pix)
             parts_pol.append(np.full(pix.shape, 1 - p, dtype=np.int8))
@@ -207,18 +246,19 @@ def assemble_frame(n_f, ts1_f, kk_f, b_f, frame_index, H, W, k: Consts, draw_fn)
 
 
 def sample_voxel_statistical_oracle(y, t0=0, fps=30, seed=0, frame_base=0, flavor='cuda',
-                                    draws=None, return_seg_counts=False):
-    """Oracle of sample_voxel_statistical(y, fps=fps, bidirectional=False,
-    additional_events_strategy='slope', pooling_type='none').
+                                    draws=None, return_seg_counts=False, additional_events_strategy='slope',
+                                    bidirectional=False):
+    """Oracle of sample_voxel_statistical(y, fps=fps, bidirectional=False | True,
+    additional_events_strategy='slope' | 'random' | 'none', pooling_type='none').
 
     y: (B,2,10,H,W) any real dtype.  draws: optional dense (B,2,9,H,W,M) float32
     array of injected uniforms; default = the Philox stream of oracle/philox.py
     keyed by `seed`, with global frame index frame_base + b."""
     y = np.asarray(y)
     B, P, C, H, W = y.shape
-    assert P == 2
+    assert P == 2 and additional_events_strategy in ('slope', 'random', 'none')
     k = Consts(fps, t0, flavor, C - 1)
-    n, tend = relocate_counts(y.astype(F32))
+    n, tend = (relocate_counts_bidirectional if bidirectional else relocate_counts)(y.astype(F32))
     ts1 = single_timestamps(tend, k)
     kk, b = slope_params(n, k)
     out, counts = [], []
@@ -229,7 +269,8 @@ def sample_voxel_statistical_oracle(y, t0=0, fps=30, seed=0, frame_base=0, flavo
         else:
             def draw_fn(idx, j, frame, p, c, pix, _f=f):
                 return draws[_f, p, c].reshape(H * W, -1)[pix, j].astype(F32)
-        rec, sc = assemble_frame(n[f], ts1[f], kk[f], b[f], frame_base + f, H, W, k, draw_fn)
+        rec, sc = assemble_frame(n[f], ts1[f], kk[f], b[f], frame_base + f, H, W, k, draw_fn,
+                                 strategy=additional_events_strategy)
         out.append(rec)
         counts.append(sc)
     if return_seg_counts:

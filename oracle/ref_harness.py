@@ -123,7 +123,7 @@ def injected_draws(seed, frame_base=0):
         torch.rand = old
 
 
-def run_reference_ldati(y, fps=30, seed=0, frame_base=0):
+def run_reference_ldati(y, fps=30, seed=0, frame_base=0, additional_events_strategy='slope', bidirectional=False):
     """sample_voxel_statistical exactly as v2ce.py:356 calls it, on CPU, with injected draws."""
     import torch
     import warnings
@@ -131,8 +131,8 @@ def run_reference_ldati(y, fps=30, seed=0, frame_base=0):
     yt = torch.as_tensor(np.asarray(y))
     with injected_draws(seed, frame_base), warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        out = ld.sample_voxel_statistical(yt, fps=fps, bidirectional=False,
-                                          additional_events_strategy='slope')
+        out = ld.sample_voxel_statistical(yt, fps=fps, bidirectional=bidirectional,
+                                          additional_events_strategy=additional_events_strategy)
     return [np.asarray(r) for r in out]
 
 

@@ -59,6 +59,31 @@ def ldati_cases():
     return meta
 
 
+OPTION_CASES = [(inp, strat, bid) for inp in ('mixed24', 'randint') for strat in ('slope', 'random', 'none')
+                for bid in (False, True) if not (strat == 'slope' and not bid)]
+
+
+def ldati_option_cases():
+    """The options of sample_voxel_statistical the CLI does not use: additional_events_strategy
+    'random' (LDATI.py:173-174) and 'none' (LDATI.py:206-207,241-244), and bidirectional=True (LDATI.py:107-122),
+    on the 'mixed24' and 'randint' voxels already stored in ldati_golden.npz."""
+    vox = np.load(os.path.join(HERE, 'ldati_golden.npz'))
+    with open(os.path.join(HERE, 'golden_meta.json')) as f:
+        base = json.load(f)['ldati']
+    out, meta = {}, {}
+    for inp, strat, bid in OPTION_CASES:
+        m = base[inp]
+        ref = rh.run_reference_ldati(vox[f'{inp}_voxel'], fps=m['fps'], seed=m['seed'], frame_base=m['frame_base'],
+                                     additional_events_strategy=strat, bidirectional=bid)
+        name = f"{inp}-{strat}-{'bi' if bid else 'uni'}"
+        for i, r in enumerate(ref):
+            out[f'{name}_events_{i}'] = np.ascontiguousarray(lo.canonicalize(r)).view(np.uint8)
+        meta[name] = dict(input=inp, fps=m['fps'], seed=m['seed'], frame_base=m['frame_base'], frames=len(ref),
+                          additional_events_strategy=strat, bidirectional=bid, counts=[int(len(r)) for r in ref])
+    np.savez_compressed(os.path.join(HERE, 'ldati_options_golden.npz'), **out)
+    return meta
+
+
 def ef_cases():
     out = {}
     meta = {}
@@ -121,8 +146,18 @@ def pipeline_cases():
 
 if __name__ == '__main__':
     import cv2
-    meta = dict(versions=dict(torch=torch.__version__, numpy=np.__version__, cv2=cv2.__version__),
-                ldati=ldati_cases(), ef=ef_cases(), unet=unet_cases(), pipeline=pipeline_cases())
+    if '--only-ldati-options' in sys.argv:
+        # incremental: (re)generate only the LDATI option goldens, keep the rest of the meta file
+        with open(os.path.join(HERE, 'golden_meta.json')) as f:
+            meta = json.load(f)
+        meta.pop('ldati_none', None)
+        meta['ldati_options'] = ldati_option_cases()
+    else:
+        meta = dict(versions=dict(torch=torch.__version__, numpy=np.__version__, cv2=cv2.__version__),
+                    ldati=ldati_cases(), ef=ef_cases(), unet=unet_cases(), pipeline=pipeline_cases())
+        with open(os.path.join(HERE, 'golden_meta.json'), 'w') as f:
+            json.dump(meta, f, indent=1)
+        meta['ldati_options'] = ldati_option_cases()
     with open(os.path.join(HERE, 'golden_meta.json'), 'w') as f:
         json.dump(meta, f, indent=1)
     print(json.dumps(meta, indent=1)[:3000])

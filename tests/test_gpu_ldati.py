@@ -21,17 +21,20 @@ def _assert_rows_equal(got, want, what):
         assert np.array_equal(np.asarray(got[f]), np.asarray(want[f])), f'{what}: field {f} differs'
 
 
-def test_relocate_counts_bit_exact():
-    import ctypes
+@pytest.mark.parametrize('bidirectional', [False, True])
+def test_relocate_counts_bit_exact(bidirectional):
+    """y_relocate alone (LDATI.py:80-123), both directions: counts and float32 tendencies bit for bit."""
     from v2ce_toolbox_b200 import _lib
     lib = _lib.load()
+    relocate = lo.relocate_counts_bidirectional if bidirectional else lo.relocate_counts
     for (F, H, W) in ((3, 40, 52), (2, 33, 47), (1, 260, 346)):
         v = synth.make_voxels('mixed', F, H, W, seed=11)
-        n, tend = lo.relocate_counts(v)
+        n, tend = relocate(v)
         vd = torch.from_numpy(v).cuda()
         cd = torch.empty((F, 2, 9, H, W), dtype=torch.int32, device='cuda')
         td = torch.empty((F, 2, 9, H, W), dtype=torch.float32, device='cuda')
-        _lib.check(lib.v2ce_ldati_relocate(_lib.ptr(vd), F, H, W, _lib.ptr(cd), _lib.ptr(td), _lib.stream_ptr()))
+        _lib.check(lib.v2ce_ldati_relocate(_lib.ptr(vd), F, H, W, int(bidirectional), _lib.ptr(cd), _lib.ptr(td),
+                                           _lib.stream_ptr()))
         assert np.array_equal(cd.cpu().numpy(), n.astype(np.int32))
         assert np.array_equal(td.cpu().numpy().view(np.uint32), tend.view(np.uint32))
 
@@ -140,7 +143,66 @@ def test_rejects_cpu_tensor_and_unsupported_modes():
     with pytest.raises(V2ceError):
         sample_voxel_statistical(torch.zeros(1, 2, 10, 4, 4))
     with pytest.raises(NotImplementedError):
-        sample_voxel_statistical(torch.zeros(1, 2, 10, 4, 4, device='cuda'), bidirectional=True)
+        sample_voxel_statistical(torch.zeros(1, 2, 10, 4, 4, device='cuda'), pooling_type='avg')
+    with pytest.raises(AssertionError):                      # the reference's own assert (LDATI.py:136)
+        sample_voxel_statistical(torch.zeros(1, 2, 10, 4, 4, device='cuda'), additional_events_strategy='other')
+
+
+OPTIONS = [(s_, b_) for s_ in ('slope', 'random', 'none') for b_ in (False, True) if (s_, b_) != ('slope', False)]
+
+
+@pytest.mark.parametrize('strategy,bidirectional', OPTIONS)
+@pytest.mark.parametrize('kind,F,H,W,fps', [('mixed', 2, 33, 47, 30), ('randint', 2, 24, 30, 24), ('rand', 2, 40, 52, 120),
+                                            ('mixed', 1, 260, 346, 30)])
+def test_options_bit_exact_vs_oracle(strategy, bidirectional, kind, F, H, W, fps):
+    """additional_events_strategy 'random' / 'none' and bidirectional=True through the same
+    kernels, bit-exact against the oracle (torch-CUDA flavour), V=1 and V=4 pixel paths, full-size plane."""
+    v = synth.make_voxels(kind, F, H, W, seed=31)
+    kw = dict(fps=fps, seed=77, frame_base=3, additional_events_strategy=strategy, bidirectional=bidirectional)
+    got = _run(v, **kw)
+    want = lo.sample_voxel_statistical_oracle(v, flavor='cuda', **kw)
+    for i, (g, w) in enumerate(zip(got, want)):
+        _assert_rows_equal(g, w, f'{kind} {strategy} bidirectional={bidirectional} frame {i}')
+
+
+@pytest.mark.parametrize('name', [f"{inp}-{s_}-{'bi' if b_ else 'uni'}" for inp in ('mixed24', 'randint')
+                                  for (s_, b_) in OPTIONS])
+def test_options_cpu_flavour_against_reference_goldens(name, golden, golden_meta):
+    """Kernel in torch-CPU scalar semantics vs the unmodified reference's events for the off-CLI options.
+    'random' and 'none' involve no sqrt, so they must match bit for bit (modulo the reference's undefined tie
+    order); 'slope' is held to the criterion of test_cpu_flavour_against_reference_goldens."""
+    m = golden_meta['ldati_options'][name]
+    v = golden('ldati')[f"{m['input']}_voxel"]
+    got = _run(v, fps=m['fps'], seed=m['seed'], frame_base=m['frame_base'], flavor='cpu',
+               additional_events_strategy=m['additional_events_strategy'], bidirectional=m['bidirectional'])
+    assert [len(e) for e in got] == m['counts']
+    for i, ev in enumerate(got):
+        ref = golden('ldati_options')[f'{name}_events_{i}'].view(lo.EVENT_DTYPE)
+        if m['additional_events_strategy'] != 'slope':
+            assert np.array_equal(lo.canonicalize(ev), ref), f'{name} frame {i}'
+        else:
+            d = np.abs(np.sort(ev['timestamp']) - np.sort(ref['timestamp']))
+            assert d.max() <= 1 and (d != 0).mean() <= 1e-3
+
+
+def test_bidirectional_tendency_beyond_sort_window_raises():
+    """bidirectional: bin 8's tendency is the tenth voxel bin itself (LDATI.py:108,111).  The sort-key window covers
+    tendencies up to ldati.BIDIR_MAX_TENDENCY bins (rounded up to a power of two of microseconds, so < 2x that);
+    a timestamp beyond it must fail loudly, never clamp silently."""
+    from v2ce_toolbox_b200 import V2ceError, ldati
+    v = np.zeros((1, 2, 10, 8, 12), np.float32)
+    # one SINGLE event in bin 8 (floor(y8 + y9) == 1) whose tendency y9 is 4x outside the window; this needs a
+    # negative voxel -- with the model's non-negative output a single event's tendency stays below 2 bins
+    v[0, 0, 8, 3, 5] = -(4 * ldati.BIDIR_MAX_TENDENCY + 99.25)
+    v[0, 0, 9, 3, 5] = 4 * ldati.BIDIR_MAX_TENDENCY + 100.5
+    assert lo.relocate_counts_bidirectional(v)[0][0, 0, 8, 3, 5] == 1
+    with pytest.raises(V2ceError):
+        _run(v, bidirectional=True)
+    v[0, 0, 8, 3, 5], v[0, 0, 9, 3, 5] = -2.0, 3.25          # tendency 3.25 bins: inside the window
+    got = _run(v, bidirectional=True, seed=1)
+    want = lo.sample_voxel_statistical_oracle(v, bidirectional=True, seed=1, flavor='cuda')
+    assert want[0]['timestamp'].max() > int(1e6 / 30)                          # lands beyond the frame's end
+    _assert_rows_equal(got[0], want[0], 'bidirectional tendency 3.25')
 
 
 def test_empty_and_negative_inputs():

@@ -52,6 +52,35 @@ def test_ldati_oracle_matches_reference(name, golden, golden_meta):
         assert o.dtype.itemsize == 13
 
 
+OPTION_CASES = [f"{inp}-{strat}-{d}" for inp in ('mixed24', 'randint') for strat in ('slope', 'random', 'none')
+                for d in ('uni', 'bi') if (strat, d) != ('slope', 'uni')]
+
+
+@pytest.mark.parametrize('name', OPTION_CASES)
+def test_ldati_oracle_options_match_reference(name, golden, golden_meta):
+    """additional_events_strategy 'random' / 'none' and bidirectional=True against the
+    unmodified reference's events."""
+    m = golden_meta['ldati_options'][name]
+    g = golden('ldati_options')
+    v = golden('ldati')[f"{m['input']}_voxel"]
+    ora = lo.sample_voxel_statistical_oracle(v, fps=m['fps'], seed=m['seed'], frame_base=m['frame_base'], flavor='cpu',
+                                             additional_events_strategy=m['additional_events_strategy'],
+                                             bidirectional=m['bidirectional'])
+    assert [len(o) for o in ora] == m['counts']
+    for i, o in enumerate(ora):
+        assert np.array_equal(lo.canonicalize(o), g[f'{name}_events_{i}'].view(lo.EVENT_DTYPE)), f'{name} frame {i}'
+
+
+def test_bidirectional_relocation_shape():
+    """LDATI.py:107-122: bin 4 is never written; bin 8's tendency is the tenth voxel bin itself."""
+    v = synth.make_voxels('mixed', 1, 16, 20, seed=2)
+    n, tend = lo.relocate_counts_bidirectional(v)
+    assert (n[:, :, 4] == 0).all() and (tend[:, :, 4] == 0).all()
+    assert np.array_equal(tend[:, :, 8], v[:, :, 9])
+    n_uni, tend_uni = lo.relocate_counts(v)
+    assert np.array_equal(n[:, :, :4], n_uni[:, :, :4]) and np.array_equal(tend[:, :, :4], tend_uni[:, :, :4])
+
+
 @pytest.mark.parametrize('kind', ['rand', 'sparse', 'randint'])
 def test_ldati_oracle_full_size_digest(kind, golden_meta):
     m = golden_meta['ldati'][f'full_{kind}']

@@ -26,6 +26,7 @@ class LdatiParams(Structure):
         ('six32', c_float), ('r6_32', c_float), ('eps6', c_float), ('eps8', c_float),
         ('binstart_t0_32', c_float * 16), ('bin_base_us', c_int64 * 16),
         ('key_span', c_int32), ('add_frame_offset', c_int32),
+        ('multi_events', c_int32), ('bidirectional', c_int32),
     ]
 
 
@@ -38,7 +39,7 @@ _SIGNATURES = {
     'v2ce_ldati_count': (c_int, [c_void_p, POINTER(LdatiParams), c_void_p, c_size_t, c_void_p, c_void_p]),
     'v2ce_ldati_emit': (c_int, [c_void_p, POINTER(LdatiParams), c_void_p, c_void_p, c_size_t, c_void_p, c_int32,
                                 c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    'v2ce_ldati_relocate': (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    'v2ce_ldati_relocate': (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     'v2ce_ef_accumulate': (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'v2ce_ef_select_workspace_bytes': (c_int, [POINTER(c_size_t)]),
     'v2ce_ef_select': (c_int, [c_void_p, c_int64, c_double, c_int32, c_void_p, c_size_t, c_void_p, c_void_p]),

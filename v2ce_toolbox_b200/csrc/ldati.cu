@@ -1,6 +1,8 @@
 // LDATI (stage 2) on sm_100a: event-count relocation, slot assignment in the reference's
 // generation order, inverse-CDF timestamps, stable per-(frame,bin) radix sort and 13-byte
-// record packing.  Replaces /root/reference/scripts/LDATI.py:13-51,80-106,126-310.
+// record packing.  Replaces /root/reference/scripts/LDATI.py:13-51,80-106,126-310, plus the
+// options the CLI leaves at their defaults: bidirectional relocation (:107-122) and the
+// 'random' / 'none' strategies for multi-event pixel-bins (:173-174, :206-207, :241-244).
 //
 // Data layout in HBM
 //   voxels   float32 (F,2,10,H,W): planes of H*W pixels; a thread owns V=4 consecutive
@@ -95,6 +97,8 @@ struct DevParams {
   int pix_bits, key_bits;
   int draws_m;
   int add_frame_offset;
+  int multi_events;   // additional_events_strategy: 0 'none' (multi-event pixel-bins emit nothing), 1 'slope',
+                      // 2 'random' (the raw draw is the time offset in seconds, LDATI.py:173-174)
   long long nan_ts;   // float NaN -> int64: INT64_MIN on x86 (cvttss2si) and on torch-CUDA (measured on B200)
 };
 
@@ -112,6 +116,7 @@ static DevParams make_dev_params(const v2ce_ldati_params* p, const Geometry& g) 
   d.pix_bits = g.pix_bits; d.key_bits = g.key_bits;
   d.draws_m = 0;
   d.add_frame_offset = p->add_frame_offset;
+  d.multi_events = p->multi_events;
   d.nan_ts = LLONG_MIN;
   return d;
 }
@@ -128,6 +133,40 @@ __device__ __forceinline__ void relocate_pixel(const float (&y)[10], float eps6,
     tend[c] = debt;
   }
   n[kBins - 1] += __float2int_rz(__fsub_rn(y[9], debt));   // `.int()` truncation, LDATI.py:106
+}
+
+// y_relocate(bidirectional=True) (LDATI.py:91-94,96-104,107-122) for one pixel: bins 0..3 carry the debt from
+// the left, bins 8,7,6 carry `bless` from the right (seeded with the tenth voxel bin), bin 5 settles both, and
+// bin 4 is never written by the reference (n = 0, tend = 0).
+__device__ __forceinline__ void relocate_pixel_bidir(const float (&y)[10], float eps6, int (&n)[kBins], float (&tend)[kBins]) {
+  float debt = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float x = __fsub_rn(y[c], debt);
+    float nc = ceilf(__fsub_rn(x, eps6));
+    debt = __fsub_rn(nc, x);
+    n[c] = __float2int_rz(nc);
+    tend[c] = debt;
+  }
+  n[4] = 0;
+  tend[4] = 0.f;
+  float bless = y[9];
+#pragma unroll
+  for (int c = 8; c > 5; --c) {
+    tend[c] = bless;
+    const float fl = floorf(__fadd_rn(__fadd_rn(y[c], bless), eps6));
+    bless = __fadd_rn(__fsub_rn(y[c], fl), bless);
+    bless = (bless < 0.f) ? 0.f : bless;            // torch.clamp(min=0): NaN stays NaN
+    n[c] = __float2int_rz(fl);
+  }
+  tend[5] = __fsub_rn(bless, debt);
+  n[5] = __float2int_rz(ceilf(__fsub_rn(__fadd_rn(y[5], bless), debt)));
+}
+
+template <bool BIDIR>
+__device__ __forceinline__ void relocate_any(const float (&y)[10], float eps6, int (&n)[kBins], float (&tend)[kBins]) {
+  if (BIDIR) relocate_pixel_bidir(y, eps6, n, tend);
+  else relocate_pixel(y, eps6, n, tend);
 }
 
 template <int V>
@@ -194,7 +233,7 @@ __device__ __forceinline__ float philox_uniform(unsigned long long idx, unsigned
 // ---------------------------------------------------------------------------------------
 // K3: count pass.  grid (NB, 2, F), 256 threads, V pixels per thread.
 // ---------------------------------------------------------------------------------------
-template <int V>
+template <int V, bool BIDIR>
 __global__ void __launch_bounds__(kThreads) count_kernel(const float* __restrict__ vox, DevParams P,
                                                           int32_t* __restrict__ partial) {
   const int blk = blockIdx.x, p = blockIdx.y, f = blockIdx.z;
@@ -209,11 +248,11 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const float* __restrict
     for (int v = 0; v < V; ++v) {
       int n[kBins];
       float tend[kBins];
-      relocate_pixel(y[v], P.eps6, n, tend);
+      relocate_any<BIDIR>(y[v], P.eps6, n, tend);
 #pragma unroll
       for (int c = 0; c < kBins; ++c) {
         tot[c] += (n[c] == 1);
-        tot[kBins + c] += (n[c] >= 2) ? n[c] : 0;
+        tot[kBins + c] += (n[c] >= 2 && P.multi_events) ? n[c] : 0;
       }
     }
   }
@@ -347,7 +386,7 @@ __device__ __forceinline__ void load_bin(const float* __restrict__ plane0, int H
   }
 }
 
-template <int V, typename Elem>
+template <int V, typename Elem, bool BIDIR>
 __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict__ vox, DevParams P,
                                                          const int32_t* __restrict__ block_base,
                                                          const int32_t* __restrict__ group_base,
@@ -373,11 +412,11 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
       for (int v = 0; v < V; ++v) {
         int n[kBins];
         float tend[kBins];
-        relocate_pixel(y[v], P.eps6, n, tend);
+        relocate_any<BIDIR>(y[v], P.eps6, n, tend);
 #pragma unroll
         for (int c = 0; c < kBins; ++c) {
           tot[c] += (n[c] == 1);
-          tot[kBins + c] += (n[c] >= 2) ? n[c] : 0;
+          tot[kBins + c] += (n[c] >= 2 && P.multi_events) ? n[c] : 0;
         }
       }
     }
@@ -399,7 +438,27 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
   int n_prev[V], n_cur[V], n_next[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) { debt[v] = 0.f; n_prev[v] = n_cur[v] = n_next[v] = 0; tend_cur[v] = tend_next[v] = 0.f; y9[v] = 0.f; }
-  if (active) {
+  // BIDIR: the right-to-left chain of bins 8..5 cannot be walked with the sliding window, so this (cold, off-CLI)
+  // instantiation keeps the nine counts and tendencies of its pixels in local arrays and feeds the window from them.
+  int n_all[BIDIR ? V : 1][kBins];
+  float tend_all[BIDIR ? V : 1][kBins];
+  if (BIDIR) {
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int c = 0; c < kBins; ++c) { n_all[v][c] = 0; tend_all[v][c] = 0.f; }
+    if (active) {
+      float y[V][10];
+      load_pixels<V>(plane0, P.HW, pix0, y);
+#pragma unroll
+      for (int v = 0; v < V; ++v) relocate_pixel_bidir(y[v], P.eps6, n_all[v], tend_all[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      n_cur[v] = n_all[v][0]; tend_cur[v] = tend_all[v][0];
+      n_next[v] = n_all[v][1]; tend_next[v] = tend_all[v][1];
+    }
+  } else if (active) {
     float y0[V], y1[V];
     load_bin<V>(plane0, P.HW, pix0, 0, y0);
     load_bin<V>(plane0, P.HW, pix0, 1, y1);
@@ -415,7 +474,7 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
     // slots: [segment start] + [group base] + [blocks before] + [warps before] + [lanes before]
     int ts1 = 0, tsm = 0;
 #pragma unroll
-    for (int v = 0; v < V; ++v) { ts1 += (n_cur[v] == 1); tsm += (n_cur[v] >= 2) ? n_cur[v] : 0; }
+    for (int v = 0; v < V; ++v) { ts1 += (n_cur[v] == 1); tsm += (n_cur[v] >= 2 && P.multi_events) ? n_cur[v] : 0; }
     const int ex1 = warp_incl_scan(ts1) - ts1, exm = warp_incl_scan(tsm) - tsm;
     int ws = 0, wm = 0;
     for (int w = 0; w < warp; ++w) { ws += wtot[w][c]; wm += wtot[w][kBins + c]; }
@@ -451,7 +510,7 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const int nc = n_cur[v];
-      cnt[v] = (active && nc >= 2) ? nc : 0;
+      cnt[v] = (active && nc >= 2 && P.multi_events) ? nc : 0;
       float kk = 0.f, b = 0.f;
       if (cnt[v]) {
         float S = 0.f;
@@ -504,7 +563,9 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
             u = philox_uniform(idx, (unsigned)j, P.seed);
           }
           float t;
-          if (kk == 0.f) {
+          if (P.multi_events == 2) {
+            t = u;                                   // 'random': additional_ts = raw draw (LDATI.py:173-174)
+          } else if (kk == 0.f) {
             t = P.true_div ? __fdiv_rn(__fdiv_rn(u, P.fps32), P.nbins32)
                            : __fmul_rn(__fmul_rn(u, P.r_fps32), P.r_nbins32);
           } else {
@@ -540,7 +601,9 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
             u = philox_uniform(idx, (unsigned)j, P.seed);
           }
           float t;
-          if (kk == 0.f) {
+          if (P.multi_events == 2) {
+            t = u;                                   // 'random': additional_ts = raw draw (LDATI.py:173-174)
+          } else if (kk == 0.f) {
             t = P.true_div ? __fdiv_rn(__fdiv_rn(u, P.fps32), P.nbins32)
                            : __fmul_rn(__fmul_rn(u, P.r_fps32), P.r_nbins32);
           } else {
@@ -559,7 +622,12 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
     // advance the window: bin c+2 becomes `next`
 #pragma unroll
     for (int v = 0; v < V; ++v) { n_prev[v] = n_cur[v]; n_cur[v] = n_next[v]; tend_cur[v] = tend_next[v]; n_next[v] = 0; }
-    if (active && c + 2 < kBins) {
+    if (BIDIR) {
+      if (c + 2 < kBins) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { n_next[v] = n_all[v][c + 2]; tend_next[v] = tend_all[v][c + 2]; }
+      }
+    } else if (active && c + 2 < kBins) {
       float yn[V];
       load_bin<V>(plane0, P.HW, pix0, c + 2, yn);
 #pragma unroll
@@ -842,8 +910,8 @@ __global__ void __launch_bounds__(kThreads) pack_kernel(const Elem* __restrict__
 }
 
 template <int V>
-__global__ void relocate_debug_kernel(const float* __restrict__ vox, int HW, float eps6, int32_t* __restrict__ counts,
-                                      float* __restrict__ tend_out) {
+__global__ void relocate_debug_kernel(const float* __restrict__ vox, int HW, float eps6, int bidirectional,
+                                      int32_t* __restrict__ counts, float* __restrict__ tend_out) {
   const int plane = blockIdx.y;   // f*2+p
   const int pix = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (pix >= HW) return;
@@ -853,7 +921,8 @@ __global__ void relocate_debug_kernel(const float* __restrict__ vox, int HW, flo
   for (int v = 0; v < V; ++v) {
     int n[kBins];
     float tend[kBins];
-    relocate_pixel(y[v], eps6, n, tend);
+    if (bidirectional) relocate_pixel_bidir(y[v], eps6, n, tend);
+    else relocate_pixel(y[v], eps6, n, tend);
 #pragma unroll
     for (int c = 0; c < kBins; ++c) {
       counts[((size_t)plane * kBins + c) * HW + pix + v] = n[c];
@@ -870,6 +939,8 @@ static int validate(const v2ce_ldati_params* p) {
   V2CE_REQUIRE((long long)p->height * p->width < (1LL << 30), "plane too large");
   V2CE_REQUIRE(p->n_frames <= 65535, "at most 65535 frames per call (grid.z)");
   V2CE_REQUIRE(p->key_span > 0 && p->key_span < (1 << 30), "bad key_span %d", p->key_span);
+  V2CE_REQUIRE(p->multi_events >= 0 && p->multi_events <= 2, "multi_events must be 0 ('none'), 1 ('slope') or 2 ('random')");
+  V2CE_REQUIRE(p->bidirectional == 0 || p->bidirectional == 1, "bidirectional must be 0 or 1");
   return V2CE_OK;
 }
 
@@ -907,8 +978,13 @@ extern "C" int v2ce_ldati_count(const float* voxels_dev, const v2ce_ldati_params
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DevParams P = make_dev_params(p, g);
   dim3 grid(g.NB, 2, g.F);
-  if (g.V == 4) count_kernel<4><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
-  else count_kernel<1><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
+  if (p->bidirectional) {
+    if (g.V == 4) count_kernel<4, true><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
+    else count_kernel<1, true><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
+  } else {
+    if (g.V == 4) count_kernel<4, false><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
+    else count_kernel<1, false><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
+  }
   V2CE_LAUNCH_CHECK("ldati::count_kernel");
   scan_planes_kernel<<<g.F, 64, 0, s>>>(w.partial, w.block_base, w.group_base, seg_counts_dev, g.NB);
   V2CE_LAUNCH_CHECK("ldati::scan_planes_kernel");
@@ -931,10 +1007,17 @@ static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometr
   Elem* eb = static_cast<Elem*>(sw.elem_b);
   V2CE_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), s));
   dim3 grid(g.NB, 2, g.F);
-  if (g.V == 4)
-    emit_kernel<4, Elem><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
-  else
-    emit_kernel<1, Elem><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
+  if (p->bidirectional) {
+    if (g.V == 4)
+      emit_kernel<4, Elem, true><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
+    else
+      emit_kernel<1, Elem, true><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
+  } else {
+    if (g.V == 4)
+      emit_kernel<4, Elem, false><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
+    else
+      emit_kernel<1, Elem, false><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
+  }
   V2CE_LAUNCH_CHECK("ldati::emit_kernel");
   if (total == 0) return V2CE_OK;
   build_tiles_kernel<<<1, 1024, 0, s>>>(cw.seg_start, ns, sw.tile_first, sw.tile_seg);
@@ -988,17 +1071,17 @@ extern "C" int v2ce_ldati_emit(const float* voxels_dev, const v2ce_ldati_params*
 }
 
 extern "C" int v2ce_ldati_relocate(const float* voxels_dev, int32_t n_frames, int32_t height, int32_t width,
-                                   int32_t* counts_dev, float* tend_dev, void* stream) {
+                                   int32_t bidirectional, int32_t* counts_dev, float* tend_dev, void* stream) {
   V2CE_REQUIRE(voxels_dev && counts_dev && tend_dev, "NULL device pointer");
   V2CE_REQUIRE(n_frames > 0 && height > 0 && width > 0 && n_frames * 2 <= 65535, "bad geometry");
   const int HW = height * width;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (HW % 4 == 0) {
     dim3 grid((HW / 4 + 255) / 256, n_frames * 2);
-    relocate_debug_kernel<4><<<grid, 256, 0, s>>>(voxels_dev, HW, 1e-6f, counts_dev, tend_dev);
+    relocate_debug_kernel<4><<<grid, 256, 0, s>>>(voxels_dev, HW, 1e-6f, bidirectional, counts_dev, tend_dev);
   } else {
     dim3 grid((HW + 255) / 256, n_frames * 2);
-    relocate_debug_kernel<1><<<grid, 256, 0, s>>>(voxels_dev, HW, 1e-6f, counts_dev, tend_dev);
+    relocate_debug_kernel<1><<<grid, 256, 0, s>>>(voxels_dev, HW, 1e-6f, bidirectional, counts_dev, tend_dev);
   }
   V2CE_LAUNCH_CHECK("ldati::relocate_debug_kernel");
   return V2CE_OK;

@@ -19,6 +19,8 @@ from ._lib import LdatiParams, V2ceError, check, ptr, stream_ptr
 EVENT_DTYPE = np.dtype([('timestamp', '<i8'), ('x', '<i2'), ('y', '<i2'), ('polarity', 'i1')])
 NBINS = 9
 KEY_BIAS = 8
+STRATEGIES = {'none': 0, 'slope': 1, 'random': 2}     # v2ce_ldati_params.multi_events
+BIDIR_MAX_TENDENCY = 1024                             # largest tenth-bin voxel value the bidirectional sort window accepts
 
 
 _bin_starts_cache = {}
@@ -43,8 +45,10 @@ def _bin_starts(fps, device, flavor='cuda'):
 
 
 def make_params(n_frames, height, width, fps=30, t0=0, seed=0, frame_base=0, flavor='cuda',
-                device='cuda', add_frame_offset=False):
+                device='cuda', add_frame_offset=False, additional_events_strategy='slope', bidirectional=False):
     """Scalar constants with the reference's own Python expressions."""
+    if additional_events_strategy not in STRATEGIES:
+        raise ValueError(f'additional_events_strategy must be one of {sorted(STRATEGIES)}')
     assert flavor in ('cuda', 'cpu')
     f32 = np.float32
     voxel_step = 1 / fps / NBINS                       # LDATI.py:146
@@ -68,11 +72,23 @@ def make_params(n_frames, height, width, fps=30, t0=0, seed=0, frame_base=0, fla
         raise V2ceError(f'torch.arange(0, 1/{fps}, 1/{fps}/9) has {bs.shape[0]} entries; the reference '
                         f'would fail to broadcast it against 9 bins')
     bs_t0 = (bs + f32(t0)).astype(f32)                 # `arange + t0` is a float32 add
+    # Sort-key window per bin: the key of an event is ts - bin_base_us + KEY_BIAS and must land in [1, 2^key_bits).
+    one_bin = int(math.ceil(1e6 / fps / NBINS))
+    below, span = 0, one_bin + 2                       # 'slope' / 'none': offsets in [0, voxel_step]
+    if bidirectional:
+        # bin 5's tendency is bless - debt > -1 bin (LDATI.py:121); bin 8's is the tenth voxel bin itself
+        # (LDATI.py:108,111), accepted up to BIDIR_MAX_TENDENCY bins -- beyond it the emit status flags the event
+        below = one_bin + 2
+        span = BIDIR_MAX_TENDENCY * one_bin + 2
+    if additional_events_strategy == 'random':
+        span = max(span, 1_000_000 + 64)               # the raw draw in [0, 1) is taken as seconds (LDATI.py:173-174)
     for c in range(NBINS):
         p.binstart_t0_32[c] = bs_t0[c]
-        p.bin_base_us[c] = int(math.floor(float(bs_t0[c]) * 1e6))
-    p.key_span = int(math.ceil(1e6 / fps / NBINS)) + 2 + 2 * KEY_BIAS
+        p.bin_base_us[c] = int(math.floor(float(bs_t0[c]) * 1e6)) - below
+    p.key_span = below + span + 2 * KEY_BIAS
     p.add_frame_offset = 1 if add_frame_offset else 0
+    p.multi_events = STRATEGIES[additional_events_strategy]
+    p.bidirectional = 1 if bidirectional else 0
     return p
 
 

@@ -10,6 +10,11 @@ Extra keyword-only arguments (not in the reference): ``seed`` / ``frame_base`` s
 counter-based Philox stream that replaces ``torch.rand`` (LDATI.py:171), ``draws`` injects a
 dense (B,2,9,H,W,M) tensor of uniforms instead, ``flavor`` picks the torch-CUDA ('cuda',
 default: what the reference computes on a GPU) or torch-CPU ('cpu') scalar semantics.
+
+Options: ``additional_events_strategy`` 'slope' (what v2ce.py:356 uses), 'random' and 'none', and
+``bidirectional`` False / True are all implemented by the same kernels; ``pooling_type`` other than
+'none' raises NotImplementedError.  With ``bidirectional=True`` a tenth-bin voxel value above
+``ldati.BIDIR_MAX_TENDENCY`` (1024 events in one pixel-bin) raises V2ceError.
 """
 import logging
 from typing import List
@@ -28,9 +33,10 @@ def sample_voxel_statistical(y, t0=0, fps=30, pooling_type='none', pooling_kerne
                              seed=None, frame_base=0, draws=None, flavor='cuda') -> List[np.recarray]:
     assert pooling_type in ['avg', 'weighted', 'none']
     assert additional_events_strategy in ['none', 'random', 'slope']
-    if pooling_type != 'none' or additional_events_strategy != 'slope' or bidirectional:
-        raise NotImplementedError('the B200 path implements the configuration v2ce.py:356 uses: '
-                                  "pooling_type='none', additional_events_strategy='slope', bidirectional=False")
+    if pooling_type != 'none':
+        # LDATI.py:177-182: spatial pooling of the counts before the slope fit -- not implemented on the B200 path
+        raise NotImplementedError("pooling_type 'avg' / 'weighted' is not implemented on the B200 path; every other "
+                                  'option of sample_voxel_statistical is')
     require_cuda(y, 'y')
     B, P, C, H, W = y.shape
     if P != 2 or C != 10:
@@ -45,7 +51,8 @@ def sample_voxel_statistical(y, t0=0, fps=30, pooling_type='none', pooling_kerne
     with torch.cuda.device(vox.device):
         eng = _ldati.engine_for(vox.device)
         params = _ldati.make_params(B, H, W, fps=fps, t0=t0, seed=seed, frame_base=frame_base, flavor=flavor,
-                                    device=vox.device)
+                                    device=vox.device, additional_events_strategy=additional_events_strategy,
+                                    bidirectional=bool(bidirectional))
         events, seg_counts, status = eng.run(vox, params, draws=draws)
         total = int(seg_counts.sum())
         host = torch.empty(total * 13, dtype=torch.uint8, pin_memory=True)
