@@ -344,45 +344,48 @@ def run_ours(args, rank, world, local_rank):
         'clocks': clocks,
     }
     if world == 1:
-        line['ldati'] = {'workload': 'LDATI-only microbench, 346x260x10 bins, 24 pairs per call (bounded sample of '
+        line['ldati'] = {'workload': 'LDATI-only microbench, 346x260x10 bins, 24 and 96 pairs per call (bounded sample of '
                                      'BASELINE configs[2]); includes the host read of the counts between the two phases',
                          'hbm_peak_gbs': hbm_peak, **ldati_microbench(device, hbm_peak)}
     print(json.dumps(line), flush=True)
 
 
-def ldati_microbench(device, hbm_peak, reps=5):
-    """BASELINE.json configs[2] on a bounded sample: LDATI alone on synthetic event-count voxels of 24 frame pairs
-    (the reference's stage-2 chunk, v2ce.py:301), distributions (a) torch.rand and (b) randint(0,10) taken from
-    the reference's own bench (LDATI.py:327-346).  Device-timed count -> (counts D2H) -> emit/sort/pack;
-    HBM roofline with SURVEY.md 8d's algorithmic bytes: 4*20*H*W per pair read + 13 B per event written."""
+def ldati_microbench(device, hbm_peak, reps=5, pairs=(24, 96)):
+    """BASELINE.json configs[2] on a bounded sample: LDATI alone on synthetic event-count voxels, distributions
+    (a) torch.rand and (b) randint(0,10) taken from the reference's own bench (LDATI.py:327-346), in calls of 24 frame
+    pairs (the reference's stage-2 chunk, v2ce.py:301 -- its dense (B,2,9,H,W,M) tensors do not fit more) and of 96
+    pairs (this path holds one 4-byte word per event, so the chunk is only bounded by 2^31 events per call).
+    Device-timed count -> (counts D2H) -> emit/sort/pack; HBM roofline with SURVEY.md 8d's algorithmic bytes:
+    4*20*H*W per pair read + 13 B per event written."""
     from v2ce_toolbox_b200 import ldati
     eng = ldati.LdatiEngine(device)
     out = {}
-    F = 24
-    for name in ('rand', 'randint10'):
-        g = torch.Generator(device=device).manual_seed(42)
-        if name == 'rand':
-            vox = torch.rand((F, 2, 10, H, W), generator=g, device=device)
-        else:
-            vox = torch.randint(0, 10, (F, 2, 10, H, W), generator=g, device=device).float()
-        params = ldati.make_params(F, H, W, fps=30, seed=42, frame_base=0, device=device)
-        total = 0
-        for _ in range(2):
-            ev, seg, st = eng.run(vox, params)
-            total = int(seg.sum())
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            eng.run(vox, params)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        alg = F * 4 * 20 * H * W + 13 * total
-        out[name] = {'pairs': F, 'events_per_pair': total / F, 'ms': ms, 'mevents_per_s': total / ms / 1e3,
-                     'pairs_per_s': F / ms * 1e3, 'algorithmic_bytes': alg, 'achieved_gbs': alg / ms / 1e6,
-                     'frac_of_hbm_peak': alg / ms / 1e6 / hbm_peak}
-        del ev, vox
+    for F in pairs:
+        for name in ('rand', 'randint10'):
+            g = torch.Generator(device=device).manual_seed(42)
+            if name == 'rand':
+                vox = torch.rand((F, 2, 10, H, W), generator=g, device=device)
+            else:
+                vox = torch.randint(0, 10, (F, 2, 10, H, W), generator=g, device=device).float()
+            params = ldati.make_params(F, H, W, fps=30, seed=42, frame_base=0, device=device)
+            total = 0
+            for _ in range(2):
+                ev, seg, st = eng.run(vox, params)
+                total = int(seg.sum())
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                eng.run(vox, params)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            alg = F * 4 * 20 * H * W + 13 * total
+            out[name if F == 24 else f'{name}_{F}pairs'] = {
+                'pairs': F, 'events_per_pair': total / F, 'ms': ms, 'mevents_per_s': total / ms / 1e3,
+                'pairs_per_s': F / ms * 1e3, 'algorithmic_bytes': alg, 'achieved_gbs': alg / ms / 1e6,
+                'frac_of_hbm_peak': alg / ms / 1e6 / hbm_peak}
+            del ev, vox
     return out
 
 

@@ -185,6 +185,43 @@ def test_options_cpu_flavour_against_reference_goldens(name, golden, golden_meta
             assert d.max() <= 1 and (d != 0).mean() <= 1e-3
 
 
+@pytest.fixture
+def ldati_variant(monkeypatch):
+    """Sets the per-call opt-in switches of csrc/ldati.cu (read with getenv on every emit call)."""
+    def set_(reuse, staged):
+        monkeypatch.setenv('V2CE_LDATI_REUSE_WARP_TOTALS', str(int(reuse)))
+        monkeypatch.setenv('V2CE_LDATI_STAGED_SCATTER', str(int(staged)))
+    return set_
+
+
+VARIANT_CASES = [('randint', 2, 24, 30, {}), ('mixed', 2, 33, 47, {}), ('rand', 1, 260, 346, {}),
+                 ('randint', 1, 260, 346, {}), ('mixed', 2, 40, 52, dict(additional_events_strategy='random')),
+                 ('mixed', 2, 33, 47, dict(bidirectional=True)),
+                 ('sparse', 3, 40, 52, dict(additional_events_strategy='none'))]
+_variant_oracle = {}
+
+
+def _variant_case(i):
+    if i not in _variant_oracle:
+        kind, F, H, W, opts = VARIANT_CASES[i]
+        v = synth.make_voxels(kind, F, H, W, seed=51)
+        _variant_oracle[i] = (v, lo.sample_voxel_statistical_oracle(v, fps=30, seed=9, frame_base=2, flavor='cuda', **opts))
+    return _variant_oracle[i]
+
+
+@pytest.mark.parametrize('reuse,staged', [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_kernel_variants_bit_exact(reuse, staged, ldati_variant):
+    """The opt-in kernel variants (per-warp totals handed from the count pass to the emit pass; sort tiles ordered
+    by digit in shared memory before the scatter) produce the same bytes as the oracle: dense, sparse and mixed
+    counts, V=1 and V=4 pixel paths, 32- and 64-bit elements, 2- and 3-pass sorts, both relocation directions."""
+    ldati_variant(reuse, staged)
+    for i, (kind, F, H, W, opts) in enumerate(VARIANT_CASES):
+        v, want = _variant_case(i)
+        got = _run(v, fps=30, seed=9, frame_base=2, **opts)
+        for j, (g, w) in enumerate(zip(got, want)):
+            _assert_rows_equal(g, w, f'reuse={reuse} staged={staged} {kind} {opts} frame {j}')
+
+
 def test_bidirectional_tendency_beyond_sort_window_raises():
     """bidirectional: bin 8's tendency is the tenth voxel bin itself (LDATI.py:108,111).  The sort-key window covers
     tendencies up to ldati.BIDIR_MAX_TENDENCY bins (rounded up to a power of two of microseconds, so < 2x that);

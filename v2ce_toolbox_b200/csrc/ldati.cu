@@ -24,6 +24,7 @@
 #include "common.cuh"
 
 #include <limits.h>
+#include <stdlib.h>
 
 namespace v2ce {
 namespace ldati {
@@ -63,6 +64,7 @@ static Geometry make_geometry(const v2ce_ldati_params* p) {
 // count workspace layout
 struct CountWs {
   int32_t* partial;     // [F][2][NB][18]
+  int32_t* warp_partial;  // [F][2][NB][8 warps][18]: the count pass's per-warp totals, reused by the emit pass
   int32_t* block_base;  // [F][2][NB][18]
   int32_t* group_base;  // [F][9][4]
   int64_t* seg_start;   // [F*9+1]
@@ -77,6 +79,7 @@ static CountWs carve_count_ws(void* ws, const Geometry& g) {
   w.block_base = a.take<int32_t>(n);
   w.group_base = a.take<int32_t>((size_t)g.F * kBins * 4);
   w.seg_start = a.take<int64_t>((size_t)g.F * kBins + 1);
+  w.warp_partial = a.take<int32_t>(n * (kThreads / 32));
   w.bytes = align_up(a.off, 256);
   return w;
 }
@@ -235,7 +238,8 @@ __device__ __forceinline__ float philox_uniform(unsigned long long idx, unsigned
 // ---------------------------------------------------------------------------------------
 template <int V, bool BIDIR>
 __global__ void __launch_bounds__(kThreads) count_kernel(const float* __restrict__ vox, DevParams P,
-                                                          int32_t* __restrict__ partial) {
+                                                          int32_t* __restrict__ partial,
+                                                          int32_t* __restrict__ warp_partial) {
   const int blk = blockIdx.x, p = blockIdx.y, f = blockIdx.z;
   const int pix = (blk * kThreads + threadIdx.x) * V;
   int tot[kQ];
@@ -271,6 +275,8 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const float* __restrict
     for (int w = 0; w < kThreads / 32; ++w) s += red[w][threadIdx.x];
     partial[(((size_t)f * 2 + p) * P.NB + blk) * kQ + threadIdx.x] = s;
   }
+  if (threadIdx.x < (kThreads / 32) * kQ)
+    warp_partial[(((size_t)f * 2 + p) * P.NB + blk) * ((kThreads / 32) * kQ) + threadIdx.x] = (&red[0][0])[threadIdx.x];
 }
 
 // K4a: per frame, exclusive scan of the block partials over the plane; group bases; segment counts.
@@ -391,6 +397,7 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
                                                          const int32_t* __restrict__ block_base,
                                                          const int32_t* __restrict__ group_base,
                                                          const int64_t* __restrict__ seg_start,
+                                                         const int32_t* __restrict__ warp_partial,
                                                          const float* __restrict__ draws, Elem* __restrict__ elems,
                                                          int32_t* __restrict__ status) {
   const int blk = blockIdx.x, p = blockIdx.y, f = blockIdx.z;
@@ -401,7 +408,12 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
   // ---- pass A: per-warp totals of the 18 quantities (singles / multi-event totals per bin) ----
   __shared__ int wtot[kThreads / 32][kQ];
   __shared__ float2 s_par[kThreads / 32][32][V];      // (k, b) of every pixel of the block for the current bin
-  {
+  if (warp_partial != nullptr) {
+    // the count pass left this block's per-warp totals in its workspace: no second relocation pass over the voxels
+    if (threadIdx.x < (kThreads / 32) * kQ)
+      (&wtot[0][0])[threadIdx.x] =
+          warp_partial[(((size_t)f * 2 + p) * P.NB + blk) * ((kThreads / 32) * kQ) + threadIdx.x];
+  } else {
     int tot[kQ];
 #pragma unroll
     for (int q = 0; q < kQ; ++q) tot[q] = 0;
@@ -791,7 +803,10 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(int32_t* __restrict__ d
   }
 }
 
-template <typename Elem>
+// STAGED: the tile is first ordered by digit in shared memory (same stable rank), then written out run by run, so
+// consecutive threads store consecutive addresses of a digit's run; unstaged, every lane stores to its own digit's
+// position (one 32-byte sector per 4-byte key).
+template <typename Elem, bool STAGED>
 __global__ void __launch_bounds__(kThreads) sort_scatter_kernel(const Elem* __restrict__ in, Elem* __restrict__ out,
                                                                  const int64_t* __restrict__ seg_start,
                                                                  const int32_t* __restrict__ tile_first,
@@ -837,6 +852,7 @@ __global__ void __launch_bounds__(kThreads) sort_scatter_kernel(const Elem* __re
   }
   __syncthreads();
   // exclusive prefix over warps per digit; fetch the scanned global base of (seg, digit, tile)
+  int digit_total = 0;                  // radix <= kThreads: thread d owns digit d
   for (int d = threadIdx.x; d < radix; d += kThreads) {
     int run = 0;
 #pragma unroll
@@ -845,12 +861,36 @@ __global__ void __launch_bounds__(kThreads) sort_scatter_kernel(const Elem* __re
       wcnt[w][d] = run;
       run += c;
     }
+    digit_total = run;
     gbase[d] = scanned[(size_t)radix * tile_first[seg] + (size_t)d * ntile_seg + tin];
   }
-  __syncthreads();
+  if (!STAGED) {
+    __syncthreads();
 #pragma unroll
-  for (int r = 0; r < kKeysPerThread; ++r) {
-    if (dig[r] != 0xFFFFu) out[(size_t)gbase[dig[r]] + wcnt[warp][dig[r]] + rank[r]] = key[r];
+    for (int r = 0; r < kKeysPerThread; ++r) {
+      if (dig[r] != 0xFFFFu) out[(size_t)gbase[dig[r]] + wcnt[warp][dig[r]] + rank[r]] = key[r];
+    }
+  } else {
+    __shared__ int lbase[256];          // tile-local position of each digit's first key
+    __shared__ int wsum[kWarps];
+    __shared__ Elem stage[kTile];
+    const int inc = warp_incl_scan(digit_total);
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += wsum[w];
+    if ((int)threadIdx.x < radix) lbase[threadIdx.x] = woff + inc - digit_total;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kKeysPerThread; ++r) {
+      if (dig[r] != 0xFFFFu) stage[lbase[dig[r]] + wcnt[warp][dig[r]] + rank[r]] = key[r];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += kThreads) {
+      const Elem k = stage[i];
+      const unsigned d = (unsigned)(k >> shift) & (radix - 1);
+      out[(size_t)gbase[d] + (i - lbase[d])] = k;
+    }
   }
 }
 
@@ -979,11 +1019,11 @@ extern "C" int v2ce_ldati_count(const float* voxels_dev, const v2ce_ldati_params
   DevParams P = make_dev_params(p, g);
   dim3 grid(g.NB, 2, g.F);
   if (p->bidirectional) {
-    if (g.V == 4) count_kernel<4, true><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
-    else count_kernel<1, true><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
+    if (g.V == 4) count_kernel<4, true><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial);
+    else count_kernel<1, true><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial);
   } else {
-    if (g.V == 4) count_kernel<4, false><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
-    else count_kernel<1, false><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
+    if (g.V == 4) count_kernel<4, false><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial);
+    else count_kernel<1, false><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial);
   }
   V2CE_LAUNCH_CHECK("ldati::count_kernel");
   scan_planes_kernel<<<g.F, 64, 0, s>>>(w.partial, w.block_base, w.group_base, seg_counts_dev, g.NB);
@@ -992,6 +1032,18 @@ extern "C" int v2ce_ldati_count(const float* voxels_dev, const v2ce_ldati_params
   V2CE_LAUNCH_CHECK("ldati::scan_i64_kernel");
   return V2CE_OK;
 }
+
+// Opt-in variants, read per call so one process can compare them (tests/test_gpu_ldati.py, tools/ldati_bench.py):
+//   V2CE_LDATI_REUSE_WARP_TOTALS=1  the emit pass reads the per-warp totals the count pass stored instead of
+//                                   relocating every pixel a second time to rebuild them
+//   V2CE_LDATI_STAGED_SCATTER=1     every sort tile is ordered by digit in shared memory before the scatter
+//                                   (see sort_scatter_kernel)
+static bool env_flag(const char* name, bool dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) != 0 : dflt;
+}
+static bool reuse_warp_totals() { return env_flag("V2CE_LDATI_REUSE_WARP_TOTALS", false); }
+static bool staged_scatter() { return env_flag("V2CE_LDATI_STAGED_SCATTER", false); }
 
 template <typename Elem>
 static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometry& g, const CountWs& cw, void* emit_ws,
@@ -1007,16 +1059,17 @@ static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometr
   Elem* eb = static_cast<Elem*>(sw.elem_b);
   V2CE_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), s));
   dim3 grid(g.NB, 2, g.F);
+  const int32_t* wp = reuse_warp_totals() ? cw.warp_partial : nullptr;
   if (p->bidirectional) {
     if (g.V == 4)
-      emit_kernel<4, Elem, true><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
+      emit_kernel<4, Elem, true><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, wp, draws, ea, status);
     else
-      emit_kernel<1, Elem, true><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
+      emit_kernel<1, Elem, true><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, wp, draws, ea, status);
   } else {
     if (g.V == 4)
-      emit_kernel<4, Elem, false><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
+      emit_kernel<4, Elem, false><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, wp, draws, ea, status);
     else
-      emit_kernel<1, Elem, false><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, draws, ea, status);
+      emit_kernel<1, Elem, false><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, wp, draws, ea, status);
   }
   V2CE_LAUNCH_CHECK("ldati::emit_kernel");
   if (total == 0) return V2CE_OK;
@@ -1041,8 +1094,12 @@ static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometr
     V2CE_LAUNCH_CHECK("ldati::scan_block_sums_kernel");
     scan_apply_kernel<<<nblk, 256, 0, s>>>(sw.counts, ncounts, sw.block_sums);
     V2CE_LAUNCH_CHECK("ldati::scan_apply_kernel");
-    sort_scatter_kernel<Elem><<<sw.nt_max, kThreads, 0, s>>>(src, dst, cw.seg_start, sw.tile_first, sw.tile_seg, ns,
-                                                             shift, rb, sw.counts);
+    if (staged_scatter())
+      sort_scatter_kernel<Elem, true><<<sw.nt_max, kThreads, 0, s>>>(src, dst, cw.seg_start, sw.tile_first, sw.tile_seg,
+                                                                     ns, shift, rb, sw.counts);
+    else
+      sort_scatter_kernel<Elem, false><<<sw.nt_max, kThreads, 0, s>>>(src, dst, cw.seg_start, sw.tile_first, sw.tile_seg,
+                                                                      ns, shift, rb, sw.counts);
     V2CE_LAUNCH_CHECK("ldati::sort_scatter_kernel");
     Elem* t = src; src = dst; dst = t;
   }
