@@ -211,7 +211,7 @@ def _variant_case(i):
 
 @pytest.mark.parametrize('reuse,staged', [(0, 0), (1, 0), (0, 1), (1, 1)])
 def test_kernel_variants_bit_exact(reuse, staged, ldati_variant):
-    """The opt-in kernel variants (per-warp totals handed from the count pass to the emit pass; sort tiles ordered
+    """The kernel variants, every on/off combination (per-warp totals handed from the count pass to the emit pass; sort tiles ordered
     by digit in shared memory before the scatter) produce the same bytes as the oracle: dense, sparse and mixed
     counts, V=1 and V=4 pixel paths, 32- and 64-bit elements, 2- and 3-pass sorts, both relocation directions."""
     ldati_variant(reuse, staged)

@@ -1033,17 +1033,19 @@ extern "C" int v2ce_ldati_count(const float* voxels_dev, const v2ce_ldati_params
   return V2CE_OK;
 }
 
-// Opt-in variants, read per call so one process can compare them (tests/test_gpu_ldati.py, tools/ldati_bench.py):
-//   V2CE_LDATI_REUSE_WARP_TOTALS=1  the emit pass reads the per-warp totals the count pass stored instead of
-//                                   relocating every pixel a second time to rebuild them
-//   V2CE_LDATI_STAGED_SCATTER=1     every sort tile is ordered by digit in shared memory before the scatter
-//                                   (see sort_scatter_kernel)
+// Kernel variants, read per call so one process can compare them (tests/test_gpu_ldati.py, tools/ldati_bench.py);
+// both default ON: bit-exact in all four combinations, 1-4 % faster together on the microbench
+// (profiles/ldati_variants_r1.json).  Set to 0 to get the first-generation path.
+//   V2CE_LDATI_REUSE_WARP_TOTALS  the emit pass reads the per-warp totals the count pass stored instead of
+//                                 relocating every pixel a second time to rebuild them
+//   V2CE_LDATI_STAGED_SCATTER     every sort tile is ordered by digit in shared memory before the scatter
+//                                 (see sort_scatter_kernel)
 static bool env_flag(const char* name, bool dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) != 0 : dflt;
 }
-static bool reuse_warp_totals() { return env_flag("V2CE_LDATI_REUSE_WARP_TOTALS", false); }
-static bool staged_scatter() { return env_flag("V2CE_LDATI_STAGED_SCATTER", false); }
+static bool reuse_warp_totals() { return env_flag("V2CE_LDATI_REUSE_WARP_TOTALS", true); }
+static bool staged_scatter() { return env_flag("V2CE_LDATI_STAGED_SCATTER", true); }
 
 template <typename Elem>
 static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometry& g, const CountWs& cw, void* emit_ws,
