@@ -1,0 +1,117 @@
+"""Host-side I/O around the device path: frame prefetch and the .npz event sink.  CPU only."""
+import os
+import zipfile
+import zlib
+
+import numpy as np
+import pytest
+
+from v2ce_toolbox_b200 import sink
+from v2ce_toolbox_b200 import v2ce as drv
+from v2ce_toolbox_b200.ldati import EVENT_DTYPE
+
+
+def test_crc32_combine_matches_zlib():
+    rng = np.random.default_rng(0)
+    for la, lb in ((0, 5), (7, 0), (1, 1), (1000, 12345), (1 << 16, (1 << 18) + 3)):
+        a = rng.integers(0, 256, la, dtype=np.uint8).tobytes()
+        b = rng.integers(0, 256, lb, dtype=np.uint8).tobytes()
+        assert sink.crc32_combine(zlib.crc32(a), zlib.crc32(b), lb) == zlib.crc32(a + b)
+
+
+def test_save_npz_reads_back_like_np_savez(tmp_path):
+    """v2ce.py:371-372: the archive must be what np.savez(path, event_stream=...) writes -- same member name, bytes,
+    CRC and zip64 layout -- so np.load and any zip tool read it."""
+    rng = np.random.default_rng(1)
+    n = 200_003
+    ev = np.zeros(n, EVENT_DTYPE)
+    ev['timestamp'] = np.sort(rng.integers(0, 1 << 40, n))
+    ev['x'], ev['y'], ev['polarity'] = rng.integers(0, 346, n), rng.integers(0, 260, n), rng.integers(0, 2, n)
+    p = sink.save_npz(tmp_path / 'clip-events', chunk_bytes=1 << 18, workers=3, event_stream=ev,
+                      empty=np.empty(0, EVENT_DTYPE), grid=np.arange(12, dtype=np.float32).reshape(3, 4))
+    assert p.endswith('clip-events.npz')
+    np.savez(tmp_path / 'ref.npz', event_stream=ev)
+    ours, ref = zipfile.ZipFile(p), zipfile.ZipFile(tmp_path / 'ref.npz')
+    assert ours.testzip() is None
+    a, b = ours.getinfo('event_stream.npy'), ref.getinfo('event_stream.npy')
+    assert (a.CRC, a.file_size, a.compress_type, a.flag_bits, a.extract_version) == \
+           (b.CRC, b.file_size, b.compress_type, b.flag_bits, b.extract_version)
+    assert ours.read('event_stream.npy') == ref.read('event_stream.npy')
+    d = np.load(p)
+    assert d['event_stream'].dtype == EVENT_DTYPE and np.array_equal(d['event_stream'], ev)
+    assert len(d['empty']) == 0 and d['empty'].dtype == EVENT_DTYPE
+    assert np.array_equal(d['grid'], np.arange(12, dtype=np.float32).reshape(3, 4))
+
+
+def _write_pngs(folder, n, h=20, w=30, seed=0):
+    import cv2
+    rng = np.random.default_rng(seed)
+    frames = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    paths = []
+    for i, f in enumerate(frames):
+        paths.append(os.path.join(folder, f'{i:05d}.png'))
+        cv2.imwrite(paths[-1], f)
+    return frames, paths
+
+
+@pytest.mark.parametrize('n_frames', [17, 33, 40, 49])
+def test_frame_prefetcher_equals_serial_reader(tmp_path, n_frames):
+    """The threaded decode hands out exactly the windows of the serial cv2.imread loop, including the clip's
+    pulled-back last window (v2ce.py:153-154)."""
+    frames, paths = _write_pngs(str(tmp_path), n_frames)
+    starts, _mode = drv.window_schedule(n_frames, 16)
+    read, close = drv._window_reader(paths, None, starts, 16)
+    try:
+        for k, st in enumerate(starts):
+            got = read(k)
+            want = drv._read_window(paths, None, int(st), 16)
+            assert got.dtype == np.uint8 and np.array_equal(got, want) and np.array_equal(got, frames[st:st + 17])
+    finally:
+        close()
+
+
+def test_window_reader_keeps_the_serial_path_for_negative_starts(tmp_path):
+    """A 16-frame clip schedules its only window at start -1 (the reference's slice then yields one frame, SURVEY.md
+    F8a): such schedules are not prefetched, so the behaviour stays that of the reference's own loop."""
+    frames, paths = _write_pngs(str(tmp_path), 16)
+    starts, mode = drv.window_schedule(16, 16)
+    assert list(starts) == [-1] and mode == 15
+    read, close = drv._window_reader(paths, None, starts, 16)
+    assert np.array_equal(read(0), drv._read_window(paths, None, -1, 16))
+    close()
+
+
+def test_frame_prefetcher_reports_unreadable_files(tmp_path):
+    frames, paths = _write_pngs(str(tmp_path), 40)
+    with open(paths[20], 'wb') as f:
+        f.write(b'not a png')
+    starts, _ = drv.window_schedule(40, 16)
+    read, close = drv._window_reader(paths, None, starts, 16)
+    try:
+        read(0)
+        with pytest.raises(FileNotFoundError):
+            read(1)
+    finally:
+        close()
+
+
+def test_batches_generator_uses_prefetch_and_matches_preprocessing(tmp_path):
+    frames, paths = _write_pngs(str(tmp_path), 40, h=26, w=40)
+    got = list(drv._batches(paths, None, 16, 26, 2))
+    starts, _ = drv.window_schedule(40, 16)
+    want = [drv.image_pre_processing(frames[s:s + 17], 26) for s in starts]
+    flat = [u for units, _last in got for u in units]
+    assert [last for _u, last in got] == [False, True] and len(flat) == len(want)
+    for a, b in zip(flat, want):
+        assert a.shape == b.shape and bool((a == b).all())
+
+
+def test_u8_window_batches_center_crop(tmp_path):
+    """The raw-uint8 batching of stream_clip (native-resolution clips): center crop of v2ce.py:78, reference batching."""
+    frames, paths = _write_pngs(str(tmp_path), 49, h=26, w=40)
+    got = list(drv._window_batches_u8(paths, None, 16, 2, None, 30))
+    assert [tuple(x.shape) for x, _ in got] == [(2, 17, 26, 30), (1, 17, 26, 30)]
+    assert [last for _, last in got] == [False, True]
+    flat = np.concatenate([x.numpy() for x, _ in got], axis=0)
+    for k, st in enumerate(drv.window_schedule(49, 16)[0]):
+        assert np.array_equal(flat[k], frames[st:st + 17, :, 20 - 15:20 + 15])

@@ -58,3 +58,111 @@ def to_host(dev_u8, chunk_bytes=128 << 20, workers=8, out=None):
                 for f in p:
                     f.result()
     return dst
+
+
+# ------------------------------------------------------------------------------------------
+# .npz writer for the event stream (v2ce.py:371-372: np.savez(path, event_stream=...))
+# ------------------------------------------------------------------------------------------
+def _gf2_times(mat, vec):
+    s, i = 0, 0
+    while vec:
+        if vec & 1:
+            s ^= mat[i]
+        vec >>= 1
+        i += 1
+    return s
+
+
+def _gf2_square(mat):
+    return [_gf2_times(mat, m) for m in mat]
+
+
+def crc32_combine(crc1, crc2, len2):
+    """CRC-32 of A+B from crc32(A), crc32(B) and len(B) (zlib's crc32_combine: the CRC register is advanced over
+    len2 zero bytes with GF(2) matrix squaring, so the cost is O(log len2))."""
+    if len2 <= 0:
+        return crc1
+    odd = [0xEDB88320] + [1 << i for i in range(31)]      # operator for one zero bit
+    even = _gf2_square(odd)                               # two zero bits
+    odd = _gf2_square(even)                               # four zero bits
+    while True:
+        even = _gf2_square(odd)
+        if len2 & 1:
+            crc1 = _gf2_times(even, crc1)
+        len2 >>= 1
+        if not len2:
+            break
+        odd = _gf2_square(even)
+        if len2 & 1:
+            crc1 = _gf2_times(odd, crc1)
+        len2 >>= 1
+        if not len2:
+            break
+    return crc1 ^ crc2
+
+
+def save_npz(path, chunk_bytes=32 << 20, workers=8, **arrays):
+    """``np.savez(path, **arrays)`` for large arrays: the same uncompressed zip64 archive of ``<name>.npy`` members
+    (``np.load`` reads it back unchanged), but the CRC-32 every zip member needs is computed chunk-wise on a thread pool
+    (``zlib.crc32`` releases the GIL) while the main thread streams the bytes to the file, instead of serially in front of
+    every write: ``np.savez`` spends ~0.55 s per GB on it, more than the device needs for the whole clip."""
+    import io
+    import struct
+    import time
+    import zlib
+
+    path = str(path)
+    if not path.endswith('.npz'):
+        path += '.npz'
+    tm = time.localtime()
+    dos_time = (tm.tm_hour << 11) | (tm.tm_min << 5) | (tm.tm_sec // 2)
+    dos_date = (max(tm.tm_year, 1980) - 1980) << 9 | (tm.tm_mon << 5) | tm.tm_mday
+    central = []
+    with open(path, 'wb') as f, ThreadPoolExecutor(max_workers=workers) as pool:
+        for name, arr in arrays.items():
+            arr = np.ascontiguousarray(arr)
+            if arr.dtype.hasobject:
+                raise TypeError('save_npz: object arrays are not supported')
+            fname = (name + '.npy').encode()
+            hdr = io.BytesIO()
+            np.lib.format.write_array_header_1_0(hdr, np.lib.format.header_data_from_array_1_0(arr))
+            hdr = hdr.getvalue()
+            data = arr.reshape(-1).view(np.uint8) if arr.size else np.empty(0, np.uint8)
+            size = len(hdr) + data.nbytes
+            offset = f.tell()
+            # local header: sizes in the zip64 extra field, like zipfile's force_zip64=True that np.savez uses
+            extra = struct.pack('<HHQQ', 1, 16, size, size)
+            f.write(struct.pack('<IHHHHHIIIHH', 0x04034b50, 45, 0, 0, dos_time, dos_date, 0, 0xFFFFFFFF, 0xFFFFFFFF,
+                                len(fname), len(extra)) + fname + extra)
+            futures = [pool.submit(zlib.crc32, data[a:a + chunk_bytes]) for a in range(0, data.nbytes, chunk_bytes)]
+            f.write(hdr)
+            for a in range(0, data.nbytes, chunk_bytes):
+                f.write(data[a:a + chunk_bytes])
+            crc = zlib.crc32(hdr)
+            for k, fut in enumerate(futures):
+                crc = crc32_combine(crc, fut.result(), min(chunk_bytes, data.nbytes - k * chunk_bytes))
+            end = f.tell()
+            f.seek(offset + 14)
+            f.write(struct.pack('<I', crc))
+            f.seek(end)
+            central.append((fname, crc, size, offset))
+        cd_start = f.tell()
+        for fname, crc, size, offset in central:
+            big = b''
+            if size >= 0xFFFFFFFF:
+                big += struct.pack('<QQ', size, size)
+            if offset >= 0xFFFFFFFF:
+                big += struct.pack('<Q', offset)
+            extra = struct.pack('<HH', 1, len(big)) + big if big else b''
+            s32 = min(size, 0xFFFFFFFF)
+            f.write(struct.pack('<IHHHHHHIIIHHHHHII', 0x02014b50, (3 << 8) | 45, 45, 0, 0, dos_time, dos_date, crc, s32, s32,
+                                len(fname), len(extra), 0, 0, 0, 0o600 << 16, min(offset, 0xFFFFFFFF)) + fname + extra)
+        cd_size = f.tell() - cd_start
+        n = len(central)
+        if cd_start >= 0xFFFFFFFF or cd_size >= 0xFFFFFFFF or n >= 0xFFFF:
+            z64 = f.tell()
+            f.write(struct.pack('<IQHHIIQQQQ', 0x06064b50, 44, 45, 45, 0, 0, n, n, cd_size, cd_start))
+            f.write(struct.pack('<IIQI', 0x07064b50, 0, z64, 1))
+        f.write(struct.pack('<IHHHHIIH', 0x06054b50, 0, 0, min(n, 0xFFFF), min(n, 0xFFFF), min(cd_size, 0xFFFFFFFF),
+                            min(cd_start, 0xFFFFFFFF), 0))
+    return path

@@ -114,6 +114,51 @@ def infer_pano_image_unit(model, image_units, width=346):
     return _pano_device(model, image_units, width).cpu()
 
 
+class FramePrefetcher:
+    """Decodes the frames of an image folder ahead of the device pipeline (at GPU speed the serial
+    ``cv2.imread`` loop of v2ce.py:158-166 is the bottleneck of a clip).  Frames are decoded once each on a thread pool
+    (OpenCV releases the GIL), `lookahead` windows beyond the one being consumed; ``window(start, seq_len)`` returns the
+    same (seq_len+1, H, W) uint8 stack the serial loop builds."""
+
+    def __init__(self, image_paths, starts, seq_len, lookahead=8, workers=8):
+        from concurrent.futures import ThreadPoolExecutor
+        self.paths = image_paths
+        self.starts = [int(s) for s in starts]
+        self.seq_len = seq_len
+        self.lookahead = lookahead
+        self.pool = ThreadPoolExecutor(max_workers=workers)
+        self.futures = {}
+        self.next_window = 0
+
+    @staticmethod
+    def _decode(path):
+        import cv2
+        img = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+        if img is None:
+            raise FileNotFoundError(f'cv2.imread could not read {path}')
+        return img
+
+    def _submit_through(self, k):
+        while self.next_window <= min(k, len(self.starts) - 1):
+            st = self.starts[self.next_window]
+            for i in range(st, min(st + self.seq_len + 1, len(self.paths))):
+                if i not in self.futures:
+                    self.futures[i] = self.pool.submit(self._decode, self.paths[i])
+            self.next_window += 1
+
+    def window(self, k):
+        """Frames of the k-th scheduled window; windows must be requested in schedule order."""
+        self._submit_through(k + self.lookahead)
+        st = self.starts[k]
+        frames = [self.futures[i].result() for i in range(st, min(st + self.seq_len + 1, len(self.paths)))]
+        for i in [i for i in self.futures if i < st]:         # windows only move forward (the pulled-back last one
+            del self.futures[i]                               # starts inside the one before it)
+        return np.stack(frames, axis=0)
+
+    def close(self):
+        self.pool.shutdown(wait=False, cancel_futures=True)
+
+
 def _read_window(image_paths, vidcap, start, seq_len):
     import cv2
     idx = range(start, start + seq_len + 1)
@@ -122,17 +167,30 @@ def _read_window(image_paths, vidcap, start, seq_len):
     return np.stack([cv2.imread(p, cv2.IMREAD_GRAYSCALE) for p in image_paths[start:start + seq_len + 1]], axis=0)
 
 
+def _window_reader(image_paths, vidcap, starts, seq_len):
+    """k -> frames of the k-th window: prefetched decode for image folders, the reader's own access otherwise."""
+    ascending = all(int(a) <= int(b) for a, b in zip(starts[:-1], starts[1:]))
+    if vidcap is None and len(starts) > 1 and int(starts[0]) >= 0 and ascending:
+        pf = FramePrefetcher(image_paths, starts, seq_len)
+        return pf.window, pf.close
+    return (lambda k: _read_window(image_paths, vidcap, int(starts[k]), seq_len)), (lambda: None)
+
+
 def _batches(image_paths, vidcap, seq_len, height, batch_size, schedule=None):
     """Yield (image_units (b,L,2,H',W') float32 host tensor, is_last) in the reference's batching.
     `schedule` = (window starts, mode) overrides the schedule derived from the frame count (a rank's share of a clip)."""
     frame_count = vidcap.frame_count if vidcap is not None else len(image_paths)
     starts, mode = schedule if schedule is not None else window_schedule(frame_count, seq_len)
+    read, close = _window_reader(image_paths, vidcap, starts, seq_len)
     pending = []
-    for i, st in enumerate(starts):
-        pending.append(image_pre_processing(_read_window(image_paths, vidcap, st, seq_len), height)[None])
-        if len(pending) == batch_size or i == len(starts) - 1:
-            yield (torch.cat(pending, dim=0) if len(pending) > 1 else pending[0]), i == len(starts) - 1
-            pending = []
+    try:
+        for i in range(len(starts)):
+            pending.append(image_pre_processing(read(i), height)[None])
+            if len(pending) == batch_size or i == len(starts) - 1:
+                yield (torch.cat(pending, dim=0) if len(pending) > 1 else pending[0]), i == len(starts) - 1
+                pending = []
+    finally:
+        close()
 
 
 @torch.no_grad()
@@ -190,14 +248,18 @@ def _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width
     """Raw uint8 windows (b, L+1, H, width), center-cropped like v2ce.py:78, in the reference's batching."""
     frame_count = vidcap.frame_count if vidcap is not None else len(image_paths)
     starts, _ = schedule if schedule is not None else window_schedule(frame_count, seq_len)
+    read, close = _window_reader(image_paths, vidcap, starts, seq_len)
     pending = []
-    for i, st in enumerate(starts):
-        fr = np.asarray(_read_window(image_paths, vidcap, st, seq_len))
-        c = fr.shape[-1] // 2
-        pending.append(np.ascontiguousarray(fr[..., c - width // 2:c + width // 2])[None])
-        if len(pending) == batch_size or i == len(starts) - 1:
-            yield torch.from_numpy(np.concatenate(pending, axis=0)), i == len(starts) - 1
-            pending = []
+    try:
+        for i in range(len(starts)):
+            fr = np.asarray(read(i))
+            c = fr.shape[-1] // 2
+            pending.append(np.ascontiguousarray(fr[..., c - width // 2:c + width // 2])[None])
+            if len(pending) == batch_size or i == len(starts) - 1:
+                yield torch.from_numpy(np.concatenate(pending, axis=0)), i == len(starts) - 1
+                pending = []
+    finally:
+        close()
 
 
 @torch.no_grad()
@@ -327,18 +389,33 @@ def main(argv=None):
                       upper_bound_percentile=args.upper_bound_percentile, keep_polarity=args.vis_keep_polarity,
                       write_event_frames=args.write_event_frame_video, seed=seed)
     logger.info(f'Predicted voxel shape: ({res.n_pairs}, 2, 10, ...) (kept on the device)')
+    encoder, encoder_error = None, []
     if args.write_event_frame_video:
         vis_color = 'rgb' if args.vis_keep_polarity else 'gray'
         ef_video_path = op.join(args.out_folder, f'{args.infer_type}-{output_name}-pred_ef_{vis_color}.mp4')
         logger.info(f'Upper bound of the event frame value during video writing: {res.ef_upper_bound}')
-        H, W = res.ef_frames.shape[1:3]
-        video = cv2.VideoWriter(ef_video_path, cv2.VideoWriter_fourcc(*'mp4v'), args.fps, (W, H))
-        for f in res.ef_frames:
-            video.write(f)
-        video.release()
-        logger.info(f'Event frame video written to {ef_video_path}')
+
+        def encode():                                 # v2ce.py:272-279; cv2 releases the GIL, so the mp4v encode
+            try:                                      # runs beside the .npz write below
+                H, W = res.ef_frames.shape[1:3]
+                video = cv2.VideoWriter(ef_video_path, cv2.VideoWriter_fourcc(*'mp4v'), args.fps, (W, H))
+                for f in res.ef_frames:
+                    video.write(f)
+                video.release()
+            except Exception as e:                    # re-raised on the main thread
+                encoder_error.append(e)
+
+        import threading
+        encoder = threading.Thread(target=encode, name='v2ce-ef-encode')
+        encoder.start()
     logger.info(f'Generated event stream shape: , {res.event_stream.shape}')
-    np.savez(op.join(args.out_folder, f'{output_name}-events.npz'), event_stream=res.event_stream)
+    from .sink import save_npz
+    save_npz(op.join(args.out_folder, f'{output_name}-events.npz'), event_stream=res.event_stream)   # v2ce.py:371-372
+    if encoder is not None:
+        encoder.join()
+        if encoder_error:
+            raise encoder_error[0]
+        logger.info(f'Event frame video written to {ef_video_path}')
     return res
 
 
