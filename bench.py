@@ -352,7 +352,8 @@ def run_ours(args, rank, world, local_rank):
 
 def ldati_microbench(device, hbm_peak, reps=5, pairs=(24, 96)):
     """BASELINE.json configs[2] on a bounded sample: LDATI alone on synthetic event-count voxels, distributions
-    (a) torch.rand and (b) randint(0,10) taken from the reference's own bench (LDATI.py:327-346), in calls of 24 frame
+    (a) torch.rand and (b) randint(0,10) taken from the reference's own bench (LDATI.py:327-346) and (c) 0.015*rand
+    (sparse), in calls of 24 frame
     pairs (the reference's stage-2 chunk, v2ce.py:301 -- its dense (B,2,9,H,W,M) tensors do not fit more) and of 96
     pairs (this path holds one 4-byte word per event, so the chunk is only bounded by 2^31 events per call).
     Device-timed count -> (counts D2H) -> emit/sort/pack; HBM roofline with SURVEY.md 8d's algorithmic bytes:
@@ -361,10 +362,13 @@ def ldati_microbench(device, hbm_peak, reps=5, pairs=(24, 96)):
     eng = ldati.LdatiEngine(device)
     out = {}
     for F in pairs:
-        for name in ('rand', 'randint10'):
+        # (c) 0.015 * rand: the sparse, all-ties regime of a random-init network, 24 pairs only
+        for name in ('rand', 'randint10') + (('sparse',) if F == 24 else ()):
             g = torch.Generator(device=device).manual_seed(42)
             if name == 'rand':
                 vox = torch.rand((F, 2, 10, H, W), generator=g, device=device)
+            elif name == 'sparse':
+                vox = torch.rand((F, 2, 10, H, W), generator=g, device=device) * 0.015
             else:
                 vox = torch.randint(0, 10, (F, 2, 10, H, W), generator=g, device=device).float()
             params = ldati.make_params(F, H, W, fps=30, seed=42, frame_base=0, device=device)
