@@ -66,3 +66,25 @@ def test_event_frame_oracle_equals_reference_on_random_inputs(keep_polarity):
         ref = rh.run_reference_event_frames(v, 30, ceil, pct, keep_polarity)
         got, _ub, _ = ef_oracle.event_frames_oracle(v, ceil, pct, keep_polarity)
         assert np.array_equal(ref, got), f'trial {trial} shape {(N, H, W)} ceil {ceil} percentile {pct}'
+
+
+def test_unet_oracle_equals_reference_model_over_three_calls():
+    """The folded fp32 restatement vs the reference's own V2ce3d (BatchNorm modules, SpectralNorm wrappers) on a fresh
+    random checkpoint and input: three consecutive calls, because the spectral-norm state advances on every forward,
+    eval mode included.  Tolerance: fp32 re-association of the folded scale/shift, rel-L2 < 2e-6."""
+    import torch
+    from oracle import synth
+    from oracle.unet_oracle import UNetOracle
+    sd = synth.make_state_dict(23, 'lively')
+    model = rh.V2ce3d()().eval()
+    model.load_state_dict(sd)
+    ora = UNetOracle(sd)
+    g = torch.Generator().manual_seed(7)
+    for call in range(3):
+        x = torch.randn(1, 5, 2, 17, 23, generator=g)      # odd sizes: every level of the 17->9->5->3->2 chain is ragged
+        with torch.no_grad():
+            want = model(x)
+        got = ora.forward(x)
+        assert got.shape == want.shape == (1, 5, 20, 17, 23)
+        rel = float((got - want).norm() / want.norm())
+        assert rel < 2e-6, f'call {call}: rel-L2 {rel}'
