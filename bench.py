@@ -115,7 +115,7 @@ class ClockSampler:
 def make_inputs():
     """The 20 windows of the clip: preprocessed image units (20, 16, 2, 260, 346) float32 and the raw gray frames
     they come from (20, 17, 260, 346) uint8 (both host)."""
-    from oracle import synth
+    import synth_inputs as synth
     from v2ce_toolbox_b200.v2ce import image_pre_processing, window_schedule
     frames = synth.make_video(N_FRAMES, H, W, seed=0)
     starts, mode = window_schedule(N_FRAMES, L)
@@ -137,7 +137,7 @@ def cpu_port_step(orc, units_window, pair_base, fps=30):
 
 
 def time_cpu_port(units, steps, warmup):
-    from oracle import synth
+    import synth_inputs as synth
     from oracle.unet_oracle import UNetOracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -182,7 +182,7 @@ class Runner:
     pinned host inputs and host results for `e2e`."""
 
     def __init__(self, device, units_host, windows_host, rank, world):
-        from oracle import synth
+        import synth_inputs as synth
         from v2ce_toolbox_b200.runner import BatchRunner
         from v2ce_toolbox_b200.scripts.v2ce_3d import V2ce3d
         self.device = device

@@ -136,16 +136,7 @@ def run_reference_ldati(y, fps=30, seed=0, frame_base=0, additional_events_strat
     return [np.asarray(r) for r in out]
 
 
-class FakeVideoReader:
-    """Duck-types what video_to_voxels needs from scripts.video_reader.VideoReader
-    (v2ce.py:149,170): ``frame_count`` and ``read_frames_at_indices``."""
-
-    def __init__(self, frames):
-        self.frames = np.asarray(frames)
-        self.frame_count = self.frames.shape[0]
-
-    def read_frames_at_indices(self, idxs):
-        return np.stack([self.frames[max(i, 0)] for i in idxs], axis=0)
+from synth_inputs import FakeVideoReader          # noqa: E402,F401  (in-memory reader; lives with the input generators)
 
 
 def run_reference_event_frames(voxel, fps=30, ceil=10, percentile=98, keep_polarity=True):

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cv2
 import numpy as np
 import torch
-from oracle import synth
+import synth_inputs as synth
 from v2ce_toolbox_b200 import v2ce as drv
 
 
@@ -36,7 +36,7 @@ def main():
     print(f'{n} frames -> {pairs} pairs, {len(res.event_stream)} events, {dt:.3f} s wall = {pairs / dt:.1f} frame-pairs/s '
           f'(PNG decode + device pipeline + D2H + mp4v encode + npz)')
     # the same without the host-side codecs: stream_clip on in-memory frames
-    from oracle.ref_harness import FakeVideoReader
+    from synth_inputs import FakeVideoReader
     model = drv.get_trained_mode(ckpt)
     drv.stream_clip(model, vidcap=FakeVideoReader(frames), batch_size=4, seed=1)
     torch.cuda.synchronize()

@@ -14,8 +14,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import torch.distributed as dist
-from oracle import synth
-from oracle.ref_harness import FakeVideoReader
+import synth_inputs as synth
+from synth_inputs import FakeVideoReader
 from v2ce_toolbox_b200 import dist as vdist
 from v2ce_toolbox_b200.scripts.v2ce_3d import V2ce3d
 

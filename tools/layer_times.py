@@ -8,7 +8,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from oracle import synth
+import synth_inputs as synth
 from v2ce_toolbox_b200.scripts.v2ce_3d import V2ce3d
 
 H, W, L = 260, 346, 16
