@@ -4,7 +4,7 @@ reference (/root/reference) on CPU in the build container.
     python tests/golden/make_golden.py
 
 The GPU box has no /root/reference, so the parity tests there read these files.
-Inputs come from oracle/synth.py generators (seeded); small inputs are stored
+Inputs come from the synth_inputs.py generators (seeded; re-exported as oracle.synth); small inputs are stored
 next to the outputs, full-size cases store only counts and SHA-256 digests of
 the tie-canonicalised event bytes.
 """
