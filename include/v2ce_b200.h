@@ -123,6 +123,17 @@ int v2ce_ef_normalize(const float* sums_dev, int32_t n_pairs, int32_t height, in
                       int32_t keep_polarity, double upper_bound, uint8_t* frames_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Image pre-processing for frames that are NOT at the model's resolution.  Replaces v2ce.py:45-64
+ * (image_pre_processing): /255, cv2.resize(INTER_LINEAR) to the model's height, pair stacking,
+ * Normalize(0.153, 0.165) -- bit-identical to the host path (oracle/resize_oracle.py).
+ * frames_dev: uint8 gray (n_windows, frames_per_window, src_h, src_w); units_dev: float32
+ * (n_windows, frames_per_window - 1, 2, dst_h, dst_w), the input layout of v2ce_model_forward.
+ * (Frames already at the model's height go to v2ce_model_forward_frames instead.)
+ * ------------------------------------------------------------------------------------------ */
+int v2ce_image_units(const uint8_t* frames_dev, int32_t n_windows, int32_t frames_per_window, int32_t src_h,
+                     int32_t src_w, int32_t dst_h, int32_t dst_w, float* units_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stage 1 -- V2ce3d.  Replaces scripts/v2ce_3d.py:12-30 (V2ce3d), scripts/unet_2layer.py:203-379
  * (UNet3D), scripts/submodules.py:85-124,216-264 (ConvLayer3D, ResidualBlock3D) and
  * scripts/spectral_norm.py:9-64 (SpectralNorm) in eval mode.

@@ -245,7 +245,8 @@ class ClipResult:
 
 
 def _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width):
-    """Raw uint8 windows (b, L+1, H, width), center-cropped like v2ce.py:78, in the reference's batching."""
+    """Raw uint8 windows in the reference's batching: (b, L+1, H, width) center-cropped like v2ce.py:78, or the whole
+    frames (b, L+1, H, W) when `width` is None (the device then resizes them, preprocess.image_units_device)."""
     frame_count = vidcap.frame_count if vidcap is not None else len(image_paths)
     starts, _ = schedule if schedule is not None else window_schedule(frame_count, seq_len)
     read, close = _window_reader(image_paths, vidcap, starts, seq_len)
@@ -253,8 +254,11 @@ def _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width
     try:
         for i in range(len(starts)):
             fr = np.asarray(read(i))
-            c = fr.shape[-1] // 2
-            pending.append(np.ascontiguousarray(fr[..., c - width // 2:c + width // 2])[None])
+            if width is None:
+                pending.append(np.ascontiguousarray(fr)[None])
+            else:
+                c = fr.shape[-1] // 2
+                pending.append(np.ascontiguousarray(fr[..., c - width // 2:c + width // 2])[None])
             if len(pending) == batch_size or i == len(starts) - 1:
                 yield torch.from_numpy(np.concatenate(pending, axis=0)), i == len(starts) - 1
                 pending = []
@@ -265,7 +269,8 @@ def _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width
 @torch.no_grad()
 def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_len=16, width=346, height=260,
                 batch_size=1, fps=30, ceil=10, upper_bound_percentile=98, keep_polarity=True,
-                write_event_frames=True, seed=0, pair_base=0, device=None, schedule=None, events_to_host=True):
+                write_event_frames=True, seed=0, pair_base=0, device=None, schedule=None, events_to_host=True,
+                device_resize=None):
     """Device-resident, pipelined version of v2ce.py:322-372 (runner.BatchRunner: the network of batch i+1 runs over
     the event frames + LDATI of batch i, results leave on a copy stream).  Returns ClipResult with the concatenated
     event stream (timestamps offset per frame, v2ce.py:365) and the uint8 BGR preview frames (clip-global percentile,
@@ -284,9 +289,20 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
     native = (infer_type == 'center' and hasattr(model, 'forward_frames') and probe.dtype == np.uint8 and
               probe.shape[-2] == height and int(probe.shape[-1] / probe.shape[-2] * height) == probe.shape[-1] and
               probe.shape[-1] >= width and width % 2 == 0)
+    # frames at another resolution: the host path (cv2.resize per frame, float image units over PCIe) is the default;
+    # device_resize=True (or V2CE_DEVICE_RESIZE=1) uploads the raw uint8 frames and runs the same arithmetic in one
+    # kernel (preprocess.image_units_device, bit-identical) -- SURVEY.md N1
+    if device_resize is None:
+        device_resize = os.environ.get('V2CE_DEVICE_RESIZE', '0') not in ('', '0')
+    raw = (not native and device_resize and probe.dtype == np.uint8 and probe.ndim == 3 and probe.shape[-2] >= 2)
     if native:
         infer = None
         batches = _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width)
+    elif raw:
+        from .preprocess import image_units_device
+        tile = _center_device if infer_type == 'center' else _pano_device
+        infer = lambda u8: tile(model, image_units_device(u8, height), width)        # noqa: E731
+        batches = _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, None)
     else:
         infer = (lambda u: _center_device(model, u, width)) if infer_type == 'center' else \
                 (lambda u: _pano_device(model, u, width))
