@@ -115,3 +115,46 @@ def test_u8_window_batches_center_crop(tmp_path):
     flat = np.concatenate([x.numpy() for x, _ in got], axis=0)
     for k, st in enumerate(drv.window_schedule(49, 16)[0]):
         assert np.array_equal(flat[k], frames[st:st + 17, :, 20 - 15:20 + 15])
+
+
+def test_background_generator_order_errors_and_early_stop():
+    import threading
+    import time
+
+    def gen(n, fail_at=None, log=None):
+        try:
+            for i in range(n):
+                if i == fail_at:
+                    raise ValueError(f'boom at {i}')
+                time.sleep(0.001)
+                yield i, threading.current_thread().name
+        finally:
+            if log is not None:
+                log.append('closed')
+
+    items = list(drv._background(gen(20)))
+    assert [i for i, _ in items] == list(range(20))
+    assert all(name == 'v2ce-batches' for _, name in items)        # produced off the consumer's thread
+    got = []
+    with pytest.raises(ValueError, match='boom at 3'):
+        for i, _ in drv._background(gen(10, fail_at=3)):
+            got.append(i)
+    assert got == [0, 1, 2]
+    log = []
+    it = drv._background(gen(1000, log=log), depth=2)
+    assert next(it)[0] == 0
+    it.close()                                                     # consumer leaves early: the producer must stop
+    deadline = time.time() + 5
+    while not log and time.time() < deadline:
+        time.sleep(0.01)
+    assert log == ['closed']
+    assert not [t for t in threading.enumerate() if t.name == 'v2ce-batches' and t.is_alive()]
+
+
+def test_background_batches_equal_inline_batches(tmp_path):
+    frames, paths = _write_pngs(str(tmp_path), 49, h=26, w=40)
+    inline = list(drv._batches(paths, None, 16, 26, 2))
+    threaded = list(drv._background(drv._batches(paths, None, 16, 26, 2)))
+    assert len(inline) == len(threaded)
+    for (a, la), (b, lb) in zip(inline, threaded):
+        assert la == lb and bool((a == b).all())

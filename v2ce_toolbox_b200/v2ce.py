@@ -176,6 +176,52 @@ def _window_reader(image_paths, vidcap, starts, seq_len):
     return (lambda k: _read_window(image_paths, vidcap, int(starts[k]), seq_len)), (lambda: None)
 
 
+def _background(gen, depth=2):
+    """Run the batch generator `gen` on a producer thread, `depth` batches ahead of the consumer: decoding, cv2.resize
+    and batch assembly (all of which release the GIL) then overlap the consumer's CUDA submissions and waits instead of
+    alternating with them.  Items arrive in order; an exception in the producer is re-raised at the consumer; closing the
+    consumer early stops the producer."""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=depth)
+    end, stop = object(), threading.Event()
+
+    def put(item):
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.05)
+                return True
+            except queue.Full:
+                pass
+        return False
+
+    def produce():
+        try:
+            for item in gen:
+                if not put(item):
+                    break
+            else:
+                put(end)
+        except BaseException as e:                      # noqa: B902 -- handed to the consumer
+            put(e)
+        finally:
+            gen.close()
+
+    th = threading.Thread(target=produce, name='v2ce-batches', daemon=True)
+    th.start()
+    try:
+        while True:
+            item = q.get()
+            if item is end:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    finally:
+        stop.set()
+        th.join(timeout=5.0)
+
+
 def _batches(image_paths, vidcap, seq_len, height, batch_size, schedule=None):
     """Yield (image_units (b,L,2,H',W') float32 host tensor, is_last) in the reference's batching.
     `schedule` = (window starts, mode) overrides the schedule derived from the frame count (a rank's share of a clip)."""
@@ -321,7 +367,7 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
         runner.reset_collection()
         pair_idx = pair_base
         prev = None
-        for x, is_last in batches:
+        for x, is_last in _background(batches):
             t = runner.submit(x.pin_memory(), pair_idx, keep_sums=write_event_frames,
                               trim_last_window_to=mode if (is_last and mode != 0) else 0)
             pair_idx += t.n_pairs
