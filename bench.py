@@ -230,6 +230,11 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     device = torch.device('cuda', local_rank)
     torch.cuda.set_device(device)
+    affinity = None
+    if world > 1:
+        # one process per GPU: keep each rank (and the pinned staging it allocates) on its GPU's NUMA node
+        from v2ce_toolbox_b200.dist import bind_to_gpu_numa
+        affinity = bind_to_gpu_numa(local_rank)
     units, windows = make_inputs()
     r = Runner(device, units, windows, rank, world)
 
@@ -342,6 +347,7 @@ def run_ours(args, rank, world, local_rank):
                              'batch\'s event-frame / LDATI kernels share the SMs'},
         'cpu_baseline': cpu,
         'clocks': clocks,
+        'cpu_affinity': None if affinity is None else {'cpus': len(affinity), 'first': affinity[0], 'last': affinity[-1]},
     }
     if world == 1:
         try:

@@ -86,3 +86,14 @@ def test_gather_event_shards_gloo(tmp_path):
     want = np.concatenate([np.load(tmp_path / f'shard{r}.npy') for r in range(world)])
     assert merged.dtype.itemsize == 13 and np.array_equal(merged, want)
     assert (np.diff(merged['timestamp']) >= 0).all()       # concatenation by rank is the time-ordered merge
+
+
+def test_bind_to_gpu_numa_is_a_no_op_without_nvml_device():
+    """bench.py calls it on every rank at N > 1; on a host without a usable NVML device it must change nothing."""
+    import os
+    from v2ce_toolbox_b200 import dist as vdist
+    before = os.sched_getaffinity(0)
+    assert vdist.bind_to_gpu_numa(0) is None or isinstance(vdist.bind_to_gpu_numa(0), list)
+    import torch
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before

@@ -28,6 +28,9 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    if world > 1:
+        from v2ce_toolbox_b200.dist import bind_to_gpu_numa
+        bind_to_gpu_numa(local)                  # pinned staging and copy threads on the GPU's own NUMA node
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     os.environ.setdefault('MASTER_PORT', '29533')
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)

@@ -12,6 +12,36 @@ import torch.distributed as dist
 EVENT_BYTES = 13
 
 
+def bind_to_gpu_numa(device_index):
+    """Restrict this process to the CPUs NVML reports as local to CUDA device `device_index` (one process per GPU:
+    its pinned staging buffers are then first-touched on the GPU's own NUMA node and the D2H / H2D copies do not cross
+    the socket interconnect).  Returns the sorted CPU list, or None when NVML, the device or a usable mask is not
+    available (nothing is changed then).  V2CE_NO_AFFINITY=1 disables it."""
+    import os
+    if os.environ.get('V2CE_NO_AFFINITY', '0') not in ('', '0') or not hasattr(os, 'sched_setaffinity'):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + uuid).encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, (max(os.cpu_count() or 1, 1) + 63) // 64)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 4:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def shard_range(n_items, world, rank):
     """Contiguous [start, end) of `n_items` owned by `rank`: rank r gets items [r*ceil(n/R), ...)."""
     per = -(-n_items // world)
