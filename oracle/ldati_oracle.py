@@ -7,6 +7,7 @@ one rounding per operation, in the operation order of the reference:
   relocate_counts_bidirectional <- /root/reference/scripts/LDATI.py:91-94,96-104,107-122 (bidirectional=True)
   single_timestamps    <- /root/reference/scripts/LDATI.py:156-165
   slope_params         <- /root/reference/scripts/LDATI.py:13-51,184-192
+  pool_counts          <- /root/reference/scripts/LDATI.py:176-183 (pooling_type 'weighted' / 'avg')
   multi_timestamps     <- /root/reference/scripts/LDATI.py:194-196,209-212
   assemble_frame       <- /root/reference/scripts/LDATI.py:217-245,248-310 (pick_elements / pick_and_sort)
   sample_voxel_statistical_oracle <- /root/reference/scripts/LDATI.py:126-214 as called by v2ce.py:356
@@ -152,9 +153,42 @@ def single_timestamps(tend, k: Consts):
     return np.trunc(t).astype(np.int64)
 
 
-def slope_params(n, k: Consts):
-    """Per pixel-bin (k, b) of the linear density; n (...,9,H,W) int64."""
+def pool_counts(n, pooling_type='none', kernel_size=3):
+    """y_pooled of LDATI.py:176-183: the (integer) counts as float32, spatially pooled per (frame, polarity, bin) plane.
+
+    'weighted': conv2d with [[1,2,1],[2,4,2],[1,2,1]]/16, zero padding 1 (LDATI.py:177-180) -- dyadic weights on small
+                integers, so every accumulation order gives the same float32;
+    'avg':      AvgPool2d(kernel_size, stride 1, padding kernel_size//2), count_include_pad -> the zero-padded window sum
+                (exact) divided by kernel_size**2 in float32 (LDATI.py:181-182); odd kernel sizes only (an even one
+                changes the plane size and the reference's reshape fails)."""
     nf = n.astype(F32)
+    if pooling_type == 'none':
+        return nf
+    H, W = nf.shape[-2:]
+    if pooling_type == 'weighted':
+        r, w1 = 1, np.array([1, 2, 1], dtype=F32)
+        weights = np.outer(w1, w1).astype(F32) / F32(16)
+    elif pooling_type == 'avg':
+        assert kernel_size % 2 == 1, 'AvgPool2d with an even kernel changes the plane size (the reference fails too)'
+        r = kernel_size // 2
+        weights = np.ones((kernel_size, kernel_size), dtype=F32)
+    else:
+        raise ValueError(pooling_type)
+    pad = np.zeros(nf.shape[:-2] + (H + 2 * r, W + 2 * r), dtype=F32)
+    pad[..., r:r + H, r:r + W] = nf
+    out = np.zeros_like(nf)
+    for dy in range(2 * r + 1):
+        for dx in range(2 * r + 1):
+            out = (out + weights[dy, dx] * pad[..., dy:dy + H, dx:dx + W]).astype(F32)
+    if pooling_type == 'avg':
+        out = (out / F32(kernel_size * kernel_size)).astype(F32)
+    return out
+
+
+def slope_params(n, k: Consts, pooled=None):
+    """Per pixel-bin (k, b) of the linear density; n (...,9,H,W) int64.  `pooled`: pool_counts(n, ...) when the
+    slope is fitted on spatially pooled counts (LDATI.py:176-186), default the counts themselves."""
+    nf = n.astype(F32) if pooled is None else pooled.astype(F32)
     S = np.zeros_like(nf)
     S[..., 1:-1, :, :] = nf[..., 2:, :, :] - nf[..., :-2, :, :]     # reflect pad => 0 at both ends
     num = F32(3) * S - F32(0)
@@ -247,7 +281,7 @@ def assemble_frame(n_f, ts1_f, kk_f, b_f, frame_index, H, W, k: Consts, draw_fn,
 
 def sample_voxel_statistical_oracle(y, t0=0, fps=30, seed=0, frame_base=0, flavor='cuda',
                                     draws=None, return_seg_counts=False, additional_events_strategy='slope',
-                                    bidirectional=False):
+                                    bidirectional=False, pooling_type='none', pooling_kernel_size=3):
     """Oracle of sample_voxel_statistical(y, fps=fps, bidirectional=False | True,
     additional_events_strategy='slope' | 'random' | 'none', pooling_type='none').
 
@@ -260,7 +294,7 @@ def sample_voxel_statistical_oracle(y, t0=0, fps=30, seed=0, frame_base=0, flavo
     k = Consts(fps, t0, flavor, C - 1)
     n, tend = (relocate_counts_bidirectional if bidirectional else relocate_counts)(y.astype(F32))
     ts1 = single_timestamps(tend, k)
-    kk, b = slope_params(n, k)
+    kk, b = slope_params(n, k, None if pooling_type == 'none' else pool_counts(n, pooling_type, pooling_kernel_size))
     out, counts = [], []
     for f in range(B):
         if draws is None:

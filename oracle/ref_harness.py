@@ -123,7 +123,8 @@ def injected_draws(seed, frame_base=0):
         torch.rand = old
 
 
-def run_reference_ldati(y, fps=30, seed=0, frame_base=0, additional_events_strategy='slope', bidirectional=False):
+def run_reference_ldati(y, fps=30, seed=0, frame_base=0, additional_events_strategy='slope', bidirectional=False,
+                        pooling_type='none', pooling_kernel_size=3):
     """sample_voxel_statistical exactly as v2ce.py:356 calls it, on CPU, with injected draws."""
     import torch
     import warnings
@@ -132,7 +133,8 @@ def run_reference_ldati(y, fps=30, seed=0, frame_base=0, additional_events_strat
     with injected_draws(seed, frame_base), warnings.catch_warnings():
         warnings.simplefilter('ignore')
         out = ld.sample_voxel_statistical(yt, fps=fps, bidirectional=bidirectional,
-                                          additional_events_strategy=additional_events_strategy)
+                                          additional_events_strategy=additional_events_strategy,
+                                          pooling_type=pooling_type, pooling_kernel_size=pooling_kernel_size)
     return [np.asarray(r) for r in out]
 
 

@@ -84,6 +84,28 @@ def ldati_option_cases():
     return meta
 
 
+POOLING_CASES = [('weighted', 3, False), ('avg', 3, False), ('avg', 5, True)]
+
+
+def ldati_pooling_cases():
+    """pooling_type 'weighted' / 'avg' (LDATI.py:176-183) on the 'mixed24' voxels of ldati_golden.npz.  Only events of
+    multi-event pixel-bins depend on the pooling, so the fixture stores the canonicalised events of frame 0 only."""
+    vox = np.load(os.path.join(HERE, 'ldati_golden.npz'))
+    with open(os.path.join(HERE, 'golden_meta.json')) as f:
+        m = json.load(f)['ldati']['mixed24']
+    out, meta = {}, {}
+    for pt, ks, bid in POOLING_CASES:
+        ref = rh.run_reference_ldati(vox['mixed24_voxel'], fps=m['fps'], seed=m['seed'], frame_base=m['frame_base'],
+                                     bidirectional=bid, pooling_type=pt, pooling_kernel_size=ks)
+        name = f"mixed24-{pt}{ks}-{'bi' if bid else 'uni'}"
+        out[f'{name}_events_0'] = np.ascontiguousarray(lo.canonicalize(ref[0])).view(np.uint8)
+        meta[name] = dict(input='mixed24', fps=m['fps'], seed=m['seed'], frame_base=m['frame_base'], frames=len(ref),
+                          pooling_type=pt, pooling_kernel_size=ks, bidirectional=bid,
+                          counts=[int(len(r)) for r in ref], sha256=[digest(r) for r in ref])
+    np.savez_compressed(os.path.join(HERE, 'ldati_pooling_golden.npz'), **out)
+    return meta
+
+
 def ef_cases():
     out = {}
     meta = {}
@@ -146,18 +168,21 @@ def pipeline_cases():
 
 if __name__ == '__main__':
     import cv2
-    if '--only-ldati-options' in sys.argv:
-        # incremental: (re)generate only the LDATI option goldens, keep the rest of the meta file
+    if '--only-ldati-options' in sys.argv or '--only-ldati-pooling' in sys.argv:
+        # incremental: (re)generate only the LDATI option / pooling goldens, keep the rest of the meta file
         with open(os.path.join(HERE, 'golden_meta.json')) as f:
             meta = json.load(f)
-        meta.pop('ldati_none', None)
-        meta['ldati_options'] = ldati_option_cases()
+        if '--only-ldati-options' in sys.argv:
+            meta['ldati_options'] = ldati_option_cases()
+        if '--only-ldati-pooling' in sys.argv:
+            meta['ldati_pooling'] = ldati_pooling_cases()
     else:
         meta = dict(versions=dict(torch=torch.__version__, numpy=np.__version__, cv2=cv2.__version__),
                     ldati=ldati_cases(), ef=ef_cases(), unet=unet_cases(), pipeline=pipeline_cases())
         with open(os.path.join(HERE, 'golden_meta.json'), 'w') as f:
             json.dump(meta, f, indent=1)
         meta['ldati_options'] = ldati_option_cases()
+        meta['ldati_pooling'] = ldati_pooling_cases()
     with open(os.path.join(HERE, 'golden_meta.json'), 'w') as f:
         json.dump(meta, f, indent=1)
     print(json.dumps(meta, indent=1)[:3000])

@@ -71,6 +71,32 @@ def test_ldati_oracle_options_match_reference(name, golden, golden_meta):
         assert np.array_equal(lo.canonicalize(o), g[f'{name}_events_{i}'].view(lo.EVENT_DTYPE)), f'{name} frame {i}'
 
 
+@pytest.mark.parametrize('name', ['mixed24-weighted3-uni', 'mixed24-avg3-uni', 'mixed24-avg5-bi'])
+def test_ldati_oracle_pooling_matches_reference(name, golden, golden_meta):
+    """pooling_type 'weighted' / 'avg' (LDATI.py:176-183): the slope is fitted on spatially pooled counts."""
+    m = golden_meta['ldati_pooling'][name]
+    v = golden('ldati')['mixed24_voxel']
+    ora = lo.sample_voxel_statistical_oracle(v, fps=m['fps'], seed=m['seed'], frame_base=m['frame_base'], flavor='cpu',
+                                             bidirectional=m['bidirectional'], pooling_type=m['pooling_type'],
+                                             pooling_kernel_size=m['pooling_kernel_size'])
+    assert [len(o) for o in ora] == m['counts']
+    assert np.array_equal(lo.canonicalize(ora[0]), golden('ldati_pooling')[f'{name}_events_0'].view(lo.EVENT_DTYPE))
+    for o, d in zip(ora, m['sha256']):
+        assert hashlib.sha256(np.ascontiguousarray(lo.canonicalize(o)).tobytes()).hexdigest() == d
+
+
+def test_pool_counts_definitions():
+    rng = np.random.default_rng(0)
+    n = rng.integers(0, 9, (2, 9, 6, 7))
+    w = lo.pool_counts(n, 'weighted')
+    assert w[0, 0, 0, 0] == np.float32((4 * n[0, 0, 0, 0] + 2 * n[0, 0, 0, 1] + 2 * n[0, 0, 1, 0] + n[0, 0, 1, 1]) / 16)
+    a = lo.pool_counts(n, 'avg', 3)
+    assert a[1, 4, 2, 3] == np.float32(n[1, 4, 1:4, 2:5].sum()) / np.float32(9)
+    assert a[1, 4, 0, 0] == np.float32(n[1, 4, 0:2, 0:2].sum()) / np.float32(9)      # zero padding counts in the divisor
+    assert np.array_equal(lo.pool_counts(n, 'avg', 1), n.astype(np.float32))
+    assert np.array_equal(lo.pool_counts(n, 'none'), n.astype(np.float32))
+
+
 def test_bidirectional_relocation_shape():
     """LDATI.py:107-122: bin 4 is never written; bin 8's tendency is the tenth voxel bin itself."""
     v = synth.make_voxels('mixed', 1, 16, 20, seed=2)

@@ -55,6 +55,23 @@ def test_ldati_oracle_equals_reference_on_random_inputs(kind, strategy, bidirect
                 f'{kind} {strategy} bidirectional={bidirectional} trial {trial} shape {(B, H, W)} fps {fps} frame {i}'
 
 
+@pytest.mark.parametrize('pooling_type,kernel_size', [('weighted', 3), ('avg', 3), ('avg', 5), ('avg', 7)])
+@pytest.mark.parametrize('bidirectional', [False, True])
+def test_ldati_pooling_oracle_equals_reference_on_random_inputs(pooling_type, kernel_size, bidirectional):
+    rng = np.random.default_rng(kernel_size * 31 + int(bidirectional) + len(pooling_type))
+    for kind in ('counts', 'bursty', 'rand', 'signed'):
+        B, H, W = int(rng.integers(1, 3)), int(rng.integers(1, 16)), int(rng.integers(1, 20))
+        fps = int(rng.choice([24, 30, 60, 120]))
+        v = _random_voxels(rng, kind, B, H, W)
+        v[0, 0, 3, 0, 0] += np.float32(2.5)
+        kw = dict(fps=fps, seed=5, frame_base=1, bidirectional=bidirectional, pooling_type=pooling_type,
+                  pooling_kernel_size=kernel_size)
+        ref = rh.run_reference_ldati(v, **kw)
+        ora = lo.sample_voxel_statistical_oracle(v, flavor='cpu', **kw)
+        for i, (r, o) in enumerate(zip(ref, ora)):
+            assert lo.events_equal_modulo_ties(r, o), f'{pooling_type}{kernel_size} {kind} shape {(B, H, W)} frame {i}'
+
+
 @pytest.mark.parametrize('keep_polarity', [True, False])
 def test_event_frame_oracle_equals_reference_on_random_inputs(keep_polarity):
     rng = np.random.default_rng(5 + int(keep_polarity))
