@@ -46,7 +46,8 @@ int v2ce_device_check(int device, int* sm_count, int* cc_major, int* cc_minor);
  * pick_elements (:217-245) and pick_and_sort (:248-310).  The configuration v2ce.py:356 uses
  * (bidirectional=False, additional_events_strategy='slope', pooling_type='none') is the tuned path;
  * bidirectional=True and the 'random' / 'none' strategies are implemented as options of the same
- * kernels; pooling_type 'avg' / 'weighted' is not implemented (the Python shim raises).
+ * kernels, and so is pooling_type 'avg' / 'weighted' (the Python shim still raises for it unless
+ * V2CE_EXPERIMENTAL_POOLING=1: that route has not run on hardware yet).
  *
  * The scalar constants are computed by the host with the reference's own Python
  * expressions so the kernel reproduces torch's rounding.
@@ -77,6 +78,10 @@ typedef struct v2ce_ldati_params {
                               * 0 = 'none' (such pixel-bins emit nothing, LDATI.py:206-207,241-244)             */
   int32_t bidirectional;     /* 1: y_relocate(bidirectional=True), LDATI.py:107-122 (bin_base_us / key_span must
                               * then cover tendencies in (-1, y[9]] bins; see v2ce_toolbox_b200/ldati.py)        */
+  int32_t pooling;           /* pooling_type: 0 = 'none', 1 = 'weighted' (3x3 binomial / 16), 2 = 'avg' (box of
+                              * pooling_kernel_size^2, zero padded, count_include_pad) -- LDATI.py:176-183; only read when
+                              * multi_events == 1.  Compiled and pinned on CPU; first B200 run pending.            */
+  int32_t pooling_kernel_size; /* odd; 'avg' only                                                                  */
 } v2ce_ldati_params;
 
 /* Workspace needed by v2ce_ldati_count (also holds the scan results v2ce_ldati_emit reads). */

@@ -27,6 +27,7 @@ class LdatiParams(Structure):
         ('binstart_t0_32', c_float * 16), ('bin_base_us', c_int64 * 16),
         ('key_span', c_int32), ('add_frame_offset', c_int32),
         ('multi_events', c_int32), ('bidirectional', c_int32),
+        ('pooling', c_int32), ('pooling_kernel_size', c_int32),
     ]
 
 

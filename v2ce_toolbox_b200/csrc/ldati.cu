@@ -43,6 +43,7 @@ struct Geometry {
   int pix_bits;  // bits of the pixel field
   int key_bits;  // bits of the sort key
   int wide;      // 1: 64-bit elements
+  int pooling;   // != 0: the count workspace also holds every pixel-bin's count (the slope is fitted on pooled counts)
 };
 
 static Geometry make_geometry(const v2ce_ldati_params* p) {
@@ -58,6 +59,7 @@ static Geometry make_geometry(const v2ce_ldati_params* p) {
   g.key_bits = 1;
   while ((1LL << g.key_bits) < (long long)p->key_span + 1) ++g.key_bits;
   g.wide = (g.pix_bits + 1 + g.key_bits > 32) ? 1 : 0;
+  g.pooling = (p->pooling != 0 && p->multi_events == 1) ? 1 : 0;     // only the 'slope' strategy reads pooled counts
   return g;
 }
 
@@ -65,6 +67,7 @@ static Geometry make_geometry(const v2ce_ldati_params* p) {
 struct CountWs {
   int32_t* partial;     // [F][2][NB][18]
   int32_t* warp_partial;  // [F][2][NB][8 warps][18]: the count pass's per-warp totals, reused by the emit pass
+  int32_t* counts_all;    // pooling only: [F][2][9][HW] counts of every pixel-bin (neighbours feed the pooled slope)
   int32_t* block_base;  // [F][2][NB][18]
   int32_t* group_base;  // [F][9][4]
   int64_t* seg_start;   // [F*9+1]
@@ -80,6 +83,7 @@ static CountWs carve_count_ws(void* ws, const Geometry& g) {
   w.group_base = a.take<int32_t>((size_t)g.F * kBins * 4);
   w.seg_start = a.take<int64_t>((size_t)g.F * kBins + 1);
   w.warp_partial = a.take<int32_t>(n * (kThreads / 32));
+  w.counts_all = g.pooling ? a.take<int32_t>((size_t)g.F * 2 * kBins * g.HW) : nullptr;
   w.bytes = align_up(a.off, 256);
   return w;
 }
@@ -102,6 +106,8 @@ struct DevParams {
   int add_frame_offset;
   int multi_events;   // additional_events_strategy: 0 'none' (multi-event pixel-bins emit nothing), 1 'slope',
                       // 2 'random' (the raw draw is the time offset in seconds, LDATI.py:173-174)
+  int pooling;        // 0 none, 1 'weighted' (3x3 binomial / 16), 2 'avg' (pool_k x pool_k box / pool_k^2); LDATI.py:176-183
+  int pool_k;
   long long nan_ts;   // float NaN -> int64: INT64_MIN on x86 (cvttss2si) and on torch-CUDA (measured on B200)
 };
 
@@ -120,6 +126,8 @@ static DevParams make_dev_params(const v2ce_ldati_params* p, const Geometry& g) 
   d.draws_m = 0;
   d.add_frame_offset = p->add_frame_offset;
   d.multi_events = p->multi_events;
+  d.pooling = g.pooling ? p->pooling : 0;
+  d.pool_k = p->pooling_kernel_size;
   d.nan_ts = LLONG_MIN;
   return d;
 }
@@ -392,12 +400,39 @@ __device__ __forceinline__ void load_bin(const float* __restrict__ plane0, int H
   }
 }
 
-template <int V, typename Elem, bool BIDIR>
+// y_pooled (LDATI.py:176-183) of one pixel-bin from the stored counts of its plane `cp` = counts_all + ((f*2+p)*9+c)*HW:
+// 'weighted' = 3x3 binomial kernel / 16 with zero padding (dyadic weights on small integers: every accumulation order
+// gives the same float32); 'avg' = zero-padded k x k window sum (exact) divided by k*k in float32.
+__device__ __noinline__ float pooled_count(const int32_t* __restrict__ cp, int H, int W, int pix, int pooling, int k) {
+  const int h = pix / W, w = pix - h * W;
+  if (pooling == 1) {
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int hh = h + dy, ww = w + dx;
+        const float wt = ((dy == 0) ? 2.f : 1.f) * ((dx == 0) ? 2.f : 1.f) * 0.0625f;
+        const float x = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? (float)__ldg(cp + (size_t)hh * W + ww) : 0.f;
+        acc = __fadd_rn(acc, __fmul_rn(wt, x));
+      }
+    }
+    return acc;
+  }
+  const int r = k >> 1;
+  long long sum = 0;
+  for (int hh = max(h - r, 0); hh <= min(h + r, H - 1); ++hh)
+    for (int ww = max(w - r, 0); ww <= min(w + r, W - 1); ++ww) sum += __ldg(cp + (size_t)hh * W + ww);
+  return __fdiv_rn((float)sum, (float)(k * k));
+}
+
+template <int V, typename Elem, bool BIDIR, bool POOL>
 __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict__ vox, DevParams P,
                                                          const int32_t* __restrict__ block_base,
                                                          const int32_t* __restrict__ group_base,
                                                          const int64_t* __restrict__ seg_start,
                                                          const int32_t* __restrict__ warp_partial,
+                                                         const int32_t* __restrict__ counts_all,
                                                          const float* __restrict__ draws, Elem* __restrict__ elems,
                                                          int32_t* __restrict__ status) {
   const int blk = blockIdx.x, p = blockIdx.y, f = blockIdx.z;
@@ -526,11 +561,20 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
       float kk = 0.f, b = 0.f;
       if (cnt[v]) {
         float S = 0.f;
-        if (c > 0 && c < kBins - 1) S = __fsub_rn((float)n_next[v], (float)n_prev[v]);
+        float y_fit = (float)nc;                 // the counts the slope is fitted on: pooled (LDATI.py:176-186) or raw
+        if (POOL) {
+          const int32_t* cp = counts_all + (((size_t)f * 2 + p) * kBins + c) * P.HW;
+          y_fit = pooled_count(cp, P.H, P.W, pix0 + v, P.pooling, P.pool_k);
+          if (c > 0 && c < kBins - 1)
+            S = __fsub_rn(pooled_count(cp + P.HW, P.H, P.W, pix0 + v, P.pooling, P.pool_k),
+                          pooled_count(cp - P.HW, P.H, P.W, pix0 + v, P.pooling, P.pool_k));
+        } else if (c > 0 && c < kBins - 1) {
+          S = __fsub_rn((float)n_next[v], (float)n_prev[v]);
+        }
         const float num = __fsub_rn(__fmul_rn(3.f, S), 0.f);
         kk = P.true_div ? __fdiv_rn(__fdiv_rn(num, P.six32), P.vs2_32)
                         : __fmul_rn(__fmul_rn(num, P.r6_32), P.r_vs2_32);
-        kk = __fdiv_rn(kk, __fadd_rn((float)nc, P.eps8));
+        kk = __fdiv_rn(kk, __fadd_rn(y_fit, P.eps8));
         b = __fsub_rn(P.inv_vs32, __fmul_rn(__fmul_rn(P.vs32, kk), 0.5f));
       }
       s_par[warp][lane][v] = make_float2(kk, b);
@@ -966,7 +1010,7 @@ __global__ void relocate_debug_kernel(const float* __restrict__ vox, int HW, flo
 #pragma unroll
     for (int c = 0; c < kBins; ++c) {
       counts[((size_t)plane * kBins + c) * HW + pix + v] = n[c];
-      tend_out[((size_t)plane * kBins + c) * HW + pix + v] = tend[c];
+      if (tend_out != nullptr) tend_out[((size_t)plane * kBins + c) * HW + pix + v] = tend[c];
     }
   }
 }
@@ -981,6 +1025,10 @@ static int validate(const v2ce_ldati_params* p) {
   V2CE_REQUIRE(p->key_span > 0 && p->key_span < (1 << 30), "bad key_span %d", p->key_span);
   V2CE_REQUIRE(p->multi_events >= 0 && p->multi_events <= 2, "multi_events must be 0 ('none'), 1 ('slope') or 2 ('random')");
   V2CE_REQUIRE(p->bidirectional == 0 || p->bidirectional == 1, "bidirectional must be 0 or 1");
+  V2CE_REQUIRE(p->pooling >= 0 && p->pooling <= 2, "pooling must be 0 ('none'), 1 ('weighted') or 2 ('avg')");
+  V2CE_REQUIRE(p->pooling != 2 || (p->pooling_kernel_size >= 1 && (p->pooling_kernel_size & 1) && p->pooling_kernel_size <= 255),
+               "pooling_kernel_size must be odd (an even AvgPool2d kernel changes the plane size; the reference fails too)");
+  V2CE_REQUIRE(p->pooling == 0 || p->n_frames * 2 <= 65535, "pooling: at most 32767 frames per call");
   return V2CE_OK;
 }
 
@@ -1026,6 +1074,17 @@ extern "C" int v2ce_ldati_count(const float* voxels_dev, const v2ce_ldati_params
     else count_kernel<1, false><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial);
   }
   V2CE_LAUNCH_CHECK("ldati::count_kernel");
+  if (g.pooling) {
+    // the slope of a multi-event pixel-bin is fitted on spatially pooled counts: keep every pixel-bin's count
+    if (g.V == 4) {
+      dim3 rgrid((g.HW / 4 + 255) / 256, g.F * 2);
+      relocate_debug_kernel<4><<<rgrid, 256, 0, s>>>(voxels_dev, g.HW, p->eps6, p->bidirectional, w.counts_all, nullptr);
+    } else {
+      dim3 rgrid((g.HW + 255) / 256, g.F * 2);
+      relocate_debug_kernel<1><<<rgrid, 256, 0, s>>>(voxels_dev, g.HW, p->eps6, p->bidirectional, w.counts_all, nullptr);
+    }
+    V2CE_LAUNCH_CHECK("ldati::relocate_debug_kernel");
+  }
   scan_planes_kernel<<<g.F, 64, 0, s>>>(w.partial, w.block_base, w.group_base, seg_counts_dev, g.NB);
   V2CE_LAUNCH_CHECK("ldati::scan_planes_kernel");
   scan_i64_kernel<<<1, 1024, 0, s>>>(seg_counts_dev, w.seg_start, g.F * kBins);
@@ -1062,17 +1121,18 @@ static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometr
   V2CE_CUDA_CHECK(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), s));
   dim3 grid(g.NB, 2, g.F);
   const int32_t* wp = reuse_warp_totals() ? cw.warp_partial : nullptr;
-  if (p->bidirectional) {
-    if (g.V == 4)
-      emit_kernel<4, Elem, true><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, wp, draws, ea, status);
-    else
-      emit_kernel<1, Elem, true><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, wp, draws, ea, status);
+#define V2CE_LAUNCH_EMIT(V_, BIDIR_, POOL_)                                                                      \
+  emit_kernel<V_, Elem, BIDIR_, POOL_><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, \
+                                                                  wp, cw.counts_all, draws, ea, status)
+  const bool bidir = p->bidirectional != 0, pool = g.pooling != 0;
+  if (g.V == 4) {
+    if (bidir) { if (pool) V2CE_LAUNCH_EMIT(4, true, true); else V2CE_LAUNCH_EMIT(4, true, false); }
+    else { if (pool) V2CE_LAUNCH_EMIT(4, false, true); else V2CE_LAUNCH_EMIT(4, false, false); }
   } else {
-    if (g.V == 4)
-      emit_kernel<4, Elem, false><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, wp, draws, ea, status);
-    else
-      emit_kernel<1, Elem, false><<<grid, kThreads, 0, s>>>(vox, P, cw.block_base, cw.group_base, cw.seg_start, wp, draws, ea, status);
+    if (bidir) { if (pool) V2CE_LAUNCH_EMIT(1, true, true); else V2CE_LAUNCH_EMIT(1, true, false); }
+    else { if (pool) V2CE_LAUNCH_EMIT(1, false, true); else V2CE_LAUNCH_EMIT(1, false, false); }
   }
+#undef V2CE_LAUNCH_EMIT
   V2CE_LAUNCH_CHECK("ldati::emit_kernel");
   if (total == 0) return V2CE_OK;
   build_tiles_kernel<<<1, 1024, 0, s>>>(cw.seg_start, ns, sw.tile_first, sw.tile_seg);

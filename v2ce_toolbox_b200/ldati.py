@@ -20,6 +20,7 @@ EVENT_DTYPE = np.dtype([('timestamp', '<i8'), ('x', '<i2'), ('y', '<i2'), ('pola
 NBINS = 9
 KEY_BIAS = 8
 STRATEGIES = {'none': 0, 'slope': 1, 'random': 2}     # v2ce_ldati_params.multi_events
+POOLING = {'none': 0, 'weighted': 1, 'avg': 2}        # v2ce_ldati_params.pooling
 BIDIR_MAX_TENDENCY = 1024                             # largest tenth-bin voxel value the bidirectional sort window accepts
 
 
@@ -45,7 +46,8 @@ def _bin_starts(fps, device, flavor='cuda'):
 
 
 def make_params(n_frames, height, width, fps=30, t0=0, seed=0, frame_base=0, flavor='cuda',
-                device='cuda', add_frame_offset=False, additional_events_strategy='slope', bidirectional=False):
+                device='cuda', add_frame_offset=False, additional_events_strategy='slope', bidirectional=False,
+                pooling_type='none', pooling_kernel_size=3):
     """Scalar constants with the reference's own Python expressions."""
     if additional_events_strategy not in STRATEGIES:
         raise ValueError(f'additional_events_strategy must be one of {sorted(STRATEGIES)}')
@@ -89,6 +91,14 @@ def make_params(n_frames, height, width, fps=30, t0=0, seed=0, frame_base=0, fla
     p.add_frame_offset = 1 if add_frame_offset else 0
     p.multi_events = STRATEGIES[additional_events_strategy]
     p.bidirectional = 1 if bidirectional else 0
+    if pooling_type not in POOLING:
+        raise ValueError(f'pooling_type must be one of {sorted(POOLING)}')
+    if pooling_type == 'avg' and pooling_kernel_size % 2 == 0:
+        raise ValueError('pooling_kernel_size must be odd: an even AvgPool2d kernel changes the plane size '
+                         '(the reference fails in its reshape, LDATI.py:186)')
+    # only the 'slope' strategy reads the pooled counts (LDATI.py:175-183)
+    p.pooling = POOLING[pooling_type] if additional_events_strategy == 'slope' else 0
+    p.pooling_kernel_size = int(pooling_kernel_size)
     return p
 
 
