@@ -65,3 +65,31 @@ def test_slope_params_match_torch_cuda_ops():
     bt = 1 / voxel_step - voxel_step * kt / 2
     assert np.array_equal(kt.cpu().numpy().view(np.uint32), kk.view(np.uint32))
     assert np.array_equal(bt.cpu().numpy().view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.xfail(strict=False, reason='probe, first hardware run pending: XPASS = torch-CUDA runs the pooled slope in float32 '
+                                        "(the oracle's cuda flavour of pooling_type='avg' then holds as written), "
+                                        'XFAIL = cuDNN uses TF32 there and the flavour needs a TF32 rounding step')
+def test_pooled_slope_ops_are_float32_on_cuda():
+    """pooling_type 'avg' / 'weighted' (LDATI.py:176-183 then :25-39): AvgPool2d / conv2d on the counts, then the
+    [-1, 0, 1] conv1d over bins.  The oracle's cuda flavour takes all three as float32 arithmetic; cuDNN may instead
+    run the convolutions on TF32 tensor cores (torch.backends.cudnn.allow_tf32 defaults to True), which is exact for
+    'weighted' (dyadic weights, small integers) but not for the k/9-valued 'avg' counts."""
+    import torch.nn.functional as Fn
+    g = torch.Generator(device='cpu').manual_seed(5)
+    n = torch.randint(0, 12, (4, 9, 20, 24), generator=g).float()
+    n_np = n.numpy().astype(np.int64)
+    avg = torch.nn.AvgPool2d(kernel_size=3, stride=1, padding=1)(n.cuda()).cpu().numpy()
+    assert np.array_equal(avg.view(np.uint32), lo.pool_counts(n_np, 'avg', 3).view(np.uint32))
+    kern = (torch.tensor([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=torch.float) / 16).reshape(1, 1, 3, 3).cuda()
+    wgt = Fn.conv2d(n.reshape(36, 1, 20, 24).cuda(), kern, padding=1).reshape(4, 9, 20, 24).cpu().numpy()
+    assert np.array_equal(wgt.view(np.uint32), lo.pool_counts(n_np, 'weighted').view(np.uint32))
+    # the slope's conv1d on k/9-valued inputs: float32 subtraction of the two outer taps, or TF32-rounded inputs?
+    yp = torch.from_numpy(avg)
+    padded = Fn.pad(yp, (0, 0, 0, 0, 1, 1), mode='reflect')
+    flat = torch.einsum('bkhw->bhwk', padded).reshape(4 * 20 * 24, 1, 11).cuda()
+    xy = torch.tensor([-1.0, 0.0, 1.0], device='cuda').repeat(1, 1, 1)
+    got = Fn.conv1d(flat, xy, padding=0).view(4, 20, 24, 9).permute(0, 3, 1, 2).cpu().numpy()
+    want = np.zeros_like(avg)
+    want[:, 1:-1] = avg[:, 2:] - avg[:, :-2]
+    assert np.array_equal(got.view(np.uint32), want.astype(np.float32).view(np.uint32))
