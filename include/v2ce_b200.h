@@ -84,6 +84,11 @@ typedef struct v2ce_ldati_params {
   int32_t pooling_kernel_size; /* odd; 'avg' only                                                                  */
 } v2ce_ldati_params;
 
+/* Host-only guards for bindings that mirror the struct (ctypes, cgo, JNI): its size in this build, and the argument
+ * checks every LDATI entry point applies (0 or a negative error code; message in v2ce_last_error()). */
+size_t v2ce_ldati_params_size(void);
+int v2ce_ldati_params_validate(const v2ce_ldati_params* p);
+
 /* Workspace needed by v2ce_ldati_count (also holds the scan results v2ce_ldati_emit reads). */
 int v2ce_ldati_count_workspace_bytes(const v2ce_ldati_params* p, size_t* bytes);
 /* Additional workspace needed by v2ce_ldati_emit for `total_events` events. */

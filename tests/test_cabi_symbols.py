@@ -69,3 +69,38 @@ def test_host_schedule_matches_oracle():
     fr = synth.make_video(5, 40, 52, seed=1)
     assert np.array_equal(drv.image_pre_processing(fr, 40).numpy(), po.preprocess(fr, 40))
     assert drv.frame_offset_us(7, 30) == po.frame_offset_us(7, 30)
+
+
+def test_ldati_params_mirror_matches_the_c_struct():
+    """The ctypes mirror of v2ce_ldati_params must have the C struct's size, and its LAST fields must land where the
+    library reads them: the library's own argument check accepts a valid struct and names the field we then corrupt."""
+    import ctypes
+    from v2ce_toolbox_b200 import _lib, ldati
+    lib = _lib.load()
+    assert lib.v2ce_ldati_params_size() == ctypes.sizeof(_lib.LdatiParams)
+    p = ldati.make_params(2, 8, 12, fps=30, flavor='cpu', device='cpu', additional_events_strategy='slope',
+                          bidirectional=True, pooling_type='avg', pooling_kernel_size=5)
+    assert lib.v2ce_ldati_params_validate(ctypes.byref(p)) == 0
+    assert (p.multi_events, p.bidirectional, p.pooling, p.pooling_kernel_size) == (1, 1, 2, 5)
+    p.pooling_kernel_size = 4
+    assert lib.v2ce_ldati_params_validate(ctypes.byref(p)) != 0 and b'pooling_kernel_size' in lib.v2ce_last_error()
+    p.pooling_kernel_size, p.pooling = 5, 7
+    assert lib.v2ce_ldati_params_validate(ctypes.byref(p)) != 0 and b'pooling must be' in lib.v2ce_last_error()
+    p.pooling, p.bidirectional = 0, 3
+    assert lib.v2ce_ldati_params_validate(ctypes.byref(p)) != 0 and b'bidirectional' in lib.v2ce_last_error()
+    p.bidirectional, p.multi_events = 0, 9
+    assert lib.v2ce_ldati_params_validate(ctypes.byref(p)) != 0 and b'multi_events' in lib.v2ce_last_error()
+    p.multi_events, p.key_span = 1, 0
+    assert lib.v2ce_ldati_params_validate(ctypes.byref(p)) != 0 and b'key_span' in lib.v2ce_last_error()
+
+
+def test_image_units_argument_checks_run_without_a_gpu():
+    """The host-side checks of v2ce_image_units fire before any launch: binding arity and error text, on CPU."""
+    from v2ce_toolbox_b200 import _lib
+    lib = _lib.load()
+    assert lib.v2ce_image_units(None, 1, 17, 260, 346, 260, 346, None, None) != 0
+    assert b'NULL' in lib.v2ce_last_error()
+    one = ctypes_buffer = (__import__('ctypes').c_uint8 * 16)()
+    out = (__import__('ctypes').c_float * 16)()
+    assert lib.v2ce_image_units(one, 1, 1, 4, 4, 4, 4, out, None) != 0 and b'window geometry' in lib.v2ce_last_error()
+    assert lib.v2ce_image_units(one, 1, 2, 1, 4, 4, 4, out, None) != 0 and b'frame geometry' in lib.v2ce_last_error()

@@ -35,6 +35,8 @@ _SIGNATURES = {
     'v2ce_last_error': (c_char_p, []),
     'v2ce_version': (c_int, []),
     'v2ce_device_check': (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    'v2ce_ldati_params_size': (c_size_t, []),
+    'v2ce_ldati_params_validate': (c_int, [POINTER(LdatiParams)]),
     'v2ce_ldati_count_workspace_bytes': (c_int, [POINTER(LdatiParams), POINTER(c_size_t)]),
     'v2ce_ldati_emit_workspace_bytes': (c_int, [POINTER(LdatiParams), c_int64, POINTER(c_size_t)]),
     'v2ce_ldati_count': (c_int, [c_void_p, POINTER(LdatiParams), c_void_p, c_size_t, c_void_p, c_void_p]),
@@ -88,6 +90,9 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.v2ce_ldati_params_size() != ctypes.sizeof(LdatiParams):
+        raise V2ceError(f'v2ce_ldati_params is {lib.v2ce_ldati_params_size()} bytes in {LIB_PATH} but the ctypes mirror has '
+                        f'{ctypes.sizeof(LdatiParams)}: rebuild the library (python -c "import __graft_entry__ as g; g.build()")')
     _lib = lib
     return lib
 

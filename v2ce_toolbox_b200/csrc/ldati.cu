@@ -1038,6 +1038,10 @@ static int validate(const v2ce_ldati_params* p) {
 using namespace v2ce;
 using namespace v2ce::ldati;
 
+extern "C" size_t v2ce_ldati_params_size(void) { return sizeof(v2ce_ldati_params); }
+
+extern "C" int v2ce_ldati_params_validate(const v2ce_ldati_params* p) { return validate(p); }
+
 extern "C" int v2ce_ldati_count_workspace_bytes(const v2ce_ldati_params* p, size_t* bytes) {
   if (int e = validate(p)) return e;
   V2CE_REQUIRE(bytes != nullptr, "bytes is NULL");
