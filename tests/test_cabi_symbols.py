@@ -100,7 +100,7 @@ def test_image_units_argument_checks_run_without_a_gpu():
     lib = _lib.load()
     assert lib.v2ce_image_units(None, 1, 17, 260, 346, 260, 346, None, None) != 0
     assert b'NULL' in lib.v2ce_last_error()
-    one = ctypes_buffer = (__import__('ctypes').c_uint8 * 16)()
-    out = (__import__('ctypes').c_float * 16)()
+    import ctypes
+    one, out = (ctypes.c_uint8 * 16)(), (ctypes.c_float * 16)()
     assert lib.v2ce_image_units(one, 1, 1, 4, 4, 4, 4, out, None) != 0 and b'window geometry' in lib.v2ce_last_error()
     assert lib.v2ce_image_units(one, 1, 2, 1, 4, 4, 4, out, None) != 0 and b'frame geometry' in lib.v2ce_last_error()
