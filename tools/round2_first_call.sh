@@ -28,6 +28,7 @@ timeout 240 ncu --set full --clock-control none --import-source on -k regex:'hea
 
 # 5. the drop-in CLI end to end with the new host side (prefetch, background batches, threaded encode, npz sink)
 timeout 180 python tools/cli_e2e.py 321 > "$OUT/cli_e2e.txt" 2>&1
+timeout 120 python tools/sink_bench.py 2 > "$OUT/sink_bench.txt" 2>&1
 grep -E "frame-pairs/s" "$OUT/cli_e2e.txt"
 
 # 6. per-layer times and the bench line
