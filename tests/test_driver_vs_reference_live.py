@@ -69,3 +69,69 @@ def test_window_schedule_and_tiles_equal_reference_arithmetic():
         # a remainder of 0 with total % 346 != 0 keeps the whole pulled-back tile (`out[..., -0:]` in the reference,
         # v2ce.py:120-127): the driver comparison above ('pano', 20, 2, 26, 40, 20) covers that quirk end to end
         assert sum((k if k else width) for _, _, k in tiles) == total
+
+
+def _write_mp4(path, n_frames, H, W, seed=0):
+    import cv2
+    frames = synth.make_video(n_frames, H, W, seed=seed)
+    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*'mp4v'), 30, (W, H))
+    for f in frames:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    vw.release()
+    return frames
+
+
+def test_video_reader_equals_reference_reader(tmp_path):
+    """scripts/video_reader.py as the CLI uses it (v2ce.py:333-335,170): same frame count and the same gray frames for
+    the index patterns the driver issues -- consecutive windows, the one-frame overlap between windows, a pulled-back
+    window (a backward seek) -- although this reader decodes consecutive indices sequentially where the reference
+    re-seeks before every frame (video_reader.py:307)."""
+    import sys
+    from v2ce_toolbox_b200.scripts.video_reader import VideoReader
+    ref_mod = sys.modules.get('_v2ce_ref.video_reader')
+    if ref_mod is None:
+        rh.main_module()
+        ref_mod = sys.modules['_v2ce_ref.video_reader']
+    path = tmp_path / 'clip.mp4'
+    _write_mp4(path, 40, 64, 96)
+    ours, ref = VideoReader(str(path), color_mode='GRAY'), ref_mod.VideoReader(str(path), color_mode='GRAY')
+    assert ours.frame_count == ref.frame_count == 40
+    assert (ours.width, ours.height) == (ref.width, ref.height) == (96, 64)
+    assert ours.fps == ref.fps
+    for idx in (range(0, 17), range(16, 33), range(23, 40), range(5, 8), [39], range(0, 40)):
+        a, b = ours.read_frames_at_indices(idx), ref.read_frames_at_indices(idx)
+        assert a.dtype == b.dtype == np.uint8 and a.shape == b.shape == (len(idx), 64, 96)
+        assert np.array_equal(a, b), f'indices {list(idx)[:3]}...'
+    ours.frame_count = 20                                     # --max_frame_num (v2ce.py:335)
+    assert ours.frame_count == 20
+    ours.close()
+
+
+def test_cli_flags_equal_the_reference_parser():
+    """Drop-in boundary: every flag of the reference's argparse block (v2ce.py:283-302), with its option
+    strings, type, default, nargs and const, exists unchanged in the product's parser; the product adds only --seed."""
+    import ast
+    import os
+    from v2ce_toolbox_b200 import v2ce as drv
+    src = open(os.path.join(rh.REF_ROOT, 'v2ce.py')).read()
+    ref = {}
+    for node in ast.walk(ast.parse(src)):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr == 'add_argument':
+            flags = tuple(a.value for a in node.args if isinstance(a, ast.Constant))
+            kw = {}
+            for k in node.keywords:
+                if k.arg == 'help':
+                    continue
+                kw[k.arg] = k.value.id if isinstance(k.value, ast.Name) else ast.literal_eval(k.value)
+            ref[flags] = kw
+    assert len(ref) >= 18
+    ours = {tuple(a.option_strings): a for a in drv.build_parser()._actions if a.option_strings and a.dest != 'help'}
+    for flags, kw in ref.items():
+        assert flags in ours, f'missing flag {flags}'
+        a = ours[flags]
+        assert a.default == kw.get('default'), (flags, a.default, kw.get('default'))
+        want_type = kw.get('type')
+        got_type = getattr(a.type, '__name__', None) if a.type is not None else None
+        assert got_type == want_type, (flags, got_type, want_type)
+        assert a.nargs == kw.get('nargs') and a.const == kw.get('const'), flags
+    assert set(ours) - set(ref) == {('--seed',)}
