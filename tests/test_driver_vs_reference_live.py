@@ -135,3 +135,26 @@ def test_cli_flags_equal_the_reference_parser():
         assert got_type == want_type, (flags, got_type, want_type)
         assert a.nargs == kw.get('nargs') and a.const == kw.get('const'), flags
     assert set(ours) - set(ref) == {('--seed',)}
+
+
+def test_drop_in_signatures_equal_the_reference():
+    """Same names, positional order and defaults for every callable of the boundary; the product may add
+    keyword-only extensions (seed / frame_base / draws / flavor on sample_voxel_statistical) and nothing else."""
+    import inspect
+    from v2ce_toolbox_b200 import v2ce as drv
+    from v2ce_toolbox_b200.scripts import LDATI as our_ldati
+    main, ref_ldati = rh.main_module(), rh.ldati_module()
+
+    def params(fn):
+        return [(p.name, p.default) for p in inspect.signature(fn).parameters.values()
+                if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+
+    for name in ('get_trained_mode', 'image_pre_processing', 'infer_center_image_unit', 'infer_pano_image_unit',
+                 'video_to_voxels', 'merge_voxels', 'write_event_frame_video', 'SBool'):
+        assert params(getattr(drv, name)) == params(getattr(main, name)), name
+    assert params(our_ldati.sample_voxel_statistical) == params(ref_ldati.sample_voxel_statistical)
+    extra = [p.name for p in inspect.signature(our_ldati.sample_voxel_statistical).parameters.values()
+             if p.kind == p.KEYWORD_ONLY]
+    assert extra == ['seed', 'frame_base', 'draws', 'flavor']
+    from v2ce_toolbox_b200.scripts.v2ce_3d import V2ce3d
+    assert params(V2ce3d.__init__)[1:] == params(rh.V2ce3d().__init__)[1:]
