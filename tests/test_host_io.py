@@ -158,3 +158,20 @@ def test_background_batches_equal_inline_batches(tmp_path):
     assert len(inline) == len(threaded)
     for (a, la), (b, lb) in zip(inline, threaded):
         assert la == lb and bool((a == b).all())
+
+
+def test_percentile_from_order_statistics_equals_numpy():
+    """Host half of the exact percentile (v2ce.py:262-264): the device hands back the two neighbouring order statistics,
+    the host interpolates like np.percentile -- also for the gray preview, whose array is every value three times."""
+    from v2ce_toolbox_b200 import event_frames as ef
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 7, 100, 4097):
+        v = np.sort((rng.random(n) * 12).astype(np.float32))
+        for mult in (1, 3):
+            full = np.sort(np.repeat(v, mult)).astype(np.float64)
+            for q in (0, 1, 37, 50, 90, 98, 99, 100):
+                vi = (n * mult - 1) * (q / 100.0)
+                lo = int(np.floor(vi))
+                hi = min(lo + 1, n * mult - 1)
+                got = ef.percentile_from_order_statistics(n, mult, q, np.float32(full[lo]), np.float32(full[hi]))
+                assert got == np.percentile(full, q), (n, mult, q)

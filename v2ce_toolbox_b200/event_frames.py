@@ -34,6 +34,15 @@ def numpy_lerp(a, b, t):
     return float(a + d * t if t < 0.5 else b - d * (1 - t))
 
 
+def percentile_from_order_statistics(n_positive, multiplicity, percentile, value_lo, value_hi):
+    """np.percentile(v, percentile) for the array v = the positive sums, each repeated `multiplicity` times
+    (np.repeat(efs, 3, axis=1) in gray mode, v2ce.py:260), given the two order statistics the device selected:
+    value_lo = v_sorted[floor(vi)], value_hi = v_sorted[min(floor(vi) + 1, len - 1)] with vi = (len - 1) * percentile / 100.
+    Host part of v2ce.py:262-264: numpy's float64 linear interpolation."""
+    vi = (n_positive * multiplicity - 1) * (percentile / 100.0)
+    return numpy_lerp(value_lo, value_hi, vi - math.floor(vi))
+
+
 def upper_bound(sums, percentile=98, ceil=10, keep_polarity=True):
     """min(np.percentile(sums[sums>0], percentile), ceil) (v2ce.py:262-264) by radix select on the device."""
     lib = _lib.load()
@@ -47,11 +56,9 @@ def upper_bound(sums, percentile=98, ceil=10, keep_polarity=True):
     npos, lo, bits_lo, bits_hi = (int(x) for x in res.cpu().numpy())
     if npos == 0:
         raise ValueError('event frames hold no positive value: np.percentile of an empty array')
-    vi = (npos * mult - 1) * (percentile / 100.0)
-    t = vi - math.floor(vi)
     a = np.array([bits_lo], dtype=np.uint32).view(np.float32)[0]
     b = np.array([bits_hi], dtype=np.uint32).view(np.float32)[0]
-    return min(numpy_lerp(a, b, t), ceil)
+    return min(percentile_from_order_statistics(npos, mult, percentile, a, b), ceil)
 
 
 def normalize(sums, ub, keep_polarity=True, out=None):

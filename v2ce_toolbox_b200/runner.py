@@ -21,7 +21,6 @@ and the tests drive it; it composes the same C-ABI calls as the one-by-one publi
 (``V2ce3d.__call__``, ``event_frames.*``, ``LdatiEngine.count/emit``).
 """
 import ctypes
-import math
 
 import numpy as np
 import torch
@@ -200,10 +199,9 @@ class BatchRunner:
                 if npos == 0:
                     raise ValueError('event frames hold no positive value: np.percentile of an empty array')
                 mult = 1 if self.keep else 3
-                vi = (npos * mult - 1) * (self.percentile / 100.0)
                 a = np.array([bits_lo], dtype=np.uint32).view(np.float32)[0]
                 b = np.array([bits_hi], dtype=np.uint32).view(np.float32)[0]
-                t.ub = min(_ef.numpy_lerp(a, b, vi - math.floor(vi)), self.ceil)
+                t.ub = min(_ef.percentile_from_order_statistics(npos, mult, self.percentile, a, b), self.ceil)
                 fr = self._buf(self._fr_dev, slot, n * H * W * 3)
                 frames = _ef.normalize(t.sums, t.ub, self.keep, out=fr[:n * H * W * 3].view(n, H, W, 3))
                 self.launches += 1
