@@ -175,3 +175,43 @@ def test_percentile_from_order_statistics_equals_numpy():
                 hi = min(lo + 1, n * mult - 1)
                 got = ef.percentile_from_order_statistics(n, mult, q, np.float32(full[lo]), np.float32(full[hi]))
                 assert got == np.percentile(full, q), (n, mult, q)
+
+
+@pytest.mark.parametrize('fps', [24, 25, 30, 50, 60, 120, 240, 1000])
+def test_ldati_params_constants_equal_the_oracle(fps):
+    """The scalar constants the product hands to the kernels (ldati.make_params) against the oracle's (oracle.Consts,
+    pinned to the reference): every reciprocal, step and bin start, bit for bit, plus the sort-key window."""
+    from oracle import ldati_oracle as lo
+    from v2ce_toolbox_b200 import ldati
+    p = ldati.make_params(3, 8, 12, fps=fps, t0=0, seed=5, frame_base=2, flavor='cpu', device='cpu')
+    k = lo.Consts(fps, 0, 'cpu')
+    f32 = np.float32
+    assert (p.fps64, p.nbins64, p.r_fps64, p.r_nbins64) == (float(fps), 9.0, k.r_fps64, k.r_c64)
+    for got, want in ((p.r_fps32, k.r_fps32), (p.r_nbins32, k.r_c32), (p.vs32, k.vs32), (p.inv_vs32, k.inv_vs32),
+                      (p.vs2_32, f32(k.vs2)), (p.r_vs2_32, k.r_vs2_32), (p.r6_32, k.r6_32), (p.eps6, k.eps6),
+                      (p.eps8, k.eps8), (p.six32, f32(6)), (p.fps32, f32(fps)), (p.nbins32, f32(9))):
+        assert f32(got).view(np.uint32) == f32(want).view(np.uint32)
+    got_bs = np.array(p.binstart_t0_32[:9], dtype=np.float32)
+    assert np.array_equal(got_bs.view(np.uint32), k.binstart_t0_32.view(np.uint32))
+    one_bin = int(np.ceil(1e6 / fps / 9))
+    for c in range(9):
+        assert p.bin_base_us[c] == int(np.floor(float(k.binstart_t0_32[c]) * 1e6))
+        # every in-contract timestamp of bin c lands inside the key window [1, 2^key_bits)
+        assert p.key_span >= one_bin + 2 * ldati.KEY_BIAS
+    assert (p.true_div, p.multi_events, p.bidirectional, p.pooling, p.frame_base, p.seed) == (1, 1, 0, 0, 2, 5)
+    wide = ldati.make_params(3, 8, 12, fps=fps, flavor='cpu', device='cpu', bidirectional=True,
+                             additional_events_strategy='random')
+    assert wide.key_span >= 1_000_000 and wide.bin_base_us[0] < 0 and wide.multi_events == 2 and wide.bidirectional == 1
+
+
+def test_split_frames_and_status_check():
+    from v2ce_toolbox_b200 import V2ceError, ldati
+    ev = np.zeros(10, ldati.EVENT_DTYPE)
+    ev['timestamp'] = np.arange(10)
+    seg = np.zeros((3, 9), np.int64)
+    seg[0, 0], seg[0, 8], seg[2, 4] = 2, 3, 5
+    parts = ldati.split_frames(ev.view(np.uint8), seg)
+    assert [len(x) for x in parts] == [5, 0, 5] and parts[2]['timestamp'][0] == 5 and isinstance(parts[0], np.recarray)
+    ldati.check_status(np.array([0, 3, 0, 0], np.int32))                 # NaN timestamps alone are legal (INT64_MIN)
+    with pytest.raises(V2ceError):
+        ldati.check_status(np.array([1, 0, 0, 0], np.int32))
