@@ -215,3 +215,27 @@ def test_split_frames_and_status_check():
     ldati.check_status(np.array([0, 3, 0, 0], np.int32))                 # NaN timestamps alone are legal (INT64_MIN)
     with pytest.raises(V2ceError):
         ldati.check_status(np.array([1, 0, 0, 0], np.int32))
+
+
+def test_v2ce3d_checkpoint_handling_without_a_device():
+    """load_state_dict accepts the reference's layout (BatchNorm's num_batches_tracked entries are dropped), nothing is
+    built before a CUDA device is named, and there is no CPU path."""
+    import torch
+    from oracle import synth
+    from v2ce_toolbox_b200 import V2ceError
+    from v2ce_toolbox_b200.scripts.v2ce_3d import V2ce3d
+    sd = synth.make_state_dict(0, 'reference')
+    sd['UNet.encoders.0.bn1.num_batches_tracked'] = torch.tensor(7)
+    m = V2ce3d()
+    assert m.load_state_dict({k: v.double() for k, v in sd.items()}) is m
+    got = m.state_dict()
+    assert 'UNet.encoders.0.bn1.num_batches_tracked' not in got
+    assert set(got) == {k for k in sd if not k.endswith('num_batches_tracked')}
+    assert all(v.dtype == torch.float32 and v.device.type == 'cpu' for v in got.values())
+    assert m.eval() is m and m.to(None) is m
+    with pytest.raises(V2ceError):
+        m.to('cpu')
+    with pytest.raises(V2ceError):
+        m(torch.zeros(1, 16, 2, 8, 8))                      # CPU tensor: no fallback
+    with pytest.raises(V2ceError):
+        V2ce3d(in_channels=3)
