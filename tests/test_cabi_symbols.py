@@ -104,3 +104,36 @@ def test_image_units_argument_checks_run_without_a_gpu():
     one, out = (ctypes.c_uint8 * 16)(), (ctypes.c_float * 16)()
     assert lib.v2ce_image_units(one, 1, 1, 4, 4, 4, 4, out, None) != 0 and b'window geometry' in lib.v2ce_last_error()
     assert lib.v2ce_image_units(one, 1, 2, 1, 4, 4, 4, out, None) != 0 and b'frame geometry' in lib.v2ce_last_error()
+
+
+def test_ldati_workspace_queries_are_host_only_and_consistent():
+    """Workspace sizing runs without a device: the count workspace grows by exactly the per-pixel-bin count planes when
+    the slope is fitted on pooled counts, the emit workspace grows with the event count and with 64-bit elements."""
+    import ctypes
+    from v2ce_toolbox_b200 import _lib, ldati
+    lib = _lib.load()
+
+    def count_bytes(**kw):
+        p = ldati.make_params(24, 260, 346, flavor='cpu', device='cpu', **kw)
+        n = ctypes.c_size_t()
+        assert lib.v2ce_ldati_count_workspace_bytes(ctypes.byref(p), ctypes.byref(n)) == 0
+        return n.value
+
+    def emit_bytes(total, **kw):
+        p = ldati.make_params(24, 260, 346, flavor='cpu', device='cpu', **kw)
+        n = ctypes.c_size_t()
+        assert lib.v2ce_ldati_emit_workspace_bytes(ctypes.byref(p), total, ctypes.byref(n)) == 0
+        return n.value
+
+    base = count_bytes()
+    planes = 24 * 2 * 9 * 260 * 346 * 4
+    assert 0 < base < 64 << 20
+    assert planes <= count_bytes(pooling_type='weighted') - base < planes + 4096
+    assert count_bytes(pooling_type='avg', additional_events_strategy='none') == base      # pooling only feeds 'slope'
+    small, big = emit_bytes(1_000_000), emit_bytes(100_000_000)
+    assert 8 * 1_000_000 <= small < big and big >= 8 * 100_000_000
+    assert emit_bytes(1_000_000, additional_events_strategy='random') >= small + 8 * 1_000_000 - 4096   # 64-bit elements
+    p = ldati.make_params(24, 260, 346, flavor='cpu', device='cpu')
+    n = ctypes.c_size_t()
+    assert lib.v2ce_ldati_emit_workspace_bytes(ctypes.byref(p), 1 << 31, ctypes.byref(n)) != 0
+    assert b'split the frames' in lib.v2ce_last_error()
