@@ -137,3 +137,21 @@ def test_ldati_workspace_queries_are_host_only_and_consistent():
     n = ctypes.c_size_t()
     assert lib.v2ce_ldati_emit_workspace_bytes(ctypes.byref(p), 1 << 31, ctypes.byref(n)) != 0
     assert b'split the frames' in lib.v2ce_last_error()
+
+
+def test_entry_points_fail_loudly_without_a_device():
+    """No CUDA device (this test is skipped where one exists): the library reports an error code and a message; it never
+    crashes and there is nothing to fall back to."""
+    import ctypes
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a CUDA device is present')
+    from v2ce_toolbox_b200 import _lib
+    lib = _lib.load()
+    a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.v2ce_device_check(0, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)) < 0 and lib.v2ce_last_error()
+    h = ctypes.c_void_p()
+    assert lib.v2ce_model_create(ctypes.byref(h), 0) < 0 and not h.value
+    assert lib.v2ce_ef_accumulate(None, 1, 4, 4, 1, None, None) < 0 and b'NULL' in lib.v2ce_last_error()
+    with pytest.raises(_lib.V2ceError):
+        _lib.check(lib.v2ce_model_create(ctypes.byref(h), 0))
