@@ -75,6 +75,18 @@ def _worker(rank, world, port, out_dir):
         merged, counts = vdist.gather_event_shards(t, n if rank == 0 else 0)
         if rank == 0:
             assert merged.numel() == 1000 * 13 and counts == [1000, 0]
+        # event-frame sums of a sharded clip: ragged leading dimension, one rank possibly without any window
+        for rows_per_rank in ([5, 3], [4, 0], [0, 2]):
+            k = rows_per_rank[rank]
+            base = sum(rows_per_rank[:rank])
+            rows = (torch.arange(k * 2 * 3 * 4, dtype=torch.float32).reshape(k, 2, 3, 4) + 1000 * base)
+            got = vdist.gather_row_shards(rows)
+            if rank == 0:
+                want = torch.cat([torch.arange(r * 24, dtype=torch.float32).reshape(r, 2, 3, 4) + 1000 * sum(rows_per_rank[:i])
+                                  for i, r in enumerate(rows_per_rank)], dim=0)
+                assert got.shape == want.shape and torch.equal(got, want)
+            else:
+                assert got is None
     finally:
         dist.destroy_process_group()
 

@@ -73,3 +73,47 @@ def test_sharded_clip_equals_single_process(case, tmp_path):
     assert got.dtype.itemsize == 13 and len(got) == len(want) and len(want) > 0
     for f in ('timestamp', 'x', 'y', 'polarity'):
         assert np.array_equal(got[f], want[f]), (case, f)
+
+
+def _preview_worker(rank, world, port, out_dir, case):
+    import torch.distributed as dist
+    from v2ce_toolbox_b200 import dist as vdist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        n_frames, H, W, infer_type, width, height, bs = CASES[case]
+        frames = synth.make_video(n_frames, H, W, seed=5)
+        preview = {}
+        ev, n = vdist.stream_clip_sharded(_model(31, dev), FakeVideoReader(frames), n_frames, world, rank, seq_len=16,
+                                          batch_size=bs, infer_type=infer_type, width=width, height=height, fps=30, seed=9,
+                                          device=dev, preview=preview, ceil=10, upper_bound_percentile=98)
+        if rank == 0:
+            np.save(os.path.join(out_dir, f'{case}_frames.npy'), preview['frames'])
+            np.save(os.path.join(out_dir, f'{case}_ub.npy'), np.float64(preview['upper_bound']))
+            np.save(os.path.join(out_dir, f'{case}_events.npy'), ev)
+        else:
+            assert 'frames' not in preview
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.xfail(strict=False, reason='first hardware run pending (added after the GPU budget of round 1)')
+@pytest.mark.parametrize('case,world', [('center', 1), ('center', 2), ('pano', 2)])
+def test_sharded_preview_equals_single_process(case, world, tmp_path):
+    """the event-frame preview of a sharded clip -- per-rank sums gathered to rank 0, ONE clip-global
+    percentile -- is the single-process preview, byte for byte (world 1 runs the same code on one GPU)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
+    import torch.multiprocessing as mp
+    from v2ce_toolbox_b200 import v2ce as drv
+    n_frames, H, W, infer_type, width, height, bs = CASES[case]
+    mp.spawn(_preview_worker, args=(world, _free_port(), str(tmp_path), case), nprocs=world, join=True)
+    frames = synth.make_video(n_frames, H, W, seed=5)
+    res = drv.stream_clip(_model(31, 'cuda:0'), vidcap=FakeVideoReader(frames), infer_type=infer_type, seq_len=16,
+                          width=width, height=height, batch_size=bs, fps=30, seed=9, write_event_frames=True,
+                          ceil=10, upper_bound_percentile=98)
+    assert float(np.load(tmp_path / f'{case}_ub.npy')) == res.ef_upper_bound
+    assert np.array_equal(np.load(tmp_path / f'{case}_frames.npy'), res.ef_frames)
+    assert np.array_equal(np.load(tmp_path / f'{case}_events.npy').view(np.uint8), res.event_stream.view(np.uint8))

@@ -77,6 +77,27 @@ def gather_event_shards(events_u8, n_events, group=None, dst=0):
     return None, counts
 
 
+def gather_row_shards(rows, group=None, dst=0):
+    """rows: (n, ...) tensor whose leading length differs per rank (device for NCCL, CPU for gloo).  Returns on `dst`
+    the concatenation over ranks, in rank order, None elsewhere -- the event-frame sums of a sharded clip
+    (the preview's percentile is global over the clip, v2ce.py:262-264, so rank 0 needs all of them)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = rows.device
+    cnt = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    pad = torch.zeros((mx,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=dev)
+    pad[:rows.shape[0]] = rows
+    if rank == dst:
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.gather(pad, bufs, dst=dst, group=group)
+        return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+    dist.gather(pad, None, dst=dst, group=group)
+    return None
+
+
 def shard_schedule(starts, mode, b0, b1, batch_size, seq_len=16):
     """Batches [b0, b1) of a clip's window schedule (v2ce.window_schedule) as a clip of their own:
     (first frame, frame count, is_tail, index of the first frame pair, (window starts relative to `first`, mode)).
@@ -91,11 +112,27 @@ def shard_schedule(starts, mode, b0, b1, batch_size, seq_len=16):
     return first, frame_count, is_tail, w0 * seq_len, (np.asarray(starts[w0:w1]) - first, mode if is_tail else 0)
 
 
-def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=16, batch_size=1, to_host=True, **kw):
+def _preview_plane(frames_reader, kw):
+    """(H, W) of the voxel planes stream_clip produces for this reader and these settings."""
+    probe = np.asarray(frames_reader.read_frames_at_indices([0]))
+    height, width = kw.get('height', 260), kw.get('width', 346)
+    if kw.get('infer_type', 'center') == 'center':
+        return height, width
+    return height, int(probe.shape[-1] / probe.shape[-2] * height)       # pano: the resized frame's full width
+
+
+def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=16, batch_size=1, to_host=True,
+                        preview=None, **kw):
     """Run v2ce.stream_clip on this rank's contiguous share of the batches of a clip and gather the
     event shards on rank 0 (the shards never visit the host on their way).  `frames_reader` duck-types VideoReader.
     Returns (event_stream | None, total events); with to_host=False rank 0 gets the merged stream as a device uint8
-    tensor instead of a host recarray."""
+    tensor instead of a host recarray.
+
+    preview: a dict to receive the event-frame preview of the WHOLE clip on rank 0 (v2ce.py:241-280) --
+    ``preview['frames']`` uint8 (N,H,W,3) BGR and ``preview['upper_bound']``.  Every rank keeps the per-pair sums of its
+    shard on the device, rank 0 gathers them (0.72 MB per pair at 346x260), takes the clip-global percentile and
+    normalises: identical to the single-process preview.  The ceil / percentile / polarity settings are read from
+    **kw like stream_clip's."""
     from . import v2ce as drv
     starts, mode = drv.window_schedule(frame_count, seq_len)
     n_batches = -(-len(starts) // batch_size)
@@ -123,15 +160,29 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
 
     shard = _Shard()
     dev = kw.pop('device', torch.device('cuda', torch.cuda.current_device()))
+    sums = None
     if shard.frame_count > 1:
         res = drv.stream_clip(model, vidcap=shard, seq_len=seq_len, batch_size=batch_size,
                               pair_base=shard.pair_base, device=dev, write_event_frames=False, schedule=shard.schedule,
-                              events_to_host=False, **kw)
+                              events_to_host=False, keep_event_frame_sums=preview is not None, **kw)
         n = res.n_events
         ev = res.event_stream_dev if n else torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev)
+        sums = res.ef_sums_dev
     else:
         ev, n = torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev), 0
     out, counts = gather_event_shards(ev, n)
+    if preview is not None:
+        from . import event_frames as _ef
+        keep = kw.get('keep_polarity', True)
+        if sums is None:                       # a rank without windows still takes part in the collective
+            h, w = _preview_plane(frames_reader, kw)
+            sums = torch.zeros((0, 2 if keep else 1, h, w), dtype=torch.float32, device=dev)
+        all_sums = gather_row_shards(sums.contiguous())
+        if all_sums is not None:
+            with torch.cuda.device(dev):
+                ub = _ef.upper_bound(all_sums, kw.get('upper_bound_percentile', 98), kw.get('ceil', 10), keep)
+                preview['frames'] = _ef.normalize(all_sums, ub, keep).cpu().numpy()
+                preview['upper_bound'] = ub
     if out is not None:
         from .ldati import EVENT_DTYPE
         from .sink import to_host as _sink

@@ -287,6 +287,7 @@ class ClipResult:
         self.ef_upper_bound = ef_upper_bound
         self.n_pairs = n_pairs
         self.event_stream_dev = None
+        self.ef_sums_dev = None            # (n_pairs, 2 | 1, H, W) float32 per-pair sums (keep_event_frame_sums=True)
         self.n_events = 0 if event_stream is None else len(event_stream)
 
 
@@ -316,7 +317,7 @@ def _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width
 def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_len=16, width=346, height=260,
                 batch_size=1, fps=30, ceil=10, upper_bound_percentile=98, keep_polarity=True,
                 write_event_frames=True, seed=0, pair_base=0, device=None, schedule=None, events_to_host=True,
-                device_resize=None):
+                device_resize=None, keep_event_frame_sums=False):
     """Device-resident, pipelined version of v2ce.py:322-372 (runner.BatchRunner: the network of batch i+1 runs over
     the event frames + LDATI of batch i, results leave on a copy stream).  Returns ClipResult with the concatenated
     event stream (timestamps offset per frame, v2ce.py:365) and the uint8 BGR preview frames (clip-global percentile,
@@ -368,7 +369,7 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
         pair_idx = pair_base
         prev = None
         for x, is_last in _background(batches):
-            t = runner.submit(x.pin_memory(), pair_idx, keep_sums=write_event_frames,
+            t = runner.submit(x.pin_memory(), pair_idx, keep_sums=write_event_frames or keep_event_frame_sums,
                               trim_last_window_to=mode if (is_last and mode != 0) else 0)
             pair_idx += t.n_pairs
             if prev is not None:
@@ -377,13 +378,15 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
         if prev is not None:
             runner.wait(prev)
         events_dev, stream = runner.collected_events(to_host=events_to_host)   # False: ClipResult.event_stream is None
-        frames, ub = None, None
-        if write_event_frames:
+        frames, ub, sums = None, None, None
+        if write_event_frames or keep_event_frame_sums:
             torch.cuda.current_stream(device).wait_stream(runner.post_stream)
             sums = torch.cat(runner.sums, dim=0) if len(runner.sums) > 1 else runner.sums[0]
+        if write_event_frames:
             ub = _ef.upper_bound(sums, upper_bound_percentile, ceil, keep_polarity)
             frames = _ef.normalize(sums, ub, keep_polarity).cpu().numpy()
     res = ClipResult(stream, frames, ub, pair_idx - pair_base)
+    res.ef_sums_dev = sums if keep_event_frame_sums else None   # a sharded clip takes its percentile over all ranks (dist.py)
     res.event_stream_dev = events_dev            # the same bytes on the device (dist.py gathers from here)
     res.n_events = 0 if events_dev is None else events_dev.numel() // 13
     return res
