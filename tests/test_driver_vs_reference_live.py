@@ -98,7 +98,9 @@ def test_video_reader_equals_reference_reader(tmp_path):
     assert ours.frame_count == ref.frame_count == 40
     assert (ours.width, ours.height) == (ref.width, ref.height) == (96, 64)
     assert ours.fps == ref.fps
-    for idx in (range(0, 17), range(16, 33), range(23, 40), range(5, 8), [39], range(0, 40)):
+    # range(-1, 16): the only window of a 16-frame clip starts at -1; both readers must resolve the
+    # negative seek the same way
+    for idx in (range(0, 17), range(16, 33), range(23, 40), range(5, 8), [39], range(0, 40), range(-1, 16)):
         a, b = ours.read_frames_at_indices(idx), ref.read_frames_at_indices(idx)
         assert a.dtype == b.dtype == np.uint8 and a.shape == b.shape == (len(idx), 64, 96)
         assert np.array_equal(a, b), f'indices {list(idx)[:3]}...'
