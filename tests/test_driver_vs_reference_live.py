@@ -31,7 +31,9 @@ class StandIn(torch.nn.Module):
         return x.repeat_interleave(10, dim=2) * (1.0 + 0.125 * self.calls) + ramp + pos
 
 
-CASES = [('center', 17, 1, 26, 40, 36), ('center', 20, 2, 26, 40, 36), ('center', 33, 1, 26, 40, 36),
+CASES = [('center', 16, 1, 26, 40, 36),                       # one window starting at frame -1
+         ('center', 2, 1, 26, 40, 36), ('center', 3, 2, 26, 40, 36),
+         ('center', 17, 1, 26, 40, 36), ('center', 20, 2, 26, 40, 36), ('center', 33, 1, 26, 40, 36),
          ('center', 36, 4, 26, 40, 36), ('center', 49, 3, 26, 40, 40), ('center', 18, 2, 26, 40, 30),
          ('center', 40, 2, 52, 80, 36),                       # resized 52x80 -> 26x40, then cropped
          ('pano', 18, 1, 26, 52, 20), ('pano', 20, 2, 26, 40, 20), ('pano', 35, 2, 26, 47, 20),
