@@ -34,7 +34,7 @@ def bind_to_gpu_numa(device_index):
             pynvml.nvmlShutdown()
         cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
         cpus &= os.sched_getaffinity(0)
-        if len(cpus) < 4:
+        if len(cpus) < 8:                     # a mask this small would crowd the rank's copy and decode threads
             return None
         os.sched_setaffinity(0, cpus)
         return sorted(cpus)
