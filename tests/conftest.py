@@ -29,6 +29,18 @@ def pytest_collection_modifyitems(config, items):
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 
+def record_measurement(kind, **fields):
+    """Append one measured figure (voxel deviations per shape, ...) to gpurun_out/measurements_r2.jsonl on the GPU box:
+    the stated tolerances in the tests are set from these."""
+    import json
+    try:
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', 'measurements_r2.jsonl'), 'a') as f:
+            f.write(json.dumps({'kind': kind, **fields}) + '\n')
+    except OSError:
+        pass
+
+
 @pytest.fixture(scope='session')
 def golden_meta():
     import json

@@ -99,7 +99,6 @@ def _preview_worker(rank, world, port, out_dir, case):
         dist.destroy_process_group()
 
 
-@pytest.mark.xfail(strict=False, reason='first hardware run pending (added after the GPU budget of round 1)')
 @pytest.mark.parametrize('case,world', [('center', 1), ('center', 2), ('pano', 2)])
 def test_sharded_preview_equals_single_process(case, world, tmp_path):
     """the event-frame preview of a sharded clip -- per-rank sums gathered to rank 0, ONE clip-global

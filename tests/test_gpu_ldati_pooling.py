@@ -1,32 +1,26 @@
 """GPU parity of LDATI's pooling_type 'weighted' / 'avg' (LDATI.py:176-183: the slope of a multi-event pixel-bin is
 fitted on spatially pooled counts) against the oracle and the reference goldens.
 
-Written after this round's GPU budget had been spent: the oracle is pinned to the reference (goldens + live
-differential tests) and a host build of the device function ``pooled_count`` equals the oracle, but the kernel route has
-not run on hardware.  It is therefore opt-in (V2CE_EXPERIMENTAL_POOLING=1) and these tests are ``xfail(strict=False)``
-until their first run on the B200 has been seen.
+The oracle is pinned to the reference (goldens + live differential tests).  First hardware run: round-1 driver box,
+16/16 green; the route is on by default since round 2.
 
 Flavour note: in the torch-CUDA flavour the reference pools with cuDNN.  'weighted' is exact in any arithmetic (dyadic
-weights on small integers); for 'avg' the oracle assumes float32 (not TF32) arithmetic in the slope's conv1d, which
-still has to be checked against torch-CUDA on the device (tests/test_gpu_torch_semantics.py is where that belongs)."""
+weights on small integers); for 'avg' the oracle assumes float32 (not TF32) arithmetic in the slope's conv1d --
+tests/test_gpu_torch_semantics.py::test_pooled_slope_ops_are_float32_on_cuda checks exactly that against torch-CUDA
+(green on the B200: torch runs those ops in float32)."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import ldati_oracle as lo, synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='first hardware run pending (added after the GPU budget of round 1)')]
+pytestmark = [pytest.mark.gpu]
 
 
 def _run(vox, **kw):
     from v2ce_toolbox_b200.scripts.LDATI import sample_voxel_statistical
     return sample_voxel_statistical(torch.as_tensor(vox).cuda(), **kw)
 
-
-@pytest.fixture(autouse=True)
-def _opt_in(monkeypatch):
-    monkeypatch.setenv('V2CE_EXPERIMENTAL_POOLING', '1')
 
 
 @pytest.mark.parametrize('pooling_type,kernel_size', [('weighted', 3), ('avg', 3), ('avg', 5)])
@@ -60,11 +54,9 @@ def test_pooling_cpu_flavour_against_reference_goldens(name, golden, golden_meta
     assert d.max() <= 1 and (d != 0).mean() <= 1e-3
 
 
-def test_pooling_needs_the_opt_in_and_an_odd_kernel(monkeypatch):
+def test_pooling_needs_an_odd_kernel():
     from v2ce_toolbox_b200.scripts.LDATI import sample_voxel_statistical
     y = torch.zeros(1, 2, 10, 4, 4, device='cuda')
     with pytest.raises(ValueError):
         sample_voxel_statistical(y, pooling_type='avg', pooling_kernel_size=4)
-    monkeypatch.setenv('V2CE_EXPERIMENTAL_POOLING', '0')
-    with pytest.raises(NotImplementedError):
-        sample_voxel_statistical(y, pooling_type='weighted')
+    assert [len(e) for e in sample_voxel_statistical(y, pooling_type='weighted')] == [0]

@@ -41,7 +41,6 @@ def test_stream_clip_events_and_frames_bit_exact_on_device_voxels(n_frames, bs):
     _check_stream_clip(n_frames, bs)
 
 
-@pytest.mark.xfail(strict=False, reason='first hardware run pending (added after the GPU budget of round 1)')
 @pytest.mark.parametrize('n_frames,bs', [(16, 1), (2, 1), (3, 2), (17, 4)])
 def test_stream_clip_tiny_clips(n_frames, bs):
     """Clips of one window or less: a 16-frame clip's only window starts at frame -1 and keeps 15 pairs (SURVEY.md

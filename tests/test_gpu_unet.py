@@ -9,6 +9,7 @@ import torch.nn.functional as F
 
 from oracle import synth
 from oracle.unet_oracle import UNetOracle
+from conftest import record_measurement
 
 pytestmark = pytest.mark.gpu
 
@@ -181,6 +182,7 @@ def test_forward_vs_fp32_oracle(init, shape):
         assert y.shape == ref.shape and (y >= 0).all()
         rel = float((y - ref).norm() / ref.norm())
         mx = float((y - ref).abs().max() / ref.abs().max())
+        record_measurement('voxel_vs_fp32_oracle', init=init, shape=list(shape), call=call, rel_l2=rel, max_abs_over_max=mx)
         assert rel <= 2e-2 and mx <= 5e-2, (init, shape, call, rel, mx)
     assert m.call_count() == 2 and orc.calls == 2
 
@@ -209,6 +211,8 @@ def test_forward_matches_reference_golden(golden, golden_meta):
             y = m(x).cpu().numpy()
             ref = g[f'{name}_y{call}']
             rel = np.linalg.norm(y - ref) / np.linalg.norm(ref)
+            record_measurement('voxel_vs_reference_golden', name=name, call=call, rel_l2=float(rel),
+                               max_abs_over_max=float(np.abs(y - ref).max() / np.abs(ref).max()))
             assert rel <= 2e-2, (name, call, rel)
 
 

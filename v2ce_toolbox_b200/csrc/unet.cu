@@ -824,8 +824,9 @@ extern "C" int v2ce_model_finalize(v2ce_model* m) {
       const std::string bn = L.bn;
       const std::vector<float>*g = find(m, bn + ".weight"), *b = find(m, bn + ".bias"), *mu = find(m, bn + ".running_mean"),
                               *var = find(m, bn + ".running_var");
-      if (!g || !b || !mu || !var || (int)g->size() != L.cout)
-        return set_error(V2CE_ERR_STATE, "missing BatchNorm tensors %s.*", L.bn);
+      if (!g || !b || !mu || !var || (int)g->size() != L.cout || (int)b->size() != L.cout ||
+          (int)mu->size() != L.cout || (int)var->size() != L.cout)
+        return set_error(V2CE_ERR_STATE, "missing or mis-sized BatchNorm tensors %s.* (expected %d channels)", L.bn, L.cout);
       for (int c = 0; c < L.cout; ++c) {
         const float sc = (*g)[c] / sqrtf((*var)[c] + kBnEps);
         scale[c] = sc;

@@ -55,47 +55,76 @@ def model_calls_before(first_batch, infer_type='center', tiles=1):
     return first_batch * (1 if infer_type == 'center' else tiles)
 
 
-def gather_event_shards(events_u8, n_events, group=None, dst=0):
-    """events_u8: 1-D uint8 tensor holding n_events*13 bytes (device for NCCL, CPU for gloo).
-    Returns on `dst` the concatenation of all shards in rank order (a uint8 tensor), None elsewhere.
-    Ranks own contiguous, increasing frame ranges, so concatenation by rank IS the time-ordered merge."""
+def init_process_group(backend='nccl', device=None, max_ctas=4, **kw):
+    """torch.distributed.init_process_group with the NCCL settings this path wants: the only collectives are tiny
+    count exchanges and point-to-point shard transfers that run UNDER the persistent conv CTAs of the next batch, so
+    NCCL gets at most `max_ctas` CTAs per operation (it would otherwise take up to 32 SMs' worth of channels away from
+    the network: forward time grew 9.8 -> 10.5 ms from 1 to 8 ranks in round 1)."""
+    if backend == 'nccl':
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = int(max_ctas)
+        opts.config.min_ctas = 1
+        return dist.init_process_group('nccl', device_id=device, pg_options=opts, **kw)
+    return dist.init_process_group(backend, **kw)
+
+
+def exchange_counts(n, group=None, device=None):
+    """One all_gather of this rank's count and ONE host read: the list of all ranks' counts."""
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    dev = events_u8.device
-    cnt = torch.tensor([n_events], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, cnt, group=group)
-    counts = [int(c.item()) for c in counts]
-    mx = max(max(counts), 1)
-    pad = torch.zeros(mx * EVENT_BYTES, dtype=torch.uint8, device=dev)
-    pad[:n_events * EVENT_BYTES] = events_u8[:n_events * EVENT_BYTES]
-    if rank == dst:
-        bufs = [torch.empty(mx * EVENT_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
-        dist.gather(pad, bufs, dst=dst, group=group)
-        return torch.cat([b[:c * EVENT_BYTES] for b, c in zip(bufs, counts)]), counts
-    dist.gather(pad, None, dst=dst, group=group)
-    return None, counts
+    mine = torch.tensor([int(n)], dtype=torch.int64, device=device)
+    every = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(every, mine, group=group)
+    return [int(v) for v in every.cpu().tolist()]
+
+
+def _gather_exact(flat, counts, unit, group, dst, out):
+    """Rank-ordered concatenation of the ranks' `flat[:counts[r]*unit]` on `dst`: every shard travels at its exact
+    length, point to point, straight into its place in the merged buffer (no padding to the longest shard, no staging
+    copy, no torch.cat)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if rank != dst:
+        if counts[rank]:
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, flat[:counts[rank] * unit], dst, group)]):
+                w.wait()
+        return None
+    total = sum(counts) * unit
+    if out is None or out.numel() < total:
+        out = torch.empty(max(total, 1), dtype=flat.dtype, device=flat.device)
+    ops, off = [], 0
+    for r in range(world):
+        n = counts[r] * unit
+        if r == rank:
+            out[off:off + n].copy_(flat[:n])
+        elif n:
+            ops.append(dist.P2POp(dist.irecv, out[off:off + n], r, group))
+        off += n
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out[:total]
+
+
+def gather_event_shards(events_u8, n_events, group=None, dst=0, out=None):
+    """events_u8: 1-D uint8 tensor holding n_events*13 bytes (device for NCCL, CPU for gloo).
+    Returns on `dst` the concatenation of all shards in rank order (a uint8 tensor; a view of `out` when that
+    preallocated buffer is large enough), None elsewhere, and the per-rank event counts everywhere.
+    Ranks own contiguous, increasing frame ranges, so concatenation by rank IS the time-ordered merge."""
+    counts = exchange_counts(n_events, group, events_u8.device)
+    return _gather_exact(events_u8, counts, EVENT_BYTES, group, dst, out), counts
 
 
 def gather_row_shards(rows, group=None, dst=0):
     """rows: (n, ...) tensor whose leading length differs per rank (device for NCCL, CPU for gloo).  Returns on `dst`
     the concatenation over ranks, in rank order, None elsewhere -- the event-frame sums of a sharded clip
     (the preview's percentile is global over the clip, v2ce.py:262-264, so rank 0 needs all of them)."""
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    dev = rows.device
-    cnt = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, cnt, group=group)
-    counts = [int(c.item()) for c in counts]
-    mx = max(max(counts), 1)
-    pad = torch.zeros((mx,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=dev)
-    pad[:rows.shape[0]] = rows
-    if rank == dst:
-        bufs = [torch.empty_like(pad) for _ in range(world)]
-        dist.gather(pad, bufs, dst=dst, group=group)
-        return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
-    dist.gather(pad, None, dst=dst, group=group)
-    return None
+    counts = exchange_counts(rows.shape[0], group, rows.device)
+    unit = 1
+    for d in rows.shape[1:]:
+        unit *= int(d)
+    merged = _gather_exact(rows.contiguous().reshape(-1), counts, unit, group, dst, None)
+    if merged is None:
+        return None
+    return merged.reshape((sum(counts),) + tuple(rows.shape[1:]))
 
 
 def shard_schedule(starts, mode, b0, b1, batch_size, seq_len=16):
@@ -146,7 +175,11 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
         h0, w0 = probe.shape[-2], probe.shape[-1]
         height = kw.get('height', 260)
         tiles = len(drv.pano_tiles(int(w0 / h0 * height), kw.get('width', 346)))     # width after image_pre_processing
-    model.sn_advance(model_calls_before(b0, infer_type, tiles) - model.call_count())
+    # the single-process schedule continues the spectral-norm iteration from clip to clip: every rank enters a clip
+    # at the same call index (`base`), replays the calls of the batches before its share and, when the clip is done,
+    # the calls of the batches after it, so that all ranks leave at base + (calls of the whole clip)
+    base = model.call_count()
+    model.sn_advance(model_calls_before(b0, infer_type, tiles))
 
     class _Shard:
         """Presents windows [b0*bs, b1*bs) of the clip as a clip of its own."""
@@ -170,6 +203,7 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
         sums = res.ef_sums_dev
     else:
         ev, n = torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev), 0
+    model.sn_advance(base + model_calls_before(n_batches, infer_type, tiles) - model.call_count())
     out, counts = gather_event_shards(ev, n)
     if preview is not None:
         from . import event_frames as _ef

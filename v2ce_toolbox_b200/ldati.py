@@ -169,6 +169,14 @@ def engine_for(device):
     return _engines[key]
 
 
+def frame_offsets_us(pair_base, n, fps):
+    """int64 (n,): the per-frame timestamp offsets `int(i * 1 / fps * 1e6)` of v2ce.py:365 for i = pair_base ..
+    pair_base+n-1 -- Python's int/int true division is the correctly rounded quotient, which for |i|, fps < 2^53 is the
+    float64 division numpy does; then one float64 multiply and a truncation."""
+    i = np.arange(pair_base, pair_base + n, dtype=np.int64).astype(np.float64)
+    return (i / np.float64(fps) * np.float64(1e6)).astype(np.int64)
+
+
 def check_status(status_host):
     if int(status_host[0]) != 0:
         raise V2ceError(f'LDATI: {int(status_host[0])} timestamps fell outside the sort-key range '

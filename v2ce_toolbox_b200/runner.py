@@ -133,7 +133,9 @@ class BatchRunner:
         n = b * L
         t.vox = y.reshape(n, 2, 10, H, W)
         if trim_last_window_to:                   # merge_voxels: drop the re-inferred overlap of the pulled-back window
-            keep = trim_last_window_to
+            # a short image folder delivers a last window of fewer than `keep` pairs: the reference's [-mode:] slice
+            # (v2ce.py:229-230) then keeps them all
+            keep = min(trim_last_window_to, L)
             t.vox = torch.cat([t.vox[:(b - 1) * L], t.vox[(b - 1) * L + (L - keep):]], dim=0).contiguous()
             n = t.vox.shape[0]
         t.n_pairs, t.hw = n, (H, W)
@@ -171,7 +173,7 @@ class BatchRunner:
                 :4 + n * _ldati.NBINS]
             t.small_host.copy_(small[:4 + n * _ldati.NBINS], non_blocking=True)
             offs_host = self._buf(self._offs_host, slot, 8 * n, pinned=True).view(torch.int64)[:n]
-            offs_host.copy_(torch.tensor([int((pair_base + i) * 1 / self.fps * 1e6) for i in range(n)], dtype=torch.int64))
+            offs_host.copy_(torch.from_numpy(_ldati.frame_offsets_us(pair_base, n, self.fps)))
             t.offs = self._buf(self._offs_dev, slot, 8 * n).view(torch.int64)[:n]
             t.offs.copy_(offs_host, non_blocking=True)
             t.counts_ready = torch.cuda.Event()
@@ -248,8 +250,20 @@ class BatchRunner:
 
     keep_vox = False                            # tests may set this to inspect the voxels a ticket was computed from
 
-    def reset_collection(self):
+    def reset_collection(self, reserve_bytes=0):
+        """Start a new clip: forget the events collected so far and any batch an aborted clip left half-way through
+        the pipeline (its ticket would otherwise be staged into the new clip).  reserve_bytes > 0 sizes the device
+        buffer up front (the caller's estimate from the schedule) so that it does not regrow by copy."""
+        if self._pending is not None or any(f is not None for f in self._free):
+            torch.cuda.synchronize(self.device)
+        self._pending = None
+        self._next = 0
+        self._free = [None] * self.slots
+        self.sums = []
         self._all_bytes = 0
+        if reserve_bytes and (self._all_ev is None or self._all_ev.numel() < reserve_bytes):
+            self._all_ev = None
+            self._all_ev = torch.empty(int(reserve_bytes), dtype=torch.uint8, device=self.device)
 
     def collected_events(self, to_host=True):
         """All events appended since reset_collection(), as (device uint8 tensor, host recarray view of one D2H or

@@ -12,13 +12,11 @@ dense (B,2,9,H,W,M) tensor of uniforms instead, ``flavor`` picks the torch-CUDA 
 default: what the reference computes on a GPU) or torch-CPU ('cpu') scalar semantics.
 
 Options: ``additional_events_strategy`` 'slope' (what v2ce.py:356 uses), 'random' and 'none', and
-``bidirectional`` False / True are all implemented by the same kernels; ``pooling_type`` 'weighted' / 'avg'
-is implemented too but raises NotImplementedError unless ``V2CE_EXPERIMENTAL_POOLING=1`` (pinned on CPU, first
-hardware run pending).  With ``bidirectional=True`` a tenth-bin voxel value above
+``bidirectional`` False / True, and ``pooling_type`` 'none' / 'weighted' / 'avg' are all implemented by the same
+kernels.  With ``bidirectional=True`` a tenth-bin voxel value above
 ``ldati.BIDIR_MAX_TENDENCY`` (1024 events in one pixel-bin) raises V2ceError.
 """
 import logging
-import os
 from typing import List
 
 import numpy as np
@@ -35,12 +33,6 @@ def sample_voxel_statistical(y, t0=0, fps=30, pooling_type='none', pooling_kerne
                              seed=None, frame_base=0, draws=None, flavor='cuda') -> List[np.recarray]:
     assert pooling_type in ['avg', 'weighted', 'none']
     assert additional_events_strategy in ['none', 'random', 'slope']
-    if pooling_type != 'none' and os.environ.get('V2CE_EXPERIMENTAL_POOLING', '0') in ('', '0'):
-        # LDATI.py:176-183 (spatial pooling of the counts before the slope fit) is implemented in csrc/ldati.cu and its
-        # oracle is pinned to the reference, but the kernel route has not run on hardware yet: opt in explicitly
-        raise NotImplementedError("pooling_type 'avg' / 'weighted': the B200 kernel route awaits its first hardware "
-                                  'run; set V2CE_EXPERIMENTAL_POOLING=1 to use it.  Every other option of '
-                                  'sample_voxel_statistical is verified')
     require_cuda(y, 'y')
     B, P, C, H, W = y.shape
     if P != 2 or C != 10:

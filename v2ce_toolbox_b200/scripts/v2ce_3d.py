@@ -35,13 +35,19 @@ class V2ce3d(nn.Module):
 
     # -- checkpoint -----------------------------------------------------------------------
     def load_state_dict(self, state_dict, strict=True):
-        """Accepts the reference's state_dict (218 entries, keys ``UNet.*``)."""
+        """Accepts the reference's state_dict (218 entries, keys ``UNet.*``).  Returns torch's ``_IncompatibleKeys``
+        result like ``nn.Module.load_state_dict``; missing or mis-sized tensors raise when the device model is built
+        (`strict` or not: the network cannot run without them)."""
+        from torch.nn.modules.module import _IncompatibleKeys
         self._state = {k: v.detach().to('cpu', torch.float32).contiguous()
                        for k, v in state_dict.items() if not k.endswith(_SKIP_SUFFIX)}
+        unexpected = [k for k in self._state if not k.startswith('UNet.')]
+        if strict and unexpected:
+            raise V2ceError(f'unexpected key(s) in state_dict: {unexpected[:4]}')
         self._release()
         if self._device is not None:
             self._build()
-        return self
+        return _IncompatibleKeys([], unexpected)
 
     def state_dict(self, *a, **k):
         return dict(self._state or {})

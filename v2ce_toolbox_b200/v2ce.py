@@ -332,15 +332,16 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
         return ClipResult(np.empty(0, _ldati.EVENT_DTYPE), None, None, 0)
     # raw uint8 windows when the frames already have the model's height (the resize of image_pre_processing is then
     # the identity and the rest of it runs inside the head conv); float image units otherwise
-    probe = np.asarray(_read_window(image_paths, vidcap, int(starts[0]), 0))
+    # (a clip of <= seq_len frames has a negative first start, v2ce.py:150-154: probe a frame that exists)
+    probe = np.asarray(_read_window(image_paths, vidcap, max(int(starts[0]), 0), 0))
     native = (infer_type == 'center' and hasattr(model, 'forward_frames') and probe.dtype == np.uint8 and
               probe.shape[-2] == height and int(probe.shape[-1] / probe.shape[-2] * height) == probe.shape[-1] and
               probe.shape[-1] >= width and width % 2 == 0)
-    # frames at another resolution: the host path (cv2.resize per frame, float image units over PCIe) is the default;
-    # device_resize=True (or V2CE_DEVICE_RESIZE=1) uploads the raw uint8 frames and runs the same arithmetic in one
-    # kernel (preprocess.image_units_device, bit-identical) -- SURVEY.md N1
+    # frames at another resolution: the raw uint8 frames are uploaded and /255, the cv2-exact bilinear resize, pair
+    # stacking and Normalize run in one kernel (preprocess.image_units_device, bit-identical to the host path) --
+    # SURVEY.md N1.  device_resize=False (or V2CE_DEVICE_RESIZE=0) keeps cv2.resize on the host, float units over PCIe.
     if device_resize is None:
-        device_resize = os.environ.get('V2CE_DEVICE_RESIZE', '0') not in ('', '0')
+        device_resize = os.environ.get('V2CE_DEVICE_RESIZE', '1') not in ('', '0')
     raw = (not native and device_resize and probe.dtype == np.uint8 and probe.ndim == 3 and probe.shape[-2] >= 2)
     if native:
         infer = None
