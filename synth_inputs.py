@@ -130,6 +130,45 @@ def make_video(n_frames, height=260, width=346, seed=0, shift=2):
     return frames
 
 
+class SynthVideoReader:
+    """make_video's clip, frame by frame on demand (duck-types VideoReader like FakeVideoReader): a rank of a sharded
+    9000-frame or 1080p clip synthesises only the frames it reads.  ``repeat`` > 1 tiles a small texture up by pixel
+    replication (a 1080p source from a 270x480 texture)."""
+
+    def __init__(self, n_frames, height=260, width=346, seed=0, shift=2, repeat=1):
+        assert height % repeat == 0 and width % repeat == 0
+        rng = np.random.default_rng(seed)
+        self.period, self.shift, self.repeat = 64, shift, repeat
+        self.h, self.w = height // repeat, width // repeat
+        base = rng.random((self.h, self.w + self.period)).astype(np.float64)
+        base = _blur1d(_blur1d(base, 3.0, 0), 3.0, 1)
+        self.base = (base - base.min()) / (base.max() - base.min())
+        self.frame_count = n_frames
+        self.shape = (height, width)
+
+    def cache_range(self, a, b):
+        """Materialise frames [a, b) so that reading them is a memory copy (benchmarks exclude the synthesis)."""
+        a, b = max(int(a), 0), min(int(b), self.frame_count)
+        self._cache_first = a
+        self._cache = np.stack([self.frame(i) for i in range(a, b)], axis=0) if b > a else None
+
+    _cache, _cache_first = None, 0
+
+    def frame(self, i):
+        i = max(int(i), 0)
+        if self._cache is not None and self._cache_first <= i < self._cache_first + len(self._cache):
+            return self._cache[i - self._cache_first]
+        off = (i * self.shift) % self.period
+        gain = 0.9 + 0.2 * (i / max(self.frame_count - 1, 1))
+        f = np.clip(self.base[:, off:off + self.w] * 255.0 * gain, 0, 255).astype(np.uint8)
+        if self.repeat > 1:
+            f = np.repeat(np.repeat(f, self.repeat, axis=0), self.repeat, axis=1)
+        return f
+
+    def read_frames_at_indices(self, idxs):
+        return np.stack([self.frame(i) for i in idxs], axis=0)
+
+
 def make_voxels(kind, n, height=260, width=346, seed=42):
     """(n,2,10,H,W) float32 voxel grids of the LDATI microbench distributions."""
     rng = np.random.default_rng(seed)

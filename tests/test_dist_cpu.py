@@ -87,6 +87,21 @@ def _worker(rank, world, port, out_dir):
                 assert got.shape == want.shape and torch.equal(got, want)
             else:
                 assert got is None
+        # the shared host ring of the multi-GPU e2e leg (page-locking skipped on CPU): every rank's bytes land in its
+        # slice of the rank-ordered merged array, ragged and empty shards included
+        ring = vdist.SharedHostRing(2, 4096, register=False)
+        for slot, sizes in ((0, [100, 37]), (1, [0, 500]), (0, [13, 0])):
+            view = ring.place(slot, sizes[rank])
+            view[:sizes[rank]] = rank + 1
+            dist.barrier()
+            assert ring.layout(slot) == [(0, sizes[0]), (sizes[0], sizes[1])]
+            merged = ring.merged(slot)
+            assert merged.numel() == sum(sizes)
+            assert bool((merged[:sizes[0]] == 1).all()) and bool((merged[sizes[0]:] == 2).all())
+            dist.barrier()
+        with pytest.raises(ValueError):
+            ring.place(0, 5000)
+        ring.close()
     finally:
         dist.destroy_process_group()
 

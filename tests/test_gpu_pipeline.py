@@ -49,14 +49,30 @@ def test_stream_clip_tiny_clips(n_frames, bs):
     _check_stream_clip(n_frames, bs)
 
 
-def _check_stream_clip(n_frames, bs):
+@pytest.mark.parametrize('n_frames,bs', [(2, 1), (3, 1), (8, 2), (9, 1), (10, 2), (17, 1), (40, 2)])
+def test_stream_clip_image_folders_incl_tiny_ones(n_frames, bs, tmp_path):
+    """an image folder of <= 16 frames has a negative window start; image_paths[start:] then clamps
+    to the frames that exist (a 9-frame folder yields 7 pairs, a 10-frame one 6: the reference's [-mode:] slice keeps
+    what is there), and the device-resident path must do what the host driver / the reference do."""
+    import cv2
+    H, W = 28, 36
+    frames = synth.make_video(n_frames, H, W, seed=9)
+    paths = []
+    for i, f in enumerate(frames):
+        paths.append(str(tmp_path / f'{i:04d}.png'))
+        cv2.imwrite(paths[-1], f)
+    _check_stream_clip(n_frames, bs, image_paths=paths)
+
+
+def _check_stream_clip(n_frames, bs, image_paths=None):
     from v2ce_toolbox_b200 import v2ce as drv
     H, W = 28, 36
     frames = synth.make_video(n_frames, H, W, seed=9)
-    vox = drv.video_to_voxels(_model(6), vidcap=FakeVideoReader(frames), infer_type='center', seq_len=16, width=W,
-                              height=H, batch_size=bs)
+    src = dict(image_paths=image_paths) if image_paths is not None else dict(vidcap=FakeVideoReader(frames))
+    vox = drv.video_to_voxels(_model(6), infer_type='center', seq_len=16, width=W, height=H, batch_size=bs, **src)
     vox = vox * np.float32(3)                                 # the check below feeds the same scaled voxels to both sides
-    assert vox.shape[0] == n_frames - 1
+    if image_paths is None:
+        assert vox.shape[0] == n_frames - 1
 
     class Scaled(torch.nn.Module):                            # same model, outputs scaled like `vox`
         def __init__(self, inner):
@@ -66,8 +82,10 @@ def _check_stream_clip(n_frames, bs):
         def forward(self, x):
             return self.inner(x) * 3.0
 
-    res = drv.stream_clip(Scaled(_model(6)), vidcap=FakeVideoReader(frames), infer_type='center', seq_len=16, width=W,
-                          height=H, batch_size=bs, fps=30, ceil=10, upper_bound_percentile=98, seed=77)
+    src = dict(image_paths=image_paths) if image_paths is not None else dict(vidcap=FakeVideoReader(frames))
+    res = drv.stream_clip(Scaled(_model(6)), infer_type='center', seq_len=16, width=W,
+                          height=H, batch_size=bs, fps=30, ceil=10, upper_bound_percentile=98, seed=77, **src)
+    assert res.n_pairs == vox.shape[0]
     want_frames, want_ub, _ = ef_oracle.event_frames_oracle(vox, 10, 98, True)
     assert res.ef_upper_bound == want_ub
     assert np.array_equal(res.ef_frames, want_frames)

@@ -227,7 +227,11 @@ def test_v2ce3d_checkpoint_handling_without_a_device():
     sd = synth.make_state_dict(0, 'reference')
     sd['UNet.encoders.0.bn1.num_batches_tracked'] = torch.tensor(7)
     m = V2ce3d()
-    assert m.load_state_dict({k: v.double() for k, v in sd.items()}) is m
+    res = m.load_state_dict({k: v.double() for k, v in sd.items()})       # nn.Module's result type
+    assert list(res.missing_keys) == [] and list(res.unexpected_keys) == []
+    with pytest.raises(V2ceError):
+        V2ce3d().load_state_dict({**sd, 'not_a_unet_key': torch.zeros(1)})
+    assert V2ce3d().load_state_dict({**sd, 'not_a_unet_key': torch.zeros(1)}, strict=False).unexpected_keys == ['not_a_unet_key']
     got = m.state_dict()
     assert 'UNet.encoders.0.bn1.num_batches_tracked' not in got
     assert set(got) == {k for k in sd if not k.endswith('num_batches_tracked')}

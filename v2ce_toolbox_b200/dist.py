@@ -127,6 +127,122 @@ def gather_row_shards(rows, group=None, dst=0):
     return merged.reshape((sum(counts),) + tuple(rows.shape[1:]))
 
 
+_merge_seq = [0]
+
+
+def merge_event_shards_to_host(events_u8, n_events, group=None, dst=0, workers=8):
+    """The merged, time-ordered event stream of a sharded clip as ONE host array on `dst`, without funnelling the
+    shards through dst's GPU and its single PCIe link: rank `dst` creates a POSIX shared-memory array of the merged
+    size, every rank copies its own device shard (sink.to_host: pinned double buffering + parallel first touch) into
+    its slice of it -- all PCIe links and all ranks' host threads in parallel.  Ranks own contiguous, increasing frame
+    ranges, so the rank-ordered layout IS the merge.  Returns (uint8 numpy array on dst | None, per-rank counts).
+    Single node only (all ranks see the same /dev/shm); when shared memory is unavailable or too small the shards are
+    gathered over NCCL instead and rank `dst` copies the merged buffer down (gather_event_shards + sink.to_host)."""
+    import os
+    from .sink import to_host as _sink
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = events_u8.device
+    counts = exchange_counts(n_events, group, dev)
+    total = sum(counts) * EVENT_BYTES
+    if world == 1:
+        return _sink(events_u8[:total], workers=workers), counts
+    _merge_seq[0] += 1
+    path = f"/dev/shm/v2ce_merge_{os.environ.get('MASTER_PORT', '0')}_{_merge_seq[0]}"
+    ok = torch.zeros(1, dtype=torch.int64, device=dev)
+    if rank == dst:
+        try:
+            st = os.statvfs('/dev/shm')
+            if st.f_bavail * st.f_frsize > total + (64 << 20) and int(os.environ.get('LOCAL_WORLD_SIZE', world)) == world:
+                with open(path, 'wb') as f:
+                    f.truncate(max(total, 1))
+                ok[0] = 1
+        except OSError:
+            ok[0] = 0
+    dist.broadcast(ok, src=dst, group=group)        # also orders "file exists" before the other ranks open it
+    if int(ok.item()) == 0:
+        merged, _ = gather_event_shards(events_u8, n_events, group, dst)
+        return (_sink(merged, workers=workers) if merged is not None else None), counts
+    try:
+        mm = np.memmap(path, dtype=np.uint8, mode='r+', shape=(max(total, 1),))
+        off = sum(counts[:rank]) * EVENT_BYTES
+        n = counts[rank] * EVENT_BYTES
+        if n:
+            _sink(events_u8[:n], out=mm[off:off + n], workers=workers)
+        dist.barrier(group=group)
+    finally:
+        if rank == dst and os.path.exists(path):
+            os.unlink(path)                          # the mapping keeps the pages alive
+    return (mm[:total] if rank == dst else None), counts
+
+
+class SharedHostRing:
+    """Per-step host destination of a multi-GPU run: `slots` shared-memory arrays that every rank maps and page-locks
+    (cudaHostRegister), so each rank's D2H lands directly in ITS slice of the merged, rank-ordered stream of the step
+    -- no NCCL gather through one GPU, no second host copy.  place(slot, nbytes) exchanges the ranks' byte counts (one
+    gloo all_gather on the host: the counts are host values already, runner._stage_b) and returns this rank's pinned
+    slice; layout(slot) gives every rank's (offset, nbytes) of the last placement.  Single node only."""
+
+    def __init__(self, slots, bytes_per_slot, group=None, register=True):
+        import os
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.cpu_group = dist.new_group(backend='gloo')
+        self.cap = int(bytes_per_slot)
+        self.path = f"/dev/shm/v2ce_ring_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        total = slots * self.cap
+        flag = torch.zeros(1, dtype=torch.int64)
+        if self.rank == 0:
+            try:
+                st = os.statvfs('/dev/shm')
+                if st.f_bavail * st.f_frsize > total + (64 << 20):
+                    with open(self.path, 'wb') as f:
+                        f.truncate(total)
+                    flag[0] = 1
+            except OSError:
+                pass
+        dist.broadcast(flag, src=0, group=self.cpu_group)
+        if int(flag.item()) == 0:
+            raise OSError('/dev/shm cannot hold the shared host ring')
+        self.buf = torch.from_file(self.path, shared=True, size=total, dtype=torch.uint8)
+        rc = torch.cuda.cudart().cudaHostRegister(self.buf.data_ptr(), total, 0) if register else 0     # False: CPU tests
+        ok = torch.tensor([1 if int(rc) == 0 else 0], dtype=torch.int64)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.cpu_group)
+        if self.rank == 0:
+            os.unlink(self.path)                     # every rank has it mapped; the pages live until the last unmap
+        self.registered = register and int(rc) == 0
+        if int(ok.item()) == 0:
+            self.close()
+            raise OSError(f'cudaHostRegister of the shared host ring failed on some rank (rc {int(rc)} here)')
+        self.slots = slots
+        self._layout = [None] * slots
+
+    def place(self, slot, nbytes):
+        mine = torch.tensor([int(nbytes)], dtype=torch.int64)
+        every = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
+        dist.all_gather(every, mine, group=self.cpu_group)
+        sizes = [int(v.item()) for v in every]
+        if sum(sizes) > self.cap:
+            raise ValueError(f'shared host ring slot too small: {sum(sizes)} > {self.cap} bytes')
+        offs = [sum(sizes[:r]) for r in range(self.world)]
+        self._layout[slot] = list(zip(offs, sizes))
+        base = slot * self.cap + offs[self.rank]
+        return self.buf[base:base + max(int(nbytes), 1)]
+
+    def layout(self, slot):
+        return self._layout[slot]
+
+    def merged(self, slot):
+        """uint8 view of the merged stream of the last placement in `slot` (valid on every rank once all ranks' copies
+        have completed)."""
+        offs_sizes = self._layout[slot]
+        n = offs_sizes[-1][0] + offs_sizes[-1][1]
+        return self.buf[slot * self.cap:slot * self.cap + n]
+
+    def close(self):
+        if getattr(self, 'registered', False):
+            torch.cuda.cudart().cudaHostUnregister(self.buf.data_ptr())
+            self.registered = False
+
+
 def shard_schedule(starts, mode, b0, b1, batch_size, seq_len=16):
     """Batches [b0, b1) of a clip's window schedule (v2ce.window_schedule) as a clip of their own:
     (first frame, frame count, is_tail, index of the first frame pair, (window starts relative to `first`, mode)).
@@ -204,7 +320,11 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
     else:
         ev, n = torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev), 0
     model.sn_advance(base + model_calls_before(n_batches, infer_type, tiles) - model.call_count())
-    out, counts = gather_event_shards(ev, n)
+    if to_host and ev.is_cuda:
+        host, counts = merge_event_shards_to_host(ev, n)
+        out = None
+    else:
+        out, counts = gather_event_shards(ev, n)
     if preview is not None:
         from . import event_frames as _ef
         keep = kw.get('keep_polarity', True)
@@ -217,8 +337,9 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
                 ub = _ef.upper_bound(all_sums, kw.get('upper_bound_percentile', 98), kw.get('ceil', 10), keep)
                 preview['frames'] = _ef.normalize(all_sums, ub, keep).cpu().numpy()
                 preview['upper_bound'] = ub
+    from .ldati import EVENT_DTYPE
+    if to_host and ev.is_cuda:
+        return (host.view(EVENT_DTYPE) if host is not None else None), sum(counts)
     if out is not None:
-        from .ldati import EVENT_DTYPE
-        from .sink import to_host as _sink
-        return (_sink(out).view(EVENT_DTYPE) if to_host else out), sum(counts)
+        return (out.numpy().view(EVENT_DTYPE) if to_host else out), sum(counts)
     return None, sum(counts)

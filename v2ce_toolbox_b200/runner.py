@@ -34,7 +34,7 @@ from ._lib import check, ptr, stream_ptr
 class Ticket:
     __slots__ = ('slot', 'n_pairs', 'total', 'seg_counts', 'done', 'status', 'ub', 'h2d_bytes', 'd2h_bytes', 'hw',
                  'pair_base', 'vox', 'sums', 'small_host', 'counts_ready', 'staged', 'params', 'offs', 'fwd_events',
-                 'events_dev', 'packed')
+                 'events_dev', 'packed', 'ev_host')
 
 
 class BatchRunner:
@@ -53,8 +53,13 @@ class BatchRunner:
         # back once by collected_events(): one D2H and one host array for a whole clip instead of a staging copy,
         # a pageable copy and a concatenation per batch (v2ce.stream_clip)
         self.collect_on_device = collect_on_device
+        # multi-GPU e2e: an object whose place(slot, nbytes) returns the pinned host bytes this batch's events go to
+        # (dist.SharedHostRing: this rank's slice of a shared-memory array that holds the merged stream of all ranks)
+        self.host_sink = None
         self._all_ev = None
         self._all_bytes = 0
+        self.clip_pairs = 0                     # pairs of the clip being collected (v2ce.stream_clip sets it): sizes
+        self._pairs_collected = 0               # the clip-wide buffer after the first batch instead of regrowing it
         self.lib = _lib.load()
         self.post_stream = torch.cuda.Stream(device=self.device)      # event frames + LDATI, one batch behind
         self.copy_stream = torch.cuda.Stream(device=self.device)      # D2H of results
@@ -223,16 +228,25 @@ class BatchRunner:
             self.copy_stream.wait_event(t.packed)
             if self.collect_on_device and total > 0:
                 need = self._all_bytes + total * 13
+                self._pairs_collected += n
                 if self._all_ev is None or self._all_ev.numel() < need:
-                    grown = torch.empty(max(2 * need, 64 << 20), dtype=torch.uint8, device=self.device)
+                    # events per pair seen so far x the pairs of the whole clip (+15 %), at least double
+                    est = int(need * max(self.clip_pairs, self._pairs_collected) / self._pairs_collected * 1.15)
+                    grown = torch.empty(max(est if self.clip_pairs else 2 * need, need, 64 << 20), dtype=torch.uint8,
+                                        device=self.device)
                     if self._all_bytes:
                         grown[:self._all_bytes].copy_(self._all_ev[:self._all_bytes])
                     self._all_ev = grown
                 self._all_ev[self._all_bytes:need].copy_(ev[:total * 13])
                 self._all_bytes = need
+            t.ev_host = None
             if self.copy_out:
-                evh = self._buf(self._ev_host, slot, max(total, 1) * 13, pinned=True)
+                if self.host_sink is not None:
+                    evh = self.host_sink.place(slot, total * 13)
+                else:
+                    evh = self._buf(self._ev_host, slot, max(total, 1) * 13, pinned=True)
                 evh[:total * 13].copy_(ev[:total * 13], non_blocking=True)
+                t.ev_host = evh[:total * 13]
                 t.d2h_bytes = total * 13 + (4 + n * _ldati.NBINS) * 8 + 16
                 if frames is not None:
                     frh = self._buf(self._fr_host, slot, frames.numel(), pinned=True)
@@ -261,6 +275,7 @@ class BatchRunner:
         self._free = [None] * self.slots
         self.sums = []
         self._all_bytes = 0
+        self._pairs_collected = 0
         if reserve_bytes and (self._all_ev is None or self._all_ev.numel() < reserve_bytes):
             self._all_ev = None
             self._all_ev = torch.empty(int(reserve_bytes), dtype=torch.uint8, device=self.device)
@@ -289,7 +304,7 @@ class BatchRunner:
         _ldati.check_status(t.status.numpy())
         if not self.copy_out:
             return None, None
-        ev = self._ev_host[t.slot][:t.total * 13].numpy().view(_ldati.EVENT_DTYPE)
+        ev = t.ev_host.numpy().view(_ldati.EVENT_DTYPE)
         fr = None
         if self.per_batch_frames:
             n, (H, W) = t.n_pairs, t.hw

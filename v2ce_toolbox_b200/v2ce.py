@@ -367,6 +367,7 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
         runner.infer = infer
         runner.sums = []
         runner.reset_collection()
+        runner.clip_pairs = int(len(starts) * seq_len - ((seq_len - mode) if mode else 0))
         pair_idx = pair_base
         prev = None
         for x, is_last in _background(batches):
