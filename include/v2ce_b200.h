@@ -80,7 +80,7 @@ typedef struct v2ce_ldati_params {
                               * then cover tendencies in (-1, y[9]] bins; see v2ce_toolbox_b200/ldati.py)        */
   int32_t pooling;           /* pooling_type: 0 = 'none', 1 = 'weighted' (3x3 binomial / 16), 2 = 'avg' (box of
                               * pooling_kernel_size^2, zero padded, count_include_pad) -- LDATI.py:176-183; only read when
-                              * multi_events == 1.  Compiled and pinned on CPU; first B200 run pending.            */
+                              * multi_events == 1.                                                                 */
   int32_t pooling_kernel_size; /* odd; 'avg' only                                                                  */
 } v2ce_ldati_params;
 
@@ -99,6 +99,12 @@ int v2ce_ldati_emit_workspace_bytes(const v2ce_ldati_params* p, int64_t total_ev
  * reference's pre-sort concatenation order.  seg_counts_dev: int64 [F][9]. */
 int v2ce_ldati_count(const float* voxels_dev, const v2ce_ldati_params* p, void* count_ws_dev, size_t count_ws_bytes,
                      int64_t* seg_counts_dev, void* stream);
+
+/* v2ce_ldati_count that also writes the per-polarity event-frame sums of v2ce_ef_accumulate(keep_polarity = 1)
+ * (v2ce.py:255: float32 [F][2][H][W], the 10 bins added left to right) from the SAME read of the voxels: in the CLI
+ * pipeline both stages consume the network output of a batch, 7.2 MB per frame pair each.  ef_sums_dev may be NULL. */
+int v2ce_ldati_count_ef(const float* voxels_dev, const v2ce_ldati_params* p, void* count_ws_dev, size_t count_ws_bytes,
+                        int64_t* seg_counts_dev, float* ef_sums_dev, void* stream);
 
 /* Pass 2 (LDATI.py:156-212, :248-310): timestamps, stable per-segment sort by timestamp,
  * 13-byte packed records {int64 timestamp; int16 x; int16 y; int8 polarity}.

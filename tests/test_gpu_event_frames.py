@@ -52,3 +52,18 @@ def test_all_zero_raises_like_numpy():
     from v2ce_toolbox_b200 import event_frames as ef
     with pytest.raises(ValueError):
         ef.event_frames(torch.zeros(1, 2, 10, 8, 8, device='cuda'))
+
+
+def test_count_pass_writes_the_same_sums_as_accumulate():
+    """v2ce_ldati_count_ef: the per-polarity event-frame sums written by the LDATI count pass (one read of the voxels
+    for both stages, runner.BatchRunner) are bit for bit those of v2ce_ef_accumulate -- V=4 and V=1 pixel paths."""
+    from v2ce_toolbox_b200 import event_frames as ef, ldati
+    for (n, H, W) in ((3, 20, 28), (2, 9, 11), (2, 260, 346)):
+        g = torch.Generator(device='cuda').manual_seed(H)
+        vox = torch.rand((n, 2, 10, H, W), generator=g, device='cuda') * 0.3
+        eng = ldati.LdatiEngine('cuda')
+        params = ldati.make_params(n, H, W, fps=30, seed=1, device='cuda')
+        sums = torch.full((n, 2, H, W), float('nan'), device='cuda')
+        seg = eng.count(vox, params, ef_sums=sums)
+        assert torch.equal(sums, ef.accumulate(vox, True))
+        assert torch.equal(seg, ldati.LdatiEngine('cuda').count(vox, params))

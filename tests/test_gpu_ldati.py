@@ -142,8 +142,8 @@ def test_rejects_cpu_tensor_and_unsupported_modes():
     from v2ce_toolbox_b200.scripts.LDATI import sample_voxel_statistical
     with pytest.raises(V2ceError):
         sample_voxel_statistical(torch.zeros(1, 2, 10, 4, 4))
-    with pytest.raises(NotImplementedError):
-        sample_voxel_statistical(torch.zeros(1, 2, 10, 4, 4, device='cuda'), pooling_type='avg')
+    with pytest.raises(AssertionError):                      # the reference's own assert (LDATI.py:135)
+        sample_voxel_statistical(torch.zeros(1, 2, 10, 4, 4, device='cuda'), pooling_type='max')
     with pytest.raises(AssertionError):                      # the reference's own assert (LDATI.py:136)
         sample_voxel_statistical(torch.zeros(1, 2, 10, 4, 4, device='cuda'), additional_events_strategy='other')
 
@@ -188,9 +188,10 @@ def test_options_cpu_flavour_against_reference_goldens(name, golden, golden_meta
 @pytest.fixture
 def ldati_variant(monkeypatch):
     """Sets the per-call opt-in switches of csrc/ldati.cu (read with getenv on every emit call)."""
-    def set_(reuse, staged):
+    def set_(reuse, staged, onesweep=1):
         monkeypatch.setenv('V2CE_LDATI_REUSE_WARP_TOTALS', str(int(reuse)))
         monkeypatch.setenv('V2CE_LDATI_STAGED_SCATTER', str(int(staged)))
+        monkeypatch.setenv('V2CE_LDATI_ONESWEEP', str(int(onesweep)))
     return set_
 
 
@@ -209,17 +210,17 @@ def _variant_case(i):
     return _variant_oracle[i]
 
 
-@pytest.mark.parametrize('reuse,staged', [(0, 0), (1, 0), (0, 1), (1, 1)])
-def test_kernel_variants_bit_exact(reuse, staged, ldati_variant):
+@pytest.mark.parametrize('reuse,staged,onesweep', [(0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0), (0, 0, 1), (1, 1, 1)])
+def test_kernel_variants_bit_exact(reuse, staged, onesweep, ldati_variant):
     """The kernel variants, every on/off combination (per-warp totals handed from the count pass to the emit pass; sort tiles ordered
     by digit in shared memory before the scatter) produce the same bytes as the oracle: dense, sparse and mixed
     counts, V=1 and V=4 pixel paths, 32- and 64-bit elements, 2- and 3-pass sorts, both relocation directions."""
-    ldati_variant(reuse, staged)
+    ldati_variant(reuse, staged, onesweep)
     for i, (kind, F, H, W, opts) in enumerate(VARIANT_CASES):
         v, want = _variant_case(i)
         got = _run(v, fps=30, seed=9, frame_base=2, **opts)
         for j, (g, w) in enumerate(zip(got, want)):
-            _assert_rows_equal(g, w, f'reuse={reuse} staged={staged} {kind} {opts} frame {j}')
+            _assert_rows_equal(g, w, f'reuse={reuse} staged={staged} onesweep={onesweep} {kind} {opts} frame {j}')
 
 
 def test_bidirectional_tendency_beyond_sort_window_raises():

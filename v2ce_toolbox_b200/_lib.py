@@ -40,6 +40,7 @@ _SIGNATURES = {
     'v2ce_ldati_count_workspace_bytes': (c_int, [POINTER(LdatiParams), POINTER(c_size_t)]),
     'v2ce_ldati_emit_workspace_bytes': (c_int, [POINTER(LdatiParams), c_int64, POINTER(c_size_t)]),
     'v2ce_ldati_count': (c_int, [c_void_p, POINTER(LdatiParams), c_void_p, c_size_t, c_void_p, c_void_p]),
+    'v2ce_ldati_count_ef': (c_int, [c_void_p, POINTER(LdatiParams), c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     'v2ce_ldati_emit': (c_int, [c_void_p, POINTER(LdatiParams), c_void_p, c_void_p, c_size_t, c_void_p, c_int32,
                                 c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'v2ce_ldati_relocate': (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),

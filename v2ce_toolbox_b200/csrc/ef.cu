@@ -36,87 +36,149 @@ __global__ void __launch_bounds__(kThreads) accumulate_kernel(const float* __res
 
 // E2 (v2ce.py:262-264): radix select.  Positive floats are order-isomorphic to their bit
 // patterns, so the k-th smallest positive sum is found with four 8-bit histogram passes.
+// One kernel per pass: every block histograms its share into per-warp shared-memory copies, adds them to the global
+// histogram of the pass, and the LAST block to finish (atomic ticket) picks the bucket of both ranks and extends the
+// prefixes for the next pass -- round 1 ran a single-thread kernel between the passes (7-34 us each, pure latency;
+// profiles/ncu_ef_r2_a.txt) and read the sums with scalar loads (1.8 TB/s).
 struct SelectState {
-  unsigned long long hist[2][256];
+  unsigned long long hist[4][2][256];
   unsigned long long npos;
   unsigned long long remaining[2];   // rank still to skip inside the current prefix bucket
   unsigned int prefix[2];
-  unsigned int pad[2];
+  unsigned int done[4];              // blocks that have added their histogram of pass p
 };
 
-__global__ void select_init_kernel(SelectState* st) {
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&st->hist[0][0])[i] = 0ull;
-  if (threadIdx.x == 0) {
-    st->npos = 0; st->remaining[0] = st->remaining[1] = 0; st->prefix[0] = st->prefix[1] = 0;
+// block-wide (256 threads): first bucket d in [0, 255) whose inclusive count exceeds k (255 if none), and the count
+// before it -- what a serial walk over the 256 buckets yields.
+__device__ __forceinline__ void pick_bucket(const unsigned long long* h, unsigned long long k,
+                                            unsigned long long* sh_warp /*8*/, unsigned long long* sh_out /*2*/) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned long long c = __ldcg(h + t);          // written by other blocks' atomics in this launch: L2, not L1
+  unsigned long long inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
   }
+  if (lane == 31) sh_warp[warp] = inc;
+  if (t == 0) { sh_out[0] = 255ull; sh_out[1] = ~0ull; }
+  __syncthreads();
+  unsigned long long off = 0ull;
+  for (int w = 0; w < warp; ++w) off += sh_warp[w];
+  inc += off;
+  const unsigned long long exc = inc - c;
+  if (t < 255 && inc > k && exc <= k) { sh_out[0] = (unsigned long long)t; sh_out[1] = exc; }     // exactly one thread
+  if (t == 255) sh_warp[8] = exc;                       // count before bucket 255 (the fall-through case)
+  __syncthreads();
+  if (t == 0 && sh_out[1] == ~0ull) sh_out[1] = sh_warp[8];
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kThreads) select_hist_kernel(const float* __restrict__ v, long long n, int pass,
-                                                                SelectState* st) {
-  __shared__ unsigned int h[2][256];
-  for (int i = threadIdx.x; i < 512; i += kThreads) (&h[0][0])[i] = 0u;
+                                                                double percentile, int multiplicity, SelectState* st,
+                                                                long long* __restrict__ result) {
+  __shared__ unsigned int h[kThreads / 32][2][256];     // per-warp copies: 8x less contention on a hot bucket
+  __shared__ unsigned long long sh_warp[9], sh_out[2];
+  __shared__ unsigned int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (kThreads / 32) * 512; i += kThreads) (&h[0][0][0])[i] = 0u;
   __syncthreads();
   const int shift = 24 - 8 * pass;
   const unsigned int p0 = st->prefix[0], p1 = st->prefix[1];
-  const long long stride = (long long)gridDim.x * kThreads;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-    const float x = __ldg(v + i);
-    if (x > 0.f) {
-      const unsigned int b = __float_as_uint(x);
-      const unsigned int d = (b >> shift) & 255u;
-      if (pass == 0) {
-        atomicAdd(&h[0][d], 1u);
-      } else {
-        const unsigned int hi = b >> (shift + 8);
-        if (hi == p0) atomicAdd(&h[0][d], 1u);
-        if (hi == p1) atomicAdd(&h[1][d], 1u);
-      }
+
+  auto add = [&](float x, bool in_range) {
+    const unsigned int b = __float_as_uint(x);
+    const bool pos = in_range && x > 0.f;
+    const unsigned int d = (b >> shift) & 255u;
+    const unsigned int hi = (pass == 0) ? 0u : (b >> (shift + 8));
+    const bool m0 = pos && (pass == 0 || hi == p0), m1 = pos && pass != 0 && hi == p1;
+    // the top byte of small positive floats is one or two exponent buckets: aggregate a warp that agrees
+    const unsigned vm0 = __ballot_sync(0xffffffffu, m0);
+    if (vm0) {
+      const int first = __ffs(vm0) - 1;
+      const unsigned d0 = __shfl_sync(0xffffffffu, d, first);
+      if (__all_sync(0xffffffffu, !m0 || d == d0)) { if (lane == first) atomicAdd(&h[warp][0][d0], (unsigned)__popc(vm0)); }
+      else if (m0) atomicAdd(&h[warp][0][d], 1u);
     }
+    const unsigned vm1 = __ballot_sync(0xffffffffu, m1);
+    if (vm1) {
+      const int first = __ffs(vm1) - 1;
+      const unsigned d0 = __shfl_sync(0xffffffffu, d, first);
+      if (__all_sync(0xffffffffu, !m1 || d == d0)) { if (lane == first) atomicAdd(&h[warp][1][d0], (unsigned)__popc(vm1)); }
+      else if (m1) atomicAdd(&h[warp][1][d], 1u);
+    }
+  };
+
+  const long long stride = (long long)gridDim.x * kThreads;
+  const bool vec = (reinterpret_cast<uintptr_t>(v) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  // whole warps iterate together (the ballots above need every lane): round the trip count up per warp
+  const long long first4 = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long trips4 = (n4 + stride - 1) / stride;
+  for (long long it = 0; it < trips4; ++it) {
+    const long long i = first4 + it * stride;
+    const bool ok = i < n4;
+    const float4 x = ok ? __ldg(reinterpret_cast<const float4*>(v) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    add(x.x, ok); add(x.y, ok); add(x.z, ok); add(x.w, ok);
+  }
+  const long long tail0 = n4 * 4;
+  const long long tripst = (n - tail0 + stride - 1) / stride;
+  for (long long it = 0; it < tripst; ++it) {
+    const long long i = tail0 + first4 + it * stride;
+    const bool ok = i < n;
+    add(ok ? __ldg(v + i) : 0.f, ok);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 512; i += kThreads) {
-    const unsigned int c = (&h[0][0])[i];
-    if (c) atomicAdd(&st->hist[0][0] + i, (unsigned long long)c);
+    unsigned int c = 0u;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) c += (&h[w][0][0])[i];
+    if (c) atomicAdd(&st->hist[pass][0][0] + i, (unsigned long long)c);
   }
-}
-
-// one thread: pick the bucket of both ranks, extend the prefixes, clear the histograms
-__global__ void select_step_kernel(SelectState* st, int pass, double percentile, int multiplicity,
-                                   long long* __restrict__ result) {
-  if (threadIdx.x != 0) return;
+  // ---- the last block to arrive closes the pass ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&st->done[pass], 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const unsigned long long* h0 = &st->hist[pass][0][0];
+  const unsigned long long* h1 = (pass == 0) ? h0 : &st->hist[pass][1][0];       // pass 0: both ranks share one histogram
   if (pass == 0) {
-    unsigned long long n = 0;
-    for (int d = 0; d < 256; ++d) { n += st->hist[0][d]; st->hist[1][d] = st->hist[0][d]; }
-    st->npos = n;
-    result[0] = (long long)n;
-    if (n == 0) { result[1] = 0; result[2] = 0; result[3] = 0; return; }
-    // numpy 'linear' method: virtual index (n-1)*q with q = percentile/100 (float64)
-    const double q = __ddiv_rn(percentile, 100.0);
-    const double nn = (double)(n * (unsigned long long)multiplicity);
-    const double vi = __dmul_rn(nn - 1.0, q);
-    long long lo = (long long)floor(vi);
-    long long last = (long long)(n * (unsigned long long)multiplicity) - 1;
-    if (lo < 0) lo = 0;
-    if (lo > last) lo = last;
-    long long hi = lo + 1 > last ? last : lo + 1;
-    st->remaining[0] = (unsigned long long)(lo / multiplicity);
-    st->remaining[1] = (unsigned long long)(hi / multiplicity);
-    result[1] = lo;
+    // total count of positive values, then numpy's 'linear' method: virtual index (n-1)*q with q = percentile/100 (float64)
+    pick_bucket(h0, ~0ull - 1ull, sh_warp, sh_out);                              // never found: sh_out[1] = count before bucket 255
+    if (threadIdx.x == 0) {
+      const unsigned long long npos = sh_out[1] + __ldcg(h0 + 255);
+      st->npos = npos;
+      result[0] = (long long)npos;
+      if (npos == 0) {
+        result[1] = 0; result[2] = 0; result[3] = 0;
+      } else {
+        const double q = __ddiv_rn(percentile, 100.0);
+        const double nn = (double)(npos * (unsigned long long)multiplicity);
+        const double vi = __dmul_rn(nn - 1.0, q);
+        long long lo = (long long)floor(vi);
+        const long long last = (long long)(npos * (unsigned long long)multiplicity) - 1;
+        if (lo < 0) lo = 0;
+        if (lo > last) lo = last;
+        const long long hi = lo + 1 > last ? last : lo + 1;
+        st->remaining[0] = (unsigned long long)(lo / multiplicity);
+        st->remaining[1] = (unsigned long long)(hi / multiplicity);
+        result[1] = lo;
+      }
+    }
+    __syncthreads();
   }
   if (st->npos == 0) return;
   for (int r = 0; r < 2; ++r) {
-    unsigned long long cum = 0;
-    int d = 0;
-    for (; d < 255; ++d) {
-      const unsigned long long c = st->hist[r][d];
-      if (cum + c > st->remaining[r]) break;
-      cum += c;
+    pick_bucket(r == 0 ? h0 : h1, st->remaining[r], sh_warp, sh_out);
+    if (threadIdx.x == 0) {
+      st->remaining[r] -= sh_out[1];
+      st->prefix[r] = (st->prefix[r] << 8) | (unsigned int)sh_out[0];
     }
-    st->remaining[r] -= cum;
-    st->prefix[r] = (st->prefix[r] << 8) | (unsigned int)d;
+    __syncthreads();
   }
-  for (int i = 0; i < 512; ++i) (&st->hist[0][0])[i] = 0ull;
-  if (pass == 3) {
+  if (pass == 3 && threadIdx.x == 0) {
     result[2] = (long long)st->prefix[0];
     result[3] = (long long)st->prefix[1];
   }
@@ -206,15 +268,14 @@ extern "C" int v2ce_ef_select(const float* sums_dev, int64_t n_values, double pe
     return set_error(V2CE_ERR_WORKSPACE, "select workspace too small: need %zu, got %zu", sizeof(SelectState), ws_bytes);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SelectState* st = static_cast<SelectState*>(ws_dev);
-  select_init_kernel<<<1, 256, 0, s>>>(st);
-  V2CE_LAUNCH_CHECK("ef::select_init_kernel");
-  long long want = (n_values + kThreads * 8 - 1) / (kThreads * 8);
-  const int grid = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+  V2CE_CUDA_CHECK(cudaMemsetAsync(st, 0, sizeof(SelectState), s));
+  long long want = (n_values / 4 + kThreads * 4 - 1) / (kThreads * 4);
+  const int cap = sm_count_cached() * 8;
+  const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
   for (int pass = 0; pass < 4; ++pass) {
-    select_hist_kernel<<<grid, kThreads, 0, s>>>(sums_dev, n_values, pass, st);
+    select_hist_kernel<<<grid, kThreads, 0, s>>>(sums_dev, n_values, pass, percentile, multiplicity, st,
+                                                 reinterpret_cast<long long*>(result_dev));
     V2CE_LAUNCH_CHECK("ef::select_hist_kernel");
-    select_step_kernel<<<1, 32, 0, s>>>(st, pass, percentile, multiplicity, reinterpret_cast<long long*>(result_dev));
-    V2CE_LAUNCH_CHECK("ef::select_step_kernel");
   }
   return V2CE_OK;
 }

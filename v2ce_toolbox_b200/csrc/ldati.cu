@@ -35,6 +35,13 @@ constexpr int kThreads = 256;
 constexpr int kKeyBias = 8;       // slack below the bin origin (ts may undershoot it by 1 us)
 constexpr int kTile = 2048;       // sort tile: 256 threads x 8 keys
 constexpr int kKeysPerThread = kTile / kThreads;
+// one-sweep sort (osw_*): 256 threads x 16 keys, <= 6-bit digits (64 digits = 32 counter lanes x 2 packed 16-bit counters)
+constexpr int kOswKpt = 16;
+constexpr int kOswTile = kThreads * kOswKpt;
+constexpr int kOswRadixBits = 6;
+constexpr int kOswRadix = 1 << kOswRadixBits;
+constexpr int kOswMaxPasses = 6;
+static inline int osw_passes(int key_bits) { return (key_bits + kOswRadixBits - 1) / kOswRadixBits; }
 
 struct Geometry {
   int H, W, HW, F;
@@ -247,7 +254,8 @@ __device__ __forceinline__ float philox_uniform(unsigned long long idx, unsigned
 template <int V, bool BIDIR>
 __global__ void __launch_bounds__(kThreads) count_kernel(const float* __restrict__ vox, DevParams P,
                                                           int32_t* __restrict__ partial,
-                                                          int32_t* __restrict__ warp_partial) {
+                                                          int32_t* __restrict__ warp_partial,
+                                                          float* __restrict__ ef_sums) {
   const int blk = blockIdx.x, p = blockIdx.y, f = blockIdx.z;
   const int pix = (blk * kThreads + threadIdx.x) * V;
   int tot[kQ];
@@ -256,6 +264,19 @@ __global__ void __launch_bounds__(kThreads) count_kernel(const float* __restrict
   if (pix < P.HW) {
     float y[V][10];
     load_pixels<V>(vox + ((size_t)(f * 2 + p) * 10) * P.HW, P.HW, pix, y);
+    if (ef_sums != nullptr) {
+      // event-frame sums (v2ce.py:255): s = y0; s += y1; ...; s += y9 -- sequential float32 adds, numpy's order
+      float sum[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        sum[v] = y[v][0];
+#pragma unroll
+        for (int c = 1; c < 10; ++c) sum[v] = __fadd_rn(sum[v], y[v][c]);
+      }
+      float* dst = ef_sums + (size_t)(f * 2 + p) * P.HW + pix;
+      if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(sum[0], sum[1 % V], sum[2 % V], sum[3 % V]);
+      else dst[0] = sum[0];
+    }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       int n[kBins];
@@ -481,6 +502,21 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
   const int grp = (p == 1) ? 0 : 2;              // negative plane is emitted first
   const size_t bb = (((size_t)f * 2 + p) * P.NB + blk) * kQ;
   const unsigned long long frame = (unsigned long long)(P.frame_base + f);
+  // slots: [segment start] + [group base] + [blocks before] + [warps before] + [lanes before].  The first three do not
+  // depend on the lane and the fourth only on the warp: 18 threads fetch them once per block instead of every thread
+  // loading five words and summing up to seven per-warp totals in every bin iteration.
+  __shared__ long long s_base[kQ];               // q < 9: singles of bin q, q >= 9: multi-events of bin q - 9
+  __shared__ int s_wpre[kThreads / 32][kQ];      // events of the warps before this one
+  if (threadIdx.x < kQ) {
+    const int q = threadIdx.x, c = q % kBins;
+    const int32_t* gb = group_base + ((size_t)f * kBins + c) * 4;
+    s_base[q] = seg_start[(size_t)f * kBins + c] + gb[grp + (q >= kBins ? 1 : 0)] + block_base[bb + q];
+    int run = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) { s_wpre[w][q] = run; run += wtot[w][q]; }
+  }
+  __syncthreads();
+  __shared__ int4 s_lane[kThreads / 32][32];     // per lane and bin: {quads before, events before, counts of pixels 0..2, count of pixel 3}
   float debt[V], tend_cur[V], tend_next[V], y9[V];
   int n_prev[V], n_cur[V], n_next[V];
 #pragma unroll
@@ -518,26 +554,31 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
   }
 #pragma unroll 1
   for (int c = 0; c < kBins; ++c) {
-    // slots: [segment start] + [group base] + [blocks before] + [warps before] + [lanes before]
     int ts1 = 0, tsm = 0;
 #pragma unroll
     for (int v = 0; v < V; ++v) { ts1 += (n_cur[v] == 1); tsm += (n_cur[v] >= 2 && P.multi_events) ? n_cur[v] : 0; }
-    const int ex1 = warp_incl_scan(ts1) - ts1, exm = warp_incl_scan(tsm) - tsm;
-    int ws = 0, wm = 0;
-    for (int w = 0; w < warp; ++w) { ws += wtot[w][c]; wm += wtot[w][kBins + c]; }
+    // one scan for both quantities while the multi-event total of a lane stays below 2^16 (singles: <= 4 per lane)
+    const bool small = tsm < 65536;
+    int ex1, exm;
+    if (__all_sync(0xffffffffu, small)) {
+      const int both = warp_incl_scan(ts1 | (tsm << 8));
+      ex1 = (both & 255) - ts1;
+      exm = (both >> 8) - tsm;
+    } else {
+      ex1 = warp_incl_scan(ts1) - ts1;
+      exm = warp_incl_scan(tsm) - tsm;
+    }
     // Single events: one lane per pixel group (cheap, float64 path).
     // Multi-event pixel-bins: WARP-COOPERATIVE.  A lane looping over its own pixels' events runs to the warp's
     // maximum count (~15 on dense inputs) while the mean is 4.5: 5.3 active lanes per warp instruction (ncu).  The
-    // warp's events of this bin are instead numbered e = 0..T-1 in generation order -- which IS their slot order,
-    // slot = warp base + e -- and dealt out 32 at a time: lane e%32 finds the source lane by binary search over the
-    // shuffled exclusive scan, reads that pixel's slope parameters from shared memory and writes slot base+e
-    // (consecutive lanes, consecutive 4-byte slots).
-    const int32_t* gb = group_base + ((size_t)f * kBins + c) * 4;
-    const long long seg = seg_start[(size_t)f * kBins + c];
+    // warp's events of this bin are instead cut into QUADS -- four consecutive events j = 4q .. 4q+3 of one pixel-bin,
+    // i.e. the four words of ONE Philox block -- numbered in generation order and dealt out 32 at a time: a lane finds
+    // its quad's source lane by binary search over the shuffled exclusive scan, reads that pixel's slope parameters
+    // and counts from shared memory, evaluates one Philox block and writes up to four consecutive slots.
     const long long bin_base = P.bin_base[c];
     const float bstart = P.binstart[c];
     if (active) {
-      long long slot_s = seg + gb[grp] + block_base[bb + c] + ws + ex1;
+      long long slot_s = s_base[c] + s_wpre[warp][c] + ex1;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         if (n_cur[v] == 1) {
@@ -579,65 +620,78 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const float* __restrict_
       }
       s_par[warp][lane][v] = make_float2(kk, b);
     }
-    // event thresholds of this lane's pixels, packed 4 x 16 bit (cumulative counts; a pixel-bin holds < 65536 events)
-    const int c0 = cnt[0], c1 = c0 + cnt[1 % V] * (V > 1), c2 = c1 + cnt[2 % V] * (V > 2), c3 = c2 + cnt[3 % V] * (V > 3);
-    const bool fits = c3 < 65536;
-    const unsigned long long thr = (unsigned long long)(unsigned)c0 | ((unsigned long long)(unsigned)c1 << 16) |
-                                   ((unsigned long long)(unsigned)c2 << 32) | ((unsigned long long)(unsigned)c3 << 48);
-    const int T_warp = __shfl_sync(0xffffffffu, exm + tsm, 31);
+    // quads of this lane's pixels; the fast path holds while every pixel-bin has < 1024 events (three counts pack
+    // into one word) -- beyond that (out-of-contract voxel values) the per-lane loop below takes over
+    const int q0 = (cnt[0] + 3) >> 2, q1 = (cnt[1 % V] * (V > 1) + 3) >> 2, q2 = (cnt[2 % V] * (V > 2) + 3) >> 2,
+              q3 = (cnt[3 % V] * (V > 3) + 3) >> 2;
+    const int tq = q0 + q1 + q2 + q3;
+    const bool fits = (cnt[0] | cnt[1 % V] | cnt[2 % V] | cnt[3 % V]) < 1024;
+    const int incq = warp_incl_scan(tq);
+    const int exq = incq - tq;
+    const int TQ_warp = __shfl_sync(0xffffffffu, incq, 31);
+    s_lane[warp][lane] = make_int4(exq, exm, cnt[0] | ((cnt[1 % V] * (V > 1)) << 10) | ((cnt[2 % V] * (V > 2)) << 20),
+                                   cnt[3 % V] * (V > 3));
     __syncwarp();
     if (__all_sync(0xffffffffu, fits)) {
-      const long long warp_slot = seg + gb[grp + 1] + block_base[bb + kBins + c] + wm;
-      for (int e0 = 0; e0 < T_warp; e0 += 32) {
+      const long long warp_slot = s_base[kBins + c] + s_wpre[warp][kBins + c];
+      for (int e0 = 0; e0 < TQ_warp; e0 += 32) {
         const int e = e0 + lane;
-        // source lane: the last one whose exclusive offset is <= e
+        // source lane: the last one whose exclusive quad offset is <= e
         int src = 0;
 #pragma unroll
         for (int step = 16; step > 0; step >>= 1) {
           const int probe = src + step;
-          const int off = __shfl_sync(0xffffffffu, exm, probe & 31);
+          const int off = __shfl_sync(0xffffffffu, exq, probe & 31);
           if (probe < 32 && off <= e) src = probe;
         }
-        const int off_s = __shfl_sync(0xffffffffu, exm, src);
-        const unsigned long long thr_s = __shfl_sync(0xffffffffu, thr, src);
-        if (e < T_warp) {
-          const int le = e - off_s;
-          const int t0 = (int)(thr_s & 0xffffu), t1 = (int)((thr_s >> 16) & 0xffffu), t2 = (int)((thr_s >> 32) & 0xffffu);
+        if (e < TQ_warp) {
+          const int4 sl = s_lane[warp][src];
+          const int c0 = sl.z & 1023, c1 = (sl.z >> 10) & 1023, c2 = (sl.z >> 20) & 1023, c3 = sl.w;
+          const int t0 = (c0 + 3) >> 2, t1 = t0 + ((c1 + 3) >> 2), t2 = t1 + ((c2 + 3) >> 2);
+          const int le = e - sl.x;
           const int v = (le >= t0) + (le >= t1) + (le >= t2);
-          const int j = le - (v == 0 ? 0 : v == 1 ? t0 : v == 2 ? t1 : t2);
+          const int qi = le - (v == 0 ? 0 : v == 1 ? t0 : v == 2 ? t1 : t2);        // quad index inside the pixel-bin
+          const int nv = v == 0 ? c0 : v == 1 ? c1 : v == 2 ? c2 : c3;              // events of the pixel-bin
+          const int ebefore = sl.y + (v == 0 ? 0 : v == 1 ? c0 : v == 2 ? c0 + c1 : c0 + c1 + c2) + 4 * qi;
+          const int nev = min(4, nv - 4 * qi);
           const float2 par = s_par[warp][src][v];
           const float kk = par.x, b = par.y;
           const float bb2 = __fmul_rn(b, b);
           const float k2 = __fmul_rn(2.f, kk);
           const int pix = (blk * kThreads + warp * 32 + src) * V + v;
           const unsigned long long idx = ((frame * 2ull + (unsigned)p) * 9ull + (unsigned)c) * (unsigned long long)P.HW + (unsigned)pix;
-          float u;
-          if (draws != nullptr) {
-            const size_t di = ((((size_t)f * 2 + p) * kBins + c) * P.HW + pix) * (size_t)P.draws_m + j;
-            u = (j < P.draws_m) ? __ldg(draws + di) : 0.f;
-          } else {
-            u = philox_uniform(idx, (unsigned)j, P.seed);
+          unsigned w4[4] = {0u, 0u, 0u, 0u};
+          if (draws == nullptr) philox_block(idx, (unsigned)qi, P.seed, w4);
+          const size_t di = ((((size_t)f * 2 + p) * kBins + c) * P.HW + pix) * (size_t)P.draws_m + 4 * qi;
+          Elem* dst = elems + warp_slot + ebefore;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < nev) {
+              float u;
+              if (draws != nullptr) u = (4 * qi + i < P.draws_m) ? __ldg(draws + di + i) : 0.f;
+              else u = __fmul_rn((float)(w4[i] >> 8), 5.9604644775390625e-08f);   // 2^-24
+              float t;
+              if (P.multi_events == 2) {
+                t = u;                                   // 'random': additional_ts = raw draw (LDATI.py:173-174)
+              } else if (kk == 0.f) {
+                t = P.true_div ? __fdiv_rn(__fdiv_rn(u, P.fps32), P.nbins32)
+                               : __fmul_rn(__fmul_rn(u, P.r_fps32), P.r_nbins32);
+              } else {
+                const float disc = __fadd_rn(bb2, __fmul_rn(k2, u));
+                t = __fdiv_rn(__fadd_rn(-b, __fsqrt_rn(disc)), kk);
+              }
+              t = __fadd_rn(t, bstart);
+              t = __fmul_rn(t, 1e6f);
+              const bool is_nan = (t != t);
+              const long long ts = is_nan ? P.nan_ts : (long long)t;
+              dst[i] = make_elem<Elem>(ts, is_nan, bin_base, pol, pix, P.pix_bits, P.key_bits, status);
+            }
           }
-          float t;
-          if (P.multi_events == 2) {
-            t = u;                                   // 'random': additional_ts = raw draw (LDATI.py:173-174)
-          } else if (kk == 0.f) {
-            t = P.true_div ? __fdiv_rn(__fdiv_rn(u, P.fps32), P.nbins32)
-                           : __fmul_rn(__fmul_rn(u, P.r_fps32), P.r_nbins32);
-          } else {
-            const float disc = __fadd_rn(bb2, __fmul_rn(k2, u));
-            t = __fdiv_rn(__fadd_rn(-b, __fsqrt_rn(disc)), kk);
-          }
-          t = __fadd_rn(t, bstart);
-          t = __fmul_rn(t, 1e6f);
-          const bool is_nan = (t != t);
-          const long long ts = is_nan ? P.nan_ts : (long long)t;
-          elems[warp_slot + e] = make_elem<Elem>(ts, is_nan, bin_base, pol, pix, P.pix_bits, P.key_bits, status);
         }
       }
     } else if (active) {
-      // a pixel-bin with >= 65536 events (out-of-contract voxel values): per-lane loop
-      long long slot_m = seg + gb[grp + 1] + block_base[bb + kBins + c] + wm + exm;
+      // a pixel-bin with >= 1024 events (out-of-contract voxel values): per-lane loop
+      long long slot_m = s_base[kBins + c] + s_wpre[warp][kBins + c] + exm;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int nc = cnt[v];
@@ -703,8 +757,17 @@ struct SortWs {
   int32_t* tile_seg;     // [NT_max]
   int32_t* counts;       // [NT_max * radix]  (segment-major, digit-major, tile-minor)
   int32_t* block_sums;   // scan scratch
+  // one-sweep path (osw_*): 4096-key tiles, per-segment digit histograms, decoupled look-back state
+  int32_t* tile_first4;  // [NS+1]
+  int32_t* tile_seg4;    // [NT4_max]
+  char* osw_zero;        // start of the region cleared before every call: tickets, histograms, look-back state
+  size_t osw_zero_bytes;
+  int32_t* tickets;      // [kOswMaxPasses]
+  int32_t* seg_hist;     // [kOswMaxPasses][NS][64]
+  unsigned long long* tstate;   // [kOswMaxPasses][NT4_max][64]
   size_t bytes;
   int nt_max;
+  int nt4_max;
 };
 
 static SortWs carve_sort_ws(void* ws, const Geometry& g, int64_t total, int elem_bytes) {
@@ -718,13 +781,21 @@ static SortWs carve_sort_ws(void* ws, const Geometry& g, int64_t total, int elem
   s.tile_seg = a.take<int32_t>((size_t)s.nt_max);
   s.counts = a.take<int32_t>((size_t)s.nt_max * 256 + 1);
   s.block_sums = a.take<int32_t>((size_t)s.nt_max * 256 / 1024 + 2);
+  s.nt4_max = (int)((total + kOswTile - 1) / kOswTile) + ns;
+  s.tile_first4 = a.take<int32_t>((size_t)ns + 1);
+  s.tile_seg4 = a.take<int32_t>((size_t)s.nt4_max);
+  const int passes = osw_passes(g.key_bits);
+  s.tickets = a.take<int32_t>(kOswMaxPasses);
+  s.osw_zero = reinterpret_cast<char*>(s.tickets);
+  s.seg_hist = a.take<int32_t>((size_t)passes * ns * kOswRadix);
+  s.tstate = a.take<unsigned long long>((size_t)passes * s.nt4_max * kOswRadix);
+  s.osw_zero_bytes = (size_t)((a.base + a.off) - s.osw_zero);
   s.bytes = align_up(a.off, 256);
   return s;
 }
 
 // one block: tiles per segment -> tile_first (exclusive scan) and tile_seg
-__global__ void build_tiles_kernel(const int64_t* __restrict__ seg_start, int ns, int32_t* __restrict__ tile_first,
-                                   int32_t* __restrict__ tile_seg) {
+__global__ void build_tiles_kernel(const int64_t* __restrict__ seg_start, int ns, int tile, int32_t* __restrict__ tile_first) {
   __shared__ int carry_s;
   __shared__ int wsum[32];
   if (threadIdx.x == 0) carry_s = 0;
@@ -732,7 +803,7 @@ __global__ void build_tiles_kernel(const int64_t* __restrict__ seg_start, int ns
   for (int base = 0; base < ns; base += blockDim.x) {
     const int s = base + threadIdx.x;
     int nt = 0;
-    if (s < ns) nt = (int)((seg_start[s + 1] - seg_start[s] + kTile - 1) / kTile);
+    if (s < ns) nt = (int)((seg_start[s + 1] - seg_start[s] + tile - 1) / tile);
     int inc = warp_incl_scan(nt);
     if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
     __syncthreads();
@@ -743,15 +814,25 @@ __global__ void build_tiles_kernel(const int64_t* __restrict__ seg_start, int ns
     }
     __syncthreads();
     const int first = carry_s + wsum[threadIdx.x >> 5] + inc - nt;
-    if (s < ns) {
-      tile_first[s] = first;
-      for (int i = 0; i < nt; ++i) tile_seg[first + i] = s;
-    }
+    if (s < ns) tile_first[s] = first;
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry_s = first + nt;
     __syncthreads();
   }
   if (threadIdx.x == 0) tile_first[ns] = carry_s;
+}
+
+// tile -> segment: one thread per tile, binary search over tile_first (a dense segment owns hundreds of tiles; one
+// thread per SEGMENT writing them serially cost 53 us on the dense microbench)
+__global__ void fill_tile_seg_kernel(const int32_t* __restrict__ tile_first, int ns, int32_t* __restrict__ tile_seg) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= tile_first[ns]) return;
+  int lo = 0, hi = ns - 1;                       // last segment s with tile_first[s] <= t (empty segments repeat values)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_first[mid] <= t) lo = mid; else hi = mid - 1;
+  }
+  tile_seg[t] = lo;
 }
 
 template <typename Elem>
@@ -993,6 +1074,221 @@ __global__ void __launch_bounds__(kThreads) pack_kernel(const Elem* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// K6': one-sweep segmented stable LSD radix sort (the default path).
+//
+// ncu on the first-generation scatter (profiles/ncu_ldati_r2_a.txt): 88 % of the ADU pipe -- eight dependent
+// __match_any_sync rounds per thread rank the keys -- at 1.4 instructions per cycle per SM, 140 us per pass for
+// 21.6 M keys, plus a histogram kernel, three scan kernels and a second read of every key per pass.  Here a pass is
+// ONE kernel over 4096-key tiles:
+//   * ranking without match/atomics: every thread counts the digits of its 16 CONSECUTIVE keys in private packed
+//     16-bit counters in shared memory ([32 lanes][256 threads] words, two digits per word), one padded raking scan
+//     over (digit, thread) turns the counters into tile-local stable positions;
+//   * the tile's digit counts are chained to the tiles before it IN ITS SEGMENT by decoupled look-back (one 64-bit
+//     status word per (tile, digit): flag | count); tiles take tickets from an atomic counter, so a tile only ever
+//     waits for tiles that already run;
+//   * the digit bases inside a segment come from per-segment histograms of ALL passes, built in one read of the keys
+//     (osw_hist_kernel);
+//   * the tile is ordered by digit in shared memory and leaves as runs of consecutive addresses.
+// Keys are loaded coalesced and transposed to the blocked arrangement through (padded) shared memory.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int osw_pad(int i) { return i + (i >> 5); }        // counters: one pad word per 32
+__device__ __forceinline__ int osw_pad16(int i) { return i + (i >> 4); }      // key transpose: one pad slot per 16
+
+constexpr unsigned long long kOswFlagAgg = 1ull << 62, kOswFlagIncl = 2ull << 62, kOswValMask = (1ull << 62) - 1ull;
+constexpr int kOswCounterWords = 32 * kThreads + (32 * kThreads >> 5);         // 8448
+constexpr int kOswStageSlots = kOswTile + (kOswTile >> 4);                     // 4352
+
+template <typename Elem>
+__global__ void __launch_bounds__(kThreads) osw_hist_kernel(const Elem* __restrict__ in, const int64_t* __restrict__ seg_start,
+                                                             const int32_t* __restrict__ tile_first,
+                                                             const int32_t* __restrict__ tile_seg, int ns, int shift0, int rb,
+                                                             int passes, int32_t* __restrict__ seg_hist) {
+  const int tile = blockIdx.x;
+  if (tile >= tile_first[ns]) return;
+  const int seg = tile_seg[tile];
+  const int tin = tile - tile_first[seg];
+  const long long start = seg_start[seg] + (long long)tin * kOswTile;
+  const int cnt = (int)min((long long)kOswTile, seg_start[seg + 1] - start);
+  __shared__ int h[kOswMaxPasses][kOswRadix];
+  for (int i = threadIdx.x; i < kOswMaxPasses * kOswRadix; i += kThreads) (&h[0][0])[i] = 0;
+  __syncthreads();
+  const unsigned mask = (1u << rb) - 1u;
+  const int lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int k = 0; k < kOswKpt; ++k) {
+    const int i = k * kThreads + threadIdx.x;
+    const bool valid = i < cnt;
+    const Elem key = valid ? in[start + i] : (Elem)0;
+    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+    if (vm == 0u) continue;
+    const int first = __ffs(vm) - 1;
+    for (int p = 0; p < passes; ++p) {
+      const unsigned d = (unsigned)(key >> (shift0 + p * rb)) & mask;
+      // massive ties (a sparse clip: thousands of events share one timestamp) would serialise on one counter
+      const unsigned d0 = __shfl_sync(0xffffffffu, d, first);
+      if (__all_sync(0xffffffffu, !valid || d == d0)) {
+        if (lane == first) atomicAdd(&h[p][d0], __popc(vm));
+      } else if (valid) {
+        atomicAdd(&h[p][d], 1);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * kOswRadix; i += kThreads) {
+    const int c = (&h[0][0])[i];
+    if (c) atomicAdd(&seg_hist[((size_t)(i / kOswRadix) * ns + seg) * kOswRadix + (i % kOswRadix)], c);
+  }
+}
+
+template <typename Elem>
+__global__ void __launch_bounds__(kThreads, 4) osw_scatter_kernel(const Elem* __restrict__ in, Elem* __restrict__ out,
+                                                                const int64_t* __restrict__ seg_start,
+                                                                const int32_t* __restrict__ tile_first,
+                                                                const int32_t* __restrict__ tile_seg, int ns, int shift, int rb,
+                                                                const int32_t* __restrict__ seg_hist,      // [ns][64], this pass
+                                                                unsigned long long* tstate,               // [nt][64], this pass
+                                                                int32_t* __restrict__ ticket) {
+  extern __shared__ __align__(16) unsigned char osw_smem[];
+  uint32_t* cntw = reinterpret_cast<uint32_t*>(osw_smem);      // packed digit counters, later their exclusive scan
+  Elem* stage = reinterpret_cast<Elem*>(osw_smem);             // aliases the counters (used before and after them)
+  __shared__ int s_tile;
+  __shared__ int lbase[kOswRadix + 1];                         // tile-local position of each digit's first key
+  __shared__ long long gbase[kOswRadix];                       // global position of this tile's first key of each digit
+  __shared__ uint32_t wsum[kThreads / 32];
+  __shared__ uint32_t s_total;
+  __shared__ int hsum[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile >= tile_first[ns]) return;
+  const int seg = tile_seg[tile];
+  const int tfirst = tile_first[seg];
+  const int tin = tile - tfirst;
+  const long long sstart = seg_start[seg];
+  const long long start = sstart + (long long)tin * kOswTile;
+  const int cnt = (int)min((long long)kOswTile, seg_start[seg + 1] - start);
+  const unsigned mask = (1u << rb) - 1u;
+
+  // ---- coalesced load, transpose to blocked: thread t owns keys [16t, 16t+16) of the tile ----
+#pragma unroll
+  for (int k = 0; k < kOswKpt; ++k) {
+    const int i = k * kThreads + tid;
+    stage[osw_pad16(i)] = (i < cnt) ? in[start + i] : (Elem)0;
+  }
+  __syncthreads();
+  Elem key[kOswKpt];
+#pragma unroll
+  for (int j = 0; j < kOswKpt; ++j) key[j] = stage[osw_pad16(kOswKpt * tid + j)];
+  __syncthreads();
+
+  // ---- private packed counters: digit d -> word (d & 31, tid), half (d >> 5) ----
+#pragma unroll
+  for (int l = 0; l < 32; ++l) cntw[osw_pad(l * kThreads + tid)] = 0u;
+  // (own column only: no barrier needed before the thread's own increments)
+  int lpos[kOswKpt];                                           // first the rank among the thread's own keys
+  const int nvalid = min(max(cnt - kOswKpt * tid, 0), kOswKpt);
+#pragma unroll
+  for (int j = 0; j < kOswKpt; ++j) {
+    lpos[j] = 0;
+    if (j < nvalid) {
+      const unsigned d = (unsigned)(key[j] >> shift) & mask;
+      unsigned short* c = reinterpret_cast<unsigned short*>(cntw + osw_pad((int)(d & 31u) * kThreads + tid)) + (d >> 5);
+      const unsigned short r = *c;
+      lpos[j] = r;
+      *c = (unsigned short)(r + 1);
+    }
+  }
+  __syncthreads();
+  // ---- raking exclusive scan over the flat (lane-major, thread-minor) counter array; both halves at once ----
+  {
+    uint32_t sum = 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sum += cntw[33 * tid + j];                        // osw_pad(32*tid + j) == 33*tid + j
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0u, total = 0u;
+#pragma unroll
+    for (int wv = 0; wv < kThreads / 32; ++wv) { const uint32_t t = wsum[wv]; if (wv < warp) woff += t; total += t; }
+    if (tid == 0) s_total = total;
+    uint32_t run = woff + inc - sum;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const uint32_t wv = cntw[33 * tid + j]; cntw[33 * tid + j] = run; run += wv; }
+  }
+  __syncthreads();
+  const int total_lo = (int)(s_total & 0xffffu);                // keys whose digit is < 32
+  // ---- tile-local stable positions; digit starts ----
+#pragma unroll
+  for (int j = 0; j < kOswKpt; ++j) {
+    const unsigned d = (unsigned)(key[j] >> shift) & mask;
+    const uint32_t wv = cntw[osw_pad((int)(d & 31u) * kThreads + tid)];
+    lpos[j] += (d >> 5) ? total_lo + (int)(wv >> 16) : (int)(wv & 0xffffu);
+  }
+  int my_start = 0;
+  if (tid < kOswRadix) {
+    const uint32_t wv = cntw[osw_pad((tid & 31) * kThreads)];
+    my_start = (tid >> 5) ? total_lo + (int)(wv >> 16) : (int)(wv & 0xffffu);
+    lbase[tid] = my_start;
+  }
+  if (tid == 0) lbase[kOswRadix] = cnt;
+  // digit bases inside the segment: exclusive scan of the segment's histogram of this pass (64 values, two warps)
+  int hcount = 0, hinc = 0;
+  if (tid < kOswRadix) {
+    hcount = seg_hist[(size_t)seg * kOswRadix + tid];
+    hinc = hcount;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, hinc, o);
+      if (lane >= o) hinc += t;
+    }
+    if (lane == 31) hsum[warp] = hinc;
+  }
+  __syncthreads();                                             // counters are dead from here: `stage` may be written
+  // ---- decoupled look-back over the earlier tiles of this segment, one thread per digit ----
+  if (tid < kOswRadix) {
+    const long long digit_base = (long long)(hinc - hcount) + (warp == 1 ? hsum[0] : 0);
+    const unsigned long long mine = (unsigned long long)(lbase[tid + 1] - my_start);
+    volatile unsigned long long* st = tstate + (size_t)tile * kOswRadix + tid;
+    unsigned long long excl = 0ull;
+    if (tin == 0) {
+      *st = kOswFlagIncl | mine;
+    } else {
+      *st = kOswFlagAgg | mine;
+      int look = tile - 1;
+      while (true) {
+        const unsigned long long v = *(volatile unsigned long long*)(tstate + (size_t)look * kOswRadix + tid);
+        if ((v >> 62) == 0ull) continue;                       // not published yet: that tile holds an earlier ticket
+        excl += v & kOswValMask;
+        if ((v >> 62) == 2ull) break;
+        --look;
+      }
+      *st = kOswFlagIncl | (excl + mine);
+    }
+    gbase[tid] = sstart + digit_base + (long long)excl;
+  }
+  // ---- order the tile by digit in shared memory, then write every digit's run to consecutive addresses ----
+#pragma unroll
+  for (int j = 0; j < kOswKpt; ++j)
+    if (j < nvalid) stage[lpos[j]] = key[j];
+  __syncthreads();
+#pragma unroll 4
+  for (int k = 0; k < kOswKpt; ++k) {
+    const int i = k * kThreads + tid;
+    if (i < cnt) {
+      const Elem e = stage[i];
+      const unsigned d = (unsigned)(e >> shift) & mask;
+      out[gbase[d] + (long long)(i - lbase[d])] = e;
+    }
+  }
+}
+
 template <int V>
 __global__ void relocate_debug_kernel(const float* __restrict__ vox, int HW, float eps6, int bidirectional,
                                       int32_t* __restrict__ counts, float* __restrict__ tend_out) {
@@ -1061,6 +1357,11 @@ extern "C" int v2ce_ldati_emit_workspace_bytes(const v2ce_ldati_params* p, int64
 
 extern "C" int v2ce_ldati_count(const float* voxels_dev, const v2ce_ldati_params* p, void* count_ws_dev,
                                 size_t count_ws_bytes, int64_t* seg_counts_dev, void* stream) {
+  return v2ce_ldati_count_ef(voxels_dev, p, count_ws_dev, count_ws_bytes, seg_counts_dev, nullptr, stream);
+}
+
+extern "C" int v2ce_ldati_count_ef(const float* voxels_dev, const v2ce_ldati_params* p, void* count_ws_dev,
+                                   size_t count_ws_bytes, int64_t* seg_counts_dev, float* ef_sums_dev, void* stream) {
   if (int e = validate(p)) return e;
   V2CE_REQUIRE(voxels_dev && count_ws_dev && seg_counts_dev, "NULL device pointer");
   Geometry g = make_geometry(p);
@@ -1071,11 +1372,11 @@ extern "C" int v2ce_ldati_count(const float* voxels_dev, const v2ce_ldati_params
   DevParams P = make_dev_params(p, g);
   dim3 grid(g.NB, 2, g.F);
   if (p->bidirectional) {
-    if (g.V == 4) count_kernel<4, true><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial);
-    else count_kernel<1, true><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial);
+    if (g.V == 4) count_kernel<4, true><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial, ef_sums_dev);
+    else count_kernel<1, true><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial, ef_sums_dev);
   } else {
-    if (g.V == 4) count_kernel<4, false><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial);
-    else count_kernel<1, false><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial);
+    if (g.V == 4) count_kernel<4, false><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial, ef_sums_dev);
+    else count_kernel<1, false><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial, w.warp_partial, ef_sums_dev);
   }
   V2CE_LAUNCH_CHECK("ldati::count_kernel");
   if (g.pooling) {
@@ -1109,6 +1410,9 @@ static bool env_flag(const char* name, bool dflt) {
 }
 static bool reuse_warp_totals() { return env_flag("V2CE_LDATI_REUSE_WARP_TOTALS", true); }
 static bool staged_scatter() { return env_flag("V2CE_LDATI_STAGED_SCATTER", true); }
+//   V2CE_LDATI_ONESWEEP           1 (default): one-sweep sort passes (osw_* kernels); 0: the first-generation
+//                                 histogram / scan / scatter passes on 2048-key tiles
+static bool onesweep() { return env_flag("V2CE_LDATI_ONESWEEP", true); }
 
 template <typename Elem>
 static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometry& g, const CountWs& cw, void* emit_ws,
@@ -1139,13 +1443,38 @@ static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometr
 #undef V2CE_LAUNCH_EMIT
   V2CE_LAUNCH_CHECK("ldati::emit_kernel");
   if (total == 0) return V2CE_OK;
-  build_tiles_kernel<<<1, 1024, 0, s>>>(cw.seg_start, ns, sw.tile_first, sw.tile_seg);
+  build_tiles_kernel<<<1, 1024, 0, s>>>(cw.seg_start, ns, kTile, sw.tile_first);
   V2CE_LAUNCH_CHECK("ldati::build_tiles_kernel");
-  // LSD passes over the key field, <= 8 bits each
-  const int passes = (g.key_bits + 7) / 8;
-  const int rb = (g.key_bits + passes - 1) / passes;
+  fill_tile_seg_kernel<<<(sw.nt_max + 255) / 256, 256, 0, s>>>(sw.tile_first, ns, sw.tile_seg);
+  V2CE_LAUNCH_CHECK("ldati::fill_tile_seg_kernel");
   Elem* src = ea;
   Elem* dst = eb;
+  const bool osw = onesweep();
+  if (osw) {
+    // one-sweep LSD passes over the key field, <= 6 bits each
+    const int passes = osw_passes(g.key_bits);
+    const int rb = (g.key_bits + passes - 1) / passes;
+    build_tiles_kernel<<<1, 1024, 0, s>>>(cw.seg_start, ns, kOswTile, sw.tile_first4);
+    V2CE_LAUNCH_CHECK("ldati::build_tiles_kernel");
+    fill_tile_seg_kernel<<<(sw.nt4_max + 255) / 256, 256, 0, s>>>(sw.tile_first4, ns, sw.tile_seg4);
+    V2CE_LAUNCH_CHECK("ldati::fill_tile_seg_kernel");
+    V2CE_CUDA_CHECK(cudaMemsetAsync(sw.osw_zero, 0, sw.osw_zero_bytes, s));
+    osw_hist_kernel<Elem><<<sw.nt4_max, kThreads, 0, s>>>(src, cw.seg_start, sw.tile_first4, sw.tile_seg4, ns, g.pix_bits + 1, rb,
+                                                          passes, sw.seg_hist);
+    V2CE_LAUNCH_CHECK("ldati::osw_hist_kernel");
+    const size_t smem = (size_t)kOswCounterWords * 4 > (size_t)kOswStageSlots * sizeof(Elem)
+                            ? (size_t)kOswCounterWords * 4 : (size_t)kOswStageSlots * sizeof(Elem);
+    for (int pass = 0; pass < passes; ++pass) {
+      osw_scatter_kernel<Elem><<<sw.nt4_max, kThreads, smem, s>>>(
+          src, dst, cw.seg_start, sw.tile_first4, sw.tile_seg4, ns, g.pix_bits + 1 + pass * rb, rb,
+          sw.seg_hist + (size_t)pass * ns * kOswRadix, sw.tstate + (size_t)pass * sw.nt4_max * kOswRadix, sw.tickets + pass);
+      V2CE_LAUNCH_CHECK("ldati::osw_scatter_kernel");
+      Elem* t = src; src = dst; dst = t;
+    }
+  }
+  // first-generation path: LSD passes over the key field, <= 8 bits each
+  const int passes = osw ? 0 : (g.key_bits + 7) / 8;
+  const int rb = osw ? 0 : (g.key_bits + passes - 1) / passes;
   for (int pass = 0; pass < passes; ++pass) {
     const int shift = g.pix_bits + 1 + pass * rb;
     const int radix = 1 << rb;

@@ -119,14 +119,16 @@ class LdatiEngine:
             setattr(self, attr, buf)
         return buf
 
-    def count(self, voxels, params, out=None):
-        """voxels (F,2,10,H,W) float32 CUDA contiguous -> seg_counts int64 (F,9) on device (`out` if given)."""
+    def count(self, voxels, params, out=None, ef_sums=None):
+        """voxels (F,2,10,H,W) float32 CUDA contiguous -> seg_counts int64 (F,9) on device (`out` if given).
+        ef_sums: optional float32 (F,2,H,W) CUDA tensor that receives the per-polarity event-frame sums
+        (event_frames.accumulate(keep_polarity=True)) from the same read of the voxels."""
         n = ctypes.c_size_t()
         check(self.lib.v2ce_ldati_count_workspace_bytes(ctypes.byref(params), ctypes.byref(n)))
         ws = self._ws('_count_ws', n.value)
         seg = out if out is not None else torch.empty((params.n_frames, NBINS), dtype=torch.int64, device=self.device)
-        check(self.lib.v2ce_ldati_count(ptr(voxels), ctypes.byref(params), ptr(ws), ws.numel(), ptr(seg),
-                                        stream_ptr()))
+        check(self.lib.v2ce_ldati_count_ef(ptr(voxels), ctypes.byref(params), ptr(ws), ws.numel(), ptr(seg),
+                                           ptr(ef_sums), stream_ptr()))
         self.launches += 3
         return seg
 
@@ -145,8 +147,9 @@ class LdatiEngine:
                                        ptr(draws), m, ptr(frame_offsets), total_events, ptr(out), ptr(status),
                                        stream_ptr()))
         key_bits = max(1, math.ceil(math.log2(params.key_span + 1)))
-        passes = (key_bits + 7) // 8
-        self.launches += 2 + (1 + 5 * passes + 1 if total_events > 0 else 0)
+        passes = (key_bits + 5) // 6                 # one-sweep passes of <= 6 bits (csrc/ldati.cu, osw_*)
+        # emit + [2 tile tables x (build, fill)] + digit histograms + one kernel per pass + pack
+        self.launches += 1 + (4 + 1 + passes + 1 if total_events > 0 else 0)
         return out, status
 
     def run(self, voxels, params, draws=None, frame_offsets=None):

@@ -158,10 +158,19 @@ class BatchRunner:
         with torch.cuda.stream(self.post_stream):
             self.post_stream.wait_event(vox_ready)
             eng = self.engines[slot]
-            t.sums = _ef.accumulate(t.vox, self.keep)
+            # keep_polarity: the per-polarity sums come out of the LDATI count pass below (one read of the voxels for
+            # both stages); gray mode sums over both polarities and keeps its own pass
+            fused = bool(self.keep)
+            t.sums = torch.empty((n, 2, H, W), dtype=torch.float32, device=self.device) if fused else \
+                _ef.accumulate(t.vox, self.keep)
             if keep_sums:
                 self.sums.append(t.sums)
             small = self._buf(self._small_dev, slot, 8 * (4 + n * _ldati.NBINS)).view(torch.int64)
+            t.params = _ldati.make_params(n, H, W, fps=self.fps, seed=self.seed, frame_base=pair_base,
+                                          device=self.device, add_frame_offset=True)
+            l0 = eng.launches
+            seg = eng.count(t.vox, t.params, out=small[4:4 + n * _ldati.NBINS].view(n, _ldati.NBINS),
+                            ef_sums=t.sums if fused else None)
             if self.per_batch_frames:
                 nb = ctypes.c_size_t()
                 check(self.lib.v2ce_ef_select_workspace_bytes(ctypes.byref(nb)))
@@ -169,11 +178,7 @@ class BatchRunner:
                 mult = 1 if self.keep else 3
                 check(self.lib.v2ce_ef_select(ptr(t.sums), t.sums.numel(), float(self.percentile), mult, ptr(ws),
                                               ws.numel(), ptr(small), stream_ptr()))
-            t.params = _ldati.make_params(n, H, W, fps=self.fps, seed=self.seed, frame_base=pair_base,
-                                          device=self.device, add_frame_offset=True)
-            l0 = eng.launches
-            seg = eng.count(t.vox, t.params, out=small[4:4 + n * _ldati.NBINS].view(n, _ldati.NBINS))
-            self.launches += (10 if self.per_batch_frames else 1) + (eng.launches - l0)
+            self.launches += (0 if fused else 1) + (4 if self.per_batch_frames else 0) + (eng.launches - l0)
             t.small_host = self._buf(self._small_host, slot, 8 * (4 + n * _ldati.NBINS), pinned=True).view(torch.int64)[
                 :4 + n * _ldati.NBINS]
             t.small_host.copy_(small[:4 + n * _ldati.NBINS], non_blocking=True)
