@@ -1081,186 +1081,168 @@ __global__ void __launch_bounds__(kThreads) pack_kernel(const Elem* __restrict__
 // __match_any_sync rounds per thread rank the keys -- at 1.4 instructions per cycle per SM, 140 us per pass for
 // 21.6 M keys, plus a histogram kernel, three scan kernels and a second read of every key per pass.  Here a pass is
 // ONE kernel over 4096-key tiles:
-//   * ranking without match/atomics: every thread counts the digits of its 16 CONSECUTIVE keys in private packed
-//     16-bit counters in shared memory ([32 lanes][256 threads] words, two digits per word), one padded raking scan
-//     over (digit, thread) turns the counters into tile-local stable positions;
 //   * the tile's digit counts are chained to the tiles before it IN ITS SEGMENT by decoupled look-back (one 64-bit
 //     status word per (tile, digit): flag | count); tiles take tickets from an atomic counter, so a tile only ever
 //     waits for tiles that already run;
-//   * the digit bases inside a segment come from per-segment histograms of ALL passes, built in one read of the keys
-//     (osw_hist_kernel);
+//   * the digit bases inside a segment come from a per-segment histogram: of the first pass from one read of the keys
+//     (osw_hist_kernel), of every later pass from the scatter pass before it, which has the keys in registers;
 //   * the tile is ordered by digit in shared memory and leaves as runs of consecutive addresses.
-// Keys are loaded coalesced and transposed to the blocked arrangement through (padded) shared memory.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ int osw_pad(int i) { return i + (i >> 5); }        // counters: one pad word per 32
-__device__ __forceinline__ int osw_pad16(int i) { return i + (i >> 4); }      // key transpose: one pad slot per 16
-
 constexpr unsigned long long kOswFlagAgg = 1ull << 62, kOswFlagIncl = 2ull << 62, kOswValMask = (1ull << 62) - 1ull;
-constexpr int kOswCounterWords = 32 * kThreads + (32 * kThreads >> 5);         // 8448
-constexpr int kOswStageSlots = kOswTile + (kOswTile >> 4);                     // 4352
 
+// digit histogram of the FIRST pass per segment (the later passes get theirs from the scatter pass before them)
 template <typename Elem>
 __global__ void __launch_bounds__(kThreads) osw_hist_kernel(const Elem* __restrict__ in, const int64_t* __restrict__ seg_start,
                                                              const int32_t* __restrict__ tile_first,
-                                                             const int32_t* __restrict__ tile_seg, int ns, int shift0, int rb,
-                                                             int passes, int32_t* __restrict__ seg_hist) {
+                                                             const int32_t* __restrict__ tile_seg, int ns, int shift, int rb,
+                                                             int32_t* __restrict__ seg_hist) {
   const int tile = blockIdx.x;
   if (tile >= tile_first[ns]) return;
   const int seg = tile_seg[tile];
   const int tin = tile - tile_first[seg];
   const long long start = seg_start[seg] + (long long)tin * kOswTile;
   const int cnt = (int)min((long long)kOswTile, seg_start[seg + 1] - start);
-  __shared__ int h[kOswMaxPasses][kOswRadix];
-  for (int i = threadIdx.x; i < kOswMaxPasses * kOswRadix; i += kThreads) (&h[0][0])[i] = 0;
+  __shared__ int h[kOswRadix];
+  if (threadIdx.x < kOswRadix) h[threadIdx.x] = 0;
   __syncthreads();
   const unsigned mask = (1u << rb) - 1u;
   const int lane = threadIdx.x & 31;
-#pragma unroll 4
-  for (int k = 0; k < kOswKpt; ++k) {
+  Elem key[kOswKpt];
+#pragma unroll
+  for (int k = 0; k < kOswKpt; ++k) {                       // all loads in flight before the first use
     const int i = k * kThreads + threadIdx.x;
-    const bool valid = i < cnt;
-    const Elem key = valid ? in[start + i] : (Elem)0;
+    key[k] = (i < cnt) ? in[start + i] : (Elem)0;
+  }
+#pragma unroll
+  for (int k = 0; k < kOswKpt; ++k) {
+    const bool valid = k * kThreads + (int)threadIdx.x < cnt;
     const unsigned vm = __ballot_sync(0xffffffffu, valid);
     if (vm == 0u) continue;
     const int first = __ffs(vm) - 1;
-    for (int p = 0; p < passes; ++p) {
-      const unsigned d = (unsigned)(key >> (shift0 + p * rb)) & mask;
-      // massive ties (a sparse clip: thousands of events share one timestamp) would serialise on one counter
-      const unsigned d0 = __shfl_sync(0xffffffffu, d, first);
-      if (__all_sync(0xffffffffu, !valid || d == d0)) {
-        if (lane == first) atomicAdd(&h[p][d0], __popc(vm));
-      } else if (valid) {
-        atomicAdd(&h[p][d], 1);
-      }
+    const unsigned d = (unsigned)(key[k] >> shift) & mask;
+    // massive ties (a sparse clip: thousands of events share one timestamp) would serialise on one counter
+    const unsigned d0 = __shfl_sync(0xffffffffu, d, first);
+    if (__all_sync(0xffffffffu, !valid || d == d0)) {
+      if (lane == first) atomicAdd(&h[d0], __popc(vm));
+    } else if (valid) {
+      atomicAdd(&h[d], 1);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < passes * kOswRadix; i += kThreads) {
-    const int c = (&h[0][0])[i];
-    if (c) atomicAdd(&seg_hist[((size_t)(i / kOswRadix) * ns + seg) * kOswRadix + (i % kOswRadix)], c);
-  }
+  if (threadIdx.x < kOswRadix && h[threadIdx.x]) atomicAdd(&seg_hist[(size_t)seg * kOswRadix + threadIdx.x], h[threadIdx.x]);
 }
 
+// One pass.  Ranking (second generation): warp w owns keys [512w, 512w+512) of the tile in 16 rounds of 32 consecutive
+// keys -- memory order == (warp, round, lane), loads are coalesced as they are -- and every round the lanes find their
+// equal-digit peers with one ballot per digit bit; the lowest peer bumps the warp's private counter of the digit.
+// Per key that is two shared-memory wavefronts where the private-counter / raking-scan version moved ~28 bytes of
+// shared memory per key byte (73 % of the LSU wavefront peak at 103 us per pass, profiles/ncu_ldati_r2_b.txt) and the
+// first generation spent 88 % of the ADU pipe on match.any.
 template <typename Elem>
 __global__ void __launch_bounds__(kThreads, 4) osw_scatter_kernel(const Elem* __restrict__ in, Elem* __restrict__ out,
-                                                                const int64_t* __restrict__ seg_start,
-                                                                const int32_t* __restrict__ tile_first,
-                                                                const int32_t* __restrict__ tile_seg, int ns, int shift, int rb,
-                                                                const int32_t* __restrict__ seg_hist,      // [ns][64], this pass
-                                                                unsigned long long* tstate,               // [nt][64], this pass
-                                                                int32_t* __restrict__ ticket) {
-  extern __shared__ __align__(16) unsigned char osw_smem[];
-  uint32_t* cntw = reinterpret_cast<uint32_t*>(osw_smem);      // packed digit counters, later their exclusive scan
-  Elem* stage = reinterpret_cast<Elem*>(osw_smem);             // aliases the counters (used before and after them)
+                                                                   const int64_t* __restrict__ seg_start,
+                                                                   const int32_t* __restrict__ tile_first,
+                                                                   const int32_t* __restrict__ tile_seg, int ns, int shift, int rb,
+                                                                   const int32_t* __restrict__ seg_hist,   // [ns][64], this pass
+                                                                   int32_t* __restrict__ seg_hist_next,    // [ns][64] of the next pass | NULL
+                                                                   unsigned long long* tstate,             // [nt][64], this pass
+                                                                   int32_t* __restrict__ ticket) {
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kPerWarp = kOswTile / kWarps;                  // 512
+  __shared__ Elem stage[kOswTile];
+  __shared__ int wcnt[kWarps][kOswRadix];                      // per-warp digit counters, then tile-local start positions
+  __shared__ int hnext[kOswRadix];
+  __shared__ int delta[kOswRadix];                             // (position in the segment) - (position in the tile) per digit
+  __shared__ int dcount[kOswRadix];
+  __shared__ int wtot[2];
   __shared__ int s_tile;
-  __shared__ int lbase[kOswRadix + 1];                         // tile-local position of each digit's first key
-  __shared__ long long gbase[kOswRadix];                       // global position of this tile's first key of each digit
-  __shared__ uint32_t wsum[kThreads / 32];
-  __shared__ uint32_t s_total;
-  __shared__ int hsum[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1);
+  for (int i = tid; i < kWarps * kOswRadix; i += kThreads) (&wcnt[0][0])[i] = 0;
+  if (tid < kOswRadix) hnext[tid] = 0;
   __syncthreads();
   const int tile = s_tile;
   if (tile >= tile_first[ns]) return;
   const int seg = tile_seg[tile];
-  const int tfirst = tile_first[seg];
-  const int tin = tile - tfirst;
+  const int tin = tile - tile_first[seg];
   const long long sstart = seg_start[seg];
   const long long start = sstart + (long long)tin * kOswTile;
   const int cnt = (int)min((long long)kOswTile, seg_start[seg + 1] - start);
   const unsigned mask = (1u << rb) - 1u;
+  const unsigned lt = (1u << lane) - 1u;
+  const bool has_next = seg_hist_next != nullptr;
+  const int next_shift = shift + rb;
 
-  // ---- coalesced load, transpose to blocked: thread t owns keys [16t, 16t+16) of the tile ----
-#pragma unroll
-  for (int k = 0; k < kOswKpt; ++k) {
-    const int i = k * kThreads + tid;
-    stage[osw_pad16(i)] = (i < cnt) ? in[start + i] : (Elem)0;
-  }
-  __syncthreads();
   Elem key[kOswKpt];
 #pragma unroll
-  for (int j = 0; j < kOswKpt; ++j) key[j] = stage[osw_pad16(kOswKpt * tid + j)];
-  __syncthreads();
-
-  // ---- private packed counters: digit d -> word (d & 31, tid), half (d >> 5) ----
+  for (int r = 0; r < kOswKpt; ++r) {
+    const int i = warp * kPerWarp + r * 32 + lane;
+    key[r] = (i < cnt) ? in[start + i] : (Elem)0;
+  }
+  int lpos[kOswKpt];
 #pragma unroll
-  for (int l = 0; l < 32; ++l) cntw[osw_pad(l * kThreads + tid)] = 0u;
-  // (own column only: no barrier needed before the thread's own increments)
-  int lpos[kOswKpt];                                           // first the rank among the thread's own keys
-  const int nvalid = min(max(cnt - kOswKpt * tid, 0), kOswKpt);
+  for (int r = 0; r < kOswKpt; ++r) {
+    const bool valid = warp * kPerWarp + r * 32 + lane < cnt;
+    const unsigned d = (unsigned)(key[r] >> shift) & mask;
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+    const unsigned vm = peers;
 #pragma unroll
-  for (int j = 0; j < kOswKpt; ++j) {
-    lpos[j] = 0;
-    if (j < nvalid) {
-      const unsigned d = (unsigned)(key[j] >> shift) & mask;
-      unsigned short* c = reinterpret_cast<unsigned short*>(cntw + osw_pad((int)(d & 31u) * kThreads + tid)) + (d >> 5);
-      const unsigned short r = *c;
-      lpos[j] = r;
-      *c = (unsigned short)(r + 1);
+    for (int b = 0; b < kOswRadixBits; ++b) {
+      const bool bit = (d >> b) & 1u;
+      const unsigned bal = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? bal : ~bal;
     }
-  }
-  __syncthreads();
-  // ---- raking exclusive scan over the flat (lane-major, thread-minor) counter array; both halves at once ----
-  {
-    uint32_t sum = 0u;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) sum += cntw[33 * tid + j];                        // osw_pad(32*tid + j) == 33*tid + j
-    uint32_t inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
+    const int before = __popc(peers & lt);
+    int old = 0;
+    if (valid && before == 0) {                                // the lowest lane of every digit group
+      old = wcnt[warp][d];
+      wcnt[warp][d] = old + __popc(peers);
     }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    uint32_t woff = 0u, total = 0u;
-#pragma unroll
-    for (int wv = 0; wv < kThreads / 32; ++wv) { const uint32_t t = wsum[wv]; if (wv < warp) woff += t; total += t; }
-    if (tid == 0) s_total = total;
-    uint32_t run = woff + inc - sum;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) { const uint32_t wv = cntw[33 * tid + j]; cntw[33 * tid + j] = run; run += wv; }
+    old = __shfl_sync(0xffffffffu, old, (__ffs(peers) - 1) & 31);
+    lpos[r] = old + before;
+    if (has_next && vm) {                                      // digit histogram of the next pass, from the same registers
+      const unsigned d2 = (unsigned)(key[r] >> next_shift) & mask;
+      const int first = __ffs(vm) - 1;
+      const unsigned d0 = __shfl_sync(0xffffffffu, d2, first);
+      if (__all_sync(0xffffffffu, !valid || d2 == d0)) {
+        if (lane == first) atomicAdd(&hnext[d0], __popc(vm));
+      } else if (valid) {
+        atomicAdd(&hnext[d2], 1);
+      }
+    }
+    __syncwarp();
   }
   __syncthreads();
-  const int total_lo = (int)(s_total & 0xffffu);                // keys whose digit is < 32
-  // ---- tile-local stable positions; digit starts ----
+  // ---- per digit: exclusive prefix over the warps, tile totals, digit starts, segment-level digit bases ----
+  int mine = 0, hcount = 0, hinc = 0, dinc = 0;
+  if (tid < kOswRadix) {
+    int run = 0;
 #pragma unroll
-  for (int j = 0; j < kOswKpt; ++j) {
-    const unsigned d = (unsigned)(key[j] >> shift) & mask;
-    const uint32_t wv = cntw[osw_pad((int)(d & 31u) * kThreads + tid)];
-    lpos[j] += (d >> 5) ? total_lo + (int)(wv >> 16) : (int)(wv & 0xffffu);
-  }
-  int my_start = 0;
-  if (tid < kOswRadix) {
-    const uint32_t wv = cntw[osw_pad((tid & 31) * kThreads)];
-    my_start = (tid >> 5) ? total_lo + (int)(wv >> 16) : (int)(wv & 0xffffu);
-    lbase[tid] = my_start;
-  }
-  if (tid == 0) lbase[kOswRadix] = cnt;
-  // digit bases inside the segment: exclusive scan of the segment's histogram of this pass (64 values, two warps)
-  int hcount = 0, hinc = 0;
-  if (tid < kOswRadix) {
+    for (int w = 0; w < kWarps; ++w) { const int t = wcnt[w][tid]; wcnt[w][tid] = run; run += t; }
+    mine = run;
     hcount = seg_hist[(size_t)seg * kOswRadix + tid];
     hinc = hcount;
+    dinc = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, hinc, o);
-      if (lane >= o) hinc += t;
+      const int u = __shfl_up_sync(0xffffffffu, dinc, o);
+      if (lane >= o) { hinc += t; dinc += u; }
     }
-    if (lane == 31) hsum[warp] = hinc;
+    if (tid == 31) { wtot[0] = hinc; wtot[1] = dinc; }
   }
-  __syncthreads();                                             // counters are dead from here: `stage` may be written
-  // ---- decoupled look-back over the earlier tiles of this segment, one thread per digit ----
+  __syncthreads();
   if (tid < kOswRadix) {
-    const long long digit_base = (long long)(hinc - hcount) + (warp == 1 ? hsum[0] : 0);
-    const unsigned long long mine = (unsigned long long)(lbase[tid + 1] - my_start);
+    const int lstart = dinc - mine + (warp == 1 ? wtot[1] : 0);          // tile-local position of the digit's first key
+    const int digit_base = hinc - hcount + (warp == 1 ? wtot[0] : 0);    // keys of smaller digits in the whole segment
+    dcount[tid] = lstart;
+    // ---- decoupled look-back over the earlier tiles of this segment ----
     volatile unsigned long long* st = tstate + (size_t)tile * kOswRadix + tid;
     unsigned long long excl = 0ull;
     if (tin == 0) {
-      *st = kOswFlagIncl | mine;
+      *st = kOswFlagIncl | (unsigned long long)mine;
     } else {
-      *st = kOswFlagAgg | mine;
+      *st = kOswFlagAgg | (unsigned long long)mine;
       int look = tile - 1;
       while (true) {
         const unsigned long long v = *(volatile unsigned long long*)(tstate + (size_t)look * kOswRadix + tid);
@@ -1269,22 +1251,109 @@ __global__ void __launch_bounds__(kThreads, 4) osw_scatter_kernel(const Elem* __
         if ((v >> 62) == 2ull) break;
         --look;
       }
-      *st = kOswFlagIncl | (excl + mine);
+      *st = kOswFlagIncl | (excl + (unsigned long long)mine);
     }
-    gbase[tid] = sstart + digit_base + (long long)excl;
+    delta[tid] = digit_base + (int)excl - lstart;
+    if (has_next && hnext[tid]) atomicAdd(&seg_hist_next[(size_t)seg * kOswRadix + tid], hnext[tid]);
   }
+  __syncthreads();
   // ---- order the tile by digit in shared memory, then write every digit's run to consecutive addresses ----
 #pragma unroll
-  for (int j = 0; j < kOswKpt; ++j)
-    if (j < nvalid) stage[lpos[j]] = key[j];
+  for (int r = 0; r < kOswKpt; ++r) {
+    if (warp * kPerWarp + r * 32 + lane < cnt) {
+      const unsigned d = (unsigned)(key[r] >> shift) & mask;
+      stage[dcount[d] + wcnt[warp][d] + lpos[r]] = key[r];
+    }
+  }
   __syncthreads();
+  Elem* dst = out + sstart;
 #pragma unroll 4
   for (int k = 0; k < kOswKpt; ++k) {
     const int i = k * kThreads + tid;
     if (i < cnt) {
       const Elem e = stage[i];
       const unsigned d = (unsigned)(e >> shift) & mask;
-      out[gbase[d] + (long long)(i - lbase[d])] = e;
+      dst[delta[d] + i] = e;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K7': 13-byte records without shared memory.  A warp takes 32 consecutive sorted elements = 416 consecutive output
+// bytes; every lane builds its record in four registers and the aligned 32-bit words of the byte stream are assembled
+// from the neighbours' registers with shuffles (5 per word) and leave as 128-byte coalesced stores.  The first
+// generation staged the bytes through shared memory with 13 one-byte stores per record: 92 % of the LSU wavefront
+// peak, 103 us for 21.6 M events (profiles/ncu_ldati_r2_b.txt).
+// ---------------------------------------------------------------------------------------
+template <typename Elem>
+__global__ void __launch_bounds__(kThreads) pack_shfl_kernel(const Elem* __restrict__ in, const int64_t* __restrict__ seg_start,
+                                                              const int32_t* __restrict__ tile_first,
+                                                              const int32_t* __restrict__ tile_seg, int ns, DevParams P,
+                                                              const int64_t* __restrict__ frame_offset_us,
+                                                              uint8_t* __restrict__ out) {
+  const int tile = blockIdx.x;
+  if (tile >= tile_first[ns]) return;
+  const int seg = tile_seg[tile];
+  const int tin = tile - tile_first[seg];
+  const long long start = seg_start[seg] + (long long)tin * kOswTile;
+  const int cnt = (int)min((long long)kOswTile, seg_start[seg + 1] - start);
+  const int f = seg / kBins, c = seg % kBins;
+  const long long base_ts = P.bin_base[c] - kKeyBias;
+  long long off = 0;
+  if (P.add_frame_offset && frame_offset_us != nullptr) off = frame_offset_us[f];
+  const unsigned long long pix_mask = (1ull << P.pix_bits) - 1ull;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int chunk = warp; chunk * 32 < cnt; chunk += kThreads / 32) {
+    const int i = chunk * 32 + lane;
+    const int nrec = min(32, cnt - chunk * 32);
+    unsigned w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+    if (lane < nrec) {
+      const unsigned long long e = (unsigned long long)in[start + i];
+      const int pix = (int)(e & pix_mask);
+      const long long key = (long long)(e >> (P.pix_bits + 1));
+      long long ts = (key == 0) ? P.nan_ts : (base_ts + key);
+      ts = (long long)((unsigned long long)ts + (unsigned long long)off);
+      const unsigned y = (unsigned)(pix / P.W), x = (unsigned)pix - y * (unsigned)P.W;
+      w0 = (unsigned)((unsigned long long)ts);
+      w1 = (unsigned)((unsigned long long)ts >> 32);
+      w2 = (x & 0xffffu) | (y << 16);
+      w3 = (unsigned)((e >> P.pix_bits) & 1ull);
+    }
+    const unsigned long long gbyte = (unsigned long long)(start + chunk * 32) * 13ull;
+    const unsigned long long gaddr = (unsigned long long)(uintptr_t)out + gbyte;
+    const int mis = (int)(gaddr & 3ull);
+    const int nb = nrec * 13;                                  // bytes of this chunk
+    unsigned* gout = reinterpret_cast<unsigned*>(out + gbyte - mis);     // 4-byte aligned
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int k = lane + 32 * m;                             // aligned word k covers chunk bytes [4k - mis, 4k - mis + 4)
+      const int s0 = 4 * k - mis;
+      // record and byte offset of the word's first byte (s0 may be -3..-1 for k = 0: treated as record 0, offset < 0)
+      const int sc = max(s0, 0);
+      const int r0 = (sc * 5042) >> 16;                        // sc / 13 for sc < 2^13 (5042 = ceil(2^16 / 13))
+      const int o0 = s0 - 13 * r0;                             // may be negative only for the chunk's first word
+      const int q = max(o0, 0) >> 2;
+      const unsigned a0 = __shfl_sync(0xffffffffu, w0, r0 & 31), a1 = __shfl_sync(0xffffffffu, w1, r0 & 31);
+      const unsigned a2 = __shfl_sync(0xffffffffu, w2, r0 & 31), a3 = __shfl_sync(0xffffffffu, w3, r0 & 31);
+      const unsigned nx = __shfl_sync(0xffffffffu, w0, (r0 + 1) & 31);
+      const unsigned lo = q == 0 ? a0 : q == 1 ? a1 : q == 2 ? a2 : a3;
+      const unsigned hi = q == 0 ? a1 : q == 1 ? a2 : q == 2 ? a3 : 0u;
+      unsigned v;
+      if (o0 >= 0) {
+        v = __funnelshift_r(lo, hi, 8 * (o0 & 3));             // bytes o0 .. o0+3 of record r0
+        const int from_r0 = 13 - o0;                           // bytes left in record r0
+        if (from_r0 < 4) v = (v & ((1u << (8 * from_r0)) - 1u)) | (nx << (8 * from_r0));
+      } else {
+        v = a0 << (8 * (-o0));                                 // the chunk starts inside this word: low bytes belong to the chunk before
+      }
+      if (s0 >= 0 && s0 + 4 <= nb) {
+        gout[k] = v;
+      } else if (s0 + 4 > 0 && s0 < nb) {                      // partial word at either end of the chunk: byte stores
+        uint8_t* gb = reinterpret_cast<uint8_t*>(gout + k);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (s0 + t >= 0 && s0 + t < nb) gb[t] = (uint8_t)(v >> (8 * t));
+      }
     }
   }
 }
@@ -1443,13 +1512,15 @@ static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometr
 #undef V2CE_LAUNCH_EMIT
   V2CE_LAUNCH_CHECK("ldati::emit_kernel");
   if (total == 0) return V2CE_OK;
-  build_tiles_kernel<<<1, 1024, 0, s>>>(cw.seg_start, ns, kTile, sw.tile_first);
-  V2CE_LAUNCH_CHECK("ldati::build_tiles_kernel");
-  fill_tile_seg_kernel<<<(sw.nt_max + 255) / 256, 256, 0, s>>>(sw.tile_first, ns, sw.tile_seg);
-  V2CE_LAUNCH_CHECK("ldati::fill_tile_seg_kernel");
   Elem* src = ea;
   Elem* dst = eb;
   const bool osw = onesweep();
+  if (!osw) {
+    build_tiles_kernel<<<1, 1024, 0, s>>>(cw.seg_start, ns, kTile, sw.tile_first);
+    V2CE_LAUNCH_CHECK("ldati::build_tiles_kernel");
+    fill_tile_seg_kernel<<<(sw.nt_max + 255) / 256, 256, 0, s>>>(sw.tile_first, ns, sw.tile_seg);
+    V2CE_LAUNCH_CHECK("ldati::fill_tile_seg_kernel");
+  }
   if (osw) {
     // one-sweep LSD passes over the key field, <= 6 bits each
     const int passes = osw_passes(g.key_bits);
@@ -1460,17 +1531,20 @@ static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometr
     V2CE_LAUNCH_CHECK("ldati::fill_tile_seg_kernel");
     V2CE_CUDA_CHECK(cudaMemsetAsync(sw.osw_zero, 0, sw.osw_zero_bytes, s));
     osw_hist_kernel<Elem><<<sw.nt4_max, kThreads, 0, s>>>(src, cw.seg_start, sw.tile_first4, sw.tile_seg4, ns, g.pix_bits + 1, rb,
-                                                          passes, sw.seg_hist);
+                                                          sw.seg_hist);
     V2CE_LAUNCH_CHECK("ldati::osw_hist_kernel");
-    const size_t smem = (size_t)kOswCounterWords * 4 > (size_t)kOswStageSlots * sizeof(Elem)
-                            ? (size_t)kOswCounterWords * 4 : (size_t)kOswStageSlots * sizeof(Elem);
     for (int pass = 0; pass < passes; ++pass) {
-      osw_scatter_kernel<Elem><<<sw.nt4_max, kThreads, smem, s>>>(
+      osw_scatter_kernel<Elem><<<sw.nt4_max, kThreads, 0, s>>>(
           src, dst, cw.seg_start, sw.tile_first4, sw.tile_seg4, ns, g.pix_bits + 1 + pass * rb, rb,
-          sw.seg_hist + (size_t)pass * ns * kOswRadix, sw.tstate + (size_t)pass * sw.nt4_max * kOswRadix, sw.tickets + pass);
+          sw.seg_hist + (size_t)pass * ns * kOswRadix,
+          pass + 1 < passes ? sw.seg_hist + (size_t)(pass + 1) * ns * kOswRadix : nullptr,
+          sw.tstate + (size_t)pass * sw.nt4_max * kOswRadix, sw.tickets + pass);
       V2CE_LAUNCH_CHECK("ldati::osw_scatter_kernel");
       Elem* t = src; src = dst; dst = t;
     }
+    pack_shfl_kernel<Elem><<<sw.nt4_max, kThreads, 0, s>>>(src, cw.seg_start, sw.tile_first4, sw.tile_seg4, ns, P, frame_off, out);
+    V2CE_LAUNCH_CHECK("ldati::pack_shfl_kernel");
+    return V2CE_OK;
   }
   // first-generation path: LSD passes over the key field, <= 8 bits each
   const int passes = osw ? 0 : (g.key_bits + 7) / 8;

@@ -298,16 +298,22 @@ def _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width
     starts, _ = schedule if schedule is not None else window_schedule(frame_count, seq_len)
     read, close = _window_reader(image_paths, vidcap, starts, seq_len)
     pending = []
+    pin = torch.cuda.is_available()
     try:
         for i in range(len(starts)):
             fr = np.asarray(read(i))
-            if width is None:
-                pending.append(np.ascontiguousarray(fr)[None])
-            else:
+            if width is not None:
                 c = fr.shape[-1] // 2
-                pending.append(np.ascontiguousarray(fr[..., c - width // 2:c + width // 2])[None])
+                fr = fr[..., c - width // 2:c + width // 2]
+            pending.append(fr)
             if len(pending) == batch_size or i == len(starts) - 1:
-                yield torch.from_numpy(np.concatenate(pending, axis=0)), i == len(starts) - 1
+                # ONE copy per frame, straight into the page-locked batch the H2D transfer reads (a 1080p window is
+                # 35 MB: stacking, concatenating and pinning it separately made the host the bottleneck of a pano clip)
+                out = torch.empty((len(pending),) + tuple(pending[0].shape), dtype=torch.uint8, pin_memory=pin)
+                o = out.numpy()
+                for j, w in enumerate(pending):
+                    np.copyto(o[j], w)
+                yield out, i == len(starts) - 1
                 pending = []
     finally:
         close()
@@ -371,7 +377,7 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
         pair_idx = pair_base
         prev = None
         for x, is_last in _background(batches):
-            t = runner.submit(x.pin_memory(), pair_idx, keep_sums=write_event_frames or keep_event_frame_sums,
+            t = runner.submit(x if x.is_pinned() else x.pin_memory(), pair_idx, keep_sums=write_event_frames or keep_event_frame_sums,
                               trim_last_window_to=mode if (is_last and mode != 0) else 0)
             pair_idx += t.n_pairs
             if prev is not None:
