@@ -251,3 +251,22 @@ def test_empty_and_negative_inputs():
     got = _run(v, seed=2)
     want = lo.sample_voxel_statistical_oracle(v, seed=2, flavor='cuda')
     _assert_rows_equal(got[0], want[0], 'negative')
+
+
+@pytest.mark.parametrize('shift', [0, 1, 4, 13])
+def test_output_buffer_of_any_alignment(shift):
+    """v2ce_ldati_emit takes a caller pointer: the record writer uses 16-byte stores when the buffer allows it and word
+    or byte stores otherwise; the bytes are the same."""
+    from v2ce_toolbox_b200 import ldati
+    v = synth.make_voxels('mixed', 2, 33, 47, seed=5)
+    want = np.concatenate(lo.sample_voxel_statistical_oracle(v, fps=30, seed=3, flavor='cuda')).view(np.uint8)
+    eng = ldati.LdatiEngine('cuda')
+    vox = torch.from_numpy(v).cuda()
+    params = ldati.make_params(2, 33, 47, fps=30, seed=3, device='cuda')
+    seg = eng.count(vox, params)
+    total = int(seg.sum())
+    buf = torch.full((total * 13 + 64,), 0xAB, dtype=torch.uint8, device='cuda')
+    out, status = eng.emit(vox, params, total, out=buf[shift:])
+    got = buf.cpu().numpy()
+    assert np.array_equal(got[shift:shift + total * 13], want)
+    assert (got[:shift] == 0xAB).all() and (got[shift + total * 13:] == 0xAB).all()      # nothing outside the records

@@ -31,7 +31,9 @@ def test_video_to_voxels_matches_reference_golden(name, golden, golden_meta):
     ref = g[f'{name}_voxel']
     assert vox.shape == ref.shape and vox.dtype == np.float32
     rel = np.linalg.norm(vox - ref) / np.linalg.norm(ref)
-    assert rel <= 2e-2, rel                                   # bf16 tolerance, DESIGN.md section 2
+    from conftest import record_measurement
+    record_measurement('pipeline_voxel_vs_reference_golden', name=name, init=m['init'], rel_l2=float(rel))
+    assert rel <= 1.6e-2, rel                                 # 'lively' stress weights: see tests/test_gpu_unet.py
 
 
 @pytest.mark.parametrize('n_frames,bs', [(20, 2), (33, 1), (36, 4)])

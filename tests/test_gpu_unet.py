@@ -169,8 +169,16 @@ def _model(seed, init):
 @pytest.mark.parametrize('init,shape', [('lively', (1, 16, 2, 36, 44)), ('lively', (2, 16, 2, 20, 28)),
                                         ('reference', (1, 16, 2, 65, 87)), ('lively', (1, 16, 2, 260, 346))])
 def test_forward_vs_fp32_oracle(init, shape):
-    """Tolerance (stated): bf16 operands / fp32 accumulation against the fp32 reference:
-    rel-L2 <= 2e-2 and max-abs <= 5e-2 * max(ref), on two consecutive calls (spectral-norm state)."""
+    """Tolerance (stated): bf16 operands / fp32 accumulation / bf16 inter-layer activations against the
+    fp32 reference, on two consecutive calls (spectral-norm state).  With the reference's own initialisation (what every
+    other voxel test and the bench use) the calibrated bound holds with room: rel-L2 <= 1e-2, max-abs <= 3e-2 * max(ref)
+    (measured on the B200: 4.2e-3 / 4.5e-3 at 65x87; 2.9e-3 / 3.4e-3 at 260x346 against cuDNN fp32,
+    tests/test_gpu_torch_reference.py; cuDNN's own TF32 default deviates by 5.3e-4).  The 'lively' stress initialisation
+    (He-scaled weights 8x the reference's, random BatchNorm statistics and biases: every layer carries signal and the
+    bf16 rounding of 26 layers of activations accumulates, synth_inputs.make_state_dict) is
+    measured at 0.92e-2 .. 1.31e-2 rel-L2 and 1.2e-2 .. 2.1e-2 max-abs depending on the plane size (gpurun_out/
+    measurements_r2.jsonl, copied to profiles/voxel_tolerance_r2.jsonl): it is held to 1.6e-2 / 3e-2."""
+    tol_rel, tol_max = (1e-2, 3e-2) if init == 'reference' else (1.6e-2, 3e-2)
     m, sd = _model(3, init)
     orc = UNetOracle(sd)
     g = torch.Generator(device='cpu').manual_seed(7)
@@ -183,7 +191,7 @@ def test_forward_vs_fp32_oracle(init, shape):
         rel = float((y - ref).norm() / ref.norm())
         mx = float((y - ref).abs().max() / ref.abs().max())
         record_measurement('voxel_vs_fp32_oracle', init=init, shape=list(shape), call=call, rel_l2=rel, max_abs_over_max=mx)
-        assert rel <= 2e-2 and mx <= 5e-2, (init, shape, call, rel, mx)
+        assert rel <= tol_rel and mx <= tol_max, (init, shape, call, rel, mx)
     assert m.call_count() == 2 and orc.calls == 2
 
 
@@ -213,7 +221,7 @@ def test_forward_matches_reference_golden(golden, golden_meta):
             rel = np.linalg.norm(y - ref) / np.linalg.norm(ref)
             record_measurement('voxel_vs_reference_golden', name=name, call=call, rel_l2=float(rel),
                                max_abs_over_max=float(np.abs(y - ref).max() / np.abs(ref).max()))
-            assert rel <= 2e-2, (name, call, rel)
+            assert rel <= 1e-2, (name, call, rel)       # measured 2.9e-3 (reference init) / 7.9e-3 ('lively')
 
 
 def test_rejects_cpu_input():

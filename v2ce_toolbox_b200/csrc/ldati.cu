@@ -41,6 +41,7 @@ constexpr int kOswTile = kThreads * kOswKpt;
 constexpr int kOswRadixBits = 6;
 constexpr int kOswRadix = 1 << kOswRadixBits;
 constexpr int kOswMaxPasses = 6;
+constexpr int kPackRecsPerWarpDecl = 128;      // records per pack chunk (pack_linear_kernel)
 static inline int osw_passes(int key_bits) { return (key_bits + kOswRadixBits - 1) / kOswRadixBits; }
 
 struct Geometry {
@@ -765,6 +766,7 @@ struct SortWs {
   int32_t* tickets;      // [kOswMaxPasses]
   int32_t* seg_hist;     // [kOswMaxPasses][NS][64]
   unsigned long long* tstate;   // [kOswMaxPasses][NT4_max][64]
+  int32_t* chunk_seg;    // [ceil(total / 128)] segment of the first record of every 128-record pack chunk
   size_t bytes;
   int nt_max;
   int nt4_max;
@@ -790,6 +792,7 @@ static SortWs carve_sort_ws(void* ws, const Geometry& g, int64_t total, int elem
   s.seg_hist = a.take<int32_t>((size_t)passes * ns * kOswRadix);
   s.tstate = a.take<unsigned long long>((size_t)passes * s.nt4_max * kOswRadix);
   s.osw_zero_bytes = (size_t)((a.base + a.off) - s.osw_zero);
+  s.chunk_seg = a.take<int32_t>((size_t)(total / kPackRecsPerWarpDecl) + 2);
   s.bytes = align_up(a.off, 256);
   return s;
 }
@@ -1090,20 +1093,20 @@ __global__ void __launch_bounds__(kThreads) pack_kernel(const Elem* __restrict__
 // ---------------------------------------------------------------------------------------
 constexpr unsigned long long kOswFlagAgg = 1ull << 62, kOswFlagIncl = 2ull << 62, kOswValMask = (1ull << 62) - 1ull;
 
-// digit histogram of the FIRST pass per segment (the later passes get theirs from the scatter pass before them)
+// digit histograms of ALL passes per segment, from one read of the keys
 template <typename Elem>
 __global__ void __launch_bounds__(kThreads) osw_hist_kernel(const Elem* __restrict__ in, const int64_t* __restrict__ seg_start,
                                                              const int32_t* __restrict__ tile_first,
-                                                             const int32_t* __restrict__ tile_seg, int ns, int shift, int rb,
-                                                             int32_t* __restrict__ seg_hist) {
+                                                             const int32_t* __restrict__ tile_seg, int ns, int shift0, int rb,
+                                                             int passes, int32_t* __restrict__ seg_hist) {
   const int tile = blockIdx.x;
   if (tile >= tile_first[ns]) return;
   const int seg = tile_seg[tile];
   const int tin = tile - tile_first[seg];
   const long long start = seg_start[seg] + (long long)tin * kOswTile;
   const int cnt = (int)min((long long)kOswTile, seg_start[seg + 1] - start);
-  __shared__ int h[kOswRadix];
-  if (threadIdx.x < kOswRadix) h[threadIdx.x] = 0;
+  __shared__ int h[kOswMaxPasses][kOswRadix];
+  for (int i = threadIdx.x; i < kOswMaxPasses * kOswRadix; i += kThreads) (&h[0][0])[i] = 0;
   __syncthreads();
   const unsigned mask = (1u << rb) - 1u;
   const int lane = threadIdx.x & 31;
@@ -1119,130 +1122,156 @@ __global__ void __launch_bounds__(kThreads) osw_hist_kernel(const Elem* __restri
     const unsigned vm = __ballot_sync(0xffffffffu, valid);
     if (vm == 0u) continue;
     const int first = __ffs(vm) - 1;
-    const unsigned d = (unsigned)(key[k] >> shift) & mask;
-    // massive ties (a sparse clip: thousands of events share one timestamp) would serialise on one counter
-    const unsigned d0 = __shfl_sync(0xffffffffu, d, first);
-    if (__all_sync(0xffffffffu, !valid || d == d0)) {
-      if (lane == first) atomicAdd(&h[d0], __popc(vm));
-    } else if (valid) {
-      atomicAdd(&h[d], 1);
+    for (int p = 0; p < passes; ++p) {
+      const unsigned d = (unsigned)(key[k] >> (shift0 + p * rb)) & mask;
+      // massive ties (a sparse clip: thousands of events share one timestamp) would serialise on one counter
+      const unsigned d0 = __shfl_sync(0xffffffffu, d, first);
+      if (__all_sync(0xffffffffu, !valid || d == d0)) {
+        if (lane == first) atomicAdd(&h[p][d0], __popc(vm));
+      } else if (valid) {
+        atomicAdd(&h[p][d], 1);
+      }
     }
   }
   __syncthreads();
-  if (threadIdx.x < kOswRadix && h[threadIdx.x]) atomicAdd(&seg_hist[(size_t)seg * kOswRadix + threadIdx.x], h[threadIdx.x]);
+  for (int i = threadIdx.x; i < passes * kOswRadix; i += kThreads) {
+    const int c = (&h[0][0])[i];
+    if (c) atomicAdd(&seg_hist[((size_t)(i / kOswRadix) * ns + seg) * kOswRadix + (i % kOswRadix)], c);
+  }
 }
 
-// One pass.  Ranking (second generation): warp w owns keys [512w, 512w+512) of the tile in 16 rounds of 32 consecutive
-// keys -- memory order == (warp, round, lane), loads are coalesced as they are -- and every round the lanes find their
-// equal-digit peers with one ballot per digit bit; the lowest peer bumps the warp's private counter of the digit.
-// Per key that is two shared-memory wavefronts where the private-counter / raking-scan version moved ~28 bytes of
-// shared memory per key byte (73 % of the LSU wavefront peak at 103 us per pass, profiles/ncu_ldati_r2_b.txt) and the
-// first generation spent 88 % of the ADU pipe on match.any.
+__device__ __forceinline__ int osw_pad(int i) { return i + (i >> 5); }        // counters: one pad word per 32
+__device__ __forceinline__ int osw_pad16(int i) { return i + (i >> 4); }      // key transpose: one pad slot per 16
+constexpr int kOswCounterWords = 32 * kThreads + (32 * kThreads >> 5);         // 8448
+constexpr int kOswStageSlots = kOswTile + (kOswTile >> 4);                     // 4352
+
+// One pass.  Ranking without match / atomics: every thread counts the digits of its 16 CONSECUTIVE keys in private
+// packed 16-bit counters in shared memory ([32 lanes][256 threads] words, two digits per word); one padded raking
+// scan over (digit, thread) turns the counters into tile-local stable positions.  Keys are loaded coalesced and
+// transposed to the blocked arrangement through (padded) shared memory.  103 us per pass for 21.6 M keys (1.7 TB/s of
+// key traffic, 73 % of the shared-memory wavefront peak).  Measured and not adopted: ranking with one ballot per
+// digit bit in warp-private counters (CUB's match-by-bits): fewer shared-memory wavefronts (41 %) but 72 % of the ALU
+// pipe, 119-129 us per pass (profiles/ncu_ldati_r2_c.txt).
 template <typename Elem>
 __global__ void __launch_bounds__(kThreads, 4) osw_scatter_kernel(const Elem* __restrict__ in, Elem* __restrict__ out,
-                                                                   const int64_t* __restrict__ seg_start,
-                                                                   const int32_t* __restrict__ tile_first,
-                                                                   const int32_t* __restrict__ tile_seg, int ns, int shift, int rb,
-                                                                   const int32_t* __restrict__ seg_hist,   // [ns][64], this pass
-                                                                   int32_t* __restrict__ seg_hist_next,    // [ns][64] of the next pass | NULL
-                                                                   unsigned long long* tstate,             // [nt][64], this pass
-                                                                   int32_t* __restrict__ ticket) {
-  constexpr int kWarps = kThreads / 32;
-  constexpr int kPerWarp = kOswTile / kWarps;                  // 512
-  __shared__ Elem stage[kOswTile];
-  __shared__ int wcnt[kWarps][kOswRadix];                      // per-warp digit counters, then tile-local start positions
-  __shared__ int hnext[kOswRadix];
-  __shared__ int delta[kOswRadix];                             // (position in the segment) - (position in the tile) per digit
-  __shared__ int dcount[kOswRadix];
-  __shared__ int wtot[2];
+                                                                const int64_t* __restrict__ seg_start,
+                                                                const int32_t* __restrict__ tile_first,
+                                                                const int32_t* __restrict__ tile_seg, int ns, int shift, int rb,
+                                                                const int32_t* __restrict__ seg_hist,      // [ns][64], this pass
+                                                                unsigned long long* tstate,               // [nt][64], this pass
+                                                                int32_t* __restrict__ ticket) {
+  extern __shared__ __align__(16) unsigned char osw_smem[];
+  uint32_t* cntw = reinterpret_cast<uint32_t*>(osw_smem);      // packed digit counters, later their exclusive scan
+  Elem* stage = reinterpret_cast<Elem*>(osw_smem);             // aliases the counters (used before and after them)
   __shared__ int s_tile;
+  __shared__ int lbase[kOswRadix + 1];                         // tile-local position of each digit's first key
+  __shared__ int delta[kOswRadix];                             // (position in the segment) - (position in the tile) per digit
+  __shared__ uint32_t wsum[kThreads / 32];
+  __shared__ uint32_t s_total;
+  __shared__ int hsum[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(ticket, 1);
-  for (int i = tid; i < kWarps * kOswRadix; i += kThreads) (&wcnt[0][0])[i] = 0;
-  if (tid < kOswRadix) hnext[tid] = 0;
   __syncthreads();
   const int tile = s_tile;
   if (tile >= tile_first[ns]) return;
   const int seg = tile_seg[tile];
-  const int tin = tile - tile_first[seg];
+  const int tfirst = tile_first[seg];
+  const int tin = tile - tfirst;
   const long long sstart = seg_start[seg];
   const long long start = sstart + (long long)tin * kOswTile;
   const int cnt = (int)min((long long)kOswTile, seg_start[seg + 1] - start);
   const unsigned mask = (1u << rb) - 1u;
-  const unsigned lt = (1u << lane) - 1u;
-  const bool has_next = seg_hist_next != nullptr;
-  const int next_shift = shift + rb;
 
-  Elem key[kOswKpt];
+  // ---- coalesced load, transpose to blocked: thread t owns keys [16t, 16t+16) of the tile ----
 #pragma unroll
-  for (int r = 0; r < kOswKpt; ++r) {
-    const int i = warp * kPerWarp + r * 32 + lane;
-    key[r] = (i < cnt) ? in[start + i] : (Elem)0;
-  }
-  int lpos[kOswKpt];
-#pragma unroll
-  for (int r = 0; r < kOswKpt; ++r) {
-    const bool valid = warp * kPerWarp + r * 32 + lane < cnt;
-    const unsigned d = (unsigned)(key[r] >> shift) & mask;
-    unsigned peers = __ballot_sync(0xffffffffu, valid);
-    const unsigned vm = peers;
-#pragma unroll
-    for (int b = 0; b < kOswRadixBits; ++b) {
-      const bool bit = (d >> b) & 1u;
-      const unsigned bal = __ballot_sync(0xffffffffu, bit);
-      peers &= bit ? bal : ~bal;
-    }
-    const int before = __popc(peers & lt);
-    int old = 0;
-    if (valid && before == 0) {                                // the lowest lane of every digit group
-      old = wcnt[warp][d];
-      wcnt[warp][d] = old + __popc(peers);
-    }
-    old = __shfl_sync(0xffffffffu, old, (__ffs(peers) - 1) & 31);
-    lpos[r] = old + before;
-    if (has_next && vm) {                                      // digit histogram of the next pass, from the same registers
-      const unsigned d2 = (unsigned)(key[r] >> next_shift) & mask;
-      const int first = __ffs(vm) - 1;
-      const unsigned d0 = __shfl_sync(0xffffffffu, d2, first);
-      if (__all_sync(0xffffffffu, !valid || d2 == d0)) {
-        if (lane == first) atomicAdd(&hnext[d0], __popc(vm));
-      } else if (valid) {
-        atomicAdd(&hnext[d2], 1);
-      }
-    }
-    __syncwarp();
+  for (int k = 0; k < kOswKpt; ++k) {
+    const int i = k * kThreads + tid;
+    stage[osw_pad16(i)] = (i < cnt) ? in[start + i] : (Elem)0;
   }
   __syncthreads();
-  // ---- per digit: exclusive prefix over the warps, tile totals, digit starts, segment-level digit bases ----
-  int mine = 0, hcount = 0, hinc = 0, dinc = 0;
-  if (tid < kOswRadix) {
-    int run = 0;
+  Elem key[kOswKpt];
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) { const int t = wcnt[w][tid]; wcnt[w][tid] = run; run += t; }
-    mine = run;
+  for (int j = 0; j < kOswKpt; ++j) key[j] = stage[osw_pad16(kOswKpt * tid + j)];
+  __syncthreads();
+
+  // ---- private packed counters: digit d -> word (d & 31, tid), half (d >> 5) ----
+#pragma unroll
+  for (int l = 0; l < 32; ++l) cntw[osw_pad(l * kThreads + tid)] = 0u;
+  // (own column only: no barrier needed before the thread's own increments)
+  int lpos[kOswKpt];                                           // first the rank among the thread's own keys
+  const int nvalid = min(max(cnt - kOswKpt * tid, 0), kOswKpt);
+#pragma unroll
+  for (int j = 0; j < kOswKpt; ++j) {
+    lpos[j] = 0;
+    if (j < nvalid) {
+      const unsigned d = (unsigned)(key[j] >> shift) & mask;
+      unsigned short* c = reinterpret_cast<unsigned short*>(cntw + osw_pad((int)(d & 31u) * kThreads + tid)) + (d >> 5);
+      const unsigned short r = *c;
+      lpos[j] = r;
+      *c = (unsigned short)(r + 1);
+    }
+  }
+  __syncthreads();
+  // ---- raking exclusive scan over the flat (lane-major, thread-minor) counter array; both halves at once ----
+  {
+    uint32_t sum = 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sum += cntw[33 * tid + j];                        // osw_pad(32*tid + j) == 33*tid + j
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0u, total = 0u;
+#pragma unroll
+    for (int wv = 0; wv < kThreads / 32; ++wv) { const uint32_t t = wsum[wv]; if (wv < warp) woff += t; total += t; }
+    if (tid == 0) s_total = total;
+    uint32_t run = woff + inc - sum;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { const uint32_t wv = cntw[33 * tid + j]; cntw[33 * tid + j] = run; run += wv; }
+  }
+  __syncthreads();
+  const int total_lo = (int)(s_total & 0xffffu);                // keys whose digit is < 32
+  // ---- tile-local stable positions; digit starts ----
+#pragma unroll
+  for (int j = 0; j < kOswKpt; ++j) {
+    const unsigned d = (unsigned)(key[j] >> shift) & mask;
+    const uint32_t wv = cntw[osw_pad((int)(d & 31u) * kThreads + tid)];
+    lpos[j] += (d >> 5) ? total_lo + (int)(wv >> 16) : (int)(wv & 0xffffu);
+  }
+  int my_start = 0;
+  if (tid < kOswRadix) {
+    const uint32_t wv = cntw[osw_pad((tid & 31) * kThreads)];
+    my_start = (tid >> 5) ? total_lo + (int)(wv >> 16) : (int)(wv & 0xffffu);
+    lbase[tid] = my_start;
+  }
+  if (tid == 0) lbase[kOswRadix] = cnt;
+  // digit bases inside the segment: exclusive scan of the segment's histogram of this pass (64 values, two warps)
+  int hcount = 0, hinc = 0;
+  if (tid < kOswRadix) {
     hcount = seg_hist[(size_t)seg * kOswRadix + tid];
     hinc = hcount;
-    dinc = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, hinc, o);
-      const int u = __shfl_up_sync(0xffffffffu, dinc, o);
-      if (lane >= o) { hinc += t; dinc += u; }
+      if (lane >= o) hinc += t;
     }
-    if (tid == 31) { wtot[0] = hinc; wtot[1] = dinc; }
+    if (lane == 31) hsum[warp] = hinc;
   }
-  __syncthreads();
+  __syncthreads();                                             // counters are dead from here: `stage` may be written
+  // ---- decoupled look-back over the earlier tiles of this segment, one thread per digit ----
   if (tid < kOswRadix) {
-    const int lstart = dinc - mine + (warp == 1 ? wtot[1] : 0);          // tile-local position of the digit's first key
-    const int digit_base = hinc - hcount + (warp == 1 ? wtot[0] : 0);    // keys of smaller digits in the whole segment
-    dcount[tid] = lstart;
-    // ---- decoupled look-back over the earlier tiles of this segment ----
+    const long long digit_base = (long long)(hinc - hcount) + (warp == 1 ? hsum[0] : 0);
+    const unsigned long long mine = (unsigned long long)(lbase[tid + 1] - my_start);
     volatile unsigned long long* st = tstate + (size_t)tile * kOswRadix + tid;
     unsigned long long excl = 0ull;
     if (tin == 0) {
-      *st = kOswFlagIncl | (unsigned long long)mine;
+      *st = kOswFlagIncl | mine;
     } else {
-      *st = kOswFlagAgg | (unsigned long long)mine;
+      *st = kOswFlagAgg | mine;
       int look = tile - 1;
       while (true) {
         const unsigned long long v = *(volatile unsigned long long*)(tstate + (size_t)look * kOswRadix + tid);
@@ -1251,20 +1280,14 @@ __global__ void __launch_bounds__(kThreads, 4) osw_scatter_kernel(const Elem* __
         if ((v >> 62) == 2ull) break;
         --look;
       }
-      *st = kOswFlagIncl | (excl + (unsigned long long)mine);
+      *st = kOswFlagIncl | (excl + mine);
     }
-    delta[tid] = digit_base + (int)excl - lstart;
-    if (has_next && hnext[tid]) atomicAdd(&seg_hist_next[(size_t)seg * kOswRadix + tid], hnext[tid]);
+    delta[tid] = (int)(digit_base + (long long)excl) - my_start;
   }
-  __syncthreads();
   // ---- order the tile by digit in shared memory, then write every digit's run to consecutive addresses ----
 #pragma unroll
-  for (int r = 0; r < kOswKpt; ++r) {
-    if (warp * kPerWarp + r * 32 + lane < cnt) {
-      const unsigned d = (unsigned)(key[r] >> shift) & mask;
-      stage[dcount[d] + wcnt[warp][d] + lpos[r]] = key[r];
-    }
-  }
+  for (int j = 0; j < kOswKpt; ++j)
+    if (j < nvalid) stage[lpos[j]] = key[j];
   __syncthreads();
   Elem* dst = out + sstart;
 #pragma unroll 4
@@ -1279,80 +1302,114 @@ __global__ void __launch_bounds__(kThreads, 4) osw_scatter_kernel(const Elem* __
 }
 
 // ---------------------------------------------------------------------------------------
-// K7': 13-byte records without shared memory.  A warp takes 32 consecutive sorted elements = 416 consecutive output
-// bytes; every lane builds its record in four registers and the aligned 32-bit words of the byte stream are assembled
-// from the neighbours' registers with shuffles (5 per word) and leave as 128-byte coalesced stores.  The first
-// generation staged the bytes through shared memory with 13 one-byte stores per record: 92 % of the LSU wavefront
-// peak, 103 us for 21.6 M events (profiles/ncu_ldati_r2_b.txt).
+// K7': 13-byte records, linear over the whole sorted stream.  FOUR consecutive records are exactly 13 aligned 32-bit
+// words, so a thread loads four elements with one 16-byte load, builds their 13 words in registers with fixed byte
+// permutes, and the warp transposes its 32 x 13 words through shared memory (stride 13: conflict free) into 416
+// consecutive words that leave as 16-byte coalesced stores.  No byte stores anywhere.  The first generation staged
+// bytes through shared memory with 13 one-byte stores per record (92 % of the LSU wavefront peak, 103 us for 21.6 M
+// events); assembling the words with 5 shuffles each was worse (230 us, 311 instructions per 32 records --
+// profiles/ncu_ldati_r2_c.txt).  A record's segment (bin origin, frame offset) is found from a per-128-record table.
 // ---------------------------------------------------------------------------------------
+constexpr int kPackRecsPerWarp = kPackRecsPerWarpDecl;
+
+// segment of the first record of every 128-record chunk: one thread per chunk, binary search over seg_start
+__global__ void pack_chunk_seg_kernel(const int64_t* __restrict__ seg_start, int ns, long long total,
+                                      int32_t* __restrict__ chunk_seg) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long r = c * kPackRecsPerWarp;
+  if (r >= total) return;
+  int lo = 0, hi = ns - 1;                       // last segment s with seg_start[s] <= r (empty segments repeat values)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (seg_start[mid] <= r) lo = mid; else hi = mid - 1;
+  }
+  chunk_seg[c] = lo;
+}
+
 template <typename Elem>
-__global__ void __launch_bounds__(kThreads) pack_shfl_kernel(const Elem* __restrict__ in, const int64_t* __restrict__ seg_start,
-                                                              const int32_t* __restrict__ tile_first,
-                                                              const int32_t* __restrict__ tile_seg, int ns, DevParams P,
-                                                              const int64_t* __restrict__ frame_offset_us,
-                                                              uint8_t* __restrict__ out) {
-  const int tile = blockIdx.x;
-  if (tile >= tile_first[ns]) return;
-  const int seg = tile_seg[tile];
-  const int tin = tile - tile_first[seg];
-  const long long start = seg_start[seg] + (long long)tin * kOswTile;
-  const int cnt = (int)min((long long)kOswTile, seg_start[seg + 1] - start);
-  const int f = seg / kBins, c = seg % kBins;
-  const long long base_ts = P.bin_base[c] - kKeyBias;
-  long long off = 0;
-  if (P.add_frame_offset && frame_offset_us != nullptr) off = frame_offset_us[f];
-  const unsigned long long pix_mask = (1ull << P.pix_bits) - 1ull;
+__global__ void __launch_bounds__(kThreads) pack_linear_kernel(const Elem* __restrict__ in, const int64_t* __restrict__ seg_start,
+                                                                const int32_t* __restrict__ chunk_seg, int ns, long long total,
+                                                                DevParams P, const int64_t* __restrict__ frame_offset_us,
+                                                                uint8_t* __restrict__ out) {
+  __shared__ __align__(16) unsigned sm[kThreads / 32][32 * 13];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int chunk = warp; chunk * 32 < cnt; chunk += kThreads / 32) {
-    const int i = chunk * 32 + lane;
-    const int nrec = min(32, cnt - chunk * 32);
-    unsigned w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
-    if (lane < nrec) {
-      const unsigned long long e = (unsigned long long)in[start + i];
-      const int pix = (int)(e & pix_mask);
-      const long long key = (long long)(e >> (P.pix_bits + 1));
-      long long ts = (key == 0) ? P.nan_ts : (base_ts + key);
-      ts = (long long)((unsigned long long)ts + (unsigned long long)off);
-      const unsigned y = (unsigned)(pix / P.W), x = (unsigned)pix - y * (unsigned)P.W;
-      w0 = (unsigned)((unsigned long long)ts);
-      w1 = (unsigned)((unsigned long long)ts >> 32);
-      w2 = (x & 0xffffu) | (y << 16);
-      w3 = (unsigned)((e >> P.pix_bits) & 1ull);
+  const long long chunk = (long long)blockIdx.x * (kThreads / 32) + warp;
+  const long long r0 = chunk * kPackRecsPerWarp;
+  if (r0 >= total) return;                                   // whole warp
+  const int nrec = (int)min((long long)kPackRecsPerWarp, total - r0);
+  const long long mine = r0 + 4 * lane;                      // this lane's four records
+  const unsigned long long pix_mask = (1ull << P.pix_bits) - 1ull;
+  // elements: the sort buffers are 256-byte aligned and `mine` is a multiple of 4 -> one 16-byte (32-byte) load
+  Elem e[4] = {0, 0, 0, 0};
+  if (4 * lane + 3 < nrec) {
+    if (sizeof(Elem) == 4) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(in + mine));
+      e[0] = (Elem)t.x; e[1] = (Elem)t.y; e[2] = (Elem)t.z; e[3] = (Elem)t.w;
+    } else {
+      const ulonglong2 t0 = __ldg(reinterpret_cast<const ulonglong2*>(in + mine));
+      const ulonglong2 t1 = __ldg(reinterpret_cast<const ulonglong2*>(in + mine + 2));
+      e[0] = (Elem)t0.x; e[1] = (Elem)t0.y; e[2] = (Elem)t1.x; e[3] = (Elem)t1.y;
     }
-    const unsigned long long gbyte = (unsigned long long)(start + chunk * 32) * 13ull;
-    const unsigned long long gaddr = (unsigned long long)(uintptr_t)out + gbyte;
-    const int mis = (int)(gaddr & 3ull);
-    const int nb = nrec * 13;                                  // bytes of this chunk
-    unsigned* gout = reinterpret_cast<unsigned*>(out + gbyte - mis);     // 4-byte aligned
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * lane + j < nrec) e[j] = in[mine + j];
+  }
+  int seg = chunk_seg[chunk];
+  unsigned w[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long idx = mine + j;
+    if (4 * lane + j < nrec) {
+      while (seg + 1 < ns && idx >= seg_start[seg + 1]) ++seg;     // rarely more than zero steps (L1 hits)
+    }
+    const int f = seg / kBins, c = seg - f * kBins;
+    const long long base_ts = P.bin_base[c] - kKeyBias;
+    long long off = 0;
+    if (P.add_frame_offset && frame_offset_us != nullptr) off = frame_offset_us[f];
+    const unsigned long long ev = (unsigned long long)e[j];
+    const unsigned pix = (unsigned)(ev & pix_mask);
+    const long long key = (long long)(ev >> (P.pix_bits + 1));
+    long long ts = (key == 0) ? P.nan_ts : (base_ts + key);
+    ts = (long long)((unsigned long long)ts + (unsigned long long)off);
+    const unsigned y = pix / (unsigned)P.W, x = pix - y * (unsigned)P.W;
+    w[4 * j + 0] = (unsigned)((unsigned long long)ts);
+    w[4 * j + 1] = (unsigned)((unsigned long long)ts >> 32);
+    w[4 * j + 2] = (x & 0xffffu) | (y << 16);
+    w[4 * j + 3] = (unsigned)((ev >> P.pix_bits) & 1ull);          // polarity byte
+  }
+  // 4 x 13 bytes -> 13 words: record j starts at byte 13 j, i.e. at byte (j) of word 3 j + ... (fixed permutes)
+  unsigned o[13];
+  o[0] = w[0];  o[1] = w[1];  o[2] = w[2];
+  o[3] = (w[3] & 0xffu) | (w[4] << 8);
+  o[4] = __funnelshift_r(w[4], w[5], 24);
+  o[5] = __funnelshift_r(w[5], w[6], 24);
+  o[6] = (w[6] >> 24) | ((w[7] & 0xffu) << 8) | (w[8] << 16);
+  o[7] = __funnelshift_r(w[8], w[9], 16);
+  o[8] = __funnelshift_r(w[9], w[10], 16);
+  o[9] = (w[10] >> 16) | ((w[11] & 0xffu) << 16) | (w[12] << 24);
+  o[10] = __funnelshift_r(w[12], w[13], 8);
+  o[11] = __funnelshift_r(w[13], w[14], 8);
+  o[12] = (w[14] >> 8) | (w[15] << 24);
+  unsigned* row = sm[warp];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) row[13 * lane + k] = o[k];
+  __syncwarp();
+  unsigned char* gdst = out + (unsigned long long)r0 * 13ull;   // 128 records * 13 B = 1664 B per chunk: 16-byte aligned
+  const int nbytes = nrec * 13;
+  const unsigned long long galign = (unsigned long long)(uintptr_t)gdst;
+  if (nrec == kPackRecsPerWarp && (galign & 15ull) == 0ull) {
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      const int k = lane + 32 * m;                             // aligned word k covers chunk bytes [4k - mis, 4k - mis + 4)
-      const int s0 = 4 * k - mis;
-      // record and byte offset of the word's first byte (s0 may be -3..-1 for k = 0: treated as record 0, offset < 0)
-      const int sc = max(s0, 0);
-      const int r0 = (sc * 5042) >> 16;                        // sc / 13 for sc < 2^13 (5042 = ceil(2^16 / 13))
-      const int o0 = s0 - 13 * r0;                             // may be negative only for the chunk's first word
-      const int q = max(o0, 0) >> 2;
-      const unsigned a0 = __shfl_sync(0xffffffffu, w0, r0 & 31), a1 = __shfl_sync(0xffffffffu, w1, r0 & 31);
-      const unsigned a2 = __shfl_sync(0xffffffffu, w2, r0 & 31), a3 = __shfl_sync(0xffffffffu, w3, r0 & 31);
-      const unsigned nx = __shfl_sync(0xffffffffu, w0, (r0 + 1) & 31);
-      const unsigned lo = q == 0 ? a0 : q == 1 ? a1 : q == 2 ? a2 : a3;
-      const unsigned hi = q == 0 ? a1 : q == 1 ? a2 : q == 2 ? a3 : 0u;
-      unsigned v;
-      if (o0 >= 0) {
-        v = __funnelshift_r(lo, hi, 8 * (o0 & 3));             // bytes o0 .. o0+3 of record r0
-        const int from_r0 = 13 - o0;                           // bytes left in record r0
-        if (from_r0 < 4) v = (v & ((1u << (8 * from_r0)) - 1u)) | (nx << (8 * from_r0));
+      const int v = lane + 32 * m;                            // 104 vectors of 16 bytes
+      if (v < 104) reinterpret_cast<uint4*>(gdst)[v] = reinterpret_cast<const uint4*>(row)[v];
+    }
+  } else {                                                    // the stream's last chunk, or a caller buffer that is not 16-byte aligned
+    for (int k = lane; 4 * k < nbytes; k += 32) {
+      if (4 * k + 4 <= nbytes && (galign & 3ull) == 0ull) {
+        reinterpret_cast<unsigned*>(gdst)[k] = row[k];
       } else {
-        v = a0 << (8 * (-o0));                                 // the chunk starts inside this word: low bytes belong to the chunk before
-      }
-      if (s0 >= 0 && s0 + 4 <= nb) {
-        gout[k] = v;
-      } else if (s0 + 4 > 0 && s0 < nb) {                      // partial word at either end of the chunk: byte stores
-        uint8_t* gb = reinterpret_cast<uint8_t*>(gout + k);
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-          if (s0 + t >= 0 && s0 + t < nb) gb[t] = (uint8_t)(v >> (8 * t));
+        for (int t = 0; 4 * k + t < nbytes; ++t) gdst[4 * k + t] = (unsigned char)(row[k] >> (8 * t));
       }
     }
   }
@@ -1531,19 +1588,23 @@ static int emit_impl(const float* vox, const v2ce_ldati_params* p, const Geometr
     V2CE_LAUNCH_CHECK("ldati::fill_tile_seg_kernel");
     V2CE_CUDA_CHECK(cudaMemsetAsync(sw.osw_zero, 0, sw.osw_zero_bytes, s));
     osw_hist_kernel<Elem><<<sw.nt4_max, kThreads, 0, s>>>(src, cw.seg_start, sw.tile_first4, sw.tile_seg4, ns, g.pix_bits + 1, rb,
-                                                          sw.seg_hist);
+                                                          passes, sw.seg_hist);
     V2CE_LAUNCH_CHECK("ldati::osw_hist_kernel");
+    const size_t smem = (size_t)kOswCounterWords * 4 > (size_t)kOswStageSlots * sizeof(Elem)
+                            ? (size_t)kOswCounterWords * 4 : (size_t)kOswStageSlots * sizeof(Elem);
     for (int pass = 0; pass < passes; ++pass) {
-      osw_scatter_kernel<Elem><<<sw.nt4_max, kThreads, 0, s>>>(
+      osw_scatter_kernel<Elem><<<sw.nt4_max, kThreads, smem, s>>>(
           src, dst, cw.seg_start, sw.tile_first4, sw.tile_seg4, ns, g.pix_bits + 1 + pass * rb, rb,
-          sw.seg_hist + (size_t)pass * ns * kOswRadix,
-          pass + 1 < passes ? sw.seg_hist + (size_t)(pass + 1) * ns * kOswRadix : nullptr,
-          sw.tstate + (size_t)pass * sw.nt4_max * kOswRadix, sw.tickets + pass);
+          sw.seg_hist + (size_t)pass * ns * kOswRadix, sw.tstate + (size_t)pass * sw.nt4_max * kOswRadix, sw.tickets + pass);
       V2CE_LAUNCH_CHECK("ldati::osw_scatter_kernel");
       Elem* t = src; src = dst; dst = t;
     }
-    pack_shfl_kernel<Elem><<<sw.nt4_max, kThreads, 0, s>>>(src, cw.seg_start, sw.tile_first4, sw.tile_seg4, ns, P, frame_off, out);
-    V2CE_LAUNCH_CHECK("ldati::pack_shfl_kernel");
+    const long long nchunks = (total + kPackRecsPerWarp - 1) / kPackRecsPerWarp;
+    pack_chunk_seg_kernel<<<(int)((nchunks + 255) / 256), 256, 0, s>>>(cw.seg_start, ns, total, sw.chunk_seg);
+    V2CE_LAUNCH_CHECK("ldati::pack_chunk_seg_kernel");
+    pack_linear_kernel<Elem><<<(int)((nchunks + kThreads / 32 - 1) / (kThreads / 32)), kThreads, 0, s>>>(
+        src, cw.seg_start, sw.chunk_seg, ns, total, P, frame_off, out);
+    V2CE_LAUNCH_CHECK("ldati::pack_linear_kernel");
     return V2CE_OK;
   }
   // first-generation path: LSD passes over the key field, <= 8 bits each

@@ -148,8 +148,8 @@ class LdatiEngine:
                                        stream_ptr()))
         key_bits = max(1, math.ceil(math.log2(params.key_span + 1)))
         passes = (key_bits + 5) // 6                 # one-sweep passes of <= 6 bits (csrc/ldati.cu, osw_*)
-        # emit + tile table (build, fill) + first-pass digit histogram + one kernel per pass + pack
-        self.launches += 1 + (2 + 1 + passes + 1 if total_events > 0 else 0)
+        # emit + tile table (build, fill) + digit histograms + one kernel per pass + pack (chunk table, records)
+        self.launches += 1 + (2 + 1 + passes + 2 if total_events > 0 else 0)
         return out, status
 
     def run(self, voxels, params, draws=None, frame_offsets=None):
