@@ -53,6 +53,9 @@ struct HaloArgs {
   int SA, SB;                  // pipeline depths (patch ring / weight ring)
   int a_stage_bytes;           // bytes reserved per patch stage (multiple of 1024)
   int box_bytes;               // bytes one TMA box delivers: PW * (TH+2) * 128
+  int a_row16;                 // conv_halo_kdm only: bytes of one patch pixel row / 16 -- 8 (64 channels, SWIZZLE_128B) or
+                               // 2 (16 channels, SWIZZLE_32B: the head conv's 8-channel split pixels)
+  uint32_t a_desc_hi;          // high word of the A operand's UMMA descriptor for that layout
   const __nv_bfloat16* wpack;  // [Cout/BN][ncc][3 kd][9 taps][BN][64], rows pre-swizzled
   const float* scale;
   const float* shift;
@@ -500,6 +503,26 @@ inline int make_patch_map(CUtensorMap* map, const void* ptr, int B, int D, int H
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(V2CE_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return V2CE_OK;
+}
+
+// The head conv's input: 8-channel (16-byte) split-bf16 pixels.  Presented as overlapping 16-channel rows (the upper
+// half is the next pixel and meets zero weights) in a SWIZZLE_32B box: one K=16 step per tap reads exactly one 32-byte
+// row.  The 64-channel presentation of the same tensor moved 8x its bytes from L2 to shared memory (1.39 GB per
+// forward, the TMA producer was what the head waited for: 0.39 ms, profiles/ncu_kdm_r2_c.txt).
+inline int make_patch_map16(CUtensorMap* map, const void* ptr, int B, int D, int H, int W, int PW, int rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(V2CE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const int cpitch = 8;
+  cuuint64_t dims[5] = {16u, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)cpitch * 2, (cuuint64_t)W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2,
+                           (cuuint64_t)D * H * W * cpitch * 2};
+  cuuint32_t box[5] = {16u, (cuuint32_t)PW, (cuuint32_t)rows, 1u, 1u};
+  cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(V2CE_ERR_CUDA, "cuTensorMapEncodeTiled (16-channel view) failed with CUresult %d", (int)r);
   return V2CE_OK;
 }
 

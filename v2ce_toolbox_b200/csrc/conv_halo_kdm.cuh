@@ -273,7 +273,9 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
     uint32_t pw = 0;                                // parity of the weight slots for the current load generation
     uint32_t pw_next = 0;
     int loaded_n_tile = -1;
-    const uint32_t pw8 = (uint32_t)a.PW * 8u;       // one patch row of pixels in descriptor units (16 B)
+    const uint32_t px16 = (uint32_t)a.a_row16;      // one patch pixel in descriptor units (16 B): 8, or 2 for the head's 32-byte rows
+    const uint32_t pw8 = (uint32_t)a.PW * px16;     // one patch row of pixels
+    const uint32_t a_hi = a.a_desc_hi;
     const uint32_t idesc32 = make_idesc(BN);
     int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -324,16 +326,16 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
             for (int k = 0; k < kBlockK / 16; ++k) {
               if (k < ks) {
                 if (!lead || k != 0 || cc != 0) {
-                  tcgen05_mma_bf16_lo(col, a_t + 2 * k, b_t + 2 * k, idesc_all, 1u);
+                  tcgen05_mma_bf16_lo2(col, a_t + 2 * k, b_t + 2 * k, idesc_all, 1u, a_hi);
                 } else if (first_z) {
                   // first multiply into this tile's accumulators: nothing covered has been written yet
-                  tcgen05_mma_bf16_lo(col, a_t, b_t, idesc_all, 0u);
+                  tcgen05_mma_bf16_lo2(col, a_t, b_t, idesc_all, 0u, a_hi);
                 } else {
                   // slice z+1 (j = 2) is touched for the first time, the others accumulate
                   const int j_old_hi = jhi < 1 ? jhi : 1;
                   const uint32_t n_old = (uint32_t)((j_old_hi - jlo + 1) * BN);
-                  tcgen05_mma_bf16_lo(col, a_t, b_t, make_idesc((int)n_old), 1u);
-                  if (jhi == 2) tcgen05_mma_bf16_lo(col + n_old, a_t, b_t + n_old * 8u, idesc32, 0u);
+                  tcgen05_mma_bf16_lo2(col, a_t, b_t, make_idesc((int)n_old), 1u, a_hi);
+                  if (jhi == 2) tcgen05_mma_bf16_lo2(col + n_old, a_t, b_t + n_old * 8u, idesc32, 0u, a_hi);
                 }
               }
             }
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
               const uint32_t bs_lo = smem_desc_lo(ws_base);
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k)
-                if (k < ks) tcgen05_mma_bf16_lo(scol, a_t + 2 * k, bs_lo + 2 * k, idesc32, (cc != 0 || k != 0) ? 1u : 0u);
+                if (k < ks) tcgen05_mma_bf16_lo2(scol, a_t + 2 * k, bs_lo + 2 * k, idesc32, (cc != 0 || k != 0) ? 1u : 0u, a_hi);
             }
             if (last_z && w_release) tcgen05_commit_elect(w_empty(tap));     // last use of this generation's tap tile
           };
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
             const uint32_t a_lo = smem_desc_lo(a_base + (uint32_t)sa * a.a_stage_bytes);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap)
-              issue_tap(tap, a_lo + (uint32_t)(tap / 3) * pw8 + (uint32_t)(tap % 3) * 8u, tap == 0);
+              issue_tap(tap, a_lo + (uint32_t)(tap / 3) * pw8 + (uint32_t)(tap % 3) * px16, tap == 0);
             tcgen05_commit_elect(a_empty(sa));
             if (++sa == a.SA) { sa = 0; pa ^= 1; }
           } else {
@@ -373,15 +375,15 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
                 issue_tap(4, a_lo, true);
               } else if (q == 1) {
                 issue_tap(3, a_lo, false);
-                issue_tap(5, a_lo + 8u, false);
+                issue_tap(5, a_lo + px16, false);
               } else if (q == 2) {
                 issue_tap(1, a_lo, false);
                 issue_tap(7, a_lo + pw8, false);
               } else {
                 issue_tap(0, a_lo, false);
-                issue_tap(2, a_lo + 8u, false);
+                issue_tap(2, a_lo + px16, false);
                 issue_tap(6, a_lo + pw8, false);
-                issue_tap(8, a_lo + pw8 + 8u, false);
+                issue_tap(8, a_lo + pw8 + px16, false);
               }
               tcgen05_commit_elect(a_empty(sa));
               if (++sa == a.SA) { sa = 0; pa ^= 1; }
@@ -564,7 +566,7 @@ inline TileShape pick_tile_s2(int H, int W) {
 
 // the kernel applies to depth multiples of 8 and needs room for at least 3 patch stages beside the weights;
 // H, W = output plane
-inline KdmPlan plan_kdm(int D, int H, int W, int stride = 1) {
+inline KdmPlan plan_kdm(int D, int H, int W, int stride = 1, int row_bytes = 128) {
   KdmPlan p;
   if (stride == 2) {
     p.ts = pick_tile_s2(H, W);
@@ -575,8 +577,8 @@ inline KdmPlan plan_kdm(int D, int H, int W, int stride = 1) {
     p.TW = p.ts.PW - 2;
     p.rows = p.ts.PW * (p.ts.TH + 2);
   }
-  p.box_bytes = p.rows * 128;
-  p.a_stage_bytes = ((p.rows + 2 + 7) / 8) * 1024;
+  p.box_bytes = p.rows * row_bytes;
+  p.a_stage_bytes = ((p.rows + 2) * row_bytes + 1023) / 1024 * 1024;
   const int tail = kKdmBars * 8 + 16 + 4 * kKdmBN * 4;
   const int budget = 227 * 1024 - 1024 - tail - 9 * kKdmWTile - kKdmSTile;
   p.SA = budget / p.a_stage_bytes;

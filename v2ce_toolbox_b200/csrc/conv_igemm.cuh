@@ -158,6 +158,20 @@ __device__ __forceinline__ void tcgen05_mma_bf16_lo(uint32_t tmem_d, uint32_t a_
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
       : "memory");
 }
+// A and B operands in different shared-memory layouts: `a_hi` is the high word of A's descriptor
+// (0x40004040 = K-major SWIZZLE_128B, SBO 1024 B; 0xC0004010 = K-major SWIZZLE_32B, SBO 256 B), B stays SWIZZLE_128B
+__device__ __forceinline__ void tcgen05_mma_bf16_lo2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                     uint32_t accumulate, uint32_t a_hi) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %6};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u), "r"(a_hi)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\t"

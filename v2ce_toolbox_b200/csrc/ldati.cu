@@ -1409,7 +1409,7 @@ __global__ void __launch_bounds__(kThreads) pack_linear_kernel(const Elem* __res
       if (4 * k + 4 <= nbytes && (galign & 3ull) == 0ull) {
         reinterpret_cast<unsigned*>(gdst)[k] = row[k];
       } else {
-        for (int t = 0; 4 * k + t < nbytes; ++t) gdst[4 * k + t] = (unsigned char)(row[k] >> (8 * t));
+        for (int t = 0; t < 4 && 4 * k + t < nbytes; ++t) gdst[4 * k + t] = (unsigned char)(row[k] >> (8 * t));
       }
     }
   }

@@ -590,6 +590,7 @@ static int run_halo(v2ce_model* m, int li, const __nv_bfloat16* src0, int p0, co
   static const int kdm_max_cout = getenv("V2CE_KDM_MAX_COUT") ? atoi(getenv("V2CE_KDM_MAX_COUT")) : 64;
   const bool kdm = dl.wpack_kdm != nullptr && kplan.ok && L.cout <= kdm_max_cout;
   halo::HaloArgs a;
+  a.a_row16 = 8; a.a_desc_hi = 0x40004040u;      // 64-channel SWIZZLE_128B patch rows
   a.B = B; a.D = D; a.H = H; a.W = W;
   a.PW = plan.ts.PW; a.TH = plan.ts.TH; a.TW = plan.ts.PW - 2;
   a.tiles_w = (W + a.TW - 1) / a.TW;
@@ -649,6 +650,7 @@ static int run_enc_kdm(v2ce_model* m, int li, const __nv_bfloat16* x, int pin, i
   const halo::KdmPlan kp = halo::plan_kdm(D, Hout, Wout, 2);
   if (off || !kp.ok || dl.wpack_kdm == nullptr || sl.wpack_kdm == nullptr || Hin < 2 || Win < 2) return V2CE_OK;
   halo::HaloArgs a;
+  a.a_row16 = 8; a.a_desc_hi = 0x40004040u;      // 64-channel SWIZZLE_128B patch rows
   a.B = B; a.D = D; a.H = Hout; a.W = Wout;
   a.PW = kp.ts.PW; a.TH = kp.ts.TH; a.TW = kp.TW;
   a.tiles_w = (Wout + a.TW - 1) / a.TW;
@@ -911,7 +913,9 @@ static int forward_impl(v2ce_model* m, const void* x_dev, bool frames_u8, float*
 
   const long long M0 = d.M[0];
   static const bool head_direct = getenv("V2CE_HEAD_DIRECT") && atoi(getenv("V2CE_HEAD_DIRECT"));
-  const halo::KdmPlan hplan = halo::plan_kdm(D, H, W, 1);
+  // 32-byte patch rows (16-channel SWIZZLE_32B view of the 8-channel split pixels) unless V2CE_HEAD_SW32=0
+  static const bool head_sw32 = !(getenv("V2CE_HEAD_SW32") && atoi(getenv("V2CE_HEAD_SW32")) == 0);
+  const halo::KdmPlan hplan = halo::plan_kdm(D, H, W, 1, head_sw32 ? 32 : 128);
   if (hplan.ok && !head_direct) {
     // head conv on the tensor pipe (see head_prep_kernel): split-bf16 pixels -> depth-merged halo kernel, LeakyReLU
     const size_t total = (size_t)M0;
@@ -921,6 +925,7 @@ static int forward_impl(v2ce_model* m, const void* x_dev, bool frames_u8, float*
     V2CE_LAUNCH_CHECK("head_prep_kernel");
     const DevLayer& dl = m->layers[0];
     halo::HaloArgs a;
+  a.a_row16 = 8; a.a_desc_hi = 0x40004040u;      // 64-channel SWIZZLE_128B patch rows
     a.B = B; a.D = D; a.H = H; a.W = W;
     a.PW = hplan.ts.PW; a.TH = hplan.ts.TH; a.TW = hplan.TW;
     a.tiles_w = (W + a.TW - 1) / a.TW;
@@ -933,7 +938,18 @@ static int forward_impl(v2ce_model* m, const void* x_dev, bool frames_u8, float*
     a.up_H = 0; a.up_W = 0; a.pred_w = nullptr; a.pred_b = nullptr; a.pred_out = nullptr;
     a.error_flag = m->error_flag_dev;
     CUtensorMap tmh;
-    if (int e = get_tmap(m, buf.head_in, B, D, H, W, 8, a.PW, a.TH + 2, &tmh)) return e;
+    if (head_sw32) {
+      a.a_row16 = 2; a.a_desc_hi = 0xC0004010u;     // K-major SWIZZLE_32B, 8-row groups 256 B apart
+      // cached like the other maps; pitch key 16 marks the 16-channel view of this pointer
+      auto key = std::make_tuple((const void*)buf.head_in, B, D, H, W, 16, a.PW, a.TH + 2);
+      auto it = m->tmaps.find(key);
+      if (it == m->tmaps.end()) {
+        CUtensorMap tm;
+        if (int e = halo::make_patch_map16(&tm, buf.head_in, B, D, H, W, a.PW, a.TH + 2)) return e;
+        it = m->tmaps.emplace(key, tm).first;
+      }
+      tmh = it->second;
+    } else if (int e = get_tmap(m, buf.head_in, B, D, H, W, 8, a.PW, a.TH + 2, &tmh)) return e;
     if (int e = halo::launch_halo_kdm(tmh, tmh, a, nullptr, hplan.smem_bytes, s)) return e;
     ++launches;
   } else {
@@ -1175,6 +1191,7 @@ extern "C" int v2ce_conv3d_bf16_ex(const void* src0_dev, int32_t c0, int32_t h0,
     const halo::HaloPlan plan = halo::plan_for(bn, depth, hin, win);
     const halo::KdmPlan kplan = halo::plan_kdm(depth, hout, wout, stride_hw);
     halo::HaloArgs a;
+  a.a_row16 = 8; a.a_desc_hi = 0x40004040u;      // 64-channel SWIZZLE_128B patch rows
     a.B = batch; a.D = depth; a.H = hin; a.W = win;
     a.PW = plan.ts.PW; a.TH = plan.ts.TH; a.TW = plan.ts.PW - 2;
     a.tiles_w = (win + a.TW - 1) / a.TW; a.tiles_h = (hin + a.TH - 1) / a.TH;
