@@ -166,6 +166,10 @@ class SynthVideoReader:
         return f
 
     def read_frames_at_indices(self, idxs):
+        idxs = list(idxs)
+        if (self._cache is not None and len(idxs) > 0 and idxs[0] >= self._cache_first and
+                idxs[-1] < self._cache_first + len(self._cache) and idxs == list(range(idxs[0], idxs[-1] + 1))):
+            return self._cache[idxs[0] - self._cache_first:idxs[-1] + 1 - self._cache_first]     # a view: no copy
         return np.stack([self.frame(i) for i in idxs], axis=0)
 
 

@@ -34,7 +34,8 @@ def main():
     dt = time.perf_counter() - t0
     pairs = res.n_pairs
     print(f'{n} frames -> {pairs} pairs, {len(res.event_stream)} events, {dt:.3f} s wall = {pairs / dt:.1f} frame-pairs/s '
-          f'(PNG decode + device pipeline + D2H + mp4v encode + npz)')
+          f'(PNG decode + device pipeline + D2H + mp4v encode + npz); stages: '
+          + ', '.join(f'{k} {v:.3f}' for k, v in res.timings.items()))
     # the same without the host-side codecs: stream_clip on in-memory frames
     from synth_inputs import FakeVideoReader
     model = drv.get_trained_mode(ckpt)

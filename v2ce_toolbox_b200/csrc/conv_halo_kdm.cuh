@@ -133,6 +133,9 @@ __device__ __forceinline__ void kdm_store_chunk(const HaloArgs& a, const KdmRow&
 // encoders.0.conv1).  The block's stride-2 1x1x1 shortcut is the (1,1) tap, fused as in the stride-1 case.
 struct ParityMaps { CUtensorMap m[4]; };
 
+template <int N>
+struct KdmInt { static constexpr int value = N; };
+
 // taps in the order the stride-2 variant multiplies them
 __device__ __constant__ int kS2TapOrder[9] = {4, 3, 5, 1, 7, 0, 2, 6, 8};
 
@@ -316,27 +319,29 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
           const uint32_t b_lo = smem_desc_lo(w_base + (uint32_t)jlo * (BN * 128));
           // one tap: all K=16 steps of A(rows shifted by a_t) x the tap's [kd-merged] weight tile; `lead` marks the
           // tile's very first instruction candidates (first tap in issue order)
-          auto issue_tap = [&](const int tap, const uint32_t a_t, const bool lead) {
+          // KS = K=16 steps per tap as a compile-time constant: the MMA warp is what these kernels wait for (one warp
+          // issues ~13 uniform-datapath instructions per tcgen05.mma at ~6.6 cycles each = 86 cycles against 56 on the
+          // tensor pipe, profiles/ncu_kdm_r2_c.txt), and a per-step `k < ks` test was three of them.
+          auto issue_tap = [&](auto KS_, const int tap, const uint32_t a_t, const bool lead) {
+            constexpr int KS = decltype(KS_)::value;
             if (first_z && w_new) {
               mbar_wait(w_full(tap), pw, a.error_flag);
               tcgen05_fence_after();
             }
             const uint32_t b_t = b_lo + (uint32_t)tap * (kKdmWTile >> 4);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              if (k < ks) {
-                if (!lead || k != 0 || cc != 0) {
-                  tcgen05_mma_bf16_lo2(col, a_t + 2 * k, b_t + 2 * k, idesc_all, 1u, a_hi);
-                } else if (first_z) {
-                  // first multiply into this tile's accumulators: nothing covered has been written yet
-                  tcgen05_mma_bf16_lo2(col, a_t, b_t, idesc_all, 0u, a_hi);
-                } else {
-                  // slice z+1 (j = 2) is touched for the first time, the others accumulate
-                  const int j_old_hi = jhi < 1 ? jhi : 1;
-                  const uint32_t n_old = (uint32_t)((j_old_hi - jlo + 1) * BN);
-                  tcgen05_mma_bf16_lo2(col, a_t, b_t, make_idesc((int)n_old), 1u, a_hi);
-                  if (jhi == 2) tcgen05_mma_bf16_lo2(col + n_old, a_t, b_t + n_old * 8u, idesc32, 0u, a_hi);
-                }
+            for (int k = 0; k < KS; ++k) {
+              if (!lead || k != 0 || cc != 0) {
+                tcgen05_mma_bf16_lo2(col, a_t + 2 * k, b_t + 2 * k, idesc_all, 1u, a_hi);
+              } else if (first_z) {
+                // first multiply into this tile's accumulators: nothing covered has been written yet
+                tcgen05_mma_bf16_lo2(col, a_t, b_t, idesc_all, 0u, a_hi);
+              } else {
+                // slice z+1 (j = 2) is touched for the first time, the others accumulate
+                const int j_old_hi = jhi < 1 ? jhi : 1;
+                const uint32_t n_old = (uint32_t)((j_old_hi - jlo + 1) * BN);
+                tcgen05_mma_bf16_lo2(col, a_t, b_t, make_idesc((int)n_old), 1u, a_hi);
+                if (jhi == 2) tcgen05_mma_bf16_lo2(col + n_old, a_t, b_t + n_old * 8u, idesc32, 0u, a_hi);
               }
             }
             if (SHORT && tap == 4 && z >= tc.d0 && z < tc.d0 + T) {
@@ -348,47 +353,54 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
               const uint32_t scol = tmem_acc + kShortCols + (uint32_t)((slot0 + z - tc.d0) * BN);
               const uint32_t bs_lo = smem_desc_lo(ws_base);
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                if (k < ks) tcgen05_mma_bf16_lo2(scol, a_t + 2 * k, bs_lo + 2 * k, idesc32, (cc != 0 || k != 0) ? 1u : 0u, a_hi);
+              for (int k = 0; k < KS; ++k)
+                tcgen05_mma_bf16_lo2(scol, a_t + 2 * k, bs_lo + 2 * k, idesc32, (cc != 0 || k != 0) ? 1u : 0u, a_hi);
             }
             if (last_z && w_release) tcgen05_commit_elect(w_empty(tap));     // last use of this generation's tap tile
           };
-          if (S == 1) {
-            mbar_wait(a_full(sa), (uint32_t)pa, a.error_flag);
-            tcgen05_fence_after();
-            // descriptor low words of (tap 0, k 0); a tap adds (kh*PW + kw) rows of 128 B to A and one weight tile to
-            // B, a K=16 step adds 32 B to both (fully unrolled: the issue loop must stay well under the 56 cycles
-            // one N=96 instruction occupies the tensor pipe)
-            const uint32_t a_lo = smem_desc_lo(a_base + (uint32_t)sa * a.a_stage_bytes);
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap)
-              issue_tap(tap, a_lo + (uint32_t)(tap / 3) * pw8 + (uint32_t)(tap % 3) * px16, tap == 0);
-            tcgen05_commit_elect(a_empty(sa));
-            if (++sa == a.SA) { sa = 0; pa ^= 1; }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
+          // all taps of one input slice (one patch, or the four parity patches of the stride-2 variant)
+          auto issue_slice = [&](auto KS_) {
+            if (S == 1) {
               mbar_wait(a_full(sa), (uint32_t)pa, a.error_flag);
               tcgen05_fence_after();
+              // descriptor low words of (tap 0, k 0); a tap adds (kh*PW + kw) pixel rows to A and one weight tile to
+              // B, a K=16 step adds 32 B to both (fully unrolled: the issue loop must stay well under the 56 cycles
+              // one N=96 instruction occupies the tensor pipe)
               const uint32_t a_lo = smem_desc_lo(a_base + (uint32_t)sa * a.a_stage_bytes);
-              if (q == 0) {
-                issue_tap(4, a_lo, true);
-              } else if (q == 1) {
-                issue_tap(3, a_lo, false);
-                issue_tap(5, a_lo + px16, false);
-              } else if (q == 2) {
-                issue_tap(1, a_lo, false);
-                issue_tap(7, a_lo + pw8, false);
-              } else {
-                issue_tap(0, a_lo, false);
-                issue_tap(2, a_lo + px16, false);
-                issue_tap(6, a_lo + pw8, false);
-                issue_tap(8, a_lo + pw8 + px16, false);
-              }
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap)
+                issue_tap(KS_, tap, a_lo + (uint32_t)(tap / 3) * pw8 + (uint32_t)(tap % 3) * px16, tap == 0);
               tcgen05_commit_elect(a_empty(sa));
               if (++sa == a.SA) { sa = 0; pa ^= 1; }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                mbar_wait(a_full(sa), (uint32_t)pa, a.error_flag);
+                tcgen05_fence_after();
+                const uint32_t a_lo = smem_desc_lo(a_base + (uint32_t)sa * a.a_stage_bytes);
+                if (q == 0) {
+                  issue_tap(KS_, 4, a_lo, true);
+                } else if (q == 1) {
+                  issue_tap(KS_, 3, a_lo, false);
+                  issue_tap(KS_, 5, a_lo + px16, false);
+                } else if (q == 2) {
+                  issue_tap(KS_, 1, a_lo, false);
+                  issue_tap(KS_, 7, a_lo + pw8, false);
+                } else {
+                  issue_tap(KS_, 0, a_lo, false);
+                  issue_tap(KS_, 2, a_lo + px16, false);
+                  issue_tap(KS_, 6, a_lo + pw8, false);
+                  issue_tap(KS_, 8, a_lo + pw8 + px16, false);
+                }
+                tcgen05_commit_elect(a_empty(sa));
+                if (++sa == a.SA) { sa = 0; pa ^= 1; }
+              }
             }
-          }
+          };
+          if (ks == 4) issue_slice(KdmInt<4>{});
+          else if (ks == 2) issue_slice(KdmInt<2>{});
+          else if (ks == 1) issue_slice(KdmInt<1>{});
+          else issue_slice(KdmInt<3>{});
           if (SHORT && last_z && w_release) tcgen05_commit_elect(w_empty(9));
           if (last_cc) {
             // output slice z-1 has received its last contribution; at the end of the depth range so has slice z

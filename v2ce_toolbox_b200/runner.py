@@ -20,7 +20,9 @@ read.  Here they run on a second stream, one batch behind the network:
 and the tests drive it; it composes the same C-ABI calls as the one-by-one public functions
 (``V2ce3d.__call__``, ``event_frames.*``, ``LdatiEngine.count/emit``).
 """
+import contextlib
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -29,6 +31,22 @@ from . import _lib
 from . import event_frames as _ef
 from . import ldati as _ldati
 from ._lib import check, ptr, stream_ptr
+
+
+_NVTX = os.environ.get('V2CE_NVTX', '0') not in ('', '0')
+
+
+@contextlib.contextmanager
+def nvtx(name):
+    """NVTX range around a pipeline stage (V2CE_NVTX=1; `ncu --nvtx --nvtx-include "v2ce:unet/"` then profiles one stage)."""
+    if not _NVTX:
+        yield
+        return
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()
 
 
 class Ticket:
@@ -127,10 +145,11 @@ class BatchRunner:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(cur)
         # uint8 windows (b, L+1, H, W): pre-processing fused into the head conv (V2ce3d.forward_frames)
-        if self.infer is not None:
-            y = self.infer(x)
-        else:
-            y = self.model.forward_frames(x) if x.dtype == torch.uint8 else self.model(x)
+        with nvtx('v2ce:unet'):
+            if self.infer is not None:
+                y = self.infer(x)
+            else:
+                y = self.model.forward_frames(x) if x.dtype == torch.uint8 else self.model(x)
         if self.time_forward:
             e1.record(cur)
             t.fwd_events = (e0, e1)
@@ -155,7 +174,7 @@ class BatchRunner:
             self._stage_b(prev)
 
         # stage A of this batch on the post stream, behind the network
-        with torch.cuda.stream(self.post_stream):
+        with torch.cuda.stream(self.post_stream), nvtx('v2ce:count+event-frame-sums'):
             self.post_stream.wait_event(vox_ready)
             eng = self.engines[slot]
             # keep_polarity: the per-polarity sums come out of the LDATI count pass below (one read of the voxels for
@@ -205,7 +224,7 @@ class BatchRunner:
         t.total = total
         t.ub = None
         frames = None
-        with torch.cuda.stream(self.post_stream):
+        with torch.cuda.stream(self.post_stream), nvtx('v2ce:emit+sort+pack'):
             if self.per_batch_frames:
                 npos, lo, bits_lo, bits_hi = (int(v) for v in small[:4])
                 if npos == 0:

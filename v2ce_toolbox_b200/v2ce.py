@@ -457,10 +457,14 @@ def main(argv=None):
             vidcap.frame_count = args.max_frame_num
         logger.info(f'Now processing {args.input_video_path}, processing {vidcap.frame_count} frames.')
     seed = args.seed if args.seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+    import time
+    timings = {}
+    t_start = time.perf_counter()
     res = stream_clip(model, image_paths=image_paths, vidcap=vidcap, infer_type=args.infer_type, seq_len=args.seq_len,
                       width=args.width, height=args.height, batch_size=args.batch_size, fps=args.fps, ceil=args.ceil,
                       upper_bound_percentile=args.upper_bound_percentile, keep_polarity=args.vis_keep_polarity,
                       write_event_frames=args.write_event_frame_video, seed=seed)
+    timings['stream_clip_s'] = time.perf_counter() - t_start
     logger.info(f'Predicted voxel shape: ({res.n_pairs}, 2, 10, ...) (kept on the device)')
     encoder, encoder_error = None, []
     if args.write_event_frame_video:
@@ -470,11 +474,13 @@ def main(argv=None):
 
         def encode():                                 # v2ce.py:272-279; cv2 releases the GIL, so the mp4v encode
             try:                                      # runs beside the .npz write below
+                t_enc = time.perf_counter()
                 H, W = res.ef_frames.shape[1:3]
                 video = cv2.VideoWriter(ef_video_path, cv2.VideoWriter_fourcc(*'mp4v'), args.fps, (W, H))
                 for f in res.ef_frames:
                     video.write(f)
                 video.release()
+                timings['encode_mp4v_s'] = time.perf_counter() - t_enc
             except Exception as e:                    # re-raised on the main thread
                 encoder_error.append(e)
 
@@ -483,12 +489,17 @@ def main(argv=None):
         encoder.start()
     logger.info(f'Generated event stream shape: , {res.event_stream.shape}')
     from .sink import save_npz
+    t_npz = time.perf_counter()
     save_npz(op.join(args.out_folder, f'{output_name}-events.npz'), event_stream=res.event_stream)   # v2ce.py:371-372
+    timings['save_npz_s'] = time.perf_counter() - t_npz
     if encoder is not None:
         encoder.join()
         if encoder_error:
             raise encoder_error[0]
         logger.info(f'Event frame video written to {ef_video_path}')
+    timings['total_s'] = time.perf_counter() - t_start
+    res.timings = timings
+    logger.debug(f'stage times: {timings}')
     return res
 
 
