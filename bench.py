@@ -215,7 +215,8 @@ class Runner:
         self.units_pinned = [windows_host[i:i + BATCH].contiguous().pin_memory() for i in range(0, 20, BATCH)]
         self.n_pairs = BATCH * L
         self.comm_stream = torch.cuda.Stream(device=device) if world > 1 else None
-        self.gather_buf = None
+        self.gather_bufs = [None, None]           # rank 0: merged shards of alternate steps
+        self.gathers = 0
         self.ring_note = None
         if world > 1:
             from v2ce_toolbox_b200 import dist as vdist
@@ -231,12 +232,16 @@ class Runner:
         """Final gather of the per-rank event shards of batch t to rank 0 (NCCL over NVLink, the product's
         dist.gather_event_shards) on the comm stream, behind the pack kernel."""
         from v2ce_toolbox_b200 import dist as vdist
+        k = self.gathers & 1
+        self.gathers += 1
         with torch.cuda.stream(self.comm_stream):
-            # its own stream: the post stream already holds stage A of the next batch, which waits for the next UNet
+            # its own stream: the post stream already holds stage A of the next batch, which waits for the next UNet.
+            # Nothing here waits on the device: the counts travel over the host-side gloo group, the shards as
+            # asynchronous point-to-point transfers that run when an SM has room for NCCL's CTAs.
             self.comm_stream.wait_event(t.packed)
-            if self.rank == 0 and self.gather_buf is None:
-                self.gather_buf = torch.empty(self.world * SHARD_CAP, dtype=torch.uint8, device=self.device)
-            merged, counts = vdist.gather_event_shards(t.events_dev, t.total, out=self.gather_buf)
+            if self.rank == 0 and self.gather_bufs[k] is None:
+                self.gather_bufs[k] = torch.empty(self.world * SHARD_CAP, dtype=torch.uint8, device=self.device)
+            merged, counts = vdist.gather_event_shards(t.events_dev, t.total, out=self.gather_bufs[k])
             fin = torch.cuda.Event()
             fin.record(self.comm_stream)
         return fin
@@ -304,11 +309,14 @@ def run_ours(args, rank, world, local_rank):
         br = r.host_runner if host_io else r.dev_runner
         src = r.units_pinned if host_io else r.units_dev
         stats = {'events': 0, 'fwd': [], 'h2d': 0, 'd2h': 0}
+        pending = []                               # gathers in flight (their buffers alternate: wait for the one before last)
 
         def collect(t, timed):
             br.wait(t, copy=False)
             if world > 1 and not host_io:
-                r.gather(t).synchronize()
+                pending.append(r.gather(t))
+                if len(pending) > 1:
+                    pending.pop(0).synchronize()
             if timed:
                 stats['events'] += t.total
                 stats['h2d'], stats['d2h'] = t.h2d_bytes, t.d2h_bytes
@@ -325,6 +333,8 @@ def run_ours(args, rank, world, local_rank):
                 prev = t
             if prev is not None:
                 collect(prev, timed)
+            while pending:
+                pending.pop(0).synchronize()
 
         run(args.warmup, False)
         br.launches = 0
@@ -608,7 +618,8 @@ def clips_record(device, rank, world, args):
     and configs[3] (pano 1920x1080, 600 frames: variant A = default --height 260 -> 462x260 -> 2 tiles; variant B =
     --height 1080 -> 6 tiles of 346x1080) through dist.stream_clip_sharded.  Per clip: `device` = all ranks computed and
     the shards merged on rank 0's GPU over NCCL (to_host=False); `e2e` = the merged stream in ONE host array (every rank
-    copies its shard into shared memory).  Frame synthesis is outside the timed region."""
+    copies its shard into shared memory over its own PCIe link); `e2e_nccl_merge` (N > 1) = the same array filled from
+    rank 0's GPU after the NCCL merge.  Frame synthesis is outside the timed region."""
     import torch.distributed as dist
     import synth_inputs as synth
     from v2ce_toolbox_b200 import dist as vdist
@@ -647,12 +658,15 @@ def clips_record(device, rank, world, args):
                 warm = synth.SynthVideoReader(wn, sp['h'], sp['w'], seed=0, repeat=sp['repeat'])
                 vdist.stream_clip_sharded(model, warm, wn, world, rank, **common)
                 res = {}
-                for leg, to_host in (('device', False), ('e2e', True)):
+                legs = [('device', False, None), ('e2e', True, 'shm')]
+                if world > 1:
+                    legs.append(('e2e_nccl_merge', True, 'nccl'))     # merged on rank 0's GPU, one D2H from there
+                for leg, to_host, merge in legs:
                     m = new_model(device)
                     dist.barrier()
                     torch.cuda.synchronize()
                     t0 = time.perf_counter()
-                    ev, n_events = vdist.stream_clip_sharded(m, reader, n, world, rank, to_host=to_host, **common)
+                    ev, n_events = vdist.stream_clip_sharded(m, reader, n, world, rank, to_host=to_host, merge=merge, **common)
                     torch.cuda.synchronize()
                     dist.barrier()
                     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
@@ -710,7 +724,7 @@ def main():
     finally:
         if world > 1:
             import torch.distributed as dist
-            dist.destroy_process_group()
+            dist.destroy_process_group()            # all groups, the host-side gloo group included
 
 
 if __name__ == '__main__':

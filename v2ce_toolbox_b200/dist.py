@@ -64,13 +64,28 @@ def init_process_group(backend='nccl', device=None, max_ctas=4, **kw):
         opts = dist.ProcessGroupNCCL.Options()
         opts.config.max_ctas = int(max_ctas)
         opts.config.min_ctas = 1
-        return dist.init_process_group('nccl', device_id=device, pg_options=opts, **kw)
+        dist.init_process_group('nccl', device_id=device, pg_options=opts, **kw)
+        # host-side values (event counts are known on the host: the count pass is read back to size the outputs) are
+        # exchanged over a gloo group: no NCCL kernel, no device sync.  The conv kernels are persistent CTAs that fill
+        # every SM's shared memory, so an NCCL kernel only starts in the gap between two of them -- a host that waits
+        # for a count exchange on the device idles the GPU for that long at every step (0.65 ms of a 10.7 ms step at
+        # N = 2, profiles/bench_r2_2gpu_a.json).
+        _host_group[0] = dist.new_group(backend='gloo')
+        return None
     return dist.init_process_group(backend, **kw)
 
 
+_host_group = [None]
+
+
 def exchange_counts(n, group=None, device=None):
-    """One all_gather of this rank's count and ONE host read: the list of all ranks' counts."""
+    """Every rank's count as a list.  Over the host-side gloo group when init_process_group set one up (no device
+    work at all); otherwise one all_gather on `device` and ONE host read."""
     world = dist.get_world_size(group)
+    if group is None and _host_group[0] is not None:
+        every = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(every, torch.tensor([int(n)], dtype=torch.int64), group=_host_group[0])
+        return [int(v.item()) for v in every]
     mine = torch.tensor([int(n)], dtype=torch.int64, device=device)
     every = torch.empty(world, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(every, mine, group=group)
@@ -80,7 +95,8 @@ def exchange_counts(n, group=None, device=None):
 def _gather_exact(flat, counts, unit, group, dst, out):
     """Rank-ordered concatenation of the ranks' `flat[:counts[r]*unit]` on `dst`: every shard travels at its exact
     length, point to point, straight into its place in the merged buffer (no padding to the longest shard, no staging
-    copy, no torch.cat)."""
+    copy, no torch.cat).  On NCCL nothing here blocks the host: `wait()` orders the current stream behind the
+    transfer."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if rank != dst:
         if counts[rank]:
@@ -130,7 +146,7 @@ def gather_row_shards(rows, group=None, dst=0):
 _merge_seq = [0]
 
 
-def merge_event_shards_to_host(events_u8, n_events, group=None, dst=0, workers=8):
+def merge_event_shards_to_host(events_u8, n_events, group=None, dst=0, workers=8, via=None):
     """The merged, time-ordered event stream of a sharded clip as ONE host array on `dst`, without funnelling the
     shards through dst's GPU and its single PCIe link: rank `dst` creates a POSIX shared-memory array of the merged
     size, every rank copies its own device shard (sink.to_host: pinned double buffering + parallel first touch) into
@@ -146,6 +162,10 @@ def merge_event_shards_to_host(events_u8, n_events, group=None, dst=0, workers=8
     total = sum(counts) * EVENT_BYTES
     if world == 1:
         return _sink(events_u8[:total], workers=workers), counts
+    via = via or os.environ.get('V2CE_SHARD_MERGE', 'shm')
+    if via == 'nccl':                                # device-side merge on dst, then ONE pipelined D2H
+        merged = _gather_exact(events_u8, counts, EVENT_BYTES, group, dst, None)
+        return (_sink(merged, workers=workers) if merged is not None else None), counts
     _merge_seq[0] += 1
     path = f"/dev/shm/v2ce_merge_{os.environ.get('MASTER_PORT', '0')}_{_merge_seq[0]}"
     ok = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -163,9 +183,17 @@ def merge_event_shards_to_host(events_u8, n_events, group=None, dst=0, workers=8
         merged, _ = gather_event_shards(events_u8, n_events, group, dst)
         return (_sink(merged, workers=workers) if merged is not None else None), counts
     try:
-        mm = np.memmap(path, dtype=np.uint8, mode='r+', shape=(max(total, 1),))
         off = sum(counts[:rank]) * EVENT_BYTES
         n = counts[rank] * EVENT_BYTES
+        if n:
+            # every rank allocates its own range of the tmpfs file in the kernel (no page fault per 4 KB from the copy
+            # threads: faulting 21 GB of fresh tmpfs pages in from user space ran at 3-4 GB/s per rank)
+            fd = os.open(path, os.O_RDWR)
+            try:
+                os.posix_fallocate(fd, off, n)
+            finally:
+                os.close(fd)
+        mm = np.memmap(path, dtype=np.uint8, mode='r+', shape=(max(total, 1),))
         if n:
             _sink(events_u8[:n], out=mm[off:off + n], workers=workers)
         dist.barrier(group=group)
@@ -173,6 +201,12 @@ def merge_event_shards_to_host(events_u8, n_events, group=None, dst=0, workers=8
         if rank == dst and os.path.exists(path):
             os.unlink(path)                          # the mapping keeps the pages alive
     return (mm[:total] if rank == dst else None), counts
+
+
+def close_host_group():
+    if _host_group[0] is not None:
+        dist.destroy_process_group(_host_group[0])
+        _host_group[0] = None
 
 
 class SharedHostRing:
@@ -185,7 +219,7 @@ class SharedHostRing:
     def __init__(self, slots, bytes_per_slot, group=None, register=True):
         import os
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.cpu_group = dist.new_group(backend='gloo')
+        self.cpu_group = _host_group[0] if _host_group[0] is not None else dist.new_group(backend='gloo')
         self.cap = int(bytes_per_slot)
         self.path = f"/dev/shm/v2ce_ring_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
         total = slots * self.cap
@@ -267,7 +301,7 @@ def _preview_plane(frames_reader, kw):
 
 
 def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=16, batch_size=1, to_host=True,
-                        preview=None, **kw):
+                        preview=None, merge=None, **kw):
     """Run v2ce.stream_clip on this rank's contiguous share of the batches of a clip and gather the
     event shards on rank 0 (the shards never visit the host on their way).  `frames_reader` duck-types VideoReader.
     Returns (event_stream | None, total events); with to_host=False rank 0 gets the merged stream as a device uint8
@@ -321,7 +355,7 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
         ev, n = torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev), 0
     model.sn_advance(base + model_calls_before(n_batches, infer_type, tiles) - model.call_count())
     if to_host and ev.is_cuda:
-        host, counts = merge_event_shards_to_host(ev, n)
+        host, counts = merge_event_shards_to_host(ev, n, via=merge)     # merge: 'shm' (default) | 'nccl'; V2CE_SHARD_MERGE
         out = None
     else:
         out, counts = gather_event_shards(ev, n)
