@@ -617,9 +617,9 @@ def clips_record(device, rank, world, args):
     """BASELINE configs[4] (long clip: center 346x260, 9000 frames, temporal windows sharded over the ranks, event merge)
     and configs[3] (pano 1920x1080, 600 frames: variant A = default --height 260 -> 462x260 -> 2 tiles; variant B =
     --height 1080 -> 6 tiles of 346x1080) through dist.stream_clip_sharded.  Per clip: `device` = all ranks computed and
-    the shards merged on rank 0's GPU over NCCL (to_host=False); `e2e` = the merged stream in ONE host array (every rank
-    copies its shard into shared memory over its own PCIe link); `e2e_nccl_merge` (N > 1) = the same array filled from
-    rank 0's GPU after the NCCL merge.  Frame synthesis is outside the timed region."""
+    the shards merged on rank 0's GPU over NCCL (to_host=False); `e2e` = the merged stream in ONE host array, copied down
+    from rank 0's GPU after the NCCL merge; `e2e_shm_merge` (N > 1) = the same array in POSIX shared memory, every rank
+    copying its shard over its own PCIe link.  Frame synthesis is outside the timed region."""
     import torch.distributed as dist
     import synth_inputs as synth
     from v2ce_toolbox_b200 import dist as vdist
@@ -658,9 +658,9 @@ def clips_record(device, rank, world, args):
                 warm = synth.SynthVideoReader(wn, sp['h'], sp['w'], seed=0, repeat=sp['repeat'])
                 vdist.stream_clip_sharded(model, warm, wn, world, rank, **common)
                 res = {}
-                legs = [('device', False, None), ('e2e', True, 'shm')]
+                legs = [('device', False, None), ('e2e', True, 'nccl')]
                 if world > 1:
-                    legs.append(('e2e_nccl_merge', True, 'nccl'))     # merged on rank 0's GPU, one D2H from there
+                    legs.append(('e2e_shm_merge', True, 'shm'))       # every rank copies its shard into shared memory
                 for leg, to_host, merge in legs:
                     m = new_model(device)
                     dist.barrier()

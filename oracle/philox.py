@@ -51,12 +51,14 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
             c2.astype(np.uint32), c3.astype(np.uint32))
 
 
-def uniform_from_index(idx, j, seed):
-    """u[idx, j] as float32 in [0,1).  idx: uint64 array, j: int array (same shape)."""
+def uniform_from_index(idx, j, seed, stream=0):
+    """u[idx, j] as float32 in [0,1).  idx: uint64 array, j: int array (same shape).  `stream` is the fourth counter
+    word: 0 for LDATI and the baseline samplers' integer-part draws, 1 / 2 for their fractional-part timestamp and
+    Bernoulli draws (oracle/baseline_oracle.py)."""
     idx = np.asarray(idx, dtype=np.uint64)
     j = np.asarray(j, dtype=np.uint64)
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    w = philox4x32_10(idx & _MASK, idx >> _SH32, j >> np.uint64(2), np.uint64(0),
+    w = philox4x32_10(idx & _MASK, idx >> _SH32, j >> np.uint64(2), np.uint64(int(stream)),
                       seed & 0xFFFFFFFF, seed >> 32)
     sel = (j & np.uint64(3)).astype(np.int64)
     word = np.choose(sel, w)

@@ -138,6 +138,84 @@ def run_reference_ldati(y, fps=30, seed=0, frame_base=0, additional_events_strat
     return [np.asarray(r) for r in out]
 
 
+def baseline_module():
+    """train/scripts/stage2/sample_methods/random_even_sample.py, loaded from where it lies (its h5py / pandas imports
+    are not needed by the sampler and may be missing: stubbed for the import only)."""
+    if 'baseline' not in _cache:
+        import importlib.machinery
+        stubs = {}
+        for name in ('h5py', 'pandas'):
+            try:
+                importlib.import_module(name)
+            except Exception:                          # noqa: BLE001
+                stubs[name] = sys.modules[name] = types.ModuleType(name)
+                sys.modules[name].__spec__ = importlib.machinery.ModuleSpec(name, None)
+        try:
+            spec = importlib.util.spec_from_file_location(
+                '_v2ce_ref_baseline', os.path.join(REF_ROOT, 'train', 'scripts', 'stage2', 'sample_methods', 'random_even_sample.py'))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+        finally:
+            for name in stubs:
+                sys.modules.pop(name, None)
+        _cache['baseline'] = mod
+    return _cache['baseline']
+
+
+def run_reference_baseline(y, fps=30, seed=0, frame_base=0, even=False, random=False):
+    """sample_voxel_baseline on CPU with its torch.rand / torch.bernoulli calls served from the counter-based streams
+    of oracle/baseline_oracle.py: rand of a 5-D shape = integer-part uniforms, of a 4-D shape = fractional-part uniforms,
+    bernoulli is called once per (frame, bin, plane) in the order frame, bin, negative plane, positive plane."""
+    import torch
+    import warnings
+    from . import philox
+    from .baseline_oracle import NB, pixel_bin_index
+    mod = baseline_module()
+    yt = torch.as_tensor(np.asarray(y))
+    B, P, C, H, W = yt.shape
+    hw = H * W
+
+    def grid_idx():
+        f = np.arange(B).reshape(B, 1, 1, 1) + frame_base
+        p = np.arange(2).reshape(1, 2, 1, 1)
+        c = np.arange(C).reshape(1, 1, C, 1)
+        pix = np.arange(hw).reshape(1, 1, 1, hw)
+        return ((f.astype(np.uint64) * np.uint64(2) + p.astype(np.uint64)) * np.uint64(NB) + c.astype(np.uint64)) * np.uint64(hw) + \
+            pix.astype(np.uint64)
+
+    old_rand, old_bern = torch.rand, torch.bernoulli
+    calls = [0]
+
+    def fake_rand(*size, **kw):
+        shape = tuple(int(s) for s in (size[0] if len(size) == 1 and not isinstance(size[0], int) else size))
+        idx = grid_idx()
+        if len(shape) == 5:                              # (B*P, C, H, W, M)
+            M = shape[-1]
+            out = np.empty((B, 2, C, hw, M), np.float32)
+            for j in range(M):
+                out[..., j] = philox.uniform_from_index(idx, np.full(idx.shape, j, np.int64), seed, 0)
+            return torch.from_numpy(out.reshape(shape))
+        assert len(shape) == 4                           # (B*P, C, H, W)
+        return torch.from_numpy(philox.uniform_from_index(idx, np.zeros(idx.shape, np.int64), seed, 1).reshape(shape))
+
+    def fake_bernoulli(prob):
+        k = calls[0]
+        calls[0] += 1
+        b, c, p = k // (2 * C), (k // 2) % C, 1 - (k % 2)
+        idx = pixel_bin_index(frame_base + b, p, c, np.arange(hw), hw)
+        u = philox.uniform_from_index(idx, np.zeros(hw, np.int64), seed, 2).reshape(H, W)
+        return (torch.from_numpy(u) < prob).to(prob.dtype)
+
+    torch.rand, torch.bernoulli = fake_rand, fake_bernoulli
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            out = mod.sample_voxel_baseline(yt, fps=fps, even=even, random=random)
+    finally:
+        torch.rand, torch.bernoulli = old_rand, old_bern
+    return [np.asarray(r) for r in out]
+
+
 from synth_inputs import FakeVideoReader          # noqa: E402,F401  (in-memory reader; lives with the input generators)
 
 

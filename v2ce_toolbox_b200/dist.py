@@ -147,13 +147,14 @@ _merge_seq = [0]
 
 
 def merge_event_shards_to_host(events_u8, n_events, group=None, dst=0, workers=8, via=None):
-    """The merged, time-ordered event stream of a sharded clip as ONE host array on `dst`, without funnelling the
-    shards through dst's GPU and its single PCIe link: rank `dst` creates a POSIX shared-memory array of the merged
-    size, every rank copies its own device shard (sink.to_host: pinned double buffering + parallel first touch) into
-    its slice of it -- all PCIe links and all ranks' host threads in parallel.  Ranks own contiguous, increasing frame
-    ranges, so the rank-ordered layout IS the merge.  Returns (uint8 numpy array on dst | None, per-rank counts).
-    Single node only (all ranks see the same /dev/shm); when shared memory is unavailable or too small the shards are
-    gathered over NCCL instead and rank `dst` copies the merged buffer down (gather_event_shards + sink.to_host)."""
+    """The merged, time-ordered event stream of a sharded clip as ONE host array on `dst`.  Returns (uint8 numpy array
+    on dst | None, per-rank counts).  Two routes (`via`, default from V2CE_SHARD_MERGE):
+      'nccl'  the shards are merged on dst's GPU over NVLink (exact-length point-to-point transfers) and copied down
+              once (sink.to_host: pinned double buffering, parallel first touch, huge-page hint);
+      'shm'   rank `dst` creates a POSIX shared-memory array of the merged size and every rank copies its own device
+              shard into its slice of it -- all PCIe links and all ranks' host threads in parallel, nothing funnels
+              through one GPU.  Single node only; falls back to 'nccl' when /dev/shm cannot hold the stream.
+    Ranks own contiguous, increasing frame ranges, so the rank-ordered layout IS the merge."""
     import os
     from .sink import to_host as _sink
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -162,10 +163,15 @@ def merge_event_shards_to_host(events_u8, n_events, group=None, dst=0, workers=8
     total = sum(counts) * EVENT_BYTES
     if world == 1:
         return _sink(events_u8[:total], workers=workers), counts
-    via = via or os.environ.get('V2CE_SHARD_MERGE', 'shm')
-    if via == 'nccl':                                # device-side merge on dst, then ONE pipelined D2H
+    # 'nccl' (default): device-side merge on dst over NVLink, then ONE pipelined D2H from there -- measured faster than
+    # 'shm' at N = 2 (1.78 s against 3.9 s for the 21 GB of a 9000-frame clip, profiles/bench_r2_2gpu_b.json: first-touch
+    # of fresh tmpfs pages costs more than rank 0's single PCIe link saves)
+    via = via or os.environ.get('V2CE_SHARD_MERGE', 'nccl')
+    if via == 'nccl':
         merged = _gather_exact(events_u8, counts, EVENT_BYTES, group, dst, None)
-        return (_sink(merged, workers=workers) if merged is not None else None), counts
+        if merged is None:
+            return None, counts
+        return _sink(merged, workers=max(workers, min(32, (os.cpu_count() or 8) // 2))), counts
     _merge_seq[0] += 1
     path = f"/dev/shm/v2ce_merge_{os.environ.get('MASTER_PORT', '0')}_{_merge_seq[0]}"
     ok = torch.zeros(1, dtype=torch.int64, device=dev)

@@ -24,10 +24,31 @@ def _buffers(chunk_bytes):
         return b
 
 
+def _advise_huge_pages(arr):
+    """Ask for transparent huge pages under a freshly allocated destination (madvise(MADV_HUGEPAGE) on the 2 MB-aligned
+    interior): the copy threads then take one page fault per 2 MB instead of per 4 KB while they first-touch it.  A hint
+    only -- ignored where THP is off."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        addr, nbytes = arr.ctypes.data, arr.nbytes
+        lo = (addr + (2 << 20) - 1) & ~((2 << 20) - 1)
+        hi = (addr + nbytes) & ~((2 << 20) - 1)
+        if hi > lo:
+            libc.madvise(ctypes.c_void_p(lo), ctypes.c_size_t(hi - lo), 14)      # MADV_HUGEPAGE
+    except Exception:                                   # noqa: BLE001
+        pass
+
+
 def to_host(dev_u8, chunk_bytes=128 << 20, workers=8, out=None):
     """dev_u8: 1-D uint8 CUDA tensor -> numpy uint8 array with the same bytes (``out`` if given)."""
     n = dev_u8.numel()
-    dst = out if out is not None else np.empty(n, dtype=np.uint8)
+    if out is not None:
+        dst = out
+    else:
+        dst = np.empty(n, dtype=np.uint8)
+        if n >= (64 << 20):
+            _advise_huge_pages(dst)
     if n == 0:
         return dst
     if n <= chunk_bytes:
