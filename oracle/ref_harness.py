@@ -138,10 +138,13 @@ def run_reference_ldati(y, fps=30, seed=0, frame_base=0, additional_events_strat
     return [np.asarray(r) for r in out]
 
 
+_baseline_cache = {}
+
+
 def baseline_module():
     """train/scripts/stage2/sample_methods/random_even_sample.py, loaded from where it lies (its h5py / pandas imports
     are not needed by the sampler and may be missing: stubbed for the import only)."""
-    if 'baseline' not in _cache:
+    if 'baseline' not in _baseline_cache:
         import importlib.machinery
         stubs = {}
         for name in ('h5py', 'pandas'):
@@ -158,8 +161,8 @@ def baseline_module():
         finally:
             for name in stubs:
                 sys.modules.pop(name, None)
-        _cache['baseline'] = mod
-    return _cache['baseline']
+        _baseline_cache['baseline'] = mod
+    return _baseline_cache['baseline']
 
 
 def run_reference_baseline(y, fps=30, seed=0, frame_base=0, even=False, random=False):
