@@ -121,6 +121,48 @@ int v2ce_ldati_emit(const float* voxels_dev, const v2ce_ldati_params* p, const v
 int v2ce_ldati_relocate(const float* voxels_dev, int32_t n_frames, int32_t height, int32_t width, int32_t bidirectional,
                         int32_t* counts_dev, float* tend_dev, void* stream);
 
+/* ---- baseline samplers 'random' / 'even'  -------------------------------------------------------
+ * Replaces /root/reference/train/scripts/stage2/sample_methods/random_even_sample.py:118-170 (sample_voxel_baseline and
+ * its pick_and_sort): every value y of the TEN voxel bins yields floor(y) events plus one more with probability frac(y);
+ * a frame's events are sorted by timestamp.  Same two-phase protocol and record format as LDATI. */
+typedef struct v2ce_baseline_params {
+  int32_t height, width;     /* H, W of one voxel plane                                                  */
+  int32_t n_frames;          /* F frame pairs in this call; voxels are (F,2,10,H,W) float32              */
+  int32_t mode;              /* 1 = 'random' (uniform draw per event), 2 = 'even' (j / (floor(y)+1))      */
+  int64_t frame_base;        /* global index of frame 0 (Philox counter)                                  */
+  uint64_t seed;             /* Philox key; streams 0 / 1 / 2 = integer-part, fractional-part, Bernoulli  */
+  float delta32;             /* float32(1 / (fps * 10)): the multiplier of `ts * delta`                   */
+  float binstart_t0_32[10];  /* torch.arange(0, 1/fps, 1/fps/10) + t0 as float32, evaluated like the reference's device */
+  int64_t key_base_us;       /* timestamps are sorted as ts - key_base_us + 8; <= the frame's first timestamp */
+  int32_t key_span;          /* largest ts - key_base_us accepted (status counts events outside)          */
+  int32_t add_frame_offset;  /* 1: add frame_offset_us_dev[f] to the records' timestamps                  */
+} v2ce_baseline_params;
+
+size_t v2ce_baseline_params_size(void);
+int v2ce_baseline_count_workspace_bytes(const v2ce_baseline_params* p, size_t* bytes);
+int v2ce_baseline_emit_workspace_bytes(const v2ce_baseline_params* p, int64_t total_events, size_t* bytes);
+/* frame_counts_dev: int64 [F] events per frame */
+int v2ce_baseline_count(const float* voxels_dev, const v2ce_baseline_params* p, void* count_ws_dev, size_t count_ws_bytes,
+                        int64_t* frame_counts_dev, void* stream);
+/* status_dev: int32[4] = {timestamps outside the key range (non-finite or negative voxels in 'even' mode), 0, 0, 0} */
+int v2ce_baseline_emit(const float* voxels_dev, const v2ce_baseline_params* p, const void* count_ws_dev, void* emit_ws_dev,
+                       size_t emit_ws_bytes, const int64_t* frame_offset_us_dev, int64_t total_events,
+                       uint8_t* events_out_dev, int32_t* status_dev, void* stream);
+
+/* ---- stage-2 evaluation metric ------------------------------------------------------------------
+ * Replaces /root/reference/train/scripts/stage2/stage2_metrics.py:22-88 (ts_diff_metric): for every ground-truth event the
+ * smallest |t_pred - t_gt| over the predicted events of the same polarity at the pixels within search_range (clamped to
+ * the width x height sensor), capped at cap_us = 1e6/fps/10*3.  Both event sets are packed 13-byte records on the device
+ * (ground-truth polarity -1 counts as 0, :38-41).  result_dev: int64[4] = {sum of the uncapped integer distances, number
+ * of capped ground-truth events ("overflow"), ground-truth events outside the sensor, predicted events outside the
+ * sensor}; the metric is (result[0] + result[1] * cap_us) / n_gt. */
+int v2ce_ts_diff_workspace_bytes(int32_t width, int32_t height, int64_t n_pred, size_t* bytes);
+int v2ce_ts_diff_metric(const uint8_t* gt_records_dev, int64_t n_gt, const uint8_t* pred_records_dev, int64_t n_pred,
+                        int32_t width, int32_t height, int32_t search_range, double cap_us, void* ws_dev, size_t ws_bytes,
+                        int64_t* result_dev, void* stream);
+
+
+
 /* ------------------------------------------------------------------------------------------
  * Event frames.  Replaces v2ce.py:241-280 (write_event_frame_video) up to the cv2 encoder.
  * ------------------------------------------------------------------------------------------ */

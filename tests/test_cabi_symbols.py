@@ -155,3 +155,20 @@ def test_entry_points_fail_loudly_without_a_device():
     assert lib.v2ce_ef_accumulate(None, 1, 4, 4, 1, None, None) < 0 and b'NULL' in lib.v2ce_last_error()
     with pytest.raises(_lib.V2ceError):
         _lib.check(lib.v2ce_model_create(ctypes.byref(h), 0))
+
+
+def test_baseline_params_mirror_matches_the_c_struct():
+    import ctypes
+    from v2ce_toolbox_b200 import _lib
+    from v2ce_toolbox_b200.sample_methods import random_even_sample as rs
+    lib = _lib.load()
+    assert lib.v2ce_baseline_params_size() == ctypes.sizeof(_lib.BaselineParams)
+    p = rs.make_params(2, 8, 12, fps=30, mode='even', flavor='cpu', device='cpu')
+    n = ctypes.c_size_t()
+    assert lib.v2ce_baseline_count_workspace_bytes(ctypes.byref(p), ctypes.byref(n)) == 0 and n.value > 0
+    assert lib.v2ce_baseline_emit_workspace_bytes(ctypes.byref(p), 1000, ctypes.byref(n)) == 0 and n.value >= 16000
+    p.mode = 5                                            # the LAST fields land where the library reads them
+    assert lib.v2ce_baseline_count_workspace_bytes(ctypes.byref(p), ctypes.byref(n)) != 0 and b'mode' in lib.v2ce_last_error()
+    p.mode, p.key_span = 1, 0
+    assert lib.v2ce_baseline_count_workspace_bytes(ctypes.byref(p), ctypes.byref(n)) != 0 and b'key_span' in lib.v2ce_last_error()
+    assert lib.v2ce_ts_diff_workspace_bytes(346, 260, 1000, ctypes.byref(n)) == 0 and n.value > 346 * 260 * 2 * 12

@@ -31,6 +31,16 @@ class LdatiParams(Structure):
     ]
 
 
+class BaselineParams(Structure):
+    """Mirror of v2ce_baseline_params (include/v2ce_b200.h)."""
+    _fields_ = [
+        ('height', c_int32), ('width', c_int32), ('n_frames', c_int32), ('mode', c_int32),
+        ('frame_base', c_int64), ('seed', c_uint64),
+        ('delta32', c_float), ('binstart_t0_32', c_float * 10),
+        ('key_base_us', c_int64), ('key_span', c_int32), ('add_frame_offset', c_int32),
+    ]
+
+
 _SIGNATURES = {
     'v2ce_last_error': (c_char_p, []),
     'v2ce_version': (c_int, []),
@@ -44,6 +54,15 @@ _SIGNATURES = {
     'v2ce_ldati_emit': (c_int, [c_void_p, POINTER(LdatiParams), c_void_p, c_void_p, c_size_t, c_void_p, c_int32,
                                 c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'v2ce_ldati_relocate': (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    'v2ce_baseline_params_size': (c_size_t, []),
+    'v2ce_baseline_count_workspace_bytes': (c_int, [POINTER(BaselineParams), POINTER(c_size_t)]),
+    'v2ce_baseline_emit_workspace_bytes': (c_int, [POINTER(BaselineParams), c_int64, POINTER(c_size_t)]),
+    'v2ce_baseline_count': (c_int, [c_void_p, POINTER(BaselineParams), c_void_p, c_size_t, c_void_p, c_void_p]),
+    'v2ce_baseline_emit': (c_int, [c_void_p, POINTER(BaselineParams), c_void_p, c_void_p, c_size_t, c_void_p, c_int64,
+                                   c_void_p, c_void_p, c_void_p]),
+    'v2ce_ts_diff_workspace_bytes': (c_int, [c_int32, c_int32, c_int64, POINTER(c_size_t)]),
+    'v2ce_ts_diff_metric': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_double, c_void_p,
+                                    c_size_t, c_void_p, c_void_p]),
     'v2ce_ef_accumulate': (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'v2ce_ef_select_workspace_bytes': (c_int, [POINTER(c_size_t)]),
     'v2ce_ef_select': (c_int, [c_void_p, c_int64, c_double, c_int32, c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -25,6 +25,7 @@
 
 #include <limits.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace v2ce {
 namespace ldati {
@@ -117,6 +118,7 @@ struct DevParams {
   int pooling;        // 0 none, 1 'weighted' (3x3 binomial / 16), 2 'avg' (pool_k x pool_k box / pool_k^2); LDATI.py:176-183
   int pool_k;
   long long nan_ts;   // float NaN -> int64: INT64_MIN on x86 (cvttss2si) and on torch-CUDA (measured on B200)
+  int segs_per_frame; // sort segments per frame: 9 (LDATI: one per bin) or 1 (baseline samplers: whole frames)
 };
 
 static DevParams make_dev_params(const v2ce_ldati_params* p, const Geometry& g) {
@@ -137,6 +139,7 @@ static DevParams make_dev_params(const v2ce_ldati_params* p, const Geometry& g) 
   d.pooling = g.pooling ? p->pooling : 0;
   d.pool_k = p->pooling_kernel_size;
   d.nan_ts = LLONG_MIN;
+  d.segs_per_frame = kBins;
   return d;
 }
 
@@ -227,6 +230,24 @@ __device__ __forceinline__ void philox_block(unsigned long long idx, unsigned bl
   }
   w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
 }
+// same generator with the fourth counter word as a stream id (baseline samplers: 0 integer-part uniforms, 1 fractional-part
+// uniform, 2 Bernoulli uniform; oracle/baseline_oracle.py)
+__device__ __forceinline__ float philox_uniform_stream(unsigned long long idx, unsigned j, unsigned long long seed, unsigned stream) {
+  unsigned c0 = (unsigned)idx, c1 = (unsigned)(idx >> 32), c2 = j >> 2, c3 = stream;
+  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const unsigned sel = j & 3u;
+  const unsigned w = sel == 0 ? c0 : sel == 1 ? c1 : sel == 2 ? c2 : c3;
+  return __fmul_rn((float)(w >> 8), 5.9604644775390625e-08f);   // 2^-24
+}
+
 __device__ __forceinline__ float philox_word_to_uniform(const unsigned (&w)[4], unsigned j) {
   const unsigned sel = j & 3u;
   const unsigned v = sel == 0 ? w[0] : sel == 1 ? w[1] : sel == 2 ? w[2] : w[3];
@@ -1363,7 +1384,7 @@ __global__ void __launch_bounds__(kThreads) pack_linear_kernel(const Elem* __res
     if (4 * lane + j < nrec) {
       while (seg + 1 < ns && idx >= seg_start[seg + 1]) ++seg;     // rarely more than zero steps (L1 hits)
     }
-    const int f = seg / kBins, c = seg - f * kBins;
+    const int f = seg / P.segs_per_frame, c = seg - f * P.segs_per_frame;
     const long long base_ts = P.bin_base[c] - kKeyBias;
     long long off = 0;
     if (P.add_frame_offset && frame_offset_us != nullptr) off = frame_offset_us[f];
@@ -1435,6 +1456,242 @@ __global__ void relocate_debug_kernel(const float* __restrict__ vox, int HW, flo
       if (tend_out != nullptr) tend_out[((size_t)plane * kBins + c) * HW + pix + v] = tend[c];
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Baseline samplers 'random' / 'even' (stage-2 comparison methods; SURVEY.md 8f N4;
+// /root/reference/train/scripts/stage2/sample_methods/random_even_sample.py:118-170).  No count relocation: every voxel
+// value y of the TEN bins yields floor(y) events -- at u * delta ('random') or j / (floor(y) + 1) * delta ('even') into its
+// bin -- plus one more with probability frac(y) at u * delta / floor(y) / (floor(y) + 1) * delta; a frame's events are
+// sorted by timestamp.  Same structure as LDATI: count pass -> scans -> emit to generation-order slots -> one-sweep sort
+// (one segment per FRAME, 16-bit keys at 30 fps: three passes over 64-bit elements) -> records.
+// Generation order g: [bin c][negative plane, positive plane][integer-part events (pixel, j), fractional-part events].
+// ---------------------------------------------------------------------------------------
+constexpr int kBaseBins = 10;
+constexpr int kBaseQ = 2 * kBaseBins;      // per plane: (bin, kind) with kind 0 = integer-part events, 1 = fractional-part events
+
+struct BaseDev {
+  int H, W, HW, F, NB;
+  int mode;                 // 1 random, 2 even
+  long long frame_base;
+  unsigned long long seed;
+  float delta32;
+  float start[kBaseBins];
+  long long key_base;       // timestamps are stored as key = ts - key_base + kKeyBias
+  int pix_bits, key_bits;
+};
+
+struct BaseWs {
+  int32_t* partial;       // [F][2][NB][20]
+  int32_t* block_base;    // [F][2][NB][20]
+  int32_t* group_base;    // [F][10][4]: neg int, neg frac, pos int, pos frac
+  int64_t* seg_start;     // [F+1]
+  size_t bytes;
+};
+
+static BaseWs carve_base_ws(void* ws, int F, int NB) {
+  Arena a(ws, (size_t)-1);
+  BaseWs w;
+  const size_t n = (size_t)F * 2 * NB * kBaseQ;
+  w.partial = a.take<int32_t>(n);
+  w.block_base = a.take<int32_t>(n);
+  w.group_base = a.take<int32_t>((size_t)F * kBaseBins * 4);
+  w.seg_start = a.take<int64_t>((size_t)F + 1);
+  w.bytes = align_up(a.off, 256);
+  return w;
+}
+
+// events of one pixel-bin: floor(y) integer-part events and the Bernoulli(frac) one
+__device__ __forceinline__ void base_counts(float y, unsigned long long idx, unsigned long long seed, int& n_int, int& n_frac,
+                                            float& ip) {
+  ip = floorf(y);
+  n_int = ip > 0.f ? __float2int_rz(ip) : 0;
+  const float frac = __fsub_rn(y, ip);
+  n_frac = philox_uniform_stream(idx, 0u, seed, 2u) < frac ? 1 : 0;       // torch.bernoulli(p): u < p
+}
+
+template <int V>
+__global__ void __launch_bounds__(kThreads) base_count_kernel(const float* __restrict__ vox, BaseDev P, int32_t* __restrict__ partial) {
+  const int blk = blockIdx.x, p = blockIdx.y, f = blockIdx.z;
+  const int pix = (blk * kThreads + threadIdx.x) * V;
+  int tot[kBaseQ];
+#pragma unroll
+  for (int q = 0; q < kBaseQ; ++q) tot[q] = 0;
+  if (pix < P.HW) {
+    float y[V][10];
+    load_pixels<V>(vox + ((size_t)(f * 2 + p) * 10) * P.HW, P.HW, pix, y);
+    const unsigned long long plane = ((unsigned long long)(P.frame_base + f) * 2ull + (unsigned)p) * (unsigned long long)kBaseBins;
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int c = 0; c < kBaseBins; ++c) {
+        int ni, nf;
+        float ip;
+        base_counts(y[v][c], (plane + (unsigned)c) * (unsigned long long)P.HW + (unsigned)(pix + v), P.seed, ni, nf, ip);
+        tot[2 * c] += ni;
+        tot[2 * c + 1] += nf;
+      }
+  }
+  __shared__ int red[kThreads / 32][kBaseQ];
+#pragma unroll
+  for (int q = 0; q < kBaseQ; ++q) {
+    int v = tot[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kBaseQ) {
+    int sum = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) sum += red[w][threadIdx.x];
+    partial[(((size_t)f * 2 + p) * P.NB + blk) * kBaseQ + threadIdx.x] = sum;
+  }
+}
+
+// per frame: exclusive scan of the block partials over each plane, the 40 group bases, the frame total
+__global__ void base_scan_kernel(const int32_t* __restrict__ partial, int32_t* __restrict__ block_base,
+                                 int32_t* __restrict__ group_base, int64_t* __restrict__ frame_counts, int NB) {
+  const int f = blockIdx.x;
+  __shared__ int tot[2][kBaseQ];
+  const int t = threadIdx.x;
+  if (t < 2 * kBaseQ) {
+    const int p = t / kBaseQ, q = t % kBaseQ;
+    const size_t base = ((size_t)f * 2 + p) * NB * kBaseQ + q;
+    int run = 0;
+    for (int b = 0; b < NB; ++b) {
+      block_base[base + (size_t)b * kBaseQ] = run;
+      run += partial[base + (size_t)b * kBaseQ];
+    }
+    tot[p][q] = run;
+  }
+  __syncthreads();
+  if (t == 0) {
+    long long run = 0;
+    for (int c = 0; c < kBaseBins; ++c) {
+      int32_t* gb = group_base + ((size_t)f * kBaseBins + c) * 4;
+      // negative plane (p-index 1) first, inside a plane integer-part events before fractional-part events
+      gb[0] = (int32_t)run; run += tot[1][2 * c];
+      gb[1] = (int32_t)run; run += tot[1][2 * c + 1];
+      gb[2] = (int32_t)run; run += tot[0][2 * c];
+      gb[3] = (int32_t)run; run += tot[0][2 * c + 1];
+    }
+    frame_counts[f] = run;
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kThreads) base_emit_kernel(const float* __restrict__ vox, BaseDev P,
+                                                              const int32_t* __restrict__ block_base,
+                                                              const int32_t* __restrict__ group_base,
+                                                              const int64_t* __restrict__ seg_start,
+                                                              unsigned long long* __restrict__ elems, int32_t* __restrict__ status) {
+  const int blk = blockIdx.x, p = blockIdx.y, f = blockIdx.z;
+  const int pix0 = (blk * kThreads + threadIdx.x) * V;
+  const bool active = pix0 < P.HW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pol = 1 - p;
+  const size_t bb = (((size_t)f * 2 + p) * P.NB + blk) * kBaseQ;
+  const long long frame_start = seg_start[f];
+  const unsigned long long plane = ((unsigned long long)(P.frame_base + f) * 2ull + (unsigned)p) * (unsigned long long)kBaseBins;
+  __shared__ int wsum[kThreads / 32][2];
+  float y[V][10];
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+#pragma unroll
+    for (int c = 0; c < 10; ++c) y[v][c] = 0.f;
+  if (active) load_pixels<V>(vox + ((size_t)(f * 2 + p) * 10) * P.HW, P.HW, pix0, y);
+#pragma unroll 1
+  for (int c = 0; c < kBaseBins; ++c) {
+    int ni[V], nf[V];
+    float ip[V];
+    int ti = 0, tf = 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      ni[v] = nf[v] = 0; ip[v] = 0.f;
+      if (active) {
+        float yc = y[0][0];
+#pragma unroll
+        for (int cc = 0; cc < 10; ++cc) if (cc == c) yc = y[v][cc];            // register select (c is a runtime index)
+        base_counts(yc, (plane + (unsigned)c) * (unsigned long long)P.HW + (unsigned)(pix0 + v), P.seed, ni[v], nf[v], ip[v]);
+      }
+      ti += ni[v]; tf += nf[v];
+    }
+    const int inc_i = warp_incl_scan(ti), inc_f = warp_incl_scan(tf);
+    if (lane == 31) { wsum[warp][0] = inc_i; wsum[warp][1] = inc_f; }
+    __syncthreads();
+    int wi = 0, wf = 0;
+    for (int w = 0; w < warp; ++w) { wi += wsum[w][0]; wf += wsum[w][1]; }
+    __syncthreads();
+    const int32_t* gb = group_base + ((size_t)f * kBaseBins + c) * 4;
+    const int grp = (p == 1) ? 0 : 2;
+    long long slot_i = frame_start + gb[grp] + block_base[bb + 2 * c] + wi + (inc_i - ti);
+    long long slot_f = frame_start + gb[grp + 1] + block_base[bb + 2 * c + 1] + wf + (inc_f - tf);
+    const float st = P.start[c];
+    auto put = [&](long long slot, float t, int pix) {
+      t = __fmul_rn(__fadd_rn(t, st), 1e6f);
+      const bool bad = !(t == t) || fabsf(t) > 9.0e18f;
+      const long long ts = bad ? LLONG_MIN : (long long)t;
+      long long key = ts - P.key_base + kKeyBias;
+      const long long kmax = (1LL << P.key_bits) - 1;
+      if (bad || key < 1 || key > kmax) {               // non-finite or far outside the frame: flagged, the host raises
+        atomicAdd(status + 0, 1);
+        key = key < 1 ? 1 : kmax;
+      }
+      elems[slot] = ((unsigned long long)key << (P.pix_bits + 1)) | ((unsigned long long)pol << P.pix_bits) |
+                    (unsigned long long)pix;
+    };
+    if (active) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const unsigned long long idx = (plane + (unsigned)c) * (unsigned long long)P.HW + (unsigned)(pix0 + v);
+        const float den = __fadd_rn(ip[v], 1.f);
+        for (int j = 0; j < ni[v]; ++j) {
+          const float t = P.mode == 1 ? __fmul_rn(philox_uniform_stream(idx, (unsigned)j, P.seed, 0u), P.delta32)
+                                      : __fmul_rn(__fdiv_rn((float)j, den), P.delta32);
+          put(slot_i++, t, pix0 + v);
+        }
+        if (nf[v]) {
+          const float t = P.mode == 1 ? __fmul_rn(philox_uniform_stream(idx, 0u, P.seed, 1u), P.delta32)
+                                      : __fmul_rn(__fdiv_rn(ip[v], den), P.delta32);
+          put(slot_f++, t, pix0 + v);
+        }
+      }
+    }
+  }
+}
+
+static int validate_base(const v2ce_baseline_params* p) {
+  V2CE_REQUIRE(p != nullptr, "params is NULL");
+  V2CE_REQUIRE(p->height > 0 && p->width > 0 && p->n_frames > 0, "bad geometry %dx%d x %d frames", p->height, p->width,
+               p->n_frames);
+  V2CE_REQUIRE(p->width < 32768 && p->height < 32768, "x/y are int16 fields: H,W must be < 32768");
+  V2CE_REQUIRE((long long)p->height * p->width < (1LL << 30), "plane too large");
+  V2CE_REQUIRE(p->n_frames <= 65535, "at most 65535 frames per call (grid.z)");
+  V2CE_REQUIRE(p->mode == 1 || p->mode == 2, "mode must be 1 ('random') or 2 ('even')");
+  V2CE_REQUIRE(p->key_span > 0 && p->key_span < (1 << 30), "bad key_span %d", p->key_span);
+  return V2CE_OK;
+}
+
+struct BaseGeom { int HW, V, NB, pix_bits, key_bits; };
+static BaseGeom base_geom(const v2ce_baseline_params* p) {
+  BaseGeom g;
+  g.HW = p->height * p->width;
+  g.V = (g.HW % 4 == 0) ? 4 : 1;
+  g.NB = (g.HW + kThreads * g.V - 1) / (kThreads * g.V);
+  g.pix_bits = 1;
+  while ((1LL << g.pix_bits) < g.HW) ++g.pix_bits;
+  g.key_bits = 1;
+  while ((1LL << g.key_bits) < (long long)p->key_span + 1) ++g.key_bits;
+  return g;
+}
+static BaseDev base_dev(const v2ce_baseline_params* p, const BaseGeom& g) {
+  BaseDev d;
+  d.H = p->height; d.W = p->width; d.HW = g.HW; d.F = p->n_frames; d.NB = g.NB;
+  d.mode = p->mode; d.frame_base = p->frame_base; d.seed = p->seed; d.delta32 = p->delta32;
+  for (int c = 0; c < kBaseBins; ++c) d.start[c] = p->binstart_t0_32[c];
+  d.key_base = p->key_base_us; d.pix_bits = g.pix_bits; d.key_bits = g.key_bits;
+  return d;
 }
 
 static int validate(const v2ce_ldati_params* p) {
@@ -1671,5 +1928,117 @@ extern "C" int v2ce_ldati_relocate(const float* voxels_dev, int32_t n_frames, in
     relocate_debug_kernel<1><<<grid, 256, 0, s>>>(voxels_dev, HW, 1e-6f, bidirectional, counts_dev, tend_dev);
   }
   V2CE_LAUNCH_CHECK("ldati::relocate_debug_kernel");
+  return V2CE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Baseline samplers: C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" size_t v2ce_baseline_params_size(void) { return sizeof(v2ce_baseline_params); }
+
+extern "C" int v2ce_baseline_count_workspace_bytes(const v2ce_baseline_params* p, size_t* bytes) {
+  if (int e = validate_base(p)) return e;
+  V2CE_REQUIRE(bytes != nullptr, "bytes is NULL");
+  *bytes = carve_base_ws(nullptr, p->n_frames, base_geom(p).NB).bytes;
+  return V2CE_OK;
+}
+
+static Geometry base_sort_geometry(const v2ce_baseline_params* p, const BaseGeom& bg) {
+  Geometry g;
+  g.H = p->height; g.W = p->width; g.HW = bg.HW; g.F = p->n_frames; g.V = bg.V; g.NB = bg.NB;
+  g.pix_bits = bg.pix_bits; g.key_bits = bg.key_bits; g.wide = 1; g.pooling = 0;
+  return g;
+}
+
+// the sort workspace is carved for F * 9 segments (LDATI's layout); the baseline sort uses F of them
+extern "C" int v2ce_baseline_emit_workspace_bytes(const v2ce_baseline_params* p, int64_t total_events, size_t* bytes) {
+  if (int e = validate_base(p)) return e;
+  V2CE_REQUIRE(bytes != nullptr && total_events >= 0, "bad arguments");
+  V2CE_REQUIRE(total_events < (1LL << 31) - (1LL << 20), "more than 2^31 events in one call; split the frames");
+  *bytes = carve_sort_ws(nullptr, base_sort_geometry(p, base_geom(p)), total_events, 8).bytes;
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_baseline_count(const float* voxels_dev, const v2ce_baseline_params* p, void* count_ws_dev,
+                                   size_t count_ws_bytes, int64_t* frame_counts_dev, void* stream) {
+  if (int e = validate_base(p)) return e;
+  V2CE_REQUIRE(voxels_dev && count_ws_dev && frame_counts_dev, "NULL device pointer");
+  const BaseGeom g = base_geom(p);
+  BaseWs w = carve_base_ws(count_ws_dev, p->n_frames, g.NB);
+  if (w.bytes > count_ws_bytes)
+    return set_error(V2CE_ERR_WORKSPACE, "count workspace too small: need %zu, got %zu", w.bytes, count_ws_bytes);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const BaseDev P = base_dev(p, g);
+  dim3 grid(g.NB, 2, p->n_frames);
+  if (g.V == 4) base_count_kernel<4><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
+  else base_count_kernel<1><<<grid, kThreads, 0, s>>>(voxels_dev, P, w.partial);
+  V2CE_LAUNCH_CHECK("ldati::base_count_kernel");
+  base_scan_kernel<<<p->n_frames, 64, 0, s>>>(w.partial, w.block_base, w.group_base, frame_counts_dev, g.NB);
+  V2CE_LAUNCH_CHECK("ldati::base_scan_kernel");
+  scan_i64_kernel<<<1, 1024, 0, s>>>(frame_counts_dev, w.seg_start, p->n_frames);
+  V2CE_LAUNCH_CHECK("ldati::scan_i64_kernel");
+  return V2CE_OK;
+}
+
+extern "C" int v2ce_baseline_emit(const float* voxels_dev, const v2ce_baseline_params* p, const void* count_ws_dev,
+                                  void* emit_ws_dev, size_t emit_ws_bytes, const int64_t* frame_offset_us_dev,
+                                  int64_t total_events, uint8_t* events_out_dev, int32_t* status_dev, void* stream) {
+  if (int e = validate_base(p)) return e;
+  V2CE_REQUIRE(voxels_dev && count_ws_dev && emit_ws_dev && status_dev, "NULL device pointer");
+  V2CE_REQUIRE(total_events >= 0 && total_events < (1LL << 31) - (1LL << 20), "total_events out of range");
+  V2CE_REQUIRE(total_events == 0 || events_out_dev != nullptr, "events_out_dev is NULL");
+  typedef unsigned long long Elem;
+  const BaseGeom bg = base_geom(p);
+  const Geometry g = base_sort_geometry(p, bg);
+  BaseWs cw = carve_base_ws(const_cast<void*>(count_ws_dev), p->n_frames, bg.NB);
+  SortWs sw = carve_sort_ws(emit_ws_dev, g, total_events, sizeof(Elem));
+  if (sw.bytes > emit_ws_bytes)
+    return set_error(V2CE_ERR_WORKSPACE, "emit workspace too small: need %zu, got %zu", sw.bytes, emit_ws_bytes);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const BaseDev P = base_dev(p, bg);
+  Elem* src = static_cast<Elem*>(sw.elem_a);
+  Elem* dst = static_cast<Elem*>(sw.elem_b);
+  V2CE_CUDA_CHECK(cudaMemsetAsync(status_dev, 0, 4 * sizeof(int32_t), s));
+  if (total_events == 0) return V2CE_OK;
+  dim3 grid(bg.NB, 2, p->n_frames);
+  if (bg.V == 4) base_emit_kernel<4><<<grid, kThreads, 0, s>>>(voxels_dev, P, cw.block_base, cw.group_base, cw.seg_start, src, status_dev);
+  else base_emit_kernel<1><<<grid, kThreads, 0, s>>>(voxels_dev, P, cw.block_base, cw.group_base, cw.seg_start, src, status_dev);
+  V2CE_LAUNCH_CHECK("ldati::base_emit_kernel");
+  // one sort segment per frame
+  const int ns = p->n_frames;
+  const int passes = osw_passes(g.key_bits);
+  const int rb = (g.key_bits + passes - 1) / passes;
+  build_tiles_kernel<<<1, 1024, 0, s>>>(cw.seg_start, ns, kOswTile, sw.tile_first4);
+  V2CE_LAUNCH_CHECK("ldati::build_tiles_kernel");
+  fill_tile_seg_kernel<<<(sw.nt4_max + 255) / 256, 256, 0, s>>>(sw.tile_first4, ns, sw.tile_seg4);
+  V2CE_LAUNCH_CHECK("ldati::fill_tile_seg_kernel");
+  V2CE_CUDA_CHECK(cudaMemsetAsync(sw.osw_zero, 0, sw.osw_zero_bytes, s));
+  osw_hist_kernel<Elem><<<sw.nt4_max, kThreads, 0, s>>>(src, cw.seg_start, sw.tile_first4, sw.tile_seg4, ns, g.pix_bits + 1, rb, passes,
+                                                        sw.seg_hist);
+  V2CE_LAUNCH_CHECK("ldati::osw_hist_kernel");
+  const size_t smem = (size_t)kOswCounterWords * 4 > (size_t)kOswStageSlots * sizeof(Elem) ? (size_t)kOswCounterWords * 4
+                                                                                           : (size_t)kOswStageSlots * sizeof(Elem);
+  for (int pass = 0; pass < passes; ++pass) {
+    osw_scatter_kernel<Elem><<<sw.nt4_max, kThreads, smem, s>>>(src, dst, cw.seg_start, sw.tile_first4, sw.tile_seg4, ns,
+                                                                g.pix_bits + 1 + pass * rb, rb, sw.seg_hist + (size_t)pass * ns * kOswRadix,
+                                                                sw.tstate + (size_t)pass * sw.nt4_max * kOswRadix, sw.tickets + pass);
+    V2CE_LAUNCH_CHECK("ldati::osw_scatter_kernel");
+    Elem* t = src; src = dst; dst = t;
+  }
+  // records: the LDATI record writer with one segment per frame whose key origin is the frame's
+  DevParams D;
+  memset(&D, 0, sizeof(D));
+  D.H = p->height; D.W = p->width; D.HW = bg.HW; D.F = p->n_frames; D.NB = bg.NB;
+  D.pix_bits = bg.pix_bits; D.key_bits = bg.key_bits;
+  D.add_frame_offset = p->add_frame_offset;
+  D.nan_ts = LLONG_MIN;
+  D.segs_per_frame = 1;
+  D.bin_base[0] = p->key_base_us;
+  const long long nchunks = (total_events + kPackRecsPerWarp - 1) / kPackRecsPerWarp;
+  pack_chunk_seg_kernel<<<(int)((nchunks + 255) / 256), 256, 0, s>>>(cw.seg_start, ns, total_events, sw.chunk_seg);
+  V2CE_LAUNCH_CHECK("ldati::pack_chunk_seg_kernel");
+  pack_linear_kernel<Elem><<<(int)((nchunks + kThreads / 32 - 1) / (kThreads / 32)), kThreads, 0, s>>>(
+      src, cw.seg_start, sw.chunk_seg, ns, total_events, D, frame_offset_us_dev, events_out_dev);
+  V2CE_LAUNCH_CHECK("ldati::pack_linear_kernel");
   return V2CE_OK;
 }
