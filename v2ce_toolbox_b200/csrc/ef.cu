@@ -70,8 +70,12 @@ __device__ __forceinline__ void pick_bucket(const unsigned long long* h, unsigne
   if (t < 255 && inc > k && exc <= k) { sh_out[0] = (unsigned long long)t; sh_out[1] = exc; }     // exactly one thread
   if (t == 255) sh_warp[8] = exc;                       // count before bucket 255 (the fall-through case)
   __syncthreads();
-  if (t == 0 && sh_out[1] == ~0ull) sh_out[1] = sh_warp[8];
-  __syncthreads();
+}
+// result of the last pick_bucket (any thread, after its barrier): the count before the picked bucket.  The fall-through
+// value is kept in its own word instead of being patched into sh_out by thread 0: compute-sanitizer's racecheck
+// flagged that patch (the compiler hoists the predicate's load to every thread while thread 0 stores).
+__device__ __forceinline__ unsigned long long picked_before(const unsigned long long* sh_warp, const unsigned long long* sh_out) {
+  return sh_out[1] == ~0ull ? sh_warp[8] : sh_out[1];
 }
 
 __global__ void __launch_bounds__(kThreads) select_hist_kernel(const float* __restrict__ v, long long n, int pass,
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(kThreads) select_hist_kernel(const float* __re
     // total count of positive values, then numpy's 'linear' method: virtual index (n-1)*q with q = percentile/100 (float64)
     pick_bucket(h0, ~0ull - 1ull, sh_warp, sh_out);                              // never found: sh_out[1] = count before bucket 255
     if (threadIdx.x == 0) {
-      const unsigned long long npos = sh_out[1] + __ldcg(h0 + 255);
+      const unsigned long long npos = picked_before(sh_warp, sh_out) + __ldcg(h0 + 255);
       st->npos = npos;
       result[0] = (long long)npos;
       if (npos == 0) {
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(kThreads) select_hist_kernel(const float* __re
   for (int r = 0; r < 2; ++r) {
     pick_bucket(r == 0 ? h0 : h1, st->remaining[r], sh_warp, sh_out);
     if (threadIdx.x == 0) {
-      st->remaining[r] -= sh_out[1];
+      st->remaining[r] -= picked_before(sh_warp, sh_out);
       st->prefix[r] = (st->prefix[r] << 8) | (unsigned int)sh_out[0];
     }
     __syncthreads();
