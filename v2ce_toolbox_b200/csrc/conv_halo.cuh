@@ -56,6 +56,7 @@ struct HaloArgs {
   int a_row16;                 // conv_halo_kdm only: bytes of one patch pixel row / 16 -- 8 (64 channels, SWIZZLE_128B) or
                                // 2 (16 channels, SWIZZLE_32B: the head conv's 8-channel split pixels)
   uint32_t a_desc_hi;          // high word of the A operand's UMMA descriptor for that layout
+  int tap_mask;                // conv_halo_kdm, stride 1: bit (kh*3+kw) set = the tap is multiplied (0x1FF; the head skips kw = 1)
   const __nv_bfloat16* wpack;  // [Cout/BN][ncc][3 kd][9 taps][BN][64], rows pre-swizzled
   const float* scale;
   const float* shift;
@@ -514,9 +515,10 @@ inline int make_patch_map16(CUtensorMap* map, const void* ptr, int B, int D, int
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(V2CE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const int cpitch = 8;
-  cuuint64_t dims[5] = {16u, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
-  cuuint64_t strides[4] = {(cuuint64_t)cpitch * 2, (cuuint64_t)W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2,
-                           (cuuint64_t)D * H * W * cpitch * 2};
+  const cuuint64_t Wp = (cuuint64_t)W + 1;          // rows are stored with one more (zero) pixel, see head_prep_kernel
+  cuuint64_t dims[5] = {16u, Wp, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)cpitch * 2, Wp * cpitch * 2, (cuuint64_t)H * Wp * cpitch * 2,
+                           (cuuint64_t)D * H * Wp * cpitch * 2};
   cuuint32_t box[5] = {16u, (cuuint32_t)PW, (cuuint32_t)rows, 1u, 1u};
   cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,

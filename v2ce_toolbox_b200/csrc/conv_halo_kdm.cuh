@@ -369,7 +369,8 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
               const uint32_t a_lo = smem_desc_lo(a_base + (uint32_t)sa * a.a_stage_bytes);
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap)
-                issue_tap(KS_, tap, a_lo + (uint32_t)(tap / 3) * pw8 + (uint32_t)(tap % 3) * px16, tap == 0);
+                if ((a.tap_mask >> tap) & 1)
+                  issue_tap(KS_, tap, a_lo + (uint32_t)(tap / 3) * pw8 + (uint32_t)(tap % 3) * px16, tap == 0);
               tcgen05_commit_elect(a_empty(sa));
               if (++sa == a.SA) { sa = 0; pa ^= 1; }
             } else {

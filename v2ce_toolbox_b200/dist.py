@@ -55,15 +55,18 @@ def model_calls_before(first_batch, infer_type='center', tiles=1):
     return first_batch * (1 if infer_type == 'center' else tiles)
 
 
-def init_process_group(backend='nccl', device=None, max_ctas=4, **kw):
-    """torch.distributed.init_process_group with the NCCL settings this path wants: the only collectives are tiny
-    count exchanges and point-to-point shard transfers that run UNDER the persistent conv CTAs of the next batch, so
-    NCCL gets at most `max_ctas` CTAs per operation (it would otherwise take up to 32 SMs' worth of channels away from
-    the network: forward time grew 9.8 -> 10.5 ms from 1 to 8 ranks in round 1)."""
+def init_process_group(backend='nccl', device=None, max_ctas=None, **kw):
+    """torch.distributed.init_process_group plus the host-side gloo group the count exchanges use.  `max_ctas` (or
+    V2CE_NCCL_MAX_CTAS) caps NCCL's CTAs per operation; the default leaves NCCL's own choice: capped at 4 the merge of
+    eight 150 MB shards per step on rank 0 ran at ~100 GB/s and the 8-GPU step went from 10.5 to 17.8 ms
+    (profiles/bench_r2_8gpu_a.json) -- the shard transfers need the channels more than the network needs those SMs."""
     if backend == 'nccl':
+        import os
         opts = dist.ProcessGroupNCCL.Options()
-        opts.config.max_ctas = int(max_ctas)
-        opts.config.min_ctas = 1
+        cap = max_ctas if max_ctas is not None else os.environ.get('V2CE_NCCL_MAX_CTAS')
+        if cap:
+            opts.config.max_ctas = int(cap)
+            opts.config.min_ctas = 1
         dist.init_process_group('nccl', device_id=device, pg_options=opts, **kw)
         # host-side values (event counts are known on the host: the count pass is read back to size the outputs) are
         # exchanged over a gloo group: no NCCL kernel, no device sync.  The conv kernels are persistent CTAs that fill
