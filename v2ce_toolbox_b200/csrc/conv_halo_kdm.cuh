@@ -65,19 +65,26 @@ struct KdmRow {
 __device__ __forceinline__ void kdm_store_chunk(const HaloArgs& a, const KdmRow& r, const uint32_t (&v)[32], const uint4 (&rv)[4],
                                                 const float* s_scale, const float* s_shift, int act, size_t plane, int n0,
                                                 __nv_bfloat16* out, int out_pitch, int cout, bool main_out) {
+  // scale / shift come in as 16-byte shared-memory loads (16 instead of 64 scalar ones): the epilogue warps are few
+  // (two per scheduler) and issue-latency bound, every instruction saved shortens the slice (profiles/ncu_kdm_r2_c.txt)
   float yv[32];
+  const float4* sc4 = reinterpret_cast<const float4*>(s_scale);
+  const float4* sh4 = reinterpret_cast<const float4*>(s_shift);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const __nv_bfloat162* rp2 = reinterpret_cast<const __nv_bfloat162*>(&rv[g]);
+    const float4 sa = sc4[2 * g], sb = sc4[2 * g + 1], ta = sh4[2 * g], tb = sh4[2 * g + 1];
+    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+    const float sh[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __bfloat1622float2(rp2[j]);      // zeros when there is no residual
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int n = g * 8 + 2 * j + hh;
-        float tv = fmaf(__uint_as_float(v[n]), s_scale[n], s_shift[n]) + (hh ? f.y : f.x);
+        float tv = fmaf(__uint_as_float(v[n]), sc[2 * j + hh], sh[2 * j + hh]) + (hh ? f.y : f.x);
         if (act == 1) tv = fmaxf(tv, 0.f);
-        else if (act == 2) tv = tv > 0.f ? tv : 0.01f * tv;
+        else if (act == 2) tv = fmaxf(tv, 0.01f * tv);  // LeakyReLU(0.01): max(x, 0.01 x)
         yv[n] = tv;
       }
     }
