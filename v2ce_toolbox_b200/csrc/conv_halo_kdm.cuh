@@ -146,8 +146,11 @@ struct KdmInt { static constexpr int value = N; };
 // taps in the order the stride-2 variant multiplies them
 __device__ __constant__ int kS2TapOrder[9] = {4, 3, 5, 1, 7, 0, 2, 6, 8};
 
-template <bool SHORT, int T, int S>
-__global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid_constant__ CUtensorMap tm0,
+// EW = epilogue warps: 8 (two per TMEM lane quarter, alternate slices) or 16 (four per quarter, every fourth slice).
+// The epilogue of the layers with few MMAs per slice (head: 6, 32-channel conv2: 18) is issue-latency bound -- a warp-slice
+// is ~350 dependent-ish instructions and two warps per scheduler cannot hide each other -- so those launches take 16.
+template <bool SHORT, int T, int S, int EW = 8>
+__global__ void __launch_bounds__(128 + 32 * EW) conv_halo_kdm_kernel(const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1,
                                                                      const __grid_constant__ ParityMaps pm,
                                                                      const HaloArgs a, const KdmShort sc) {
@@ -421,7 +424,8 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
   } else if (warp >= 4) {
     // ================= epilogue (warps 4-11) =================
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;             // even / odd slices of the block
+    constexpr int kParts = EW / 4;                // warps per lane quarter: they take the block's slices round robin
+    const int half = (warp - 4) >> 2;             // which of them this warp is
     const int i = quarter * 32 + lane;            // accumulator row == TMEM lane
     const int th = i / a.PW, tw = i % a.PW;
     const int etid = tid - 128;                   // 0..255 inside the epilogue group
@@ -432,8 +436,8 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const TileCoord tc = decode_tile(tile, a, T, n_tiles);
       if (tc.n_tile != cur_n_tile) {              // (re)stage the folded BatchNorm scale/shift of this channel tile
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int j = etid; j < BN; j += 256) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
+        for (int j = etid; j < BN; j += 32 * EW) {
           s_scale[j] = __ldg(a.scale + tc.n_tile * BN + j) * isg;
           s_shift[j] = __ldg(a.shift + tc.n_tile * BN + j);
           if (SHORT) {
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
             s_shift2[j] = __ldg(sc.shift + tc.n_tile * BN + j);
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
         cur_n_tile = tc.n_tile;
       }
       const int slot0 = (iter % G) * T;
@@ -470,11 +474,11 @@ __global__ void __launch_bounds__(kKdmThreads) conv_halo_kdm_kernel(const __grid
         for (int g = 0; g < 4; ++g) rv[g] = __ldg(rp + g);
       }
 #pragma unroll 1
-      for (int tt = half; tt < T; tt += 2) {
+      for (int tt = half; tt < T; tt += kParts) {
         const int slot = slot0 + tt;
         uint4 rn[4] = {rv[0], rv[1], rv[2], rv[3]};
-        if (has_res && tt + 2 < T) {
-          const uint4* rp = res_ptr(tt + 2);
+        if (has_res && tt + kParts < T) {
+          const uint4* rp = res_ptr(tt + kParts);
 #pragma unroll
           for (int g = 0; g < 4; ++g) rn[g] = __ldg(rp + g);
         }
@@ -629,18 +633,18 @@ inline int make_parity_map(CUtensorMap* map, const void* ptr, int B, int D, int 
   return V2CE_OK;
 }
 
-template <bool SHORT, int T, int S>
+template <bool SHORT, int T, int S, int EW = 8>
 inline int launch_kdm_one(const CUtensorMap& tm0, const CUtensorMap& tm1, const ParityMaps& pm, const HaloArgs& a,
                           const KdmShort& sc, int smem_bytes, cudaStream_t s) {
   static int configured[64] = {0};
   const int slot = device_slot();
   if (configured[slot] < smem_bytes) {
-    V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<SHORT, T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    V2CE_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kdm_kernel<SHORT, T, S, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured[slot] = smem_bytes;
   }
   const int total = a.B * (a.D / T) * a.tiles_h * a.tiles_w * (a.Cout / kKdmBN);
   const int grid = total < sm_count_cached() ? total : sm_count_cached();
-  V2CE_CUDA_CHECK(launch_pdl(conv_halo_kdm_kernel<SHORT, T, S>, grid, kKdmThreads, (size_t)smem_bytes, s, tm0, tm1, pm, a, sc));
+  V2CE_CUDA_CHECK(launch_pdl(conv_halo_kdm_kernel<SHORT, T, S, EW>, grid, 128 + 32 * EW, (size_t)smem_bytes, s, tm0, tm1, pm, a, sc));
   V2CE_LAUNCH_CHECK("conv_halo_kdm_kernel");
   return V2CE_OK;
 }
@@ -666,6 +670,10 @@ inline int launch_halo_kdm(const CUtensorMap& tm0, const CUtensorMap& tm1, const
     return launch_kdm_one<false, 8, 2>(tm0, tm1, *pm, b, none, smem_bytes, s);
   }
   if (sc) return launch_kdm_one<true, 8, 1>(tm0, tm1, no_pm, b, *sc, smem_bytes, s);
+  // few MMAs per slice (<= 2 K steps per tap, one chunk): the epilogue is the limit -> 16 epilogue warps (V2CE_KDM_EW16=0: 8)
+  static const bool ew16 = !(getenv("V2CE_KDM_EW16") && atoi(getenv("V2CE_KDM_EW16")) == 0);
+  static const int ew16_maxc = getenv("V2CE_KDM_EW16_MAXC") ? atoi(getenv("V2CE_KDM_EW16_MAXC")) : 32;
+  if (t16 && ew16 && a.ncc0 + a.ncc1 == 1 && a.real0 <= ew16_maxc) return launch_kdm_one<false, 16, 1, 16>(tm0, tm1, no_pm, b, none, smem_bytes, s);
   if (t16) return launch_kdm_one<false, 16, 1>(tm0, tm1, no_pm, b, none, smem_bytes, s);
   return launch_kdm_one<false, 8, 1>(tm0, tm1, no_pm, b, none, smem_bytes, s);
 }

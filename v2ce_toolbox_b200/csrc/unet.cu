@@ -239,13 +239,14 @@ __global__ void __launch_bounds__(256) head_prep_kernel(const void* __restrict__
 // kernel skips (HaloArgs::tap_mask) -- 6 MMA instructions per input slice instead of 9 for the warp that issues them.
 // (Pairing kw = 1 with kw = 2, not kw = 0 with kw = 1: the row of tap kw = 0 of output column 0 lies left of the image and
 // is zero-filled as a whole by TMA, upper half included; the right neighbour of the last column is the stored zero pixel.)
-__global__ void head_split_weights_kernel(const float* __restrict__ w, float* __restrict__ out) {
+__global__ void head_split_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int nine_taps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 32 * 16 * 27) return;
   const int tap = i % 27, c16 = (i / 27) % 16, n = i / (27 * 16);
   const int kw = tap % 3, c = c16 & 7;
   int src_tap = -1;
-  if (c16 < 8) src_tap = (kw == 2) ? -1 : tap;              // kw = 0 and kw = 1 keep their own weights in the lower half
+  if (nine_taps) src_tap = (c16 < 8) ? tap : -1;            // A/B switch V2CE_HEAD_9TAPS=1: every tap on its own, upper half zero
+  else if (c16 < 8) src_tap = (kw == 2) ? -1 : tap;         // kw = 0 and kw = 1 keep their own weights in the lower half
   else src_tap = (kw == 1) ? tap + 1 : -1;                  // upper half of kw = 1: the weights of kw = 2 (next pixel)
   float v = 0.f;
   if (src_tap >= 0 && c < 6) {
@@ -826,7 +827,8 @@ extern "C" int v2ce_model_finalize(v2ce_model* m) {
         // tensor-pipe variant: split weights in the depth-merged packing, unit scale, bias as shift
         float* w8 = nullptr;
         if (int e = dev_alloc(m, &w8, (size_t)32 * 16 * 27)) return e;
-        head_split_weights_kernel<<<(32 * 16 * 27 + 255) / 256, 256, 0, s>>>(dl.w32, w8);
+        head_split_weights_kernel<<<(32 * 16 * 27 + 255) / 256, 256, 0, s>>>(
+            dl.w32, w8, (getenv("V2CE_HEAD_9TAPS") && atoi(getenv("V2CE_HEAD_9TAPS"))) ? 1 : 0);
         V2CE_LAUNCH_CHECK("head_split_weights_kernel");
         if (int e = dev_alloc(m, &dl.wpack_kdm, (size_t)32 * 27 * 64)) return e;
         halo::pack_weights_kdm_kernel<<<(32 * 27 * 64 + 255) / 256, 256, 0, s>>>(w8, 32, 16, 64, 16, 0, 0, dl.wpack_kdm);
@@ -947,7 +949,8 @@ static int forward_impl(v2ce_model* m, const void* x_dev, bool frames_u8, float*
     a.tiles_w = (W + a.TW - 1) / a.TW;
     a.tiles_h = (H + a.TH - 1) / a.TH;
     a.ncc0 = 1; a.ncc1 = 0; a.real0 = 8; a.real1 = 0;
-    a.tap_mask = 0x0DB;                            // taps (kh, 0) and (kh, 1): the kw = 2 weights ride in the upper half of kw = 1
+    // taps (kh, 0) and (kh, 1): the kw = 2 weights ride in the upper half of kw = 1
+    a.tap_mask = (getenv("V2CE_HEAD_9TAPS") && atoi(getenv("V2CE_HEAD_9TAPS"))) ? 0x1FF : 0x0DB;
     a.Cout = 32; a.out_pitch = pitch_of(32); a.res_pitch = 0;
     a.T = halo::kKdmT; a.SA = hplan.SA; a.SB = 9; a.a_stage_bytes = hplan.a_stage_bytes; a.box_bytes = hplan.box_bytes;
     a.wpack = dl.wpack_kdm; a.scale = dl.scale; a.shift = dl.shift; a.inv_sigma = nullptr;
