@@ -146,9 +146,8 @@ struct KdmInt { static constexpr int value = N; };
 // taps in the order the stride-2 variant multiplies them
 __device__ __constant__ int kS2TapOrder[9] = {4, 3, 5, 1, 7, 0, 2, 6, 8};
 
-// EW = epilogue warps: 8 (two per TMEM lane quarter, alternate slices) or 16 (four per quarter, every fourth slice).
-// The epilogue of the layers with few MMAs per slice (head: 6, 32-channel conv2: 18) is issue-latency bound -- a warp-slice
-// is ~350 dependent-ish instructions and two warps per scheduler cannot hide each other -- so those launches take 16.
+// EW = epilogue warps: 8 (two per TMEM lane quarter, alternate slices) or, as an experiment switch, 16 (four per
+// quarter, every fourth slice; see launch_halo_kdm).
 template <bool SHORT, int T, int S, int EW = 8>
 __global__ void __launch_bounds__(128 + 32 * EW) conv_halo_kdm_kernel(const __grid_constant__ CUtensorMap tm0,
                                                                      const __grid_constant__ CUtensorMap tm1,
@@ -670,8 +669,10 @@ inline int launch_halo_kdm(const CUtensorMap& tm0, const CUtensorMap& tm1, const
     return launch_kdm_one<false, 8, 2>(tm0, tm1, *pm, b, none, smem_bytes, s);
   }
   if (sc) return launch_kdm_one<true, 8, 1>(tm0, tm1, no_pm, b, *sc, smem_bytes, s);
-  // few MMAs per slice (<= 2 K steps per tap, one chunk): the epilogue is the limit -> 16 epilogue warps (V2CE_KDM_EW16=0: 8)
-  static const bool ew16 = !(getenv("V2CE_KDM_EW16") && atoi(getenv("V2CE_KDM_EW16")) == 0);
+  // V2CE_KDM_EW16=1: 16 epilogue warps for the launches with few MMAs per slice (<= V2CE_KDM_EW16_MAXC channels, one
+  // chunk).  Measured on one box (profiles/layer_times_r2_h_*.txt) and left OFF: the head and decoders.3.conv2 do not get
+  // faster (0.470 / 0.540 ms against 0.458 / 0.530) and the whole power-capped forward gets 3 % slower (9.40 vs 9.07 ms).
+  static const bool ew16 = getenv("V2CE_KDM_EW16") && atoi(getenv("V2CE_KDM_EW16")) != 0;
   static const int ew16_maxc = getenv("V2CE_KDM_EW16_MAXC") ? atoi(getenv("V2CE_KDM_EW16_MAXC")) : 32;
   if (t16 && ew16 && a.ncc0 + a.ncc1 == 1 && a.real0 <= ew16_maxc) return launch_kdm_one<false, 16, 1, 16>(tm0, tm1, no_pm, b, none, smem_bytes, s);
   if (t16) return launch_kdm_one<false, 16, 1>(tm0, tm1, no_pm, b, none, smem_bytes, s);
