@@ -218,8 +218,18 @@ class Runner:
         self.gather_bufs = [None, None]           # rank 0: merged shards of alternate steps
         self.gathers = 0
         self.ring_note = None
+        self.window, self.gather_note = None, None
         if world > 1:
             from v2ce_toolbox_b200 import dist as vdist
+            if os.environ.get('V2CE_BENCH_GATHER', 'p2p') == 'p2p':
+                try:
+                    # merged shards of alternate steps live in two buffers on rank 0 that every rank maps (CUDA IPC)
+                    self.window = vdist.PeerWindow(world * SHARD_CAP, buffers=2, device=device)
+                    self.gather_note = 'copy-engine pushes into a peer window on rank 0 (dist.PeerWindow, CUDA IPC over NVLink)'
+                except Exception as e:                 # noqa: BLE001 -- raised on every rank alike
+                    self.gather_note = f'NCCL point-to-point gather (dist.gather_event_shards; no peer window: {e})'
+            else:
+                self.gather_note = 'NCCL point-to-point gather to rank 0 (dist.gather_event_shards)'
             try:
                 # merged events of one step: ~180 k events per pair x 64 pairs x 13 B = 150 MB per rank; one slot
                 # per runner slot
@@ -234,6 +244,17 @@ class Runner:
         from v2ce_toolbox_b200 import dist as vdist
         k = self.gathers & 1
         self.gathers += 1
+        if self.window is not None:
+            # counts over the host group, then ONE asynchronous copy per rank on the comm stream: no kernel at all.
+            # The merged buffer is complete on rank 0 once every rank's stream has drained (the barrier that closes
+            # the timed region; dist.gather_event_shards(window=...) is the blocking form).
+            counts = vdist.exchange_counts(t.total)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(t.packed)
+                self.window.push(k, t.events_dev, counts, vdist.EVENT_BYTES)
+                fin = torch.cuda.Event()
+                fin.record(self.comm_stream)
+            return fin
         with torch.cuda.stream(self.comm_stream):
             # its own stream: the post stream already holds stage A of the next batch, which waits for the next UNet.
             # Nothing here waits on the device: the counts travel over the host-side gloo group, the shards as
@@ -279,6 +300,25 @@ def check_sharded_parity(device, rank, world):
         dist.broadcast(ok, src=0)
         if int(ok.item()) != 1:
             raise AssertionError(f'sharded_parity: {name} differs from the single-process stream at {world} ranks')
+    # the per-step merge `value` times: copy-engine pushes into a peer window == the NCCL point-to-point gather
+    try:
+        win = vdist.PeerWindow(1 << 20, buffers=1, device=device)
+    except Exception as e:                             # noqa: BLE001 -- raised on every rank alike
+        out['peer_window'] = {'available': False, 'why': str(e)[:200]}
+        return out
+    ok = torch.ones(1, dtype=torch.int64, device=device)
+    for step, n in enumerate([3000 + 11 * rank, 0 if rank == 0 else 7, 0]):
+        g = torch.Generator().manual_seed(1000 * step + rank)
+        shard = torch.randint(0, 256, (n * 13 + 16,), dtype=torch.uint8, generator=g).to(device)
+        a, _ = vdist.gather_event_shards(shard, n)
+        b, counts = vdist.gather_event_shards(shard, n, window=win)
+        if rank == 0 and not (b.numel() == sum(counts) * 13 and torch.equal(a, b)):
+            ok[0] = 0
+    win.close()
+    dist.broadcast(ok, src=0)
+    if int(ok.item()) != 1:
+        raise AssertionError(f'sharded_parity: peer-window merge differs from the NCCL gather at {world} ranks')
+    out['peer_window'] = {'available': True, 'equal': True}
     return out
 
 
@@ -387,8 +427,8 @@ def run_ours(args, rank, world, local_rank):
                    'pipeline': 'event frames + LDATI of step i run on a second stream under the UNet of step i+1',
                    'e2e_input': 'uint8 gray frame windows (4 x 17 x 260 x 346) in pinned host memory; pre-processing '
                                 'fused into the head conv; events + preview frames copied back to pinned host memory',
-                   'multi_gpu': 'windows sharded per rank; value: NCCL gather of event shards to rank 0 '
-                                '(dist.gather_event_shards); e2e: ' + (r.ring_note or 'n/a')},
+                   'multi_gpu': 'windows sharded per rank; value: ' + (r.gather_note or 'n/a') + '; e2e: ' +
+                                (r.ring_note or 'n/a')},
         'e2e': {'value': e2e, 'unit': 'frame-pairs/s', 'h2d_bytes_per_step': st_e2e['h2d'],
                 'd2h_bytes_per_step': st_e2e['d2h'], 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
@@ -414,6 +454,8 @@ def run_ours(args, rank, world, local_rank):
         line['sharded_parity_cases'] = parity
     if r.host_runner.host_sink is not None:
         r.host_runner.host_sink.close()
+    if r.window is not None:
+        r.window.close()
     del r.dev_runner, r.host_runner
     free_device_memory()
 

@@ -254,6 +254,23 @@ int v2ce_model_layer_times(v2ce_model* m, int32_t cap, float* ms_out, char* name
 /* Tuning / bring-up options of a model handle: "desc_mode", "layer_timing". */
 int v2ce_model_set_option(v2ce_model* m, const char* key, int64_t value);
 
+/* ------------------------------------------------------------------------------------------
+ * Peer windows -- the shard merge of the multi-GPU clip driver (v2ce_toolbox_b200/dist.py; the reference is
+ * single-process: this replaces the concatenation of v2ce.py:226 across ranks).  One process per GPU; the
+ * destination rank allocates a window, ships its 64-byte handle to the other ranks (any host channel), and every
+ * rank copies its shard straight into place with the copy engines over NVLink: no SM, no collective kernel
+ * competing with the persistent conv CTAs.
+ *   v2ce_peer_window_alloc : cudaMalloc on the current device + cudaIpcGetMemHandle
+ *   v2ce_peer_window_open  : map another process's window (peer access enabled lazily); _close unmaps it
+ *   v2ce_peer_copy_async   : cudaMemcpyAsync(dst, src, bytes) on `stream`; dst / src may be opened windows
+ * ------------------------------------------------------------------------------------------ */
+#define V2CE_PEER_HANDLE_BYTES 64
+int v2ce_peer_window_alloc(size_t bytes, void** window_dev, uint8_t handle_out[V2CE_PEER_HANDLE_BYTES]);
+int v2ce_peer_window_free(void* window_dev);
+int v2ce_peer_window_open(const uint8_t handle[V2CE_PEER_HANDLE_BYTES], void** window_dev);
+int v2ce_peer_window_close(void* window_dev);
+int v2ce_peer_copy_async(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

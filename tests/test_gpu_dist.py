@@ -116,3 +116,47 @@ def test_sharded_preview_equals_single_process(case, world, tmp_path):
     assert float(np.load(tmp_path / f'{case}_ub.npy')) == res.ef_upper_bound
     assert np.array_equal(np.load(tmp_path / f'{case}_frames.npy'), res.ef_frames)
     assert np.array_equal(np.load(tmp_path / f'{case}_events.npy').view(np.uint8), res.event_stream.view(np.uint8))
+
+
+def _window_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from v2ce_toolbox_b200 import dist as vdist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    vdist.init_process_group('nccl', device=dev, rank=rank, world_size=world)
+    try:
+        win = vdist.PeerWindow(4 << 20, buffers=2, device=dev)
+        for step, n in enumerate([1000 + 37 * rank, 0 if rank == 0 else 5, 50000 - 9 * rank, 0]):
+            g = torch.Generator().manual_seed(100 * step + rank)
+            shard = torch.randint(0, 256, (n * 13 + 64,), dtype=torch.uint8, generator=g).to(dev)
+            via_nccl, counts = vdist.gather_event_shards(shard, n)
+            via_win, counts2 = vdist.gather_event_shards(shard, n, window=win, slot=step & 1)
+            assert counts == counts2
+            if rank == 0:
+                assert via_win.numel() == sum(counts) * 13
+                assert torch.equal(via_win, via_nccl), step
+                np.save(os.path.join(out_dir, f'win{step}.npy'), via_win.cpu().numpy())
+            else:
+                assert via_win is None
+        win.close()
+    finally:
+        vdist.close_host_group()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [1, 2])
+def test_peer_window_gather_equals_nccl_gather(world, tmp_path):
+    """dist.PeerWindow (CUDA IPC window on rank 0, one copy-engine push per rank) merges ragged shards -- including
+    empty ones -- exactly like the NCCL point-to-point gather; two alternating buffers."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
+    import torch.multiprocessing as mp
+    mp.spawn(_window_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for step, n in enumerate([1000, 0, 50000, 0]):
+        want = []
+        for rank in range(world):
+            k = [1000 + 37 * rank, 0 if rank == 0 else 5, 50000 - 9 * rank, 0][step]
+            g = torch.Generator().manual_seed(100 * step + rank)
+            want.append(torch.randint(0, 256, (k * 13 + 64,), dtype=torch.uint8, generator=g)[:k * 13].numpy())
+        assert np.array_equal(np.load(tmp_path / f'win{step}.npy'), np.concatenate(want))

@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(128 + 32 * EW) conv_halo_kdm_kernel(const __gr
     const uint32_t px16 = (uint32_t)a.a_row16;      // one patch pixel in descriptor units (16 B): 8, or 2 for the head's 32-byte rows
     const uint32_t pw8 = (uint32_t)a.PW * px16;     // one patch row of pixels
     const uint32_t a_hi = a.a_desc_hi;
+    const uint32_t tap_mask = (uint32_t)a.tap_mask;
     const uint32_t idesc32 = make_idesc(BN);
     int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -331,9 +332,12 @@ __global__ void __launch_bounds__(128 + 32 * EW) conv_halo_kdm_kernel(const __gr
           // KS = K=16 steps per tap as a compile-time constant: the MMA warp is what these kernels wait for (one warp
           // issues ~13 uniform-datapath instructions per tcgen05.mma at ~6.6 cycles each = 86 cycles against 56 on the
           // tensor pipe, profiles/ncu_kdm_r2_c.txt), and a per-step `k < ks` test was three of them.
-          auto issue_tap = [&](auto KS_, const int tap, const uint32_t a_t, const bool lead) {
+          // EDGE = this input slice may be the first / last user of the chunk's weight tiles (waits for their arrival,
+          // releases them); the slices in between carry neither test: two uniform compares and two branches per tap.
+          auto issue_tap = [&](auto KS_, auto EDGE_, const int tap, const uint32_t a_t, const bool lead) {
             constexpr int KS = decltype(KS_)::value;
-            if (first_z && w_new) {
+            constexpr bool EDGE = decltype(EDGE_)::value != 0;
+            if (EDGE && first_z && w_new) {
               mbar_wait(w_full(tap), pw, a.error_flag);
               tcgen05_fence_after();
             }
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(128 + 32 * EW) conv_halo_kdm_kernel(const __gr
             }
             if (SHORT && tap == 4 && z >= tc.d0 && z < tc.d0 + T) {
               // shortcut conv of output slice z: centre tap of input slice z times the 1x1x1 weights
-              if ((first_z || z == tc.d0) && w_new) {           // first use of the shortcut tile in this chunk
+              if (EDGE && (first_z || z == tc.d0) && w_new) {   // first use of the shortcut tile in this chunk
                 mbar_wait(w_full(9), pw, a.error_flag);
                 tcgen05_fence_after();
               }
@@ -365,10 +369,11 @@ __global__ void __launch_bounds__(128 + 32 * EW) conv_halo_kdm_kernel(const __gr
               for (int k = 0; k < KS; ++k)
                 tcgen05_mma_bf16_lo2(scol, a_t + 2 * k, bs_lo + 2 * k, idesc32, (cc != 0 || k != 0) ? 1u : 0u, a_hi);
             }
-            if (last_z && w_release) tcgen05_commit_elect(w_empty(tap));     // last use of this generation's tap tile
+            if (EDGE && last_z && w_release) tcgen05_commit_elect(w_empty(tap));   // last use of this generation's tap tile
           };
           // all taps of one input slice (one patch, or the four parity patches of the stride-2 variant)
-          auto issue_slice = [&](auto KS_) {
+          auto issue_slice = [&](auto KS_, auto EDGE_) {
+            constexpr int KS = decltype(KS_)::value;
             if (S == 1) {
               mbar_wait(a_full(sa), (uint32_t)pa, a.error_flag);
               tcgen05_fence_after();
@@ -378,8 +383,8 @@ __global__ void __launch_bounds__(128 + 32 * EW) conv_halo_kdm_kernel(const __gr
               const uint32_t a_lo = smem_desc_lo(a_base + (uint32_t)sa * a.a_stage_bytes);
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap)
-                if ((a.tap_mask >> tap) & 1)
-                  issue_tap(KS_, tap, a_lo + (uint32_t)(tap / 3) * pw8 + (uint32_t)(tap % 3) * px16, tap == 0);
+                if (KS > 1 || ((tap_mask >> tap) & 1))          // only the head (one K step per tap) masks taps
+                  issue_tap(KS_, EDGE_, tap, a_lo + (uint32_t)(tap / 3) * pw8 + (uint32_t)(tap % 3) * px16, tap == 0);
               tcgen05_commit_elect(a_empty(sa));
               if (++sa == a.SA) { sa = 0; pa ^= 1; }
             } else {
@@ -389,28 +394,36 @@ __global__ void __launch_bounds__(128 + 32 * EW) conv_halo_kdm_kernel(const __gr
                 tcgen05_fence_after();
                 const uint32_t a_lo = smem_desc_lo(a_base + (uint32_t)sa * a.a_stage_bytes);
                 if (q == 0) {
-                  issue_tap(KS_, 4, a_lo, true);
+                  issue_tap(KS_, EDGE_, 4, a_lo, true);
                 } else if (q == 1) {
-                  issue_tap(KS_, 3, a_lo, false);
-                  issue_tap(KS_, 5, a_lo + px16, false);
+                  issue_tap(KS_, EDGE_, 3, a_lo, false);
+                  issue_tap(KS_, EDGE_, 5, a_lo + px16, false);
                 } else if (q == 2) {
-                  issue_tap(KS_, 1, a_lo, false);
-                  issue_tap(KS_, 7, a_lo + pw8, false);
+                  issue_tap(KS_, EDGE_, 1, a_lo, false);
+                  issue_tap(KS_, EDGE_, 7, a_lo + pw8, false);
                 } else {
-                  issue_tap(KS_, 0, a_lo, false);
-                  issue_tap(KS_, 2, a_lo + px16, false);
-                  issue_tap(KS_, 6, a_lo + pw8, false);
-                  issue_tap(KS_, 8, a_lo + pw8 + px16, false);
+                  issue_tap(KS_, EDGE_, 0, a_lo, false);
+                  issue_tap(KS_, EDGE_, 2, a_lo + px16, false);
+                  issue_tap(KS_, EDGE_, 6, a_lo + pw8, false);
+                  issue_tap(KS_, EDGE_, 8, a_lo + pw8 + px16, false);
                 }
                 tcgen05_commit_elect(a_empty(sa));
                 if (++sa == a.SA) { sa = 0; pa ^= 1; }
               }
             }
           };
-          if (ks == 4) issue_slice(KdmInt<4>{});
-          else if (ks == 2) issue_slice(KdmInt<2>{});
-          else if (ks == 1) issue_slice(KdmInt<1>{});
-          else issue_slice(KdmInt<3>{});
+          const bool edge = first_z || last_z || (SHORT && z == tc.d0);
+          if (edge) {
+            if (ks == 4) issue_slice(KdmInt<4>{}, KdmInt<1>{});
+            else if (ks == 2) issue_slice(KdmInt<2>{}, KdmInt<1>{});
+            else if (ks == 1) issue_slice(KdmInt<1>{}, KdmInt<1>{});
+            else issue_slice(KdmInt<3>{}, KdmInt<1>{});
+          } else {
+            if (ks == 4) issue_slice(KdmInt<4>{}, KdmInt<0>{});
+            else if (ks == 2) issue_slice(KdmInt<2>{}, KdmInt<0>{});
+            else if (ks == 1) issue_slice(KdmInt<1>{}, KdmInt<0>{});
+            else issue_slice(KdmInt<3>{}, KdmInt<0>{});
+          }
           if (SHORT && last_z && w_release) tcgen05_commit_elect(w_empty(9));
           if (last_cc) {
             // output slice z-1 has received its last contribution; at the end of the depth range so has slice z

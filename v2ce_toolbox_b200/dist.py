@@ -123,13 +123,108 @@ def _gather_exact(flat, counts, unit, group, dst, out):
     return out[:total]
 
 
-def gather_event_shards(events_u8, n_events, group=None, dst=0, out=None):
+def gather_event_shards(events_u8, n_events, group=None, dst=0, out=None, window=None, slot=0):
     """events_u8: 1-D uint8 tensor holding n_events*13 bytes (device for NCCL, CPU for gloo).
     Returns on `dst` the concatenation of all shards in rank order (a uint8 tensor; a view of `out` when that
     preallocated buffer is large enough), None elsewhere, and the per-rank event counts everywhere.
-    Ranks own contiguous, increasing frame ranges, so concatenation by rank IS the time-ordered merge."""
+    Ranks own contiguous, increasing frame ranges, so concatenation by rank IS the time-ordered merge.
+    window: a PeerWindow -- the shards are then written into its buffer `slot` by the copy engines (no NCCL kernel) and
+    the call returns once every rank's copy has landed."""
     counts = exchange_counts(n_events, group, events_u8.device)
+    if window is not None:
+        window.push(slot, events_u8, counts, EVENT_BYTES)
+        window.fence()
+        return (window.view(slot, sum(counts) * EVENT_BYTES) if window.rank == window.dst else None), counts
     return _gather_exact(events_u8, counts, EVENT_BYTES, group, dst, out), counts
+
+
+class _DeviceBytes:
+    """`nbytes` of device memory at `ptr` for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {'shape': (int(nbytes),), 'typestr': '|u1', 'data': (int(ptr), False),
+                                         'version': 3, 'strides': None}
+
+
+class PeerWindow:
+    """Gather destination on rank `dst` that every rank of the node writes directly (`buffers` buffers of `nbytes`).
+    `dst` allocates it (v2ce_peer_window_alloc), the 64-byte CUDA IPC handles travel over the host group, the other
+    ranks map it (v2ce_peer_window_open), and push() is one cudaMemcpyAsync per rank -- the copy engines move the shard
+    over NVLink into its place in the merged stream.  Why not NCCL here: the conv kernels are persistent CTAs that fill
+    every SM's shared memory, so an NCCL send/recv kernel both waits for a gap between two of them and then holds SMs
+    the next conv kernel's CTAs need (forward 9.2 -> 11.0 ms inside the 8-GPU step, profiles/bench_r2_8gpu_b.json); a
+    DMA copy needs no SM.  Single node only."""
+
+    def __init__(self, nbytes, buffers=1, dst=0, group=None, device=None):
+        from . import _lib
+        import ctypes
+        self._lib, self._ct = _lib, ctypes
+        lib = _lib.load()
+        self.world, self.rank, self.dst = dist.get_world_size(group), dist.get_rank(group), dst
+        self.group = _host_group[0] if (group is None and _host_group[0] is not None) else group
+        self.nbytes = int(nbytes)
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.ptrs, self._views = [], []
+        err = None
+        with torch.cuda.device(self.device):
+            for _ in range(buffers):
+                box, p = [None], ctypes.c_void_p()
+                if self.rank == dst and err is None:
+                    h = (ctypes.c_uint8 * 64)()
+                    if lib.v2ce_peer_window_alloc(self.nbytes, ctypes.byref(p), h) == 0:
+                        box[0] = bytes(h)
+                        self._views.append(torch.as_tensor(_DeviceBytes(p.value, self.nbytes), device=self.device))
+                    else:
+                        err = lib.v2ce_last_error().decode()
+                dist.broadcast_object_list(box, src=dst, group=self.group)
+                if self.rank != dst and err is None:
+                    if box[0] is None:
+                        err = 'the destination rank could not allocate the window'
+                    elif lib.v2ce_peer_window_open((ctypes.c_uint8 * 64).from_buffer_copy(box[0]), ctypes.byref(p)) != 0:
+                        err = lib.v2ce_last_error().decode()
+                if err is None:
+                    self.ptrs.append(int(p.value))
+        # every rank learns whether every rank has the window: a one-sided failure must not leave the others waiting
+        every = [None] * self.world
+        dist.all_gather_object(every, err, group=self.group)
+        if any(e is not None for e in every):
+            self._release()
+            raise _lib.V2ceError('peer window unavailable: ' + '; '.join(f'rank {r}: {e}' for r, e in enumerate(every) if e))
+
+    def push(self, slot, flat, counts, unit=1):
+        """Enqueue, on the current stream, the copy of this rank's `flat[:counts[rank]*unit]` to its place in buffer
+        `slot` (rank-ordered, exact lengths).  Nothing waits; fence() (or any later host barrier behind a stream
+        synchronize on every rank) makes the merged buffer complete on `dst`."""
+        total = sum(counts) * unit
+        if total > self.nbytes:
+            raise ValueError(f'peer window too small: {total} > {self.nbytes} bytes')
+        off, n = sum(counts[:self.rank]) * unit, counts[self.rank] * unit
+        if n:
+            flat = self._lib.require_cuda(flat, 'shard')
+            self._lib.check(self._lib.load().v2ce_peer_copy_async(
+                self._ct.c_void_p(self.ptrs[slot] + off), self._ct.c_void_p(flat.data_ptr()), n,
+                self._lib.stream_ptr()))
+
+    def fence(self):
+        torch.cuda.current_stream(self.device).synchronize()
+        dist.barrier(group=self.group)
+
+    def view(self, slot, nbytes=None):
+        """dst only: the first `nbytes` of buffer `slot` as a uint8 device tensor."""
+        v = self._views[slot]
+        return v if nbytes is None else v[:nbytes]
+
+    def _release(self):
+        lib = self._lib.load()
+        self._views = []
+        for p in self.ptrs:
+            (lib.v2ce_peer_window_free if self.rank == self.dst else lib.v2ce_peer_window_close)(self._ct.c_void_p(p))
+        self.ptrs = []
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)               # nobody is still copying into a buffer that is about to go
+        self._release()
 
 
 def gather_row_shards(rows, group=None, dst=0):
