@@ -409,6 +409,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     fwd_alone = float(np.mean([a.elapsed_time(b) for a, b in fwd_ms]))
     clocks = sampler.stop() if rank == 0 else None
+    link = host_link_probe(device) if rank == 0 else None
 
     pairs_per_step = r.n_pairs * world
     value = pairs_per_step * args.steps / (ms_dev / 1e3)
@@ -430,7 +431,7 @@ def run_ours(args, rank, world, local_rank):
                    'multi_gpu': 'windows sharded per rank; value: ' + (r.gather_note or 'n/a') + '; e2e: ' +
                                 (r.ring_note or 'n/a')},
         'e2e': {'value': e2e, 'unit': 'frame-pairs/s', 'h2d_bytes_per_step': st_e2e['h2d'],
-                'd2h_bytes_per_step': st_e2e['d2h'], 'ms_per_step': ms_e2e / args.steps},
+                'd2h_bytes_per_step': st_e2e['d2h'], 'ms_per_step': ms_e2e / args.steps, 'host_link': link},
         'gpu_launches': launches,
         'ldati_mevents_per_s': st_dev['events'] * world / (ms_dev / 1e3) / 1e6,
         'events_per_pair': st_dev['events'] / (r.n_pairs * args.steps),
@@ -500,6 +501,27 @@ def run_ours(args, rank, world, local_rank):
             guarded('cpu_baseline', cpu)
     if rank == 0:
         print(json.dumps(line), flush=True)
+
+
+def host_link_probe(device, mb=160, reps=5):
+    """Pinned D2H / H2D rate of this box with the GPU otherwise idle (160 MB = one step's results).  The e2e leg hides a
+    step's D2H behind the next step's network only while that copy is shorter than the network (9 ms: 18 GB/s); on a
+    box whose host side delivers less (shared PCIe switch / host memory: 11-12 GB/s measured on some) e2e is the
+    copy, not the GPU -- this record says which case the line was measured in."""
+    dev = torch.empty(mb << 20, dtype=torch.uint8, device=device)
+    host = torch.empty(mb << 20, dtype=torch.uint8, pin_memory=True)
+    out = {'mb': mb}
+    for key, (dst, src) in (('d2h_gbs', (host, dev)), ('h2d_gbs', (dev, host))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        out[key] = (mb << 20) * reps / (e0.elapsed_time(e1) / 1e3) / 1e9
+    return out
 
 
 def free_device_memory():
