@@ -756,6 +756,10 @@ def clips_record(device, rank, world, args):
                         res['monotone_frames'] = bool((np.diff(ts[::step]) >= -40000).all()) if len(ts) > 1 else True
                     del ev
                     free_device_memory()
+                # `events` is the count of the last run: the spectral-norm power iteration advances with every model call
+                # (reference semantics, spectral_norm.py) and the warm-up clip has one window per rank, so the last
+                # digits of the count differ from run to run and from N to N; sharded == single-process equality is
+                # checked on fresh models (sharded_parity, tests/test_gpu_dist.py)
                 res.update({'frames': n, 'pairs': n - 1, 'events': int(n_events), 'stream_bytes': int(n_events) * 13,
                             'source': [sp['h'], sp['w']], 'batch_size': sp['bs'], **{k: v for k, v in sp['kw'].items()}})
                 out[name] = res
