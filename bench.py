@@ -348,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
         computes."""
         br = r.host_runner if host_io else r.dev_runner
         src = r.units_pinned if host_io else r.units_dev
-        stats = {'events': 0, 'fwd': [], 'h2d': 0, 'd2h': 0}
+        stats = {'events': 0, 'fwd': [], 'gap': [], 'h2d': 0, 'd2h': 0, 'last_fwd_end': None}
         pending = []                               # gathers in flight (their buffers alternate: wait for the one before last)
 
         def collect(t, timed):
@@ -362,6 +362,9 @@ def run_ours(args, rank, world, local_rank):
                 stats['h2d'], stats['d2h'] = t.h2d_bytes, t.d2h_bytes
                 if t.fwd_events is not None:
                     stats['fwd'].append(t.fwd_events[0].elapsed_time(t.fwd_events[1]))
+                    if stats['last_fwd_end'] is not None:       # main-stream time between two networks
+                        stats['gap'].append(stats['last_fwd_end'].elapsed_time(t.fwd_events[0]))
+                    stats['last_fwd_end'] = t.fwd_events[1]
 
         def run(n, timed):
             prev = None
@@ -441,6 +444,7 @@ def run_ours(args, rank, world, local_rank):
                      'forward_ms': fwd, 'forward_ms_in_step': fwd_in_step,
                      'frac_in_step': GFLOP_PER_WINDOW * BATCH / fwd_in_step / pk['tf'],
                      'forward_share_of_step': fwd / (ms_dev / args.steps),
+                     'forward_gap_ms_in_step': float(np.mean(st_dev['gap'])) if st_dev['gap'] else None,
                      'note': 'forward_ms: CUDA events around the network run alone over the same K steps; '
                              'forward_ms_in_step: the same events inside the timed steps, where the previous '
                              'batch\'s event-frame / LDATI kernels share the SMs.  peak = sustained cuBLAS bf16 '

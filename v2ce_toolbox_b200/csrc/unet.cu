@@ -706,6 +706,17 @@ static int pack_layer(v2ce_model* m, int li, const float* w_dev, cudaStream_t s)
   const int taps = L.k * L.k * L.k;
   const int cin_pad = c.pad0 + c.pad1;
   dl.bn_tile = conv::pick_bn(L.cout);
+  if (c.kind == 2 && dl.bn_tile == 256) {
+    // N tile of the 256- / 512-channel halo layers.  256-channel layers run as two N = 128 tiles: at 33 x 44 x 16 x 4
+    // an N = 256 launch has 448 items = 3.03 waves of 148 CTAs (a quarter of the last wave's time is 4 items), the
+    // N = 128 launch has 896 half-size items = 6.05 waves (3.5 full-item times) and a double-buffered accumulator, so
+    // the epilogue overlaps the next item: encoders.2.conv2 0.326 -> 0.268 ms, decoders.0.conv1 0.823 -> 0.753,
+    // decoders.0.conv2 0.381 -> 0.278 (profiles/layer_times_r2_l_*.txt).  512-channel layers (256 items = 1.73 waves
+    // either way) gain nothing and stay at 256.  V2CE_BN_COUT256 / V2CE_BN_COUT512 = 128 | 256 override.
+    const char* e = getenv(L.cout == 256 ? "V2CE_BN_COUT256" : "V2CE_BN_COUT512");
+    const int want = e ? atoi(e) : (L.cout == 256 ? 128 : 256);
+    if (want == 128) dl.bn_tile = 128;
+  }
   if (c.real0 + c.real1 != L.cin) return set_error(V2CE_ERR_STATE, "layer %s: channel split mismatch", L.name);
   if (c.kind == 2) {
     const size_t n = (size_t)L.cout * 27 * cin_pad;
