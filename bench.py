@@ -56,8 +56,8 @@ SHARD_CAP = 200 << 20                  # bytes reserved per rank and step for th
 EF_BYTES_PER_PAIR = 8_906_040          # 80 B/pixel read + 8 sum write + 8 re-read + 3 uint8 write
 METRIC = '346x260 frame-pairs/s (center, 321 frames, batch 4, voxel+LDATI+event-frame)'
 # dram__bytes_read.sum + dram__bytes_write.sum of one V2ce3d forward (batch 4), summed over its launches from the
-# ncu capture summarised in profiles/forward_traffic_r1_b.txt
-TRAFFIC_BYTES = 13.03e9        # read 8.98 GB + write 4.05 GB (L2: 59.1 GB)
+# ncu capture summarised in profiles/forward_traffic_r2.txt (tools/ncu_traffic.py)
+TRAFFIC_BYTES = 13.24e9        # read 9.17 GB + write 4.06 GB (L2: 59.2 GB): profiles/forward_traffic_r2.txt
 KERNEL_NOTE = ('V2ce3d forward (26 launches + 4 spectral-norm launches on a side stream): conv_halo_kdm_kernel x11 '
                '(head, stride-2 encoder convs and decoder convs with fused shortcuts, N<=64 convs), conv_halo_kernel x10, '
                'conv_igemm_kernel x4 (remaining 1x1x1 shortcuts, side stream), head prep')
