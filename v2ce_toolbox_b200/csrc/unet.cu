@@ -270,53 +270,93 @@ struct SnDesc {
   float* v;         // K
   float* t;         // K scratch
   float* s;         // rows scratch
-  float* partial;   // ceil(K/256) partial sums of t^2
+  float* partial;   // ceil(K/32) partial sums of t^2
   int rows, K;
 };
 
+// Every sum below has a fixed order (no atomics): a rank that replays the steps of calls it does not own
+// (v2ce_model_sn_advance) must reach bit-identical u, v and sigma.
+// t = W^T u: one block per 32 columns, its 8 warps take the rows r = w, w+8, ... with eight loads in flight per lane
+// (the first version walked all rows of a column in one thread: 151 MB of weights at 1.1 TB/s, 135 us per step, which
+// is what a sharded clip's replay of the other ranks' calls costs per call).
+constexpr int kSnCols = 32;
 __global__ void __launch_bounds__(256) sn_wtu_kernel(const SnDesc* __restrict__ descs) {
   const SnDesc d = descs[blockIdx.y];
-  const int k = blockIdx.x * 256 + threadIdx.x;
-  if (blockIdx.x * 256 >= d.K) return;
+  if (blockIdx.x * kSnCols >= d.K) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int k = blockIdx.x * kSnCols + lane;
+  __shared__ float part[8][kSnCols];
   float acc = 0.f;
   if (k < d.K) {
-    for (int r = 0; r < d.rows; ++r) acc = fmaf(__ldg(d.W + (size_t)r * d.K + k), __ldg(d.u + r), acc);
-    d.t[k] = acc;
-  }
-  float sq = (k < d.K) ? acc * acc : 0.f;
-  __shared__ float red[8];
+    const float* col = d.W + k;
+    int r = w;
+    for (; r + 56 < d.rows; r += 64) {
+      float x[8], uu[8];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+      for (int j = 0; j < 8; ++j) { x[j] = __ldg(col + (size_t)(r + 8 * j) * d.K); uu[j] = __ldg(d.u + r + 8 * j); }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(x[j], uu[j], acc);
+    }
+    for (; r < d.rows; r += 8) acc = fmaf(__ldg(col + (size_t)r * d.K), __ldg(d.u + r), acc);
+  }
+  part[w][lane] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w];
-    d.partial[blockIdx.x] = s;
+  if (w == 0) {
+    float tk = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tk += part[j][lane];
+    if (k < d.K) d.t[k] = tk;
+    float sq = (k < d.K) ? tk * tk : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) d.partial[blockIdx.x] = sq;
   }
 }
 
 __global__ void __launch_bounds__(256) sn_norm_v_kernel(const SnDesc* __restrict__ descs) {
   const SnDesc d = descs[blockIdx.x];
-  __shared__ float norm_s;
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    const int nb = (d.K + 255) / 256;
-    for (int i = 0; i < nb; ++i) s += d.partial[i];
-    norm_s = sqrtf(s) + 1e-12f;
-  }
+  __shared__ float red[256];
+  const int nb = (d.K + kSnCols - 1) / kSnCols;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nb; i += 256) s += d.partial[i];
+  red[threadIdx.x] = s;
   __syncthreads();
-  const float nrm = norm_s;
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float nrm = sqrtf(red[0]) + 1e-12f;
   for (int k = threadIdx.x; k < d.K; k += 256) d.v[k] = d.t[k] / nrm;
 }
 
+// s = W v: one warp per row, 16-byte loads (K = Cin * 27 with Cin a multiple of 4), two of them in flight per lane
 __global__ void __launch_bounds__(256) sn_wv_kernel(const SnDesc* __restrict__ descs) {
   const SnDesc d = descs[blockIdx.y];
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= d.rows) return;
   const int lane = threadIdx.x & 31;
   float acc = 0.f;
-  for (int k = lane; k < d.K; k += 32) acc = fmaf(__ldg(d.W + (size_t)row * d.K + k), d.v[k], acc);
+  if ((d.K & 3) == 0) {
+    const float4* wr = reinterpret_cast<const float4*>(d.W + (size_t)row * d.K);
+    const float4* vv = reinterpret_cast<const float4*>(d.v);
+    const int n4 = d.K >> 2;
+    float a0 = 0.f, a1 = 0.f;
+    int q = lane;
+    for (; q + 32 < n4; q += 64) {
+      const float4 x0 = __ldg(wr + q), x1 = __ldg(wr + q + 32);
+      const float4 y0 = vv[q], y1 = vv[q + 32];
+      a0 = fmaf(x0.x, y0.x, a0); a0 = fmaf(x0.y, y0.y, a0); a0 = fmaf(x0.z, y0.z, a0); a0 = fmaf(x0.w, y0.w, a0);
+      a1 = fmaf(x1.x, y1.x, a1); a1 = fmaf(x1.y, y1.y, a1); a1 = fmaf(x1.z, y1.z, a1); a1 = fmaf(x1.w, y1.w, a1);
+    }
+    if (q < n4) {
+      const float4 x0 = __ldg(wr + q);
+      const float4 y0 = vv[q];
+      a0 = fmaf(x0.x, y0.x, a0); a0 = fmaf(x0.y, y0.y, a0); a0 = fmaf(x0.z, y0.z, a0); a0 = fmaf(x0.w, y0.w, a0);
+    }
+    acc = a0 + a1;
+  } else {
+    for (int k = lane; k < d.K; k += 32) acc = fmaf(__ldg(d.W + (size_t)row * d.K + k), d.v[k], acc);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) d.s[row] = acc;
@@ -461,7 +501,7 @@ static bool known_name(const std::string& name) {
 }
 
 static int run_sn_step(v2ce_model* m, cudaStream_t s) {
-  dim3 g1((m->max_k + 255) / 256, kNumSn);
+  dim3 g1((m->max_k + kSnCols - 1) / kSnCols, kNumSn);
   sn_wtu_kernel<<<g1, 256, 0, s>>>(m->sn_descs_dev);
   V2CE_LAUNCH_CHECK("sn_wtu_kernel");
   sn_norm_v_kernel<<<kNumSn, 256, 0, s>>>(m->sn_descs_dev);
@@ -883,7 +923,7 @@ extern "C" int v2ce_model_finalize(v2ce_model* m) {
       if (int e = upload(m, &d.v, *v)) return e;
       if (int e = dev_alloc(m, &d.t, (size_t)d.K)) return e;
       if (int e = dev_alloc(m, &d.s, (size_t)d.rows)) return e;
-      if (int e = dev_alloc(m, &d.partial, (size_t)(d.K + 255) / 256)) return e;
+      if (int e = dev_alloc(m, &d.partial, (size_t)(d.K + kSnCols - 1) / kSnCols)) return e;
       m->max_rows = m->max_rows > d.rows ? m->max_rows : d.rows;
       m->max_k = m->max_k > d.K ? m->max_k : d.K;
       ++sn_count;
