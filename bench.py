@@ -403,6 +403,9 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e, st_e2e, _ = timed_loop(True)
     # the network alone (no event-frame / LDATI kernels sharing the SMs): what the roofline fraction describes
     fwd_ms = []
+    for i in range(3):                          # untimed: the timed steps ran the network on the runner's own stream, so
+        r.model(r.units_dev[i % 5])             # this stream's allocator pool has no 460 MB output block yet
+    torch.cuda.synchronize()
     for i in range(args.steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
