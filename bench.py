@@ -277,7 +277,9 @@ def check_sharded_parity(device, rank, world):
     from v2ce_toolbox_b200 import dist as vdist, v2ce as drv
     cases = {'center': (16 * 2 * world + 9, 28, 36, 'center', 36, 28, 1),
              'center_b2': (16 * 4 * world + 1, 28, 36, 'center', 36, 28, 2),
-             'pano': (16 * (world + 1) + 8, 24, 80, 'pano', 32, 24, 1)}
+             'pano': (16 * (world + 1) + 8, 24, 80, 'pano', 32, 24, 1),
+             # one window, fewer batches than ranks: its three width tiles are shared among the ranks (dist.pano_tile_owner)
+             'pano_tiles': (17, 24, 80, 'pano', 32, 24, 1)}
     out = {}
     for name, (n_frames, h, w, infer_type, width, height, bs) in cases.items():
         frames = synth.make_video(n_frames, h, w, seed=5)

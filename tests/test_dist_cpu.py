@@ -124,3 +124,19 @@ def test_bind_to_gpu_numa_is_a_no_op_without_nvml_device():
     import torch
     if not torch.cuda.is_available():
         assert os.sched_getaffinity(0) == before
+
+
+def test_pano_tile_groups():
+    """dist.pano_tile_owner: fewer batches than ranks -> groups of world // n_batches ranks share a window's tiles; the
+    first member of a group reports the batch; ranks beyond the last group idle; otherwise the window split applies."""
+    from v2ce_toolbox_b200.dist import pano_tile_owner
+    assert pano_tile_owner(1, 2, 0) == (0, [0, 1], True)
+    assert pano_tile_owner(1, 2, 1) == (0, [0, 1], False)
+    assert pano_tile_owner(2, 8, 5) == (1, [4, 5, 6, 7], False)
+    assert pano_tile_owner(3, 8, 4) == (2, [4, 5], True)
+    assert pano_tile_owner(3, 8, 7) == (None, [], False)
+    assert pano_tile_owner(5, 8, 0) is None and pano_tile_owner(8, 8, 3) is None and pano_tile_owner(0, 4, 0) is None
+    for n_batches, world in [(1, 2), (1, 8), (2, 8), (3, 8), (2, 4)]:
+        leaders = [r for r in range(world) if (pano_tile_owner(n_batches, world, r) or (None,))[0] is not None
+                   and pano_tile_owner(n_batches, world, r)[2]]
+        assert [pano_tile_owner(n_batches, world, r)[0] for r in leaders] == list(range(n_batches))

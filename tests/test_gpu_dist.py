@@ -32,6 +32,8 @@ CASES = {
     'center': (70, 28, 36, 'center', 36, 28, 1),           # 5 windows (last pulled back), ragged over 2 ranks
     'center_b2': (100, 28, 36, 'center', 36, 28, 2),
     'pano': (40, 24, 80, 'pano', 32, 24, 1),                # 3 width tiles per window, 3 windows
+    # fewer windows than ranks: the 3 tiles of the one window are shared between the ranks (dist.pano_tile_owner)
+    'pano_tiles': (17, 24, 80, 'pano', 32, 24, 1),
 }
 
 
@@ -99,7 +101,7 @@ def _preview_worker(rank, world, port, out_dir, case):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('case,world', [('center', 1), ('center', 2), ('pano', 2)])
+@pytest.mark.parametrize('case,world', [('center', 1), ('center', 2), ('pano', 2), ('pano_tiles', 2)])
 def test_sharded_preview_equals_single_process(case, world, tmp_path):
     """the event-frame preview of a sharded clip -- per-rank sums gathered to rank 0, ONE clip-global
     percentile -- is the single-process preview, byte for byte (world 1 runs the same code on one GPU)."""

@@ -404,6 +404,57 @@ def _preview_plane(frames_reader, kw):
     return height, int(probe.shape[-1] / probe.shape[-2] * height)       # pano: the resized frame's full width
 
 
+def pano_tile_owner(n_batches, world, rank):
+    """Tile-level sharding of a pano clip with fewer batches than ranks (north_star's "pano tiles" partition): ranks
+    form `n_batches` groups of g = world // n_batches; group b runs batch b, its members take the window's 346-px
+    tiles round robin and exchange the voxel tiles, and every member then holds the full-width voxels (LDATI needs
+    full-width frames).  Returns (batch index or None for an idle rank, member ranks, is_leader); None when the
+    window-level split applies (g < 2)."""
+    g = world // max(n_batches, 1)
+    if n_batches == 0 or g < 2:
+        return None
+    b = rank // g
+    if b >= n_batches:
+        return (None, [], False)
+    members = list(range(b * g, (b + 1) * g))
+    return (b, members, rank == members[0])
+
+
+def _pano_tiles_shared(members, rank):
+    """The pano_fn of a tile-sharing group (v2ce.stream_clip): each member runs the tiles j with members[j % g] == rank
+    at the call index the single-process schedule gives them (spectral-norm replay in between), sends them to the other
+    members point to point and stitches the full-width voxels exactly like v2ce._pano_device."""
+    from . import v2ce as drv
+
+    def fn(model, image_units, width=346):
+        tl = drv.pano_tiles(image_units.shape[-1], width)
+        g = len(members)
+        call0 = model.call_count()                         # every member enters the batch at the same call index
+        parts = [None] * len(tl)
+        for j, (a, b, keep) in enumerate(tl):
+            if members[j % g] == rank:
+                if call0 + j > model.call_count():
+                    model.sn_advance(call0 + j - model.call_count())
+                parts[j] = model(image_units[..., a:b].float().contiguous())
+        if call0 + len(tl) > model.call_count():
+            model.sn_advance(call0 + len(tl) - model.call_count())
+        B, L, _, H, _ = image_units.shape
+        ops = []
+        for j in range(len(tl)):
+            owner = members[j % g]
+            if owner == rank:
+                ops += [dist.P2POp(dist.isend, parts[j], r) for r in members if r != rank]
+            else:
+                parts[j] = torch.empty((B, L, 20, H, width), dtype=torch.float32, device=image_units.device)
+                ops.append(dist.P2POp(dist.irecv, parts[j], owner))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        parts = [p[..., -keep:] if keep != width else p for p, (a, b, keep) in zip(parts, tl)]
+        return torch.cat(parts, dim=-1) if len(parts) > 1 else parts[0]
+    return fn
+
+
 def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=16, batch_size=1, to_host=True,
                         preview=None, merge=None, **kw):
     """Run v2ce.stream_clip on this rank's contiguous share of the batches of a clip and gather the
@@ -432,6 +483,17 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
     # the single-process schedule continues the spectral-norm iteration from clip to clip: every rank enters a clip
     # at the same call index (`base`), replays the calls of the batches before its share and, when the clip is done,
     # the calls of the batches after it, so that all ranks leave at base + (calls of the whole clip)
+    # fewer batches than ranks: share the tiles of each window among a group of ranks instead (the voxel tiles are
+    # exchanged point to point; every member then runs the cheap post-network stages, the group leader reports them)
+    import os
+    split = pano_tile_owner(n_batches, world, rank) if (infer_type == 'pano' and tiles > 1 and dist.is_initialized() and
+                                                        os.environ.get('V2CE_PANO_TILE_SHARDING', '1') != '0') else None
+    pano_fn, reports = None, True
+    if split is not None:
+        b, members, reports = split
+        b0, b1 = (b, b + 1) if b is not None else (n_batches, n_batches)
+        if b is not None:
+            pano_fn = _pano_tiles_shared(members, rank)
     base = model.call_count()
     model.sn_advance(model_calls_before(b0, infer_type, tiles))
 
@@ -451,10 +513,10 @@ def stream_clip_sharded(model, frames_reader, frame_count, world, rank, seq_len=
     if shard.frame_count > 1:
         res = drv.stream_clip(model, vidcap=shard, seq_len=seq_len, batch_size=batch_size,
                               pair_base=shard.pair_base, device=dev, write_event_frames=False, schedule=shard.schedule,
-                              events_to_host=False, keep_event_frame_sums=preview is not None, **kw)
-        n = res.n_events
+                              events_to_host=False, keep_event_frame_sums=preview is not None, pano_fn=pano_fn, **kw)
+        n = res.n_events if reports else 0                 # tile sharing: only the group leader reports the batch
         ev = res.event_stream_dev if n else torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev)
-        sums = res.ef_sums_dev
+        sums = res.ef_sums_dev if reports else None
     else:
         ev, n = torch.zeros(EVENT_BYTES, dtype=torch.uint8, device=dev), 0
     model.sn_advance(base + model_calls_before(n_batches, infer_type, tiles) - model.call_count())

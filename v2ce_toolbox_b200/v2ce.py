@@ -323,13 +323,16 @@ def _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width
 def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_len=16, width=346, height=260,
                 batch_size=1, fps=30, ceil=10, upper_bound_percentile=98, keep_polarity=True,
                 write_event_frames=True, seed=0, pair_base=0, device=None, schedule=None, events_to_host=True,
-                device_resize=None, keep_event_frame_sums=False):
+                device_resize=None, keep_event_frame_sums=False, pano_fn=None):
     """Device-resident, pipelined version of v2ce.py:322-372 (runner.BatchRunner: the network of batch i+1 runs over
     the event frames + LDATI of batch i, results leave on a copy stream).  Returns ClipResult with the concatenated
     event stream (timestamps offset per frame, v2ce.py:365) and the uint8 BGR preview frames (clip-global percentile,
     as the reference computes it)."""
     from .runner import BatchRunner
     assert image_paths is not None or vidcap is not None
+    # pano_fn(model, image_units, width): replaces the serial tile loop of a pano batch (dist.py shares the tiles of a
+    # window among ranks when a clip has fewer batches than ranks)
+    pano = pano_fn if pano_fn is not None else _pano_device
     device = torch.device(device or 'cuda')
     frame_count = vidcap.frame_count if vidcap is not None else len(image_paths)
     # `schedule` = (window starts relative to this reader, mode): a rank's share of a longer clip (dist.py)
@@ -354,12 +357,12 @@ def stream_clip(model, image_paths=None, vidcap=None, infer_type='center', seq_l
         batches = _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, width)
     elif raw:
         from .preprocess import image_units_device
-        tile = _center_device if infer_type == 'center' else _pano_device
+        tile = _center_device if infer_type == 'center' else pano
         infer = lambda u8: tile(model, image_units_device(u8, height), width)        # noqa: E731
         batches = _window_batches_u8(image_paths, vidcap, seq_len, batch_size, schedule, None)
     else:
         infer = (lambda u: _center_device(model, u, width)) if infer_type == 'center' else \
-                (lambda u: _pano_device(model, u, width))
+                (lambda u: pano(model, u, width))
         batches = _batches(image_paths, vidcap, seq_len, height, batch_size, schedule)
     with torch.cuda.device(device):
         # the runner owns ~0.5 GB of pinned staging buffers whose allocation costs more than a short clip's compute:
